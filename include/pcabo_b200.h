@@ -1,0 +1,114 @@
+/*
+ * pcabo_b200.h -- C ABI of the B200-native PCA-BO hot path (libpcabo_b200.so).
+ *
+ * Drop-in boundary for the inner loop of IvanBanny/para-ortho-pca-bo. Every entry point replaces one
+ * Python-level operator seam of the reference (citations are relative to the reference repo root):
+ *
+ *   pcabo_weights_pca_fit   <- PCA_BO._calculate_weights                    Algorithms/BayesianOptimization/PCA_BO.py:316-341
+ *                              PCA_BO._transform_points_to_reduced_space   PCA_BO.py:343-408  (sklearn PCA().fit/.transform)
+ *   pcabo_inverse_map       <- PCA_BO._transform_point_to_original_space   PCA_BO.py:410-434  (+ the bounds test PCA_BO.py:248)
+ *   pcabo_gp_fit            <- PCA_BO._initialize_model                    PCA_BO.py:502-545  (SingleTaskGP + Normalize + Standardize,
+ *                              Vanilla_BO._initialise_model                Vanilla_BO.py:166-195; prediction caches of gpytorch)
+ *                              and the search box of optimize_acqf_and_get_observation, PCA_BO.py:558-573
+ *   pcabo_gp_mll            <- (north_star only; the reference never fits the GP)
+ *   pcabo_logei             <- LogExpectedImprovement(model, best_f, maximize)(X)   PCA_BO.py:199-203, class map :679-686
+ *   pcabo_argmax            <- torch.argmax over restarts / raw samples inside botorch.optimize_acqf, PCA_BO.py:607-614
+ *   pcabo_lbfgsb_logei      <- botorch gen_candidates_scipy (scipy L-BFGS-B, maxiter 200) inside optimize_acqf, PCA_BO.py:607-614
+ *   pcabo_ei_sweep          <- the raw-sample scoring pass of optimize_acqf scaled to 2^20..2^26 candidates (BASELINE config 4)
+ *
+ * Conventions
+ *   - All array arguments are DEVICE pointers to row-major FP64 (or int32) unless a name ends in _host.
+ *   - The batch dimension B (independent BO runs stepping in lock-step) is outermost. All runs of a batch share
+ *     n (points evaluated so far) and D; the reduced dimension k[b] differs per run.
+ *   - `ld_n` is the row capacity (leading dimension in points) of per-run arrays, ld_n >= n.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream). Calls are asynchronous.
+ *   - Return value: 0 on success, a negative PCABO_E_* code otherwise. No exceptions cross the ABI; the callee
+ *     allocates nothing that outlives the call.
+ */
+#ifndef PCABO_B200_H
+#define PCABO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCABO_ABI_VERSION 1
+
+#define PCABO_OK 0
+#define PCABO_E_INVALID (-1)      /* bad argument (null pointer, n < 2, ...) */
+#define PCABO_E_UNSUPPORTED (-2)  /* size outside what the kernels support (D > 104, n > 2048, k > 104) */
+#define PCABO_E_CUDA (-3)         /* a CUDA runtime call failed; see pcabo_last_cuda_error() */
+
+int pcabo_abi_version(void);
+const char *pcabo_error_string(int code);
+const char *pcabo_last_cuda_error(void);
+
+/* Fitted GP in eval mode (what botorch keeps inside SingleTaskGP + its prediction caches). */
+typedef struct pcabo_gp_model {
+  int B;            /* runs in the batch */
+  int n;            /* training points per run */
+  int kmax;         /* column capacity of per-run z arrays (= D) */
+  int ld_n;         /* row capacity */
+  int maximize;     /* LogExpectedImprovement(maximize=...) */
+  int pad_;
+  double lengthscale;       /* Matern-5/2 lengthscale (reference: softplus(0) = ln 2) */
+  const int *k;             /* [B] active dimensions per run */
+  const double *norm_off;   /* [B][kmax]  Normalize offset  (lo)        */
+  const double *norm_coef;  /* [B][kmax]  Normalize coefficient (hi-lo) */
+  const double *ZnT;        /* [B][kmax][ld_n] normalised training inputs, transposed */
+  const double *alpha;      /* [B][ld_n]  K^-1 y_s */
+  const double *W;          /* [B][ld_n][ld_n] L^-1, lower triangular, row-major */
+  const double *ymean;      /* [B] Standardize mean */
+  const double *ystd;       /* [B] Standardize std  */
+  const double *best_f;     /* [B] incumbent, already rounded to float32 as botorch stores it */
+} pcabo_gp_model;
+
+/* Rank weights + weighted PCA + projection, one CTA per run.
+ *   X      [B][ld_n][D]   evaluated points            f [B][ld_n] objective values
+ *   noise  [B][n][D]      the N(0,1e-8) matrix of PCA_BO.py:376 (host RNG replay)
+ *   logtab [>= n+1]       logtab[i] = numpy.log(i) (host table, keeps the weights bit-identical to numpy)
+ * outputs
+ *   w [B][ld_n], ranks [B][ld_n] (1 = best, ties by index), xbar [B][D] (data_mean), m2 [B][D] (pca.mean_),
+ *   V [B][D][D] (components_, rows, svd_flip'ed), lam [B][D] (explained_variance_), evr [B][D] (ratio),
+ *   k [B] (reduced_space_dim_num), Z [B][ld_n][D] (first k[b] columns valid, rest zero)                    */
+int pcabo_weights_pca_fit(int B, int n, int D, int ld_n,
+                          const double *X, const double *f, const double *noise, const double *logtab,
+                          double var_threshold, int n_components, int maximization,
+                          double *w, int *ranks, double *xbar, double *m2, double *V, double *lam, double *evr,
+                          int *k, double *Z, void *stream);
+
+/* x = z V_k + m2 + xbar and the bounds test. z [B][kmax=D], x [B][D], oob [B] (1 = outside [lo, hi]). */
+int pcabo_inverse_map(int B, int D, const double *z, const int *k, const double *V, const double *m2,
+                      const double *xbar, const double *lo, const double *hi, double *x, int *oob, void *stream);
+
+/* GP construction + caches.
+ *   Z [B][ld_n][kmax], k [B] (NULL: all kmax), f [B][ld_n]
+ *   mode 0 (PCA_BO): Normalize bounds [zmin-0.1r, zmax+0.1r]; search box [zmin-0.5r, zmax+0.5r], min width 0.1
+ *   mode 1 (Vanilla_BO): no input normalisation; search box = (fix_lo, fix_hi) [kmax]
+ * outputs
+ *   norm_off, norm_coef, box_lo, box_hi [B][kmax]; ymean, ystd [B]; ZnT [B][kmax][ld_n];
+ *   L [B][ld_n][ld_n] (Cholesky factor of K + noise I, lower), W [B][ld_n][ld_n] (L^-1), alpha [B][ld_n],
+ *   info [B] (0 ok, i > 0: non-positive pivot at row i -> caller should add jitter)                            */
+int pcabo_gp_fit(int B, int n, int kmax, int ld_n, int mode,
+                 const double *Z, const int *k, const double *f, const double *fix_lo, const double *fix_hi,
+                 double lengthscale, double noise,
+                 double *norm_off, double *norm_coef, double *box_lo, double *box_hi,
+                 double *ymean, double *ystd, double *ZnT, double *L, double *W, double *alpha, int *info,
+                 void *stream);
+
+/* Exact marginal log-likelihood of the standardised targets from the caches: mll [B]. ys = (f-ymean)/ystd. */
+int pcabo_gp_mll(int B, int n, int ld_n, const double *f, const double *ymean, const double *ystd,
+                 const double *L, const double *alpha, double *mll, void *stream);
+
+/* log-EI (and optionally its gradient, posterior mean and sigma) at npts raw-space points per run.
+ *   X [B][npts][kmax]; val [B][npts]; grad [B][npts][kmax] or NULL; mu, sigma [B][npts] or NULL.               */
+int pcabo_logei(const pcabo_gp_model *m, int npts, const double *X, double *val, double *grad,
+                double *mu, double *sigma, void *stream);
+
+/* Row-wise argmax with first-occurrence ties (torch.argmax): v [B][m] -> best_val [B], best_idx [B]. */
+int pcabo_argmax(int B, int m, const double *v, double *best_val, int *best_idx, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCABO_B200_H */

@@ -1,0 +1,467 @@
+// K3-K5: GP construction + prediction caches, batched over runs.
+//
+// Replaces PCA_BO._initialize_model (PCA_BO.py:502-545) / Vanilla_BO._initialise_model (Vanilla_BO.py:166-195),
+// i.e. botorch SingleTaskGP(train_z, train_obj, MaternKernel(2.5), Standardize(m=1), Normalize(d, bounds)) plus the
+// caches gpytorch builds on the first posterior call (K + sigma^2 I -> Cholesky -> alpha = K^-1 y_s, R = L^-T), and the
+// search box of PCA_BO.optimize_acqf_and_get_observation (PCA_BO.py:558-573). The GP is never fitted in the
+// reference: lengthscale and noise are the fixed prior values passed by the caller.
+//
+//   gp_prep_kernel   : per-dim min/max -> Normalize (0.1 pad) + search box (0.5 pad, min width 0.1); Standardize;
+//                      normalised inputs transposed (ZnT[c][i]) so later kernels read them coalesced.
+//   gp_kmat_kernel   : lower triangle of K = matern52(|zn_i - zn_j| / ell) + sigma^2 I, 64x64 tiles.
+//   gp_chol_kernel   : one CTA per run: blocked left-looking Cholesky (NB = 32, register-tiled FP64 panel GEMM,
+//                      diagonal blocks factored + inverted in shared memory, TRSM by forward substitution),
+//                      blocked triangular inverse W = L^-1, alpha = W^T (W y_s).
+#include "common.cuh"
+
+namespace {
+
+constexpr double SQRT5 = 2.23606797749978969640917366873128;
+constexpr int NB = 32;         // Cholesky block size
+constexpr int CH_THREADS = 256;
+constexpr int MT = 256;        // panel GEMM rows per pass
+constexpr int KB = 16;         // panel GEMM k-tile
+constexpr int AS_LD = MT + 2;  // k-major A tile leading dimension (even -> 16-byte aligned rows)
+constexpr int BS_LD = NB + 2;
+
+// --------------------------------------------------------------------------------------------- prep
+struct PrepArgs {
+  int B, n, kmax, ld_n, mode;
+  const double *Z;
+  const int *k;
+  const double *f, *fix_lo, *fix_hi;
+  double *norm_off, *norm_coef, *box_lo, *box_hi, *ymean, *ystd, *ZnT, *ys;
+};
+
+__global__ void __launch_bounds__(256) gp_prep_kernel(PrepArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int n = a.n, kmax = a.kmax;
+  const int kk = a.k ? a.k[b] : kmax;
+  double *pmin = sm;                 // [G][kmax]
+  const int G = max(1, nt / kmax);
+  double *pmax = pmin + G * kmax;    // [G][kmax]
+  double *off = pmax + G * kmax;     // [kmax]
+  double *coef = off + kmax;         // [kmax]
+  double *red = coef + kmax;         // [34]
+  const double *Zb = a.Z + (size_t)b * a.ld_n * kmax;
+  const double *fb = a.f + (size_t)b * a.ld_n;
+  // min / max per dimension
+  {
+    const int g = tid / kmax, c = tid % kmax;
+    if (g < G) {
+      double mn = INFINITY, mx = -INFINITY;
+      if (c < kk)
+        for (int i = g; i < n; i += G) {
+          const double v = Zb[(size_t)i * kmax + c];
+          mn = fmin(mn, v);
+          mx = fmax(mx, v);
+        }
+      pmin[g * kmax + c] = mn;
+      pmax[g * kmax + c] = mx;
+    }
+  }
+  __syncthreads();
+  if (tid < kmax) {
+    const int c = tid;
+    double lo_n = 0.0, cf = 1.0, blo = 0.0, bhi = 0.0;
+    if (c < kk) {
+      double mn = INFINITY, mx = -INFINITY;
+      for (int g = 0; g < G; ++g) { mn = fmin(mn, pmin[g * kmax + c]); mx = fmax(mx, pmax[g * kmax + c]); }
+      const double rng = mx - mn;
+      if (a.mode == 0) {
+        // PCA_BO.py:512-518 Normalize bounds, botorch Normalize: coefficient = hi - lo, |.| < 1e-12 -> 1
+        lo_n = mn - 0.1 * rng;
+        const double hi_n = mx + 0.1 * rng;
+        cf = hi_n - lo_n;
+        if (fabs(cf) < 1e-12) cf = 1.0;
+        // PCA_BO.py:558-573 search box
+        blo = mn - 0.5 * rng;
+        bhi = mx + 0.5 * rng;
+        if (bhi - blo < 0.1) {
+          const double mid = (bhi + blo) / 2;
+          blo = mid - 0.1 / 2;
+          bhi = mid + 0.1 / 2;
+        }
+      } else {
+        blo = a.fix_lo[c];
+        bhi = a.fix_hi[c];
+      }
+    }
+    off[c] = lo_n;
+    coef[c] = cf;
+    a.norm_off[(size_t)b * kmax + c] = lo_n;
+    a.norm_coef[(size_t)b * kmax + c] = cf;
+    a.box_lo[(size_t)b * kmax + c] = blo;
+    a.box_hi[(size_t)b * kmax + c] = bhi;
+  }
+  // Standardize(m=1): mean, unbiased std (two pass), std < 1e-8 -> 1
+  double s = 0.0;
+  for (int i = tid; i < n; i += nt) s += fb[i];
+  s = block_sum(s, red);
+  const double mean = s / (double)n;
+  double q = 0.0;
+  for (int i = tid; i < n; i += nt) { const double d = fb[i] - mean; q = fma(d, d, q); }
+  q = block_sum(q, red);
+  double sd = (n > 1) ? sqrt(q / (double)(n - 1)) : 1.0;
+  if (!(sd >= 1e-8)) sd = 1.0;
+  if (tid == 0) { a.ymean[b] = mean; a.ystd[b] = sd; }
+  for (int i = tid; i < n; i += nt) a.ys[(size_t)b * a.ld_n + i] = (fb[i] - mean) / sd;
+  __syncthreads();
+  // normalised, transposed training inputs
+  double *ZnTb = a.ZnT + (size_t)b * kmax * a.ld_n;
+  for (int idx = tid; idx < kk * n; idx += nt) {
+    const int c = idx / n, i = idx % n;
+    ZnTb[(size_t)c * a.ld_n + i] = (Zb[(size_t)i * kmax + c] - off[c]) / coef[c];
+  }
+}
+
+// --------------------------------------------------------------------------------------------- kernel matrix
+__device__ __forceinline__ double matern52_from_sq(double sq, double inv_ell2) {
+  // gpytorch: dist = sqrt(clamp_min(sq / ell^2, 1e-30)); (1 + sqrt5 d + 5/3 d^2) exp(-sqrt5 d)
+  const double d = sqrt(fmax(sq * inv_ell2, 1e-30));
+  return (SQRT5 * d + 1.0 + (5.0 / 3.0) * (d * d)) * exp(-SQRT5 * d);
+}
+
+constexpr int KT = 64;  // kernel-matrix tile
+
+__global__ void __launch_bounds__(256) gp_kmat_kernel(int n, int kmax, int ld_n, const int *k, const double *ZnT,
+                                                     double inv_ell2, double noise, double *Kout) {
+  // grid: (tiles_lower, B); tile (ti >= tj)
+  __shared__ double zi[8][KT];
+  __shared__ double zj[8][KT];
+  const int b = blockIdx.y;
+  int t = blockIdx.x, ti = 0;
+  while (t >= ti + 1) { t -= ti + 1; ++ti; }
+  const int tj = t;
+  const int kk = k ? k[b] : kmax;
+  const double *Zb = ZnT + (size_t)b * kmax * ld_n;
+  double *Kb = Kout + (size_t)b * ld_n * ld_n;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;  // thread computes rows ty*4.., cols tx*4..
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int c0 = 0; c0 < kk; c0 += 8) {
+    for (int idx = threadIdx.x; idx < 8 * KT; idx += blockDim.x) {
+      const int c = idx / KT, r = idx % KT;
+      const int gi = ti * KT + r, gj = tj * KT + r;
+      const bool vc = (c0 + c) < kk;
+      zi[c][r] = (vc && gi < n) ? Zb[(size_t)(c0 + c) * ld_n + gi] : 0.0;
+      zj[c][r] = (vc && gj < n) ? Zb[(size_t)(c0 + c) * ld_n + gj] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = zi[c][ty * 4 + i]; bv[i] = zj[c][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const double d = av[i] - bv[j]; acc[i][j] = fma(d, d, acc[i][j]); }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gi = ti * KT + ty * 4 + i, gj = tj * KT + tx * 4 + j;
+      if (gi < n && gj <= gi) {
+        double v = matern52_from_sq(acc[i][j], inv_ell2);
+        if (gi == gj) v += noise;
+        Kb[(size_t)gi * ld_n + gj] = v;
+      }
+    }
+}
+
+// --------------------------------------------------------------------------------------------- Cholesky + inverse
+// C(r, c) (r < M, c < 32) = beta * C + alpha * sum_{k < K} A(r, k) * Bm(c, k)
+//   A(r, k) = Ap[r * a_rs + k * a_ks]  (a_lower_t: treat A(r, k) as zero when k < r + a_diag_off, for transposed lower W)
+//   Bm(c, k) = Bp[c * ldb + k]
+//   C(r, c) = Cp[r * c_rs + c * c_cs]
+struct Smem {
+  double As[KB][AS_LD];
+  double Bs[KB][BS_LD];
+  double D[NB][NB + 1];     // diagonal block
+  double Di[NB][NB + 1];    // its inverse
+  int info;
+};
+
+__device__ __noinline__ void panel_gemm(Smem &s, double *Cp, long c_rs, long c_cs, const double *Ap, long a_rs, long a_ks,
+                           const double *Bp, long ldb, int M, int K, int ncols, double alpha, double beta,
+                           bool a_k_fast, bool a_lower_t) {
+  const int tid = threadIdx.x;
+  const int tr = tid / 8, tc = tid % 8;
+  for (int m0 = 0; m0 < M; m0 += MT) {
+    double acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    const int rows = min(MT, M - m0);
+    // for the transposed-lower operand, A(r, k) == 0 whenever k < r: k-tiles entirely below m0 contribute nothing
+    int kstart = 0;
+    if (a_lower_t) kstart = (m0 / KB) * KB;
+    for (int k0 = kstart; k0 < K; k0 += KB) {
+      // stage A tile (rows x KB) k-major, B tile (32 x KB) k-major
+      if (a_k_fast) {
+        for (int idx = tid; idx < MT * KB; idx += CH_THREADS) {
+          const int r = idx / KB, kk = idx % KB;
+          double v = 0.0;
+          if (r < rows && k0 + kk < K) v = Ap[(long)(m0 + r) * a_rs + (long)(k0 + kk) * a_ks];
+          s.As[kk][r] = v;
+        }
+      } else {
+        for (int idx = tid; idx < MT * KB; idx += CH_THREADS) {
+          const int kk = idx / MT, r = idx % MT;
+          double v = 0.0;
+          if (r < rows && k0 + kk < K && !(a_lower_t && (k0 + kk) < (m0 + r)))
+            v = Ap[(long)(m0 + r) * a_rs + (long)(k0 + kk) * a_ks];
+          s.As[kk][r] = v;
+        }
+      }
+      for (int idx = tid; idx < NB * KB; idx += CH_THREADS) {
+        const int c = idx / KB, kk = idx % KB;
+        double v = 0.0;
+        if (c < ncols && k0 + kk < K) v = Bp[(long)c * ldb + k0 + kk];
+        s.Bs[kk][c] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < KB; ++kk) {
+        double av[8], bv[4];
+        const double2 *ap = reinterpret_cast<const double2 *>(&s.As[kk][tr * 8]);
+        const double2 *bp = reinterpret_cast<const double2 *>(&s.Bs[kk][tc * 4]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const double2 t2 = ap[i]; av[2 * i] = t2.x; av[2 * i + 1] = t2.y; }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { const double2 t2 = bp[j]; bv[2 * j] = t2.x; bv[2 * j + 1] = t2.y; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = tr * 8 + i;
+      if (r < rows) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = tc * 4 + j;
+          if (c < ncols) {
+            double *p = Cp + (long)(m0 + r) * c_rs + (long)c * c_cs;
+            *p = (beta == 0.0 ? 0.0 : beta * (*p)) + alpha * acc[i][j];
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+struct CholArgs {
+  int B, n, ld_n;
+  double *L, *W, *alpha;  // alpha holds y_s on entry
+  int *info;
+};
+
+__global__ void __launch_bounds__(CH_THREADS, 1) gp_chol_kernel(CholArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  Smem &s = *reinterpret_cast<Smem *>(smraw);
+  double *uvec = reinterpret_cast<double *>(smraw + sizeof(Smem));  // [n]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = a.n;
+  const long ld = a.ld_n;
+  double *L = a.L + (size_t)b * ld * ld;
+  double *W = a.W + (size_t)b * ld * ld;
+  double *al = a.alpha + (size_t)b * ld;
+  if (tid == 0) s.info = 0;
+  __syncthreads();
+
+  // ---------------- blocked left-looking Cholesky
+  for (int j0 = 0; j0 < n; j0 += NB) {
+    const int nbj = min(NB, n - j0);
+    const int M = n - j0;
+    if (j0 > 0)
+      panel_gemm(s, L + (long)j0 * ld + j0, ld, 1, L + (long)j0 * ld, ld, 1, L + (long)j0 * ld, ld, M, j0, nbj, -1.0,
+                 1.0, true, false);
+    // diagonal block -> smem (lower), factor with warp 0
+    for (int idx = tid; idx < NB * NB; idx += CH_THREADS) {
+      const int r = idx / NB, c = idx % NB;
+      s.D[r][c] = (r < nbj && c <= r) ? L[(long)(j0 + r) * ld + j0 + c] : ((r == c) ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const int r = tid;
+      for (int c = 0; c < NB; ++c) {
+        // left-looking inside the block: column c
+        double v = s.D[r][c];
+        if (r >= c) {
+          for (int t = 0; t < c; ++t) v = fma(-s.D[r][t], s.D[c][t], v);
+        }
+        double dcc = __shfl_sync(0xffffffffu, v, c);
+        if (!(dcc > 0.0)) {
+          if (r == c && s.info == 0) s.info = j0 + c + 1;
+          dcc = 1e-300;
+        }
+        const double piv = sqrt(dcc);
+        if (r == c) s.D[r][c] = piv;
+        else if (r > c) s.D[r][c] = v / piv;
+        __syncwarp();
+      }
+      // inverse of the lower-triangular block: lane c solves L x = e_c
+      {
+        const int c = tid;
+        double x[NB];
+#pragma unroll
+        for (int r2 = 0; r2 < NB; ++r2) {
+          double v = (r2 == c) ? 1.0 : 0.0;
+#pragma unroll
+          for (int t = 0; t < r2; ++t) v = fma(-s.D[r2][t], x[t], v);
+          x[r2] = (r2 >= c) ? v / s.D[r2][r2] : 0.0;
+        }
+#pragma unroll
+        for (int r2 = 0; r2 < NB; ++r2) s.Di[r2][c] = x[r2];
+      }
+    }
+    __syncthreads();
+    // write back the factored diagonal block (lower; upper zero) and its inverse into W's diagonal block
+    for (int idx = tid; idx < NB * NB; idx += CH_THREADS) {
+      const int r = idx / NB, c = idx % NB;
+      if (r < nbj && c < nbj) {
+        L[(long)(j0 + r) * ld + j0 + c] = (c <= r) ? s.D[r][c] : 0.0;
+        W[(long)(j0 + r) * ld + j0 + c] = (c <= r) ? s.Di[r][c] : 0.0;
+      }
+    }
+    // TRSM below the diagonal block: row x <- x * Ljj^-T (forward substitution), one thread per row
+    for (int r = j0 + NB + tid; r < n; r += CH_THREADS) {
+      double *row = L + (long)r * ld + j0;
+      double x[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) x[c] = row[c];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        double v = x[c];
+#pragma unroll
+        for (int t = 0; t < c; ++t) v = fma(-x[t], s.D[c][t], v);
+        x[c] = v / s.D[c][c];
+      }
+#pragma unroll
+      for (int c = 0; c < NB; ++c) row[c] = x[c];
+    }
+    __syncthreads();
+  }
+
+  // ---------------- blocked inverse W = L^-1 (lower). Diagonal blocks of W already hold inv(Ljj).
+  for (int i0 = NB; i0 < n; i0 += NB) {
+    const int nbi = min(NB, n - i0);
+    // T(r, c) = sum_k W[k][r] * L[i0 + c][k],  r in [0, i0), k in [r, i0)  -> stored at W[i0 + c][r]
+    panel_gemm(s, W + (long)i0 * ld, 1, ld, W, 1, ld, L + (long)i0 * ld, ld, i0, i0, nbi, 1.0, 0.0, false, true);
+    // W[i0 + :, r] <- - Wii * T[:, r]   (Wii = inv(Lii), lower), one thread per column r
+    for (int idx = tid; idx < NB * NB; idx += CH_THREADS) {
+      const int r = idx / NB, c = idx % NB;
+      s.Di[r][c] = (r < nbi && c < nbi) ? W[(long)(i0 + r) * ld + i0 + c] : 0.0;
+    }
+    __syncthreads();
+    for (int r = tid; r < i0; r += CH_THREADS) {
+      double v[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) v[c] = (c < nbi) ? W[(long)(i0 + c) * ld + r] : 0.0;
+#pragma unroll
+      for (int c = NB - 1; c >= 0; --c) {
+        double acc = 0.0;
+#pragma unroll
+        for (int t = 0; t <= c; ++t) acc = fma(s.Di[c][t], v[t], acc);
+        if (c < nbi) W[(long)(i0 + c) * ld + r] = -acc;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---------------- alpha = W^T (W y_s)
+  {
+    const int warp = tid >> 5, lane = tid & 31, nw = CH_THREADS >> 5;
+    for (int i = warp; i < n; i += nw) {
+      double acc = 0.0;
+      for (int j = lane; j <= i; j += 32) acc = fma(W[(long)i * ld + j], al[j], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) uvec[i] = acc;
+    }
+    __syncthreads();
+    for (int j = tid; j < n; j += CH_THREADS) {
+      double acc = 0.0;
+      for (int i = j; i < n; ++i) acc = fma(W[(long)i * ld + j], uvec[i], acc);
+      al[j] = acc;
+    }
+  }
+  if (tid == 0) a.info[b] = s.info;
+}
+
+__global__ void gp_mll_kernel(int n, int ld_n, const double *f, const double *ymean, const double *ystd,
+                              const double *L, const double *alpha, double *mll) {
+  __shared__ double red[34];
+  const int b = blockIdx.x;
+  const double mean = ymean[b], sd = ystd[b];
+  double quad = 0.0, logdet = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double ys = (f[(size_t)b * ld_n + i] - mean) / sd;
+    quad = fma(ys, alpha[(size_t)b * ld_n + i], quad);
+    logdet += log(L[(size_t)b * ld_n * ld_n + (size_t)i * ld_n + i]);
+  }
+  quad = block_sum(quad, red);
+  logdet = block_sum(logdet, red);
+  if (threadIdx.x == 0) mll[b] = -0.5 * quad - logdet - 0.5 * (double)n * 1.8378770664093453;  // log(2 pi)
+}
+
+}  // namespace
+
+extern "C" int pcabo_gp_fit(int B, int n, int kmax, int ld_n, int mode, const double *Z, const int *k, const double *f,
+                            const double *fix_lo, const double *fix_hi, double lengthscale, double noise,
+                            double *norm_off, double *norm_coef, double *box_lo, double *box_hi, double *ymean,
+                            double *ystd, double *ZnT, double *L, double *W, double *alpha, int *info, void *stream) {
+  if (B <= 0 || n < 1 || kmax < 1 || ld_n < n || !Z || !f || !norm_off || !norm_coef || !box_lo || !box_hi || !ymean ||
+      !ystd || !ZnT || !L || !W || !alpha || !info || !(lengthscale > 0.0))
+    return PCABO_E_INVALID;
+  if (mode != 0 && (!fix_lo || !fix_hi)) return PCABO_E_INVALID;
+  if (kmax > 104 || n > 4096) return PCABO_E_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  {
+    PrepArgs a;
+    a.B = B; a.n = n; a.kmax = kmax; a.ld_n = ld_n; a.mode = mode;
+    a.Z = Z; a.k = k; a.f = f; a.fix_lo = fix_lo; a.fix_hi = fix_hi;
+    a.norm_off = norm_off; a.norm_coef = norm_coef; a.box_lo = box_lo; a.box_hi = box_hi;
+    a.ymean = ymean; a.ystd = ystd; a.ZnT = ZnT; a.ys = alpha;
+    const int G = 256 / kmax > 0 ? 256 / kmax : 1;
+    const size_t smem = (size_t)(2 * G * kmax + 2 * kmax + 34) * sizeof(double);
+    gp_prep_kernel<<<B, 256, smem, st>>>(a);
+    PCABO_LAUNCH_CHECK();
+  }
+  {
+    const int nt = (n + KT - 1) / KT;
+    dim3 grid(nt * (nt + 1) / 2, B);
+    gp_kmat_kernel<<<grid, 256, 0, st>>>(n, kmax, ld_n, k, ZnT, 1.0 / (lengthscale * lengthscale), noise, L);
+    PCABO_LAUNCH_CHECK();
+  }
+  {
+    CholArgs a;
+    a.B = B; a.n = n; a.ld_n = ld_n; a.L = L; a.W = W; a.alpha = alpha; a.info = info;
+    const size_t smem = sizeof(Smem) + (size_t)n * sizeof(double);
+    PCABO_CUDA_CHECK(cudaFuncSetAttribute(gp_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gp_chol_kernel<<<B, CH_THREADS, smem, st>>>(a);
+    PCABO_LAUNCH_CHECK();
+  }
+  return PCABO_OK;
+}
+
+extern "C" int pcabo_gp_mll(int B, int n, int ld_n, const double *f, const double *ymean, const double *ystd,
+                            const double *L, const double *alpha, double *mll, void *stream) {
+  if (B <= 0 || n < 1 || ld_n < n || !f || !ymean || !ystd || !L || !alpha || !mll) return PCABO_E_INVALID;
+  gp_mll_kernel<<<B, 256, 0, as_stream(stream)>>>(n, ld_n, f, ymean, ystd, L, alpha, mll);
+  PCABO_LAUNCH_CHECK();
+  return PCABO_OK;
+}

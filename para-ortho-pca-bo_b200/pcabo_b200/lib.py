@@ -1,0 +1,76 @@
+"""ctypes loader for libpcabo_b200.so and thin typed wrappers around its C ABI (include/pcabo_b200.h)."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+EXPORTED_SYMBOLS = [
+    "pcabo_abi_version", "pcabo_error_string", "pcabo_last_cuda_error",
+    "pcabo_weights_pca_fit", "pcabo_inverse_map", "pcabo_gp_fit", "pcabo_gp_mll",
+    "pcabo_logei", "pcabo_argmax",
+]
+
+
+class PcaboError(RuntimeError):
+    pass
+
+
+class GpModelStruct(ctypes.Structure):
+    """struct pcabo_gp_model (include/pcabo_b200.h)."""
+    _fields_ = [
+        ("B", ctypes.c_int), ("n", ctypes.c_int), ("kmax", ctypes.c_int), ("ld_n", ctypes.c_int),
+        ("maximize", ctypes.c_int), ("pad_", ctypes.c_int),
+        ("lengthscale", ctypes.c_double),
+        ("k", ctypes.c_void_p), ("norm_off", ctypes.c_void_p), ("norm_coef", ctypes.c_void_p),
+        ("ZnT", ctypes.c_void_p), ("alpha", ctypes.c_void_p), ("W", ctypes.c_void_p),
+        ("ymean", ctypes.c_void_p), ("ystd", ctypes.c_void_p), ("best_f", ctypes.c_void_p),
+    ]
+
+
+def library_path() -> str:
+    return os.path.join(HERE, "libpcabo_b200.so")
+
+
+def load_library(build_if_missing: bool = False):
+    """Load the shared library; raises PcaboError (never falls back) when it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        if build_if_missing:
+            from .build import build
+            build()
+        else:
+            raise PcaboError(f"{path} is missing: run `python __graft_entry__.py build` (nvcc, sm_100a). "
+                             "There is no CPU fallback for the PCA-BO hot path.")
+    lib = ctypes.CDLL(path)
+    vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    lib.pcabo_abi_version.restype = ci
+    lib.pcabo_error_string.restype = ctypes.c_char_p
+    lib.pcabo_error_string.argtypes = [ci]
+    lib.pcabo_last_cuda_error.restype = ctypes.c_char_p
+    lib.pcabo_weights_pca_fit.restype = ci
+    lib.pcabo_weights_pca_fit.argtypes = [ci, ci, ci, ci, vp, vp, vp, vp, cd, ci, ci] + [vp] * 9 + [vp]
+    lib.pcabo_inverse_map.restype = ci
+    lib.pcabo_inverse_map.argtypes = [ci, ci] + [vp] * 9 + [vp]
+    lib.pcabo_gp_fit.restype = ci
+    lib.pcabo_gp_fit.argtypes = [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, cd, cd] + [vp] * 11 + [vp]
+    lib.pcabo_gp_mll.restype = ci
+    lib.pcabo_gp_mll.argtypes = [ci, ci, ci] + [vp] * 6 + [vp]
+    lib.pcabo_logei.restype = ci
+    lib.pcabo_logei.argtypes = [ctypes.POINTER(GpModelStruct), ci, vp, vp, vp, vp, vp, vp]
+    lib.pcabo_argmax.restype = ci
+    lib.pcabo_argmax.argtypes = [ci, ci, vp, vp, vp, vp]
+    _LIB = lib
+    return lib
+
+
+def check(code: int, what: str):
+    if code != 0:
+        lib = load_library()
+        msg = lib.pcabo_error_string(code).decode()
+        if code == -3:
+            msg += ": " + lib.pcabo_last_cuda_error().decode()
+        raise PcaboError(f"{what} failed: {msg} (code {code})")

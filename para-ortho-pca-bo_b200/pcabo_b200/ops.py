@@ -1,0 +1,167 @@
+"""Torch-tensor front end of the C ABI: validates device/dtype/layout, passes raw device pointers and the current stream."""
+import ctypes
+import math
+
+import torch
+
+from .lib import GpModelStruct, PcaboError, check, load_library
+
+LENGTHSCALE = math.log(2.0)   # softplus(0): gpytorch MaternKernel default raw_lengthscale = 0
+NOISE = math.exp(-5.0)        # mode of botorch's LogNormalPrior(-4, 1) noise prior
+
+
+def _dev_ptr(t, dtype, name):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise PcaboError(f"{name}: expected a CUDA tensor (the PCA-BO hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise PcaboError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise PcaboError(f"{name}: expected a contiguous tensor")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _d(t, name):
+    return _dev_ptr(t, torch.float64, name)
+
+
+def _i(t, name):
+    return _dev_ptr(t, torch.int32, name)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def weights_pca_fit(X, f, noise, logtab, n, var_threshold=0.95, n_components=0, maximization=False, out=None):
+    """X [B, ld_n, D], f [B, ld_n], noise [B, n, D], logtab [>= n + 1]. Returns dict of device tensors."""
+    lib = load_library()
+    B, ld_n, D = X.shape
+    dev = X.device
+    if out is None:
+        out = dict(
+            w=torch.zeros(B, ld_n, dtype=torch.float64, device=dev),
+            ranks=torch.zeros(B, ld_n, dtype=torch.int32, device=dev),
+            xbar=torch.empty(B, D, dtype=torch.float64, device=dev),
+            m2=torch.empty(B, D, dtype=torch.float64, device=dev),
+            V=torch.empty(B, D, D, dtype=torch.float64, device=dev),
+            lam=torch.empty(B, D, dtype=torch.float64, device=dev),
+            evr=torch.empty(B, D, dtype=torch.float64, device=dev),
+            k=torch.empty(B, dtype=torch.int32, device=dev),
+            Z=torch.zeros(B, ld_n, D, dtype=torch.float64, device=dev),
+        )
+    if noise.shape != (B, n, D):
+        raise PcaboError(f"noise: expected shape {(B, n, D)}, got {tuple(noise.shape)}")
+    if logtab.numel() < n + 1:
+        raise PcaboError("logtab: needs at least n + 1 entries")
+    check(lib.pcabo_weights_pca_fit(B, n, D, ld_n, _d(X, "X"), _d(f, "f"), _d(noise, "noise"), _d(logtab, "logtab"),
+                                    float(var_threshold), int(n_components), int(bool(maximization)),
+                                    _d(out["w"], "w"), _i(out["ranks"], "ranks"), _d(out["xbar"], "xbar"),
+                                    _d(out["m2"], "m2"), _d(out["V"], "V"), _d(out["lam"], "lam"),
+                                    _d(out["evr"], "evr"), _i(out["k"], "k"), _d(out["Z"], "Z"), _stream()),
+          "pcabo_weights_pca_fit")
+    return out
+
+
+def inverse_map(z, k, V, m2, xbar, lo, hi, out=None):
+    """z [B, D] (first k[b] entries used) -> x [B, D], oob [B]."""
+    lib = load_library()
+    B, D = z.shape
+    if out is None:
+        out = dict(x=torch.empty(B, D, dtype=torch.float64, device=z.device),
+                   oob=torch.empty(B, dtype=torch.int32, device=z.device))
+    check(lib.pcabo_inverse_map(B, D, _d(z, "z"), _i(k, "k"), _d(V, "V"), _d(m2, "m2"), _d(xbar, "xbar"),
+                                _d(lo, "lo"), _d(hi, "hi"), _d(out["x"], "x"), _i(out["oob"], "oob"), _stream()),
+          "pcabo_inverse_map")
+    return out
+
+
+class GPBuffers:
+    """Device storage for the batched GP caches (allocated once per engine, reused every iteration)."""
+
+    def __init__(self, B, ld_n, kmax, device):
+        f64 = dict(dtype=torch.float64, device=device)
+        self.B, self.ld_n, self.kmax = B, ld_n, kmax
+        self.norm_off = torch.zeros(B, kmax, **f64)
+        self.norm_coef = torch.ones(B, kmax, **f64)
+        self.box_lo = torch.zeros(B, kmax, **f64)
+        self.box_hi = torch.zeros(B, kmax, **f64)
+        self.ymean = torch.zeros(B, **f64)
+        self.ystd = torch.ones(B, **f64)
+        self.ZnT = torch.zeros(B, kmax, ld_n, **f64)
+        self.L = torch.zeros(B, ld_n, ld_n, **f64)
+        self.W = torch.zeros(B, ld_n, ld_n, **f64)
+        self.alpha = torch.zeros(B, ld_n, **f64)
+        self.info = torch.zeros(B, dtype=torch.int32, device=device)
+        self.best_f = torch.zeros(B, **f64)
+        self.n = 0
+        self.k = None
+        self.maximize = False
+        self.lengthscale = LENGTHSCALE
+
+
+def gp_fit(buf: GPBuffers, Z, k, f, n, mode=0, fix_lo=None, fix_hi=None, lengthscale=LENGTHSCALE, noise=NOISE):
+    """Z [B, ld_n, kmax], k [B] int32 or None, f [B, ld_n]. Fills `buf`."""
+    lib = load_library()
+    B, ld_n, kmax = Z.shape
+    if (B, ld_n, kmax) != (buf.B, buf.ld_n, buf.kmax):
+        raise PcaboError("gp_fit: buffer shape mismatch")
+    check(lib.pcabo_gp_fit(B, n, kmax, ld_n, int(mode), _d(Z, "Z"), _i(k, "k"), _d(f, "f"), _d(fix_lo, "fix_lo"),
+                           _d(fix_hi, "fix_hi"), float(lengthscale), float(noise),
+                           _d(buf.norm_off, "norm_off"), _d(buf.norm_coef, "norm_coef"), _d(buf.box_lo, "box_lo"),
+                           _d(buf.box_hi, "box_hi"), _d(buf.ymean, "ymean"), _d(buf.ystd, "ystd"), _d(buf.ZnT, "ZnT"),
+                           _d(buf.L, "L"), _d(buf.W, "W"), _d(buf.alpha, "alpha"), _i(buf.info, "info"), _stream()),
+          "pcabo_gp_fit")
+    buf.n, buf.k, buf.lengthscale = n, k, lengthscale
+    return buf
+
+
+def gp_mll(buf: GPBuffers, f):
+    lib = load_library()
+    out = torch.empty(buf.B, dtype=torch.float64, device=f.device)
+    check(lib.pcabo_gp_mll(buf.B, buf.n, buf.ld_n, _d(f, "f"), _d(buf.ymean, "ymean"), _d(buf.ystd, "ystd"),
+                           _d(buf.L, "L"), _d(buf.alpha, "alpha"), _d(out, "mll"), _stream()), "pcabo_gp_mll")
+    return out
+
+
+def model_struct(buf: GPBuffers) -> GpModelStruct:
+    m = GpModelStruct()
+    m.B, m.n, m.kmax, m.ld_n = buf.B, buf.n, buf.kmax, buf.ld_n
+    m.maximize = int(bool(buf.maximize))
+    m.lengthscale = float(buf.lengthscale)
+    m.k = _i(buf.k, "k") if buf.k is not None else None
+    m.norm_off, m.norm_coef = _d(buf.norm_off, "norm_off"), _d(buf.norm_coef, "norm_coef")
+    m.ZnT, m.alpha, m.W = _d(buf.ZnT, "ZnT"), _d(buf.alpha, "alpha"), _d(buf.W, "W")
+    m.ymean, m.ystd, m.best_f = _d(buf.ymean, "ymean"), _d(buf.ystd, "ystd"), _d(buf.best_f, "best_f")
+    return m
+
+
+def logei(buf: GPBuffers, X, want_grad=False, want_posterior=False, out=None):
+    """X [B, npts, kmax] raw-space points -> dict(val [B, npts], grad [B, npts, kmax], mu, sigma)."""
+    lib = load_library()
+    B, npts, kmax = X.shape
+    if B != buf.B or kmax != buf.kmax:
+        raise PcaboError("logei: shape mismatch with the GP buffers")
+    dev = X.device
+    if out is None:
+        out = dict(val=torch.empty(B, npts, dtype=torch.float64, device=dev))
+        if want_grad:
+            out["grad"] = torch.empty(B, npts, kmax, dtype=torch.float64, device=dev)
+        if want_posterior:
+            out["mu"] = torch.empty(B, npts, dtype=torch.float64, device=dev)
+            out["sigma"] = torch.empty(B, npts, dtype=torch.float64, device=dev)
+    m = model_struct(buf)
+    check(lib.pcabo_logei(ctypes.byref(m), npts, _d(X, "X"), _d(out["val"], "val"), _d(out.get("grad"), "grad"),
+                          _d(out.get("mu"), "mu"), _d(out.get("sigma"), "sigma"), _stream()), "pcabo_logei")
+    return out
+
+
+def argmax(v):
+    """v [B, m] -> (best_val [B], best_idx [B] int32), first occurrence on ties."""
+    lib = load_library()
+    B, m = v.shape
+    bv = torch.empty(B, dtype=torch.float64, device=v.device)
+    bi = torch.empty(B, dtype=torch.int32, device=v.device)
+    check(lib.pcabo_argmax(B, m, _d(v, "v"), _d(bv, "best_val"), _i(bi, "best_idx"), _stream()), "pcabo_argmax")
+    return bv, bi

@@ -1,0 +1,240 @@
+"""GPU parity tests: every CUDA kernel, called through the C ABI (ctypes), against the CPU oracle on seeded inputs.
+
+Bars (BASELINE.md section 4 / north_star): ranks, weights and selected component counts bit-exact; eigenvalues,
+posterior mean / sigma, log-EI and gradients within 1e-8 relative in FP64.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import synthetic_history, oracle_state, batch_to_device
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-8
+
+
+def _ops():
+    from pcabo_b200 import ops
+    return ops
+
+
+def rel_err(a, b, floor=0.0):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
+
+
+CASES = [(5, 10), (10, 30), (10, 77), (20, 61), (20, 250), (40, 120), (40, 399), (40, 450), (7, 33)]
+
+
+@pytest.mark.parametrize("D,n", CASES)
+@pytest.mark.parametrize("maximization", [False, True])
+def test_weights_pca_fit(D, n, maximization):
+    ops = _ops()
+    B = 3
+    hist = [synthetic_history(D, n, 100 * D + n + b, maximization=maximization) for b in range(B)]
+    ld_n = n + 5
+    X, f, nz, logtab = batch_to_device([h[0] for h in hist], [h[1] for h in hist], [h[2] for h in hist], ld_n)
+    out = ops.weights_pca_fit(X, f, nz, logtab, n, 0.95, 0, maximization)
+    torch.cuda.synchronize()
+    for b in range(B):
+        Xb, fb, nb = hist[b]
+        st, _, _, _ = oracle_state(Xb, fb, nb, maximization=maximization)
+        # bit-exact integer / weight parity
+        assert np.array_equal(out["ranks"][b, :n].cpu().numpy(), st["ranks"]), "ranks"
+        assert np.array_equal(out["w"][b, :n].cpu().numpy(), st["weights"]), "weights must be bit-identical"
+        assert int(out["k"][b]) == st["k"], "component count"
+        k = st["k"]
+        assert rel_err(out["xbar"][b].cpu().numpy(), st["data_mean"], 1e-12) < 1e-12
+        assert np.max(np.abs(out["m2"][b].cpu().numpy() - st["pca_mean"])) < 1e-18 + 1e-10 * np.max(np.abs(st["pca_mean"]))
+        lam = out["lam"][b].cpu().numpy()
+        lam_ref = st["explained_variance"]
+        r = len(lam_ref)
+        # eigenvalues: 1e-8 relative for everything above the noise floor of the covariance
+        big = lam_ref > 1e-12 * lam_ref[0]
+        assert rel_err(lam[:r][big], lam_ref[big]) < RTOL, "eigenvalues"
+        assert rel_err(out["evr"][b].cpu().numpy()[:r][big], st["explained_variance_ratio"][big]) < RTOL
+        # components: compare each retained component where the relative eigen-gap is not tiny
+        V = out["V"][b].cpu().numpy()
+        Vr = st["components"]
+        gaps = np.abs(np.diff(lam_ref)) / lam_ref[0]
+        for c in range(min(k, r)):
+            gl = gaps[c - 1] if c > 0 else 1.0
+            gr = gaps[c] if c < r - 1 else 1.0
+            if min(gl, gr) > 1e-6:
+                assert np.max(np.abs(V[c] - Vr[c])) < 1e-8, f"component {c}"
+                assert int(np.argmax(np.abs(V[c]))) == int(np.argmax(np.abs(Vr[c])))
+        # orthonormality of the full basis
+        assert np.max(np.abs(V @ V.T - np.eye(D))) < 1e-12
+        Z = out["Z"][b, :n, :k].cpu().numpy()
+        scale = np.max(np.abs(st["Z"]))
+        assert np.max(np.abs(Z - st["Z"])) < RTOL * scale, "projection"
+        assert float(out["Z"][b, :n, k:].abs().max()) == 0.0 if k < D else True
+
+
+def test_weights_pca_fit_ncomponents_and_ties():
+    """n_components > 0 bypasses the threshold (PCA_BO.py:389-396); heavy exact ties use the index tie rule."""
+    ops = _ops()
+    D, n = 6, 40
+    Xb, fb, nb = synthetic_history(D, n, 7, penalty_fraction=0.6)
+    X, f, nz, logtab = batch_to_device([Xb], [fb], [nb], n)
+    out = ops.weights_pca_fit(X, f, nz, logtab, n, 0.95, 2, False)
+    st, _, _, _ = oracle_state(Xb, fb, nb, n_components=2)
+    assert int(out["k"][0]) == 2 == st["k"]
+    assert np.array_equal(out["ranks"][0].cpu().numpy(), st["ranks"])
+    assert np.array_equal(out["w"][0].cpu().numpy(), st["weights"])
+    assert np.max(np.abs(out["Z"][0, :, :2].cpu().numpy() - st["Z"])) < 1e-8 * np.max(np.abs(st["Z"]))
+    assert (fb == 1000.0).sum() > 5
+
+
+def _fit_gp_batch(D, n, B, maximization=False, seed0=0):
+    ops = _ops()
+    hist = [synthetic_history(D, n, seed0 + 31 * D + n + b, maximization=maximization) for b in range(B)]
+    X, f, nz, logtab = batch_to_device([h[0] for h in hist], [h[1] for h in hist], [h[2] for h in hist], n)
+    pca = ops.weights_pca_fit(X, f, nz, logtab, n, 0.95, 0, maximization)
+    buf = ops.GPBuffers(B, n, D, X.device)
+    ops.gp_fit(buf, pca["Z"], pca["k"], f, n, mode=0)
+    torch.cuda.synchronize()
+    return ops, hist, X, f, pca, buf
+
+
+@pytest.mark.parametrize("D,n", [(5, 10), (10, 77), (20, 250), (40, 120), (40, 450)])
+def test_gp_fit(D, n):
+    B = 2
+    ops, hist, X, f, pca, buf = _fit_gp_batch(D, n, B)
+    assert int(buf.info.abs().max()) == 0
+    mll = ops.gp_mll(buf, f).cpu().numpy()
+    for b in range(B):
+        # oracle GP on the GPU's own Z (isolates the GP kernels from the PCA kernel)
+        k = int(pca["k"][b])
+        Z = pca["Z"][b, :n, :k].cpu().numpy()
+        from oracle import gp, acqf
+        model = gp.GPModel(Z, hist[b][1], norm_bounds=acqf.normalize_box_pca(Z))
+        K, L, alpha, Linv = model.caches()
+        nb = acqf.normalize_box_pca(Z)
+        assert rel_err(buf.norm_off[b, :k].cpu().numpy(), nb[0], 1e-12) < 1e-13
+        assert rel_err(buf.norm_coef[b, :k].cpu().numpy(), nb[1] - nb[0], 1e-12) < 1e-13
+        box = acqf.search_box_pca(Z)
+        assert rel_err(buf.box_lo[b, :k].cpu().numpy(), box[0], 1e-12) < 1e-13
+        assert rel_err(buf.box_hi[b, :k].cpu().numpy(), box[1], 1e-12) < 1e-13
+        assert abs(float(buf.ymean[b]) - float(model.y_mean)) <= 1e-12 * abs(float(model.y_mean)) + 1e-12
+        assert abs(float(buf.ystd[b]) - float(model.y_std)) <= 1e-12 * float(model.y_std)
+        Lg = torch.tril(buf.L[b, :n, :n]).cpu().numpy()
+        assert np.max(np.abs(Lg - L.numpy())) < RTOL * np.max(np.abs(L.numpy())), "Cholesky factor"
+        Wg = torch.tril(buf.W[b, :n, :n]).cpu().numpy()
+        assert np.max(np.abs(Wg - Linv.numpy())) < RTOL * np.max(np.abs(Linv.numpy())), "L^-1"
+        ag = buf.alpha[b, :n].cpu().numpy()
+        assert np.max(np.abs(ag - alpha.numpy())) < RTOL * np.max(np.abs(alpha.numpy())), "alpha"
+        assert abs(mll[b] - model.mll()) < RTOL * abs(model.mll()), "marginal log-likelihood"
+
+
+@pytest.mark.parametrize("D,n,npts", [(5, 10, 7), (10, 77, 5), (20, 250, 16), (40, 120, 33), (40, 450, 10), (40, 450, 64)])
+@pytest.mark.parametrize("maximization", [False, True])
+def test_logei_value_grad(D, n, npts, maximization):
+    B = 2
+    ops, hist, X, f, pca, buf = _fit_gp_batch(D, n, B, maximization)
+    from oracle import gp, acqf
+    rng = np.random.RandomState(5)
+    pts = torch.zeros(B, npts, D, dtype=torch.float64)
+    models = []
+    for b in range(B):
+        k = int(pca["k"][b])
+        Z = pca["Z"][b, :n, :k].cpu().numpy()
+        fb = hist[b][1]
+        model = gp.GPModel(Z, fb, norm_bounds=acqf.normalize_box_pca(Z))
+        best = float(np.max(fb) if maximization else np.min(fb))
+        acq = gp.LogExpectedImprovement(model, best, maximize=maximization)
+        models.append((k, acq))
+        box = acqf.search_box_pca(Z)
+        P = box[0] + (box[1] - box[0]) * rng.rand(npts, k)
+        # a few points on / next to training points (tiny variance, u << -1) and on the box boundary
+        P[0] = Z[rng.randint(n)]
+        P[1] = Z[int(np.argmin(fb))] + 1e-3 * rng.randn(k)
+        P[2] = box[0]
+        pts[b, :, :k] = torch.from_numpy(P)
+        buf.best_f[b] = gp.best_f_as_botorch(best)
+    buf.maximize = maximization
+    ptsd = pts.cuda()
+    out = ops.logei(buf, ptsd, want_grad=True, want_posterior=True)
+    out_v = ops.logei(buf, ptsd, want_grad=False)
+    torch.cuda.synchronize()
+    for b in range(B):
+        k, acq = models[b]
+        Xp = pts[b, :, :k]
+        mean, sigma = acq.mean_sigma(Xp)
+        vals, grad = acq.value_and_grad(Xp)
+        assert rel_err(out["mu"][b].cpu().numpy(), mean.numpy(), 1e-9) < RTOL, "posterior mean"
+        assert rel_err(out["sigma"][b].cpu().numpy(), sigma.numpy()) < RTOL, "posterior sigma"
+        assert rel_err(out["val"][b].cpu().numpy(), vals.numpy(), 1e-6) < RTOL, "logEI"
+        assert torch.equal(out["val"][b], out_v["val"][b]) or rel_err(out_v["val"][b].cpu().numpy(), vals.numpy(), 1e-6) < RTOL
+        g = out["grad"][b, :, :k].cpu().numpy()
+        gr = grad.numpy()
+        scale = np.maximum(np.max(np.abs(gr), axis=1, keepdims=True), 1e-12)
+        assert np.max(np.abs(g - gr) / scale) < 1e-7, "logEI gradient (per-point max-norm relative)"
+        assert float(out["grad"][b, :, k:].abs().max()) == 0.0 if k < D else True
+
+
+def test_logei_branches():
+    """All three branches of log_h (u > -1, -1e6 < u <= -1, u <= -1e6) against the oracle's helper."""
+    B, D, n = 1, 5, 12
+    ops, hist, X, f, pca, buf = _fit_gp_batch(D, n, B)
+    from oracle import gp, acqf
+    k = int(pca["k"][0])
+    Z = pca["Z"][0, :n, :k].cpu().numpy()
+    model = gp.GPModel(Z, hist[0][1], norm_bounds=acqf.normalize_box_pca(Z))
+    box = acqf.search_box_pca(Z)
+    pts = torch.zeros(1, 6, D, dtype=torch.float64)
+    pts[0, :, :k] = torch.from_numpy(box[0] + (box[1] - box[0]) * np.random.RandomState(0).rand(6, k))
+    for best in [float(np.min(hist[0][1])), -1e5, -1e9, 1e4]:
+        acq = gp.LogExpectedImprovement(model, best, maximize=False)
+        buf.best_f[0] = gp.best_f_as_botorch(best)
+        out = ops.logei(buf, pts.cuda(), want_grad=True)
+        vals, grad = acq.value_and_grad(pts[0, :, :k])
+        assert rel_err(out["val"][0].cpu().numpy(), vals.numpy(), 1e-6) < RTOL, best
+        g, gr = out["grad"][0, :, :k].cpu().numpy(), grad.numpy()
+        scale = np.maximum(np.max(np.abs(gr), axis=1, keepdims=True), 1e-12)
+        assert np.max(np.abs(g - gr) / scale) < 1e-7, best
+
+
+def test_inverse_map_and_argmax():
+    ops = _ops()
+    D, n, B = 10, 40, 3
+    hist = [synthetic_history(D, n, 900 + b) for b in range(B)]
+    X, f, nz, logtab = batch_to_device([h[0] for h in hist], [h[1] for h in hist], [h[2] for h in hist], n)
+    pca = ops.weights_pca_fit(X, f, nz, logtab, n)
+    rng = np.random.RandomState(1)
+    z = torch.zeros(B, D, dtype=torch.float64)
+    from oracle import weights_pca
+    lo = torch.full((D,), -5.0, dtype=torch.float64).cuda()
+    hi = torch.full((D,), 5.0, dtype=torch.float64).cuda()
+    refs = []
+    for b in range(B):
+        k = int(pca["k"][b])
+        zz = rng.randn(k) * (0.5 if b < 2 else 30.0)
+        z[b, :k] = torch.from_numpy(zz)
+        V = pca["V"][b].cpu().numpy()
+        refs.append(weights_pca.inverse_map(zz, V[:k], pca["m2"][b].cpu().numpy(), pca["xbar"][b].cpu().numpy()))
+    out = ops.inverse_map(z.cuda(), pca["k"], pca["V"], pca["m2"], pca["xbar"], lo, hi)
+    for b in range(B):
+        assert np.max(np.abs(out["x"][b].cpu().numpy() - refs[b])) < 1e-12 * max(1.0, np.max(np.abs(refs[b])))
+        outside = (not np.all(refs[b] >= -5.0)) or (not np.all(refs[b] <= 5.0))
+        assert bool(out["oob"][b]) == outside
+    assert bool(out["oob"][2])
+    v = torch.from_numpy(rng.randn(4, 513))
+    v[1, 77] = v[1].max() + 1.0
+    v[1, 300] = v[1, 77]          # tie -> first occurrence
+    bv, bi = ops.argmax(v.cuda())
+    assert torch.equal(bi.cpu().long(), torch.argmax(v, dim=1))
+    assert torch.equal(bv.cpu(), v.max(dim=1).values)
+    assert int(bi[1]) == 77
+
+
+def test_errors_are_loud():
+    """The product path refuses CPU tensors and wrong dtypes instead of falling back."""
+    ops = _ops()
+    from pcabo_b200 import PcaboError
+    with pytest.raises(PcaboError):
+        ops.argmax(torch.zeros(2, 3, dtype=torch.float64))
+    with pytest.raises(PcaboError):
+        ops.argmax(torch.zeros(2, 3, dtype=torch.float32, device="cuda"))

@@ -1,0 +1,47 @@
+"""Library yardsticks missing from MEASURED_PEAKS.json: FP64 DGEMM peak and batched cuSOLVER Cholesky (run on the B200)."""
+import json
+import sys
+import time
+
+import torch
+
+
+def timed(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        best = min(best, s.elapsed_time(e) * 1e-3)
+    return best
+
+
+def main():
+    out = {"gpu": torch.cuda.get_device_name(0)}
+    N = 8192
+    a = torch.randn(N, N, dtype=torch.float64, device="cuda")
+    b = torch.randn(N, N, dtype=torch.float64, device="cuda")
+    t = timed(lambda: torch.matmul(a, b))
+    out["dgemm_8192_tflops"] = 2 * N ** 3 / t / 1e12
+    for (B, n) in [(90, 450), (90, 285), (150, 1050)]:
+        A = torch.randn(B, n, n, dtype=torch.float64, device="cuda")
+        A = A @ A.transpose(1, 2) + n * torch.eye(n, dtype=torch.float64, device="cuda")
+        t = timed(lambda: torch.linalg.cholesky(A))
+        out[f"potrf_batched_B{B}_n{n}_ms"] = t * 1e3
+        out[f"potrf_batched_B{B}_n{n}_gflops"] = B * n ** 3 / 3 / t / 1e9
+    # HBM copy for reference
+    x = torch.empty(1 << 28, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    t = timed(lambda: y.copy_(x))
+    out["copy_gbs"] = 2 * x.numel() * 8 / t / 1e9
+    print(json.dumps(out))
+    if len(sys.argv) > 1:
+        json.dump(out, open(sys.argv[1], "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
