@@ -36,7 +36,7 @@ __host__ __device__ inline size_t pca_smem_doubles(int n, int D, int R) {
   size_t d = 0;
   d += 2 * (size_t)n_pad;          // key, pre
   d += 2 * (size_t)D * ldc;        // C, Vm
-  d += (size_t)R * D4;             // row tile
+  d += ((size_t)R * D4 > (size_t)PCA_THREADS ? (size_t)R * D4 : (size_t)PCA_THREADS);  // row tile / partial buffers
   d += 4 * (size_t)D4;             // xb, mm2, lamv, mproj
   d += 3 * (size_t)(H + 1);        // rc, rs, rt
   d += 40;                         // reduction scratch + scalars
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(PCA_THREADS, 1) pca_fit_kernel(PcaArgs a) {
   double *C = pre + n_pad;
   double *Vm = C + (size_t)D * ldc;
   double *tile = Vm + (size_t)D * ldc;
-  double *xb = tile + (size_t)R * D4;
+  double *xb = tile + ((size_t)R * D4 > (size_t)PCA_THREADS ? (size_t)R * D4 : (size_t)PCA_THREADS);
   double *mm2 = xb + D4;
   double *lamv = mm2 + D4;
   double *mproj = lamv + D4;
@@ -443,11 +443,6 @@ extern "C" int pcabo_weights_pca_fit(int B, int n, int D, int ld_n, const double
   while (R > 4 && pca_smem_doubles(n, D, R) * sizeof(double) > limit) R /= 2;
   const size_t smem = pca_smem_doubles(n, D, R) * sizeof(double);
   if (smem > limit) return PCABO_E_UNSUPPORTED;
-  // the G x D partial buffers of phases C/E live in the row tile: need (threads / D) * D <= R * D4 doubles
-  if ((size_t)(PCA_THREADS / D) * D > (size_t)R * (((D + 3) / 4) * 4)) {
-    // enlarge R virtually is not possible; fall back to rejecting (cannot happen for D <= 104 with R >= 8)
-    if ((size_t)PCA_THREADS > (size_t)R * (((D + 3) / 4) * 4)) return PCABO_E_UNSUPPORTED;
-  }
   PCABO_CUDA_CHECK(cudaFuncSetAttribute(pca_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PcaArgs a;
   a.B = B; a.n = n; a.D = D; a.ld_n = ld_n; a.R = R;
