@@ -1,0 +1,121 @@
+"""Host-side pieces of botorch's optimize_acqf that must stay on the CPU generators for RNG-stream parity
+(SURVEY H6): scrambled Sobol raw samples, the Boltzmann selection of initial conditions, and a lock-step
+reverse-communication driver of scipy's own L-BFGS-B (`scipy.optimize._lbfgsb.setulb`) that lets B x 2 joint
+restart problems share one batched CUDA value+gradient launch per round.
+
+Reference call site: PCA_BO.optimize_acqf_and_get_observation, PCA_BO.py:547-621 (optimize_acqf at :607-614 with
+num_restarts=10, raw_samples=512, options={"batch_limit": 5, "maxiter": 200}); semantics in SURVEY App. A.5.
+The acquisition values and gradients themselves always come from the CUDA kernels (pcabo_logei).
+"""
+import numpy as np
+import torch
+from scipy.optimize import _lbfgsb
+
+MAXCOR = 10
+FTOL = 2.2204460492503131e-09
+GTOL = 1e-5
+MAXFUN = 15000
+MAXLS = 20
+
+
+def scrambled_sobol(d: int, n: int, generator: torch.Generator) -> torch.Tensor:
+    """torch.quasirandom.SobolEngine(d, scramble=True).draw(n, dtype=float64) with an explicit CPU generator.
+
+    Mirrors SobolEngine._scramble (two randint draws from the generator), so a generator seeded like the reference's
+    global torch RNG reproduces botorch.utils.sampling.draw_sobol_samples bit for bit.
+    """
+    eng = torch.quasirandom.SobolEngine(d, scramble=False)
+    maxbit = eng.MAXBIT
+    shift_ints = torch.randint(2, (d, maxbit), generator=generator)
+    eng.shift = torch.mv(shift_ints, torch.pow(2, torch.arange(0, maxbit)))
+    ltm = torch.randint(2, (d, maxbit, maxbit), generator=generator).tril()
+    torch._sobol_engine_scramble_(eng.sobolstate, ltm, d)
+    eng.quasi = eng.shift.clone(memory_format=torch.contiguous_format)
+    eng._first_point = (eng.quasi / 2 ** maxbit).reshape(1, -1)
+    return eng.draw(n, dtype=torch.float64)
+
+
+def initialize_q_batch(acq_vals: torch.Tensor, n: int, generator: torch.Generator, eta: float = 1.0):
+    """botorch initialize_q_batch: indices of the n initial conditions, or None when all values coincide
+    (botorch then warns BadInitialCandidatesWarning and the caller draws more raw samples)."""
+    n_samples = acq_vals.shape[0]
+    if n >= n_samples:
+        return torch.arange(n_samples), False
+    ystd = acq_vals.std(dim=0)
+    if bool(ystd == 0) or not bool(torch.isfinite(ystd)):
+        perm = torch.randperm(n_samples, generator=generator)[:n]
+        return perm, True
+    max_idx = torch.argmax(acq_vals)
+    z = (acq_vals - acq_vals.mean(dim=0)) / ystd
+    etaz = eta * z
+    weights = torch.exp(etaz)
+    while torch.isinf(weights).any():
+        etaz *= 0.5
+        weights = torch.exp(etaz)
+    idcs = torch.multinomial(weights, n, generator=generator)
+    if max_idx not in idcs:
+        idcs[-1] = max_idx
+    return idcs, False
+
+
+class LbfgsbProblem:
+    """One scipy L-BFGS-B minimisation driven by reverse communication (mirrors scipy _minimize_lbfgsb)."""
+
+    __slots__ = ("n", "x", "f", "g", "lo", "hi", "nbd", "wa", "iwa", "task", "ln_task", "lsave", "isave", "dsave",
+                 "nit", "nfev", "maxiter", "done", "warnflag")
+
+    def __init__(self, x0, lo, hi, maxiter=200):
+        n = x0.size
+        m = MAXCOR
+        self.n = n
+        self.x = np.array(x0, dtype=np.float64)
+        self.f = np.array(0.0, dtype=np.float64)
+        self.g = np.zeros(n, dtype=np.float64)
+        self.lo = np.array(lo, dtype=np.float64)
+        self.hi = np.array(hi, dtype=np.float64)
+        self.nbd = np.full(n, 2, dtype=np.int32)
+        self.wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m, np.float64)
+        self.iwa = np.zeros(3 * n, dtype=np.int32)
+        self.task = np.zeros(2, dtype=np.int32)
+        self.ln_task = np.zeros(2, dtype=np.int32)
+        self.lsave = np.zeros(4, dtype=np.int32)
+        self.isave = np.zeros(44, dtype=np.int32)
+        self.dsave = np.zeros(29, dtype=np.float64)
+        self.nit, self.nfev, self.maxiter = 0, 0, maxiter
+        self.done, self.warnflag = False, 0
+
+    def advance(self) -> bool:
+        """Run setulb until it asks for f,g at self.x (returns True) or terminates (returns False)."""
+        factr = FTOL / np.finfo(float).eps
+        while True:
+            _lbfgsb.setulb(MAXCOR, self.x, self.lo, self.hi, self.nbd, self.f, self.g, factr, GTOL, self.wa, self.iwa,
+                           self.task, self.lsave, self.isave, self.dsave, MAXLS, self.ln_task)
+            t = self.task[0]
+            if t == 3:
+                return True
+            if t == 1:
+                self.nit += 1
+                if self.nit >= self.maxiter:
+                    self.task[0], self.task[1] = 5, 504
+                elif self.nfev > MAXFUN:
+                    self.task[0], self.task[1] = 5, 502
+                continue
+            break
+        self.done = True
+        if self.task[0] == 4:
+            self.warnflag = 0
+        elif self.nfev > MAXFUN or self.nit >= self.maxiter:
+            self.warnflag = 1
+        else:
+            self.warnflag = 2
+        return False
+
+    def supply(self, f, g):
+        self.f = np.array(f, dtype=np.float64)
+        self.g[:] = g
+        self.nfev += 1
+
+    @property
+    def optimization_warning(self) -> bool:
+        """botorch _process_scipy_result: failure other than the iteration / evaluation limit raises OptimizationWarning."""
+        return self.warnflag == 2

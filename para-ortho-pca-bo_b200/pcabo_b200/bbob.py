@@ -1,0 +1,191 @@
+"""Batched BBOB objectives (f15 RastriginRotated, f16 Weierstrass, f17 Schaffers F7, f20 Schwefel) in torch.
+
+The reference evaluates `problem(x)` through ioh's C++ BBOB suite (PCA_BO.py:263, AbstractBayesianOptimizer.py:163);
+ioh is not installable here, so the COCO/ioh definitions are restated: instance data from the
+legacy COCO generator with `rseed = fid + 10000 * instance`, evaluation as one batched torch expression over B
+runs that works on CPU or CUDA tensors (one point per run per BO iteration). f15 and f20 are pinned against the
+reference's shipped IOHprofiler data (tests/test_bbob_doe.py); f16 / f17 are unpinned.
+This is the objective, not the hot path: plain torch ops are deliberate here.
+"""
+import math
+
+import numpy as np
+import torch
+
+NAMES = {15: "RastriginRotated", 16: "Weierstrass", 17: "Schaffers10", 20: "Schwefel"}
+
+
+def _unif(n: int, inseed: int) -> np.ndarray:
+    inseed = abs(int(inseed))
+    if inseed < 1:
+        inseed = 1
+    akt = inseed
+    table = [0] * 32
+    for i in range(39, -1, -1):
+        q = akt // 127773
+        akt = 16807 * (akt - q * 127773) - 2836 * q
+        if akt < 0:
+            akt += 2147483647
+        if i < 32:
+            table[i] = akt
+    cur = table[0]
+    out = np.empty(n)
+    for i in range(n):
+        q = akt // 127773
+        akt = 16807 * (akt - q * 127773) - 2836 * q
+        if akt < 0:
+            akt += 2147483647
+        j = cur // 67108865
+        cur = table[j]
+        table[j] = akt
+        out[i] = cur / 2.147483647e9
+        if out[i] == 0.0:
+            out[i] = 1e-99
+    return out
+
+
+def _gauss(n: int, seed: int) -> np.ndarray:
+    u = _unif(2 * n, seed)
+    g = np.sqrt(-2.0 * np.log(u[:n])) * np.cos(2.0 * math.pi * u[n:])
+    g[g == 0.0] = 1e-99
+    return g
+
+
+def _rotation(seed: int, dim: int) -> np.ndarray:
+    B = _gauss(dim * dim, seed).reshape(dim, dim).T.copy()
+    for i in range(dim):
+        for j in range(i):
+            B[:, i] -= float(B[:, i] @ B[:, j]) * B[:, j]
+        B[:, i] /= math.sqrt(float(B[:, i] @ B[:, i]))
+    return B
+
+
+def _xopt(seed: int, dim: int) -> np.ndarray:
+    x = 8.0 * np.floor(1e4 * _unif(dim, seed)) / 1e4 - 4.0
+    x[x == 0.0] = -1e-5
+    return x
+
+
+def _fopt(fid: int, instance: int) -> float:
+    rseed = {4: 3, 18: 17}.get(fid, fid) + 10000 * instance
+    g1, g2 = _gauss(1, rseed)[0], _gauss(1, rseed + 1)[0]
+    return min(1000.0, max(-1000.0, math.floor(100.0 * 100.0 * g1 / g2 + 0.5) / 100.0))
+
+
+def _t_osz(x: torch.Tensor) -> torch.Tensor:
+    ax = x.abs().clamp_min(1e-300)
+    t = ax.log() / 0.1
+    pos = torch.exp(t + 0.49 * (torch.sin(t) + torch.sin(0.79 * t))).pow(0.1)
+    neg = -torch.exp(t + 0.49 * (torch.sin(0.55 * t) + torch.sin(0.31 * t))).pow(0.1)
+    return torch.where(x > 0, pos, torch.where(x < 0, neg, torch.zeros_like(x)))
+
+
+def _t_asy(x: torch.Tensor, beta: float) -> torch.Tensor:
+    d = x.shape[-1]
+    idx = torch.arange(d, dtype=x.dtype, device=x.device) / (d - 1.0)
+    xp = x.clamp_min(0.0)
+    return torch.where(x > 0, xp.clamp_min(1e-300).pow(1.0 + beta * idx * xp.sqrt()), x)
+
+
+class BatchedBBOB:
+    """B (function id, instance) problems of one dimension evaluated together: f(X[B, D]) -> [B]."""
+
+    def __init__(self, fids, instances, dim: int, device="cpu"):
+        fids, instances = list(fids), list(instances)
+        assert len(fids) == len(instances)
+        self.B, self.D = len(fids), int(dim)
+        self.fids, self.instances = fids, instances
+        D = self.D
+        idx = np.arange(D) / (D - 1.0) if D > 1 else np.zeros(1)
+        xopt = np.zeros((self.B, D))
+        R = np.zeros((self.B, D, D))
+        M = np.zeros((self.B, D, D))
+        sign = np.ones((self.B, D))
+        fopt = np.zeros(self.B)
+        for b, (fid, inst) in enumerate(zip(fids, instances)):
+            if fid not in NAMES:
+                raise ValueError(f"BBOB f{fid} is not available")
+            rseed = fid + 10000 * inst
+            fopt[b] = _fopt(fid, inst)
+            if fid == 20:
+                u = _unif(D, rseed)
+                sign[b] = np.where(u - 0.5 < 0, -1.0, 1.0)
+                xopt[b] = sign[b] * 0.5 * 4.2096874637
+                continue
+            xopt[b] = _xopt(rseed, D)
+            rot1, rot2 = _rotation(rseed + 1000000, D), _rotation(rseed, D)
+            R[b] = rot1
+            if fid == 15:
+                M[b] = (rot1 * np.power(math.sqrt(10.0), idx)[None, :]) @ rot2
+            elif fid == 16:
+                M[b] = (rot1 * np.power(1.0 / math.sqrt(100.0), idx)[None, :]) @ rot2
+            else:
+                M[b] = np.power(math.sqrt(10.0), idx)[:, None] * rot2
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
+        self.xopt, self.R, self.M, self.sign, self.fopt = t(xopt), t(R), t(M), t(sign), t(fopt)
+        self.fid_t = torch.tensor(fids, device=device)
+        self.lam = t(np.power(math.sqrt(10.0), idx))
+        k = np.arange(12)
+        self.ak, self.bk = t(np.power(0.5, k)), t(np.power(3.0, k))
+        self.f0 = float(np.sum(np.power(0.5, k) * np.cos(2.0 * math.pi * np.power(3.0, k) * 0.5)))
+        self.bounds = np.tile(np.array([[-5.0, 5.0]]), (D, 1))
+        self.device = torch.device(device)
+        self._groups = {fid: torch.tensor([b for b in range(self.B) if fids[b] == fid], device=device)
+                        for fid in sorted(set(fids))}
+
+    def _eval_group(self, fid: int, sel: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        """x [m, D]: row i is evaluated with the instance data of problem sel[i]."""
+        D = self.D
+        if fid == 20:
+            sgn, xo = self.sign[sel], self.xopt[sel]
+            xh = 2.0 * sgn * x
+            zh = xh.clone()
+            zh[:, 1:] = xh[:, 1:] + 0.25 * (xh[:, :-1] - 2.0 * xo[:, :-1].abs())
+            z = 100.0 * (self.lam * (zh - 2.0 * xo.abs()) + 2.0 * xo.abs())
+            pen = (z.abs() - 500.0).clamp_min(0.0).pow(2).sum(-1)
+            s = (z * torch.sin(z.abs().sqrt())).sum(-1)
+            return 0.01 * (pen + 418.9828872724339 - s / D)
+        z = torch.einsum("bij,bj->bi", self.R[sel], x - self.xopt[sel])
+        pen = (x.abs() - 5.0).clamp_min(0.0).pow(2).sum(-1)
+        if fid == 15:
+            z = torch.einsum("bij,bj->bi", self.M[sel], _t_asy(_t_osz(z), 0.2))
+            return 10.0 * (D - torch.cos(2.0 * math.pi * z).sum(-1)) + (z * z).sum(-1)
+        if fid == 16:
+            z = torch.einsum("bij,bj->bi", self.M[sel], _t_osz(z))
+            s = (torch.cos(2.0 * math.pi * (z.unsqueeze(-1) + 0.5) * self.bk) * self.ak).sum((-1, -2))
+            return 10.0 * (s / D - self.f0).pow(3) + (10.0 / D) * pen
+        z = torch.einsum("bij,bj->bi", self.M[sel], _t_asy(z, 0.5))
+        s = z[:, :-1] ** 2 + z[:, 1:] ** 2
+        r = (s.pow(0.25) * (1.0 + torch.sin(50.0 * s.pow(0.1)) ** 2)).sum(-1)
+        return (r / (D - 1.0)).pow(2) + 10.0 * pen
+
+    def __call__(self, X: torch.Tensor) -> torch.Tensor:
+        """X [B, D] (one point per problem) -> objective values [B] (with f_opt added, like ioh's `problem(x)`)."""
+        out = torch.empty(self.B, dtype=torch.float64, device=X.device)
+        for fid, sel in self._groups.items():
+            out[sel] = self._eval_group(fid, sel, X[sel])
+        return out + self.fopt
+
+    def eval_many(self, b: int, X: np.ndarray) -> np.ndarray:
+        """Rows of X [m, D] on problem b (host convenience for the DoE and the tests)."""
+        Xt = torch.from_numpy(np.atleast_2d(np.asarray(X, dtype=np.float64))).to(self.device)
+        sel = torch.full((Xt.shape[0],), b, device=self.device, dtype=torch.long)
+        return (self._eval_group(self.fids[b], sel, Xt) + self.fopt[b]).cpu().numpy()
+
+    def problem(self, b: int):
+        """A single-problem callable `p(x) -> float` with .dim/.bounds, for the drop-in optimizer classes."""
+        return _SingleProblem(self, b)
+
+
+class _SingleProblem:
+    def __init__(self, batch: BatchedBBOB, b: int):
+        self._batch, self._b = batch, b
+        self.dim, self.bounds = batch.D, batch.bounds
+        self.fid, self.instance = batch.fids[b], batch.instances[b]
+        self.fopt = float(batch.fopt[b])
+        self.evaluations = 0
+        self._one = BatchedBBOB([self.fid], [self.instance], batch.D, device="cpu")
+
+    def __call__(self, x) -> float:
+        self.evaluations += 1
+        return float(self._one(torch.from_numpy(np.asarray(x, dtype=np.float64).reshape(1, -1)))[0])

@@ -1,0 +1,348 @@
+"""Lock-step batched PCA-BO / vanilla-BO engine: B independent runs advance one BO iteration per `step()`.
+
+One process drives one GPU. Every numerical stage of the reference's hot loop (PCA_BO.py:178-281) runs in the
+sm_100a kernels behind the C ABI; the host keeps only what must stay on the CPU generators for RNG-stream parity
+(LHS DoE and the 1e-8 PCA noise from numpy's legacy MT19937, Sobol scrambling and the Boltzmann multinomial from
+torch's CPU generator -- one private generator pair per run, seeded exactly like the reference seeds its global
+ones in AbstractAlgorithm.py:310-328) and, in `optimizer="scipy"` mode, scipy's own L-BFGS-B driven by reverse
+communication with all runs' restart problems sharing one value+gradient kernel launch per round.
+"""
+import math
+from time import perf_counter
+
+import numpy as np
+import torch
+
+from . import ops
+from .acq_host import LbfgsbProblem, initialize_q_batch, scrambled_sobol
+from .lib import PcaboError
+
+NUM_RESTARTS = 10      # PCA_BO.py:107
+RAW_SAMPLES = 512      # PCA_BO.py:108
+BATCH_LIMIT = 5        # PCA_BO.py:613
+MAXITER = 200          # PCA_BO.py:613
+
+
+def lhs_center(rs: np.random.RandomState, dim: int, n_samples: int) -> np.ndarray:
+    """pyDOE 0.3.8 lhs(criterion="center") on an explicit RandomState (AbstractBayesianOptimizer.py:30-51)."""
+    cut = np.linspace(0, 1, n_samples + 1)
+    rs.rand(n_samples, dim)  # pyDOE draws and discards this matrix
+    center = (cut[:n_samples] + cut[1:n_samples + 1]) / 2
+    H = np.zeros((n_samples, dim))
+    for j in range(dim):
+        H[:, j] = rs.permutation(center)
+    return H
+
+
+def rescale_lhs(raw: np.ndarray, bounds: np.ndarray) -> np.ndarray:
+    """AbstractBayesianOptimizer._rescale_lhs_points (:178-194)."""
+    out = np.empty_like(raw)
+    for d in range(raw.shape[1]):
+        out[:, d] = (bounds[d, 1] - bounds[d, 0]) * raw[:, d] + bounds[d, 0]
+    return out
+
+
+class BatchedBOEngine:
+    def __init__(self, problems, dim, bounds, budget, n_doe, seeds, algorithm="pca", var_threshold=0.95,
+                 n_components=0, maximization=False, device="cuda:0", optimizer="scipy",
+                 num_restarts=NUM_RESTARTS, raw_samples=RAW_SAMPLES, batch_limit=BATCH_LIMIT, maxiter=MAXITER,
+                 np_rngs=None, torch_gens=None, profile_timing=False, batch_objective=None):
+        if not torch.cuda.is_available():
+            raise PcaboError("BatchedBOEngine needs a CUDA device: the PCA-BO hot path has no CPU fallback")
+        if algorithm not in ("pca", "vanilla"):
+            raise ValueError(f"Invalid algorithm name: '{algorithm}'")
+        if optimizer not in ("scipy", "device"):
+            raise ValueError(f"Invalid optimizer: '{optimizer}'")
+        # `problems`: a list of B callables p(x) -> float, or one batched objective (e.g. pcabo_b200.bbob.BatchedBBOB)
+        # exposing B, eval_many(b, X[m, D]) -> ndarray and __call__(X[B, D] device tensor) -> [B] device tensor
+        self.batched_problem = problems if hasattr(problems, "eval_many") else None
+        self.problems = None if self.batched_problem is not None else list(problems)
+        self.B = self.batched_problem.B if self.batched_problem is not None else len(self.problems)
+        self.D = int(dim)
+        self.bounds = np.asarray(bounds, dtype=np.float64).reshape(self.D, 2)
+        self.budget = int(budget)
+        self.n_doe = int(n_doe) if n_doe and n_doe > 0 else self.D
+        self.seeds = list(seeds)
+        self.algorithm, self.optimizer = algorithm, optimizer
+        self.var_threshold, self.n_components = float(var_threshold), int(n_components or 0)
+        self.maximization = bool(maximization)
+        self.num_restarts, self.raw_samples = int(num_restarts), int(raw_samples)
+        self.batch_limit, self.maxiter = int(batch_limit), int(maxiter)
+        self.device = torch.device(device)
+        self.profile_timing = profile_timing
+        self.batch_objective = batch_objective
+        B, D, cap = self.B, self.D, self.budget
+        self.cap = cap
+        self.np_rngs = np_rngs if np_rngs is not None else [np.random.RandomState(s) for s in self.seeds]
+        if torch_gens is not None:
+            self.torch_gens = torch_gens
+        else:
+            self.torch_gens = []
+            for s in self.seeds:
+                g = torch.Generator()
+                g.manual_seed(int(s))
+                self.torch_gens.append(g)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self.X = torch.zeros(B, cap, D, **f64)
+        self.f = torch.zeros(B, cap, **f64)
+        self.logtab = torch.from_numpy(np.log(np.maximum(np.arange(cap + 2), 1).astype(np.float64))).to(self.device)
+        self.lo = torch.from_numpy(self.bounds[:, 0].copy()).to(self.device)
+        self.hi = torch.from_numpy(self.bounds[:, 1].copy()).to(self.device)
+        self.gp = ops.GPBuffers(B, cap, D, self.device)
+        self.gp.maximize = self.maximization
+        self.pca = None
+        self.d_noise = torch.zeros(B * cap * D, **f64)
+        self.h_noise = torch.zeros(B * cap * D, dtype=torch.float64).pin_memory()
+        self.n = 0
+        self.x_evals = [[] for _ in range(B)]
+        self.f_evals = [[] for _ in range(B)]
+        self.z_evals = [None] * B
+        self.current_best = [(-math.inf if self.maximization else math.inf)] * B
+        self.current_best_index = [0] * B
+        self.k_host = np.full(B, D, dtype=np.int64)
+        self.timing_logs = {"pca": [], "SingleTaskGP": [], "optimize_acqf": []}
+        self.stats = dict(kernel_launches=0, lbfgsb_rounds=0, h2d_bytes=0, d2h_bytes=0, retries=0)
+        self.last = {}
+
+    # ------------------------------------------------------------------ bookkeeping (AbstractBayesianOptimizer.py:196-208)
+    def _assign_new_best(self, b):
+        fe = self.f_evals[b]
+        self.current_best[b] = max(fe) if self.maximization else min(fe)
+        self.current_best_index[b] = fe.index(self.current_best[b], self.current_best_index[b])
+
+    def _evaluate(self, b, x):
+        return float(self.problems[b](x))
+
+    def initial_design(self):
+        """AbstractBayesianOptimizer.__call__ (:142-168): LHS DoE, evaluation, best tracking."""
+        B, D = self.B, self.D
+        for b in range(B):
+            pts = rescale_lhs(lhs_center(self.np_rngs[b], D, self.n_doe), self.bounds)
+            if self.batched_problem is not None:
+                vals = self.batched_problem.eval_many(b, pts)
+                for p, v in zip(pts, vals):
+                    self.x_evals[b].append(p)
+                    self.f_evals[b].append(float(v))
+            else:
+                for p in pts:
+                    self.x_evals[b].append(p)
+                    self.f_evals[b].append(self._evaluate(b, p))
+            self._assign_new_best(b)
+        n0 = self.n_doe
+        hx = torch.from_numpy(np.stack([np.stack(self.x_evals[b]) for b in range(B)]))
+        hf = torch.from_numpy(np.array([self.f_evals[b] for b in range(B)], dtype=np.float64))
+        self.X[:, :n0].copy_(hx)
+        self.f[:, :n0].copy_(hf)
+        self.stats["h2d_bytes"] += hx.numel() * 8 + hf.numel() * 8
+        self.n = n0
+
+    def attach_history(self, x_lists, f_lists):
+        """Adopt already evaluated points (the caller's own list objects are kept and appended to)."""
+        B = self.B
+        n0 = len(f_lists[0])
+        if any(len(f) != n0 for f in f_lists) or n0 > self.cap:
+            raise PcaboError("attach_history: all runs of a batch must hold the same number of points (<= budget)")
+        self.x_evals, self.f_evals = list(x_lists), list(f_lists)
+        hx = torch.from_numpy(np.stack([np.stack([np.asarray(x, dtype=np.float64) for x in x_lists[b]])
+                                        for b in range(B)]))
+        hf = torch.from_numpy(np.array([[float(v) for v in f_lists[b]] for b in range(B)], dtype=np.float64))
+        self.X[:, :n0].copy_(hx)
+        self.f[:, :n0].copy_(hf)
+        self.stats["h2d_bytes"] += hx.numel() * 8 + hf.numel() * 8
+        self.n = n0
+        self.current_best_index = [0] * B
+        for b in range(B):
+            self._assign_new_best(b)
+
+    # ------------------------------------------------------------------ one lock-step BO iteration
+    def _sync_time(self):
+        if self.profile_timing:
+            torch.cuda.synchronize(self.device)
+        return perf_counter()
+
+    def _fit_models(self):
+        B, D, n = self.B, self.D, self.n
+        if self.algorithm == "pca":
+            hv = self.h_noise[:B * n * D].view(B, n, D)
+            for b in range(B):
+                hv[b] = torch.from_numpy(self.np_rngs[b].normal(0, 1e-8, size=(n, D)))     # PCA_BO.py:376
+            dv = self.d_noise[:B * n * D].view(B, n, D)
+            dv.copy_(hv, non_blocking=True)
+            self.stats["h2d_bytes"] += hv.numel() * 8
+            t0 = self._sync_time()
+            self.pca = ops.weights_pca_fit(self.X, self.f, dv, self.logtab, n, self.var_threshold,
+                                           self.n_components, self.maximization, out=self.pca)
+            t1 = self._sync_time()
+            ops.gp_fit(self.gp, self.pca["Z"], self.pca["k"], self.f, n, mode=0)
+            t2 = self._sync_time()
+            self.stats["kernel_launches"] += 4
+            self.timing_logs["pca"].append(t1 - t0)
+            self.timing_logs["SingleTaskGP"].append(t2 - t1)
+        else:
+            t1 = self._sync_time()
+            ops.gp_fit(self.gp, self.X, None, self.f, n, mode=1, fix_lo=self.lo, fix_hi=self.hi)
+            t2 = self._sync_time()
+            self.stats["kernel_launches"] += 3
+            self.timing_logs["SingleTaskGP"].append(t2 - t1)
+        # best_f as botorch stores it: torch.as_tensor(python float) -> float32
+        bf = torch.tensor([float(torch.as_tensor(float(v))) for v in self.current_best], dtype=torch.float64)
+        self.gp.best_f.copy_(bf)
+        self.stats["h2d_bytes"] += B * 8
+
+    def _initial_conditions(self, runs, k_host, box_lo, box_hi):
+        """gen_batch_initial_conditions for the given runs: returns {b: ndarray [num_restarts, k_b]}."""
+        B, D = self.B, self.D
+        out = {}
+        pending = list(runs)
+        factor = 1
+        while pending and factor < 5:
+            nraw = self.raw_samples * factor
+            h_raw = torch.zeros(B, nraw, D, dtype=torch.float64).pin_memory()
+            for b in pending:
+                kb = int(k_host[b])
+                raw = scrambled_sobol(kb, nraw, self.torch_gens[b])
+                h_raw[b, :, :kb] = box_lo[b, :kb] + (box_hi[b, :kb] - box_lo[b, :kb]) * raw
+            d_raw = h_raw.to(self.device, non_blocking=True)
+            vals = ops.logei(self.gp, d_raw)["val"].cpu()
+            self.stats["kernel_launches"] += 1
+            self.stats["h2d_bytes"] += h_raw.numel() * 8
+            self.stats["d2h_bytes"] += vals.numel() * 8
+            still = []
+            for b in pending:
+                kb = int(k_host[b])
+                idcs, bad = initialize_q_batch(vals[b], self.num_restarts, self.torch_gens[b])
+                out[b] = h_raw[b, idcs, :kb].numpy().copy()
+                if bad:
+                    still.append(b)
+            pending = still
+            factor += 1
+        return out
+
+    def _optimize_scipy(self, runs, ics, k_host, box_lo, box_hi):
+        """gen_candidates_scipy for every chunk of batch_limit restarts of every run, in lock-step.
+
+        Returns (cands {b: [num_restarts, k_b]}, warned {b: bool})."""
+        B, D, R = self.B, self.D, self.num_restarts
+        chunks = [(s, min(s + self.batch_limit, R)) for s in range(0, R, self.batch_limit)]
+        probs = {}
+        for b in runs:
+            kb = int(k_host[b])
+            lo, hi = box_lo[b, :kb].numpy(), box_hi[b, :kb].numpy()
+            for ci, (s, e) in enumerate(chunks):
+                x0 = np.clip(ics[b][s:e], lo, hi).reshape(-1)                         # columnwise_clamp
+                probs[(b, ci)] = LbfgsbProblem(x0, np.tile(lo, e - s), np.tile(hi, e - s), self.maxiter)
+        h_x = torch.zeros(B, R, D, dtype=torch.float64).pin_memory()
+        for b in runs:
+            h_x[b, :, :int(k_host[b])] = torch.from_numpy(ics[b])
+        active = {key for key, p in probs.items() if p.advance()}
+        out = None
+        while active:
+            for (b, ci) in active:
+                s, e = chunks[ci]
+                kb = int(k_host[b])
+                h_x[b, s:e, :kb] = torch.from_numpy(probs[(b, ci)].x.reshape(e - s, kb))
+            d_x = h_x.to(self.device, non_blocking=True)
+            out = ops.logei(self.gp, d_x, want_grad=True, out=out)
+            val = out["val"].cpu().numpy()
+            grad = out["grad"].cpu().numpy()
+            self.stats["kernel_launches"] += 1
+            self.stats["lbfgsb_rounds"] += 1
+            self.stats["h2d_bytes"] += h_x.numel() * 8
+            self.stats["d2h_bytes"] += (val.size + grad.size) * 8
+            nxt = set()
+            for (b, ci) in active:
+                s, e = chunks[ci]
+                kb = int(k_host[b])
+                p = probs[(b, ci)]
+                p.supply(-float(val[b, s:e].sum()), -grad[b, s:e, :kb].reshape(-1))
+                if p.advance():
+                    nxt.add((b, ci))
+            active = nxt
+        cands, warned = {}, {}
+        for b in runs:
+            kb = int(k_host[b])
+            lo, hi = box_lo[b, :kb].numpy(), box_hi[b, :kb].numpy()
+            c = np.concatenate([probs[(b, ci)].x.reshape(-1, kb) for ci in range(len(chunks))], axis=0)
+            cands[b] = np.clip(c, lo, hi)
+            warned[b] = any(probs[(b, ci)].optimization_warning for ci in range(len(chunks)))
+            self.last.setdefault("nit", {})[b] = [probs[(b, ci)].nit for ci in range(len(chunks))]
+            self.last.setdefault("nfev", {})[b] = [probs[(b, ci)].nfev for ci in range(len(chunks))]
+        return cands, warned
+
+    def _propose(self):
+        """optimize_acqf (PCA_BO.py:607-614): returns device tensor z_new [B, D] and its log-EI values [B]."""
+        B, D, R = self.B, self.D, self.num_restarts
+        k_host = self.pca["k"].cpu().numpy().astype(np.int64) if self.algorithm == "pca" else np.full(B, D, np.int64)
+        self.k_host = k_host
+        box_lo, box_hi = self.gp.box_lo.cpu(), self.gp.box_hi.cpu()
+        self.stats["d2h_bytes"] += B * 4 + 2 * B * D * 8
+        runs = list(range(B))
+        ics = self._initial_conditions(runs, k_host, box_lo, box_hi)
+        if self.optimizer == "scipy":
+            cands, warned = self._optimize_scipy(runs, ics, k_host, box_lo, box_hi)
+            retry = [b for b in runs if warned[b]]
+            if retry:  # botorch retry_on_optimization_warning: new initial conditions, one more attempt
+                self.stats["retries"] += len(retry)
+                ics2 = self._initial_conditions(retry, k_host, box_lo, box_hi)
+                c2, _ = self._optimize_scipy(retry, ics2, k_host, box_lo, box_hi)
+                cands.update(c2)
+        else:
+            raise PcaboError("optimizer='device' is not built in this revision")
+        h_c = torch.zeros(B, R, D, dtype=torch.float64).pin_memory()
+        for b in runs:
+            h_c[b, :, :int(k_host[b])] = torch.from_numpy(cands[b])
+        d_c = h_c.to(self.device, non_blocking=True)
+        vals = ops.logei(self.gp, d_c)["val"]                        # final no-grad evaluation of the candidates
+        best_val, best_idx = ops.argmax(vals)                        # torch.argmax over the restarts
+        z_new = d_c[torch.arange(B, device=self.device), best_idx.long()]
+        self.stats["kernel_launches"] += 2
+        self.stats["h2d_bytes"] += h_c.numel() * 8
+        return z_new.contiguous(), best_val
+
+    def step(self):
+        """One BO iteration for all runs (PCA_BO.py:178-281)."""
+        if self.n >= self.budget:
+            return False
+        B, D, n = self.B, self.D, self.n
+        self._fit_models()
+        t0 = self._sync_time()
+        z_new, acq_val = self._propose()
+        t1 = self._sync_time()
+        self.timing_logs["optimize_acqf"].append(t1 - t0)
+        if self.algorithm == "pca":
+            im = ops.inverse_map(z_new, self.pca["k"], self.pca["V"], self.pca["m2"], self.pca["xbar"], self.lo, self.hi)
+            self.stats["kernel_launches"] += 1
+            x_dev = im["x"]
+            oob = im["oob"].cpu().numpy().astype(bool)
+        else:
+            x_dev = z_new
+            oob = np.zeros(B, dtype=bool)
+        f_dev = self.batched_problem(x_dev).cpu().numpy() if self.batched_problem is not None else None
+        x_new = x_dev.cpu().numpy()
+        z_host = z_new.cpu().numpy()
+        self.stats["d2h_bytes"] += 2 * B * D * 8 + B * 4
+        new_f = np.empty(B, dtype=np.float64)
+        for b in range(B):
+            if oob[b]:
+                new_f[b] = -1000.0 if self.maximization else 1000.0          # PCA_BO.py:260-261 (not evaluated)
+            else:
+                new_f[b] = f_dev[b] if f_dev is not None else self._evaluate(b, x_new[b])
+            self.x_evals[b].append(x_new[b].copy())
+            self.f_evals[b].append(float(new_f[b]))
+            self._assign_new_best(b)
+        self.X[:, n].copy_(torch.from_numpy(x_new))
+        self.f[:, n].copy_(torch.from_numpy(new_f))
+        self.stats["h2d_bytes"] += B * D * 8 + B * 8
+        self.last.update(z_new=z_host, x_new=x_new, new_f=new_f, oob=oob, acq_val=acq_val.cpu().numpy(),
+                         k=self.k_host.copy())
+        self.n = n + 1
+        return True
+
+    def run(self, max_iterations=None):
+        if self.n == 0:
+            self.initial_design()
+        it = 0
+        while self.n < self.budget and (max_iterations is None or it < max_iterations):
+            self.step()
+            it += 1
+        return self

@@ -1,0 +1,105 @@
+"""GPU tests of the lock-step engine and the drop-in classes: trajectories against the CPU oracle loop."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_run(fid, D, inst, iters, algorithm="pca"):
+    from oracle import bbob, doe, loop
+    torch.set_num_threads(1)
+    p = bbob.BBOBProblem(fid, D, inst)
+    budget, ndoe = doe.budget_and_ndoe(D)
+    r = loop.OracleRun(p, D, p.bounds, budget, ndoe, doe.run_seed(fid, D, inst), algorithm=algorithm, keep_trace=True)
+    r.run(max_iterations=iters)
+    return r
+
+
+def test_engine_trajectory_matches_oracle_c1():
+    """Config C1 (f15, D=10, instance 0, seed 15100): first BO iterations, engine vs oracle on identical seeds."""
+    from pcabo_b200.engine import BatchedBOEngine
+    from pcabo_b200.bbob import BatchedBBOB
+    fid, D, iters = 15, 10, 5
+    insts = [0, 1]
+    budget, ndoe = 10 * D + 50, 3 * D
+    prob = BatchedBBOB([fid] * len(insts), insts, D, device="cuda")
+    seeds = [1000 * fid + 10 * D + i for i in insts]
+    eng = BatchedBOEngine(prob, D, prob.bounds, budget, ndoe, seeds, algorithm="pca")
+    eng.initial_design()
+    refs = [_oracle_run(fid, D, i, iters) for i in insts]
+    for b, r in enumerate(refs):
+        assert np.array_equal(np.array(eng.x_evals[b][:ndoe]), np.array(r.x_evals[:ndoe])), "DoE must be bit-identical"
+        np.testing.assert_allclose(eng.f_evals[b][:ndoe], r.f_evals[:ndoe], rtol=1e-12)
+    matched = [0] * len(insts)
+    alive = [True] * len(insts)
+    for it in range(iters):
+        eng.step()
+        for b, r in enumerate(refs):
+            rec = r.trace[it]
+            if not alive[b]:
+                continue
+            same_k = int(eng.last["k"][b]) == rec["k"]
+            zerr = np.max(np.abs(eng.last["z_new"][b, :rec["k"]] - rec["new_z"])) / max(1.0, np.max(np.abs(rec["new_z"]))) \
+                if same_k else np.inf
+            if same_k and zerr < 1e-6 and bool(eng.last["oob"][b]) == rec["outside"]:
+                matched[b] += 1
+                assert abs(eng.last["acq_val"][b] - rec["acq_value"]) < 1e-6 * max(1.0, abs(rec["acq_value"]))
+            else:
+                alive[b] = False   # an L-BFGS-B line-search decision flipped: trajectories legitimately diverge
+    # identical seeds, designs and candidate sets: the first iterations must coincide
+    assert min(matched) >= 2, matched
+    assert eng.stats["kernel_launches"] > 0 and eng.stats["lbfgsb_rounds"] > 0
+
+
+def test_dropin_pca_bo_api():
+    """`from Algorithms import PCA_BO` keeps the reference's call protocol and attributes."""
+    from Algorithms import PCA_BO, Vanilla_BO, ExperimentRunner  # noqa: F401
+    from pcabo_b200.bbob import BatchedBBOB
+    D = 5
+    problem = BatchedBBOB([15], [0], D).problem(0)
+    opt = PCA_BO(budget=14, n_DoE=10, random_seed=15050, verbose=False,
+                 DoE_parameters={"criterion": "center", "iterations": 1000})
+    assert opt.TIME_PROFILES == ["SingleTaskGP", "optimize_acqf", "pca"]
+    assert opt.acquisition_function_name == "expected_improvement"
+    with pytest.raises(ValueError, match="Oddly defined name"):
+        opt.acquisition_function_name = "thompson"
+    opt.acquisition_function_name = "EI"
+    opt(problem, dim=D, bounds=problem.bounds)
+    assert opt.number_of_function_evaluations == 14 and len(opt.x_evals) == 14 and len(opt.f_evals) == 14
+    # DoE identical to the reference's shipped data for seed 15050 (f15, D=5, instance 0)
+    np.testing.assert_allclose(opt.x_evals[0], [-1.5, -1.5, -4.5, 3.5, 0.5], atol=1e-12)
+    assert opt.current_best == min(opt.f_evals) and opt.f_evals.index(opt.current_best) == opt.current_best_index
+    assert 1 <= opt.reduced_space_dim_num <= D and opt.component_matrix.shape == (D, D)
+    assert opt.explained_variance_ratio.shape == (D,) and opt.data_mean.shape == (D,)
+    for name in opt.TIME_PROFILES:
+        assert len(opt.timing_logs[name]) == 4 and opt.total_times[name] > 0
+    z = opt.z_evals[-1]
+    x_back = opt._transform_point_to_original_space(z)
+    np.testing.assert_allclose(x_back, opt.x_evals[-1], rtol=0, atol=1e-9)
+    w = opt._calculate_weights()
+    assert abs(w.sum() - 1.0) < 1e-12 and w.min() == 0.0
+    opt.reset()
+    assert opt.x_evals == [] and opt.pca is None
+
+    van = Vanilla_BO(budget=13, n_DoE=10, random_seed=15050)
+    van(problem, dim=D, bounds=problem.bounds)
+    assert len(van.f_evals) == 13 and van.TIME_PROFILES == ["SingleTaskGP", "optimize_acqf"]
+    X = np.array(van.x_evals)
+    assert np.all(X >= -5 - 1e-12) and np.all(X <= 5 + 1e-12)
+    with pytest.raises(TypeError):
+        PCA_BO(budget=12, n_DoE=10)(lambda x: 0.0, dim=D, bounds=[[-5, 5]] * D)
+
+
+def test_vanilla_engine_matches_oracle():
+    from pcabo_b200.engine import BatchedBOEngine
+    from pcabo_b200.bbob import BatchedBBOB
+    fid, D, inst, iters = 20, 5, 3, 3
+    prob = BatchedBBOB([fid], [inst], D, device="cuda")
+    eng = BatchedBOEngine(prob, D, prob.bounds, 10 * D + 50, 3 * D, [1000 * fid + 10 * D + inst], algorithm="vanilla")
+    eng.initial_design()
+    r = _oracle_run(fid, D, inst, iters, algorithm="vanilla")
+    eng.step()
+    rec = r.trace[0]
+    assert np.max(np.abs(eng.last["z_new"][0] - rec["new_z"])) < 1e-6 * max(1.0, np.max(np.abs(rec["new_z"])))
+    assert abs(eng.last["new_f"][0] - rec["new_f"]) < 1e-6 * max(1.0, abs(rec["new_f"]))
