@@ -103,6 +103,7 @@ class BatchedBOEngine:
         self.timing_logs = {"pca": [], "SingleTaskGP": [], "optimize_acqf": []}
         self.stats = dict(kernel_launches=0, lbfgsb_rounds=0, h2d_bytes=0, d2h_bytes=0, retries=0)
         self.last = {}
+        self.kernel_events = None   # set to [] to record CUDA-event pairs around every value+grad log-EI launch
 
     # ------------------------------------------------------------------ bookkeeping (AbstractBayesianOptimizer.py:196-208)
     def _assign_new_best(self, b):
@@ -242,7 +243,16 @@ class BatchedBOEngine:
                 kb = int(k_host[b])
                 h_x[b, s:e, :kb] = torch.from_numpy(probs[(b, ci)].x.reshape(e - s, kb))
             d_x = h_x.to(self.device, non_blocking=True)
-            out = ops.logei(self.gp, d_x, want_grad=True, out=out)
+            if self.kernel_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = ops.logei(self.gp, d_x, want_grad=True, out=out)
+                e1.record()
+                n = self.n
+                nbytes = sum(4 * n * n + 8 * n * int(kb) + 8 * n + R * (16 * int(kb) + 8) for kb in k_host)
+                self.kernel_events.append((e0, e1, nbytes))
+            else:
+                out = ops.logei(self.gp, d_x, want_grad=True, out=out)
             val = out["val"].cpu().numpy()
             grad = out["grad"].cpu().numpy()
             self.stats["kernel_launches"] += 1

@@ -1,0 +1,153 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every declared symbol (no compute
+without a GPU), the product fails loudly without CUDA, host mirrors of reference logic, and the world_size-2 gloo
+path of run sharding / candidate-sharded argmax."""
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    from pcabo_b200 import load_library, EXPORTED_SYMBOLS
+    lib = load_library()
+    header = open(os.path.join(ROOT, "include", "pcabo_b200.h")).read()
+    declared = set(re.findall(r"\b(pcabo_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(EXPORTED_SYMBOLS), declared ^ set(EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.pcabo_abi_version() == 1
+    assert lib.pcabo_error_string(-2).decode().startswith("size not supported")
+    # argument validation happens before any CUDA call
+    assert lib.pcabo_argmax(0, 0, None, None, None, None) == -1
+
+
+def test_no_cpu_fallback():
+    from pcabo_b200 import ops, PcaboError
+    with pytest.raises(PcaboError, match="CUDA tensor"):
+        ops.argmax(torch.zeros(2, 3, dtype=torch.float64))
+    if not torch.cuda.is_available():
+        from pcabo_b200.engine import BatchedBOEngine
+        with pytest.raises(PcaboError, match="no CPU fallback"):
+            BatchedBOEngine([lambda x: 0.0], 2, np.array([[-1, 1], [-1, 1.0]]), 10, 4, [1])
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "para-ortho-pca-bo_b200")
+    for base, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(base, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(base, fn)
+
+
+def test_host_doe_and_bbob_match_reference_goldens():
+    import json
+    from pcabo_b200.engine import lhs_center, rescale_lhs
+    from pcabo_b200.bbob import BatchedBBOB
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_kats.json")))
+    b5 = np.tile([[-5.0, 5.0]], (5, 1))
+    for fid in (15, 20):
+        prob = BatchedBBOB([fid] * 30, list(range(30)), 5)
+        for inst, rows in enumerate(kat["doe"][str(fid)]):
+            X = rescale_lhs(lhs_center(np.random.RandomState(1000 * fid + 50 + inst), 5, 10), b5)
+            ref = np.array([r["x"] for r in rows])
+            assert np.array_equal(np.round(X, 6), ref)
+            y = prob.eval_many(inst, X) - float(prob.fopt[inst])
+            np.testing.assert_allclose(y, [r["raw_y"] for r in rows], rtol=2e-12)
+
+
+def test_lbfgsb_reverse_communication_equals_scipy_minimize():
+    from scipy.optimize import minimize, rosen, rosen_der
+    from pcabo_b200.acq_host import LbfgsbProblem
+    rng = np.random.RandomState(0)
+    for _ in range(4):
+        n = 10
+        lo, hi = np.full(n, -1.5), np.full(n, 1.2)
+        x0 = np.clip(rng.uniform(-2, 2, n), lo, hi)
+        res = minimize(lambda x: (rosen(x), rosen_der(x)), x0, jac=True, method="L-BFGS-B",
+                       bounds=list(zip(lo, hi)), options={"maxiter": 200})
+        p = LbfgsbProblem(x0, lo, hi, 200)
+        while p.advance():
+            p.supply(rosen(p.x), rosen_der(p.x))
+        assert np.array_equal(res.x, p.x) and res.nit == p.nit and res.nfev == p.nfev
+        assert (res.status == 0) == (p.warnflag == 0)
+
+
+def test_initialize_q_batch_matches_oracle():
+    from pcabo_b200.acq_host import initialize_q_batch, scrambled_sobol
+    from oracle import acqf
+    g1, g2 = torch.Generator(), torch.Generator()
+    g1.manual_seed(3)
+    g2.manual_seed(3)
+    assert torch.equal(scrambled_sobol(7, 64, g1), acqf.scrambled_sobol(7, 64, g2))
+    vals = torch.randn(64, dtype=torch.float64)
+    X = torch.arange(64, dtype=torch.float64).reshape(64, 1)
+    idx, bad = initialize_q_batch(vals, 10, g1)
+    Xo, _ = acqf.initialize_q_batch(X, vals, 10, generator=g2)
+    assert not bad and torch.equal(X[idx], Xo) and int(torch.argmax(vals)) in idx.tolist()
+    idx, bad = initialize_q_batch(torch.zeros(64, dtype=torch.float64), 10, g1)
+    assert bad and len(idx) == 10
+
+
+def test_dropin_surface_without_gpu():
+    from Algorithms import PCA_BO, Vanilla_BO, ExperimentRunner
+    from Algorithms.BayesianOptimization.AbstractBayesianOptimizer import LHS_sampler
+    opt = PCA_BO(budget=30, n_DoE=6, var_threshold=0.9, random_seed=5, maximization=True, verbose=False)
+    assert opt.budget == 30 and opt.n_DoE == 6 and opt.maximization and opt.var_threshold == 0.9
+    assert opt.current_best == -np.inf and opt.random_seed == 5
+    opt.acquisition_function_name = " UCB "
+    assert opt.acquisition_function_name == "upper_confidence_bound"
+    with pytest.raises(ValueError):
+        opt.acquisition_function_name = "nonsense"
+    with pytest.raises(AttributeError):
+        opt.acquisition_function = object()
+    with pytest.raises(ValueError):
+        opt.number_of_function_evaluations = -1
+    with pytest.raises(AssertionError):
+        PCA_BO(budget=0)
+    with pytest.raises(ValueError):
+        LHS_sampler(criterion="bogus")
+    s = LHS_sampler(criterion="c", iterations=3)
+    assert s.criterion == "center"
+    np.random.seed(15050)
+    H = s(5, 10)
+    np.testing.assert_allclose(10 * H[0] - 5, [-1.5, -1.5, -4.5, 3.5, 0.5], atol=1e-12)
+    for crit in ("maximin", "centermaximin", "correlation"):
+        Hc = LHS_sampler(criterion=crit, iterations=3)(3, 6)
+        assert Hc.shape == (6, 3) and np.all((Hc >= 0) & (Hc <= 1))
+        assert all(sorted(np.floor(Hc[:, j] * 6).astype(int)) == list(range(6)) for j in range(3))
+    v = Vanilla_BO(budget=20, acquisition_function="EI")
+    assert v.TIME_PROFILES == ["SingleTaskGP", "optimize_acqf"] and v.torch_config["RAW_SAMPLES"] == 512
+    r = ExperimentRunner(["pca"], [40], [15, 16, 17], num_runs=30, world_size=4, rank=1)
+    assert r.shard(list(range(30))) == list(range(1, 30, 4))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_world_size_2_gloo_sharding_and_argmax():
+    """N > 1 host path on CPU: run sharding is disjoint and complete; the candidate-sharded argmax exchange
+    (value, global index) picks the global first-occurrence maximum with one all_gather."""
+    script = os.path.join(ROOT, "tests", "_gloo_worker.py")
+    port = _free_port()
+    procs = [subprocess.Popen([sys.executable, script, str(r), "2", str(port)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    assert "argmax ok" in outs[0]

@@ -1,0 +1,169 @@
+"""CPU tests: the oracle against the reference's golden vectors (tests/golden/reference_kats.json, generated from the
+reference's shipped IOHprofiler files by tests/golden/make_golden.py) and its own self-consistency checks."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import acqf, bbob, doe, gp, weights_pca
+
+KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+BOUNDS5 = np.tile([[-5.0, 5.0]], (5, 1))
+
+
+@pytest.mark.parametrize("fid", [15, 20])
+def test_doe_matches_reference_dat(fid):
+    """Rows 1..10 of every run block = center-LHS DoE for seed 1000*fid + 50 + instance."""
+    for inst, rows in enumerate(KAT["doe"][str(fid)]):
+        np.random.seed(doe.run_seed(fid, 5, inst))
+        X = doe.rescale(doe.lhs_center(5, 10), BOUNDS5)
+        ref = np.array([r["x"] for r in rows])
+        assert np.max(np.abs(X - ref)) < 5e-7          # .dat prints x with 6 decimals
+        assert np.array_equal(np.round(X, 6), ref)
+
+
+@pytest.mark.parametrize("fid", [15, 20])
+def test_bbob_known_answers(fid):
+    for inst, rows in enumerate(KAT["doe"][str(fid)]):
+        p = bbob.BBOBProblem(fid, 5, inst)
+        X = np.array([r["x"] for r in rows])
+        y = np.array([r["raw_y"] for r in rows])
+        np.testing.assert_allclose(p.batch(X) - p.fopt, y, rtol=2e-12)   # raw_y printed with 10 decimals
+    for r in KAT["best"][str(fid)]:                                      # full-precision x and y
+        p = bbob.BBOBProblem(fid, 5, r["instance"])
+        assert abs(p(np.array(r["x"])) - p.fopt - r["y"]) <= 1e-12 * abs(r["y"])
+    for r in KAT["rows"][str(fid)]:                                      # x rounded to 1e-6 -> loose
+        p = bbob.BBOBProblem(fid, 5, r["instance"])
+        assert abs(p(np.array(r["x"])) - p.fopt - r["raw_y"]) <= 1e-4 * max(1.0, abs(r["raw_y"]))
+
+
+def test_best_x_of_doe_rows_is_bit_exact():
+    """JSON `best.x` entries that are DoE points carry full precision (e.g. -1.4999999999999996)."""
+    hits = 0
+    for fid in (15, 20):
+        for r in KAT["best"][str(fid)]:
+            if r["evals"] <= 10:
+                np.random.seed(doe.run_seed(fid, 5, r["instance"]))
+                X = doe.rescale(doe.lhs_center(5, 10), BOUNDS5)
+                assert np.array_equal(X[r["evals"] - 1], np.array(r["x"]))
+                hits += 1
+    assert hits >= 3
+
+
+def test_pairwise_sum_is_numpy_sum():
+    rng = np.random.default_rng(0)
+    for n in list(range(1, 200)) + [255, 256, 257, 450, 1050, 2047]:
+        v = rng.random(n) * rng.choice([1e-3, 1.0, 1e3])
+        assert weights_pca.numpy_pairwise_sum(v) == float(v.sum())
+
+
+def test_rank_weights_reference_formula():
+    f = np.array([3.0, -1.0, 10.0, 2.5, 7.0])
+    w, r = weights_pca.rank_weights(f)
+    ref_r = np.argsort(np.argsort(f)) + 1                 # PCA_BO.py:333 on tie-free input
+    assert np.array_equal(r, ref_r)
+    pre = np.log(5) - np.log(ref_r)
+    assert np.array_equal(w, pre / pre.sum())
+    assert w[np.argmax(f)] == 0.0
+    wm, rm = weights_pca.rank_weights(f, maximization=True)
+    assert rm[np.argmax(f)] == 1
+    # ties: index order (stable), best among ties is the earliest
+    ft = np.array([1000.0, 5.0, 1000.0, 1000.0, 2.0])
+    _, rt = weights_pca.rank_weights(ft)
+    assert list(rt) == [3, 2, 4, 5, 1]
+
+
+@pytest.mark.parametrize("D,n", [(5, 12), (10, 30), (10, 120), (20, 61), (40, 130)])
+def test_restated_pca_matches_sklearn(D, n):
+    from helpers import synthetic_history
+    X, f, noise = synthetic_history(D, n, 3 * D + n)
+    a = weights_pca.weighted_pca_fit(X, f, noise)
+    for method in ("eigh", "svd"):
+        b = weights_pca.weighted_pca_restated(X, f, noise, method=method)
+        assert a["k"] == b["k"]
+        lam = a["explained_variance"]
+        big = lam > 1e-12 * lam[0]
+        np.testing.assert_allclose(b["explained_variance"][big], lam[big], rtol=1e-9)
+        np.testing.assert_allclose(b["Z"], a["Z"], atol=1e-9 * np.max(np.abs(a["Z"])))
+        k = a["k"]
+        np.testing.assert_allclose(b["components"][:k], a["components"][:k], atol=1e-8)
+    x = weights_pca.inverse_map(a["Z"][3], a["components"][:a["k"]], a["pca_mean"], a["data_mean"])
+    np.testing.assert_allclose(x, (a["pca"].inverse_transform(a["Z"][3].reshape(1, -1)) + a["data_mean"]).ravel())
+    # solver switch of sklearn's "auto" 
+    assert a["solver"] == ("covariance_eigh" if n >= 10 * D else "full")
+
+
+def test_log_ei_helper_against_direct_formula():
+    u = torch.tensor([-30.0, -8.0, -3.0, -1.0, -0.999, 0.0, 2.0], dtype=torch.float64)
+    import math
+    from scipy.special import log_ndtr, ndtr
+    direct = []
+    for v in u.tolist():
+        if v > -5:
+            direct.append(math.log(math.exp(-0.5 * v * v) / math.sqrt(2 * math.pi) + v * ndtr(v)))
+        else:   # asymptotic series of h(u) = phi(u) (1/u^2 - 3/u^4 + 15/u^6 - 105/u^8)
+            s = 1 / v ** 2 - 3 / v ** 4 + 15 / v ** 6 - 105 / v ** 8 + 945 / v ** 10
+            direct.append(-0.5 * v * v - 0.5 * math.log(2 * math.pi) + math.log(s))
+    got = gp.log_ei_helper(u).tolist()
+    for g, d, v in zip(got, direct, u.tolist()):
+        assert abs(g - d) < (1e-10 if v > -5 else 1e-6) * max(1.0, abs(d)), (v, g, d)
+    assert gp.best_f_as_botorch(73.085663910096) == 73.08566284179688
+
+
+def test_gp_model_identities():
+    from helpers import synthetic_history, oracle_state
+    X, f, noise = synthetic_history(8, 40, 11)
+    st, model, box, acq = oracle_state(X, f, noise)
+    K, L, alpha, Linv = model.caches()
+    n = model.n
+    assert torch.allclose(L @ L.T, K, atol=1e-12)
+    assert torch.allclose(Linv @ L, torch.eye(n, dtype=torch.float64), atol=1e-10)
+    assert torch.allclose(K @ alpha, model.y_s, atol=1e-9)
+    # training data sit in [1/12, 11/12] after Normalize
+    assert abs(float(model.train_xn.min()) - 1 / 12) < 1e-12 and abs(float(model.train_xn.max()) - 11 / 12) < 1e-12
+    # posterior at a training point: small variance, mean close to the observation
+    mu, var = model.posterior(model.train_x[:3])
+    assert torch.all(var < model.y_std ** 2 * 0.02)
+    # gradient by autograd == finite differences
+    Xq = torch.from_numpy(box[0] + (box[1] - box[0]) * np.random.RandomState(0).rand(4, model.k))
+    v, g = acq.value_and_grad(Xq)
+    eps = 1e-6
+    for j in range(model.k):
+        e = torch.zeros_like(Xq)
+        e[:, j] = eps
+        fd = (acq(Xq + e) - acq(Xq - e)) / (2 * eps)
+        assert torch.allclose(fd, g[:, j], rtol=1e-4, atol=1e-6)
+    assert abs(model.mll() - float(torch.distributions.MultivariateNormal(
+        torch.zeros(n, dtype=torch.float64), covariance_matrix=K).log_prob(model.y_s))) < 1e-8 * abs(model.mll())
+
+
+def test_sobol_with_generator_equals_global_stream():
+    w = torch.rand(100, dtype=torch.float64) + 0.1
+    torch.manual_seed(7)
+    a = torch.quasirandom.SobolEngine(6, scramble=True).draw(32, dtype=torch.float64)
+    ia = torch.multinomial(w, 10)
+    g = torch.Generator()
+    g.manual_seed(7)
+    b = acqf.scrambled_sobol(6, 32, g)
+    ib = torch.multinomial(w, 10, generator=g)
+    assert torch.equal(a, b) and torch.equal(ia, ib)
+
+
+def test_oracle_loop_runs_and_penalises_out_of_bounds():
+    from oracle import loop
+    torch.set_num_threads(1)
+    D = 5
+    p = bbob.BBOBProblem(15, D, 0)
+    r = loop.OracleRun(p, D, p.bounds, 10 * D + 50, 3 * D, doe.run_seed(15, D, 0), keep_trace=True,
+                       num_restarts=4, raw_samples=64)
+    r.run(max_iterations=4)
+    assert len(r.f_evals) == 3 * D + 4
+    for rec in r.trace:
+        x = rec["new_x"]
+        outside = (not np.all(x >= -5)) or (not np.all(x <= 5))
+        assert rec["outside"] == outside
+        if outside:
+            assert rec["new_f"] == 1000      # PCA_BO.py:260-261
+    assert r.current_best == min(r.f_evals)
