@@ -71,8 +71,19 @@ def oracle_throughput(steps, warmup, cores=None):
     cores = cores or os.cpu_count() or 1
     jobs = [(FIDS[j % len(FIDS)], j // len(FIDS), warmup + steps) for j in range(cores)]
     ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        res = pool.map(_oracle_worker, jobs)
+    # one BLAS/OpenMP thread per worker: with 16 processes x 16 library threads the tiny operands thrash
+    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS")}
+    for k in saved:
+        os.environ[k] = "1"
+    try:
+        with ctx.Pool(cores) as pool:
+            res = pool.map(_oracle_worker, jobs)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     # per step, all workers run concurrently: the step time is the slowest worker's
     per_step = [max(r[1][i] for r in res) for i in range(warmup + steps)]
     timed = sum(per_step[warmup:])
