@@ -108,6 +108,17 @@ int pcabo_logei(const pcabo_gp_model *m, int npts, const double *X, double *val,
 /* Row-wise argmax with first-occurrence ties (torch.argmax): v [B][m] -> best_val [B], best_idx [B]. */
 int pcabo_argmax(int B, int m, const double *v, double *best_val, int *best_idx, void *stream);
 
+/* Device-resident multi-start L-BFGS-B on -sum(log-EI): one thread block per chunk of `batch_limit` restarts of one
+ * run (botorch gen_candidates_scipy semantics: one joint problem per chunk, scipy defaults factr = 1e7, pgtol = 1e-5,
+ * m = 10, maxls = 20).  ics [B][num_restarts][kmax] raw-space initial conditions (clamped to the box on entry),
+ * box_lo / box_hi [B][kmax].  Outputs: cand [B][num_restarts][kmax] (clamped optimisers), and per chunk
+ * (nchunks = ceil(num_restarts / batch_limit)): fval [B][nchunks] (= -sum logEI), status [B][nchunks]
+ * (0 |proj g| <= pgtol, 1 relative reduction <= factr * eps, 2 iteration limit, 3 abnormal line-search termination ->
+ * botorch would raise OptimizationWarning and retry), nit, nfev [B][nchunks].                                       */
+int pcabo_lbfgsb_logei(const pcabo_gp_model *m, int num_restarts, int batch_limit, int maxiter, double factr,
+                       double pgtol, const double *ics, const double *box_lo, const double *box_hi,
+                       double *cand, double *fval, int *status, int *nit, int *nfev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

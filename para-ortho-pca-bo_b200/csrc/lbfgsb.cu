@@ -1,0 +1,185 @@
+// Device-resident multi-start optimiser: one thread block per joint restart problem (batch_limit points of one run)
+// runs the whole L-BFGS-B minimisation of -sum(log-EI) with the value+gradient evaluated in the same block, so an
+// optimize_acqf call costs ONE launch instead of hundreds of host round trips.
+//
+// Replaces botorch gen_candidates_scipy -> scipy.optimize.minimize(method="L-BFGS-B", options={"maxiter": 200})
+// inside the reference's optimize_acqf call (PCA_BO.py:607-614). The algorithm is
+// lbfgsb_core.cuh (validated on the host against scipy, tests/test_lbfgsb_core.py); tolerances are scipy's defaults
+// (factr = 2.22e-9 / eps = 1e7, pgtol = 1e-5, m = 10, maxls = 20).
+#include "lbfgsb_core.cuh"
+#include "logei_core.cuh"
+
+namespace {
+
+constexpr int LB_THREADS = logei::LE_THREADS;
+
+struct CudaTeam {
+  int tid, nt, lane, nl;
+  bool w0;
+  double *red;  // [8][M2] + [16]
+  int *ired;    // [16]
+  __device__ void sync() { __syncthreads(); }
+  __device__ void wsync() { __syncwarp(); }
+  __device__ double sum(double v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < LB_THREADS / 32; ++w) r += red[w];
+    return r;
+  }
+  __device__ double max(double v) {
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double r = red[0];
+#pragma unroll
+    for (int w = 1; w < LB_THREADS / 32; ++w) r = fmax(r, red[w]);
+    return r;
+  }
+  __device__ void sum_n(double *vals, int cnt) {
+#pragma unroll
+    for (int j = 0; j < lbfgsb::M2; ++j)
+      if (j < cnt) vals[j] = warp_sum(vals[j]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < lbfgsb::M2; ++j)
+        if (j < cnt) red[(tid >> 5) * lbfgsb::M2 + j] = vals[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < lbfgsb::M2; ++j) {
+      if (j < cnt) {
+        double r = 0.0;
+#pragma unroll
+        for (int w = 0; w < LB_THREADS / 32; ++w) r += red[w * lbfgsb::M2 + j];
+        vals[j] = r;
+      }
+    }
+  }
+  __device__ void argmin(double &val, int &idx) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, val, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov < val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { red[tid >> 5] = val; ired[tid >> 5] = idx; }
+    __syncthreads();
+    val = red[0];
+    idx = ired[0];
+#pragma unroll
+    for (int w = 1; w < LB_THREADS / 32; ++w) {
+      const double ov = red[w];
+      const int oi = ired[w];
+      if (ov < val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+    }
+  }
+};
+
+template <int PT>
+struct LogEiObjective {
+  logei::Ctx ctx;
+  int pcount, kk;
+  double *vals;  // smem [PT]
+  __device__ double operator()(CudaTeam &, const double *x, double *g) {
+    logei::eval_points<PT, true>(ctx, pcount, x, kk, vals, g, kk, kk, -1.0, nullptr, nullptr);
+    double f = 0.0;
+    for (int p = 0; p < pcount; ++p) f -= vals[p];
+    return f;
+  }
+};
+
+struct LbArgs {
+  pcabo_gp_model m;
+  int num_restarts, batch_limit, maxiter;
+  double factr, pgtol;
+  const double *ics, *box_lo, *box_hi;
+  double *cand, *fval;
+  int *status, *nit, *nfev;
+};
+
+template <int PT>
+__global__ void __launch_bounds__(LB_THREADS, 2) lbfgsb_logei_kernel(LbArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int nchunks = gridDim.x;
+  const int p0 = chunk * a.batch_limit;
+  const int pcount = min(a.batch_limit, a.num_restarts - p0);
+  LogEiObjective<PT> obj;
+  load_ctx(obj.ctx, a.m, b);
+  const int kk = obj.ctx.kk, kmax = a.m.kmax;
+  const int nvar = pcount * kk;
+  double *q = sm;
+  carve_ctx(obj.ctx, PT, true, q);
+  q += logei::scratch_doubles(PT, kmax, a.m.n, true);
+  lbfgsb::Work w;
+  lbfgsb::carve(w, nvar, q);
+  q += lbfgsb::work_doubles(nvar);
+  CudaTeam tm;
+  tm.tid = tid; tm.nt = LB_THREADS; tm.lane = tid & 31; tm.nl = 32; tm.w0 = tid < 32;
+  tm.red = q; q += 8 * lbfgsb::M2 + 16;
+  obj.vals = q; q += 8;
+  tm.ired = reinterpret_cast<int *>(q); q += 8;
+  int *flag = tm.ired + 12;
+  obj.pcount = pcount; obj.kk = kk;
+
+  const double *ic = a.ics + ((size_t)b * a.num_restarts + p0) * kmax;
+  const double *blo = a.box_lo + (size_t)b * kmax, *bhi = a.box_hi + (size_t)b * kmax;
+  for (int i = tid; i < nvar; i += LB_THREADS) {
+    const int p = i / kk, j = i % kk;
+    const double lo = blo[j], hi = bhi[j];
+    w.l[i] = lo; w.u[i] = hi;
+    w.x[i] = fmax(fmin(ic[(size_t)p * kmax + j], hi), lo);   // columnwise_clamp of the initial conditions
+  }
+  __syncthreads();
+  lbfgsb::Result r = lbfgsb::minimize(tm, w, obj, a.maxiter, a.factr, a.pgtol, flag);
+  __syncthreads();
+  double *out = a.cand + ((size_t)b * a.num_restarts + p0) * kmax;
+  for (int i = tid; i < pcount * kmax; i += LB_THREADS) {
+    const int p = i / kmax, j = i % kmax;
+    out[i] = (j < kk) ? fmax(fmin(w.x[p * kk + j], bhi[j]), blo[j]) : 0.0;
+  }
+  if (tid == 0) {
+    const size_t o = (size_t)b * nchunks + chunk;
+    a.status[o] = r.status; a.nit[o] = r.nit; a.nfev[o] = r.nfev; a.fval[o] = r.f;
+  }
+}
+
+template <int PT>
+int launch(const LbArgs &a, cudaStream_t st) {
+  const int nchunks = (a.num_restarts + a.batch_limit - 1) / a.batch_limit;
+  const int nvar_max = a.batch_limit * a.m.kmax;
+  const size_t smem = (logei::scratch_doubles(PT, a.m.kmax, a.m.n, true) + lbfgsb::work_doubles(nvar_max) +
+                       8 * lbfgsb::M2 + 16 + 8 + 8 + 8) * sizeof(double);
+  if (smem > 227 * 1024) return PCABO_E_UNSUPPORTED;
+  PCABO_CUDA_CHECK(cudaFuncSetAttribute(lbfgsb_logei_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(nchunks, a.m.B);
+  lbfgsb_logei_kernel<PT><<<grid, LB_THREADS, smem, st>>>(a);
+  PCABO_LAUNCH_CHECK();
+  return PCABO_OK;
+}
+
+}  // namespace
+
+extern "C" int pcabo_lbfgsb_logei(const pcabo_gp_model *m, int num_restarts, int batch_limit, int maxiter, double factr,
+                                  double pgtol, const double *ics, const double *box_lo, const double *box_hi,
+                                  double *cand, double *fval, int *status, int *nit, int *nfev, void *stream) {
+  if (!m || num_restarts <= 0 || batch_limit <= 0 || maxiter <= 0 || !ics || !box_lo || !box_hi || !cand || !fval ||
+      !status || !nit || !nfev || m->B <= 0 || m->n < 1 || m->ld_n < m->n || !m->norm_off || !m->norm_coef || !m->ZnT ||
+      !m->alpha || !m->W || !m->ymean || !m->ystd || !m->best_f || !(m->lengthscale > 0.0))
+    return PCABO_E_INVALID;
+  if (m->kmax > 104 || m->n > 4096 || batch_limit > 8) return PCABO_E_UNSUPPORTED;
+  LbArgs a;
+  a.m = *m; a.num_restarts = num_restarts; a.batch_limit = batch_limit; a.maxiter = maxiter;
+  a.factr = factr; a.pgtol = pgtol; a.ics = ics; a.box_lo = box_lo; a.box_hi = box_hi;
+  a.cand = cand; a.fval = fval; a.status = status; a.nit = nit; a.nfev = nfev;
+  cudaStream_t st = as_stream(stream);
+  if (batch_limit <= 5) return launch<5>(a, st);
+  return launch<8>(a, st);
+}

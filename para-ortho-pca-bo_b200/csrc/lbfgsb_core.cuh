@@ -1,0 +1,795 @@
+// L-BFGS-B (Byrd, Lu, Nocedal, Zhu 1995; subspace step of Morales & Nocedal 2011; More-Thuente line search) written as
+// team-parallel code: the same source runs on one host thread (HostTeam, used by the CPU validation harness against
+// scipy) and on one CUDA thread block (CudaTeam, one block per restart problem, all state in shared memory).
+//
+// It follows the published algorithm in the structure of L-BFGS-B 3.0 that scipy's `optimize.minimize(method=
+// "L-BFGS-B")` executes for botorch's gen_candidates_scipy inside the reference's optimize_acqf call
+// (PCA_BO.py:607-614): generalized Cauchy point -> free-variable subspace minimisation with the LEL^T factorisation
+// of the 2m x 2m indefinite matrix -> projected Newton step -> dcsrch line search (ftol 1e-3, gtol 0.9, xtol 0.1) ->
+// BFGS pair update with the curvature test -> tests pgtol (1e-5) and factr * epsmch (scipy ftol 2.22e-9).
+// All variables are box constrained (nbd = 2), which is the only case optimize_acqf produces.
+//
+// Control flow is uniform across the team: every thread keeps the scalar state in registers (computed redundantly
+// from team-reduced values); only arrays live in (shared) memory.
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define LB_HD __host__ __device__
+#else
+#define LB_HD
+#endif
+
+namespace lbfgsb {
+
+constexpr int M = 10;       // history pairs (scipy maxcor)
+constexpr int M2 = 2 * M;
+constexpr double EPSMCH = 2.220446049250313e-16;
+constexpr double FTOL_LS = 1e-3, GTOL_LS = 0.9, XTOL_LS = 0.1, STPMIN = 0.0, BIG = 1e10;
+constexpr int MAXLS = 20;
+
+enum Status { CONV_PGTOL = 0, CONV_FTOL = 1, STOP_MAXITER = 2, ABNORMAL = 3, RUNNING = 4 };
+
+struct HostTeam {
+  static constexpr int tid = 0, nt = 1, lane = 0, nl = 1;
+  static constexpr bool w0 = true;
+  void sync() {}
+  void wsync() {}
+  double sum(double v) { return v; }
+  double max(double v) { return v; }
+  void sum_n(double *, int) {}
+  void argmin(double &, int &) {}
+};
+
+struct Work {
+  int n;
+  double *x, *l, *u, *g, *z, *d, *t, *r, *xp;  // [n]
+  double *ws, *wy;                               // [M][n]  stored pairs, oldest first
+  double *sy, *ss, *wt, *jinv;                   // [M][M]
+  double *wn;                                    // [M2][M2]
+  double *p, *c, *wbp, *v, *wv;                  // [M2]
+  double *tbrk;                                  // [n] breakpoints (negative: none / consumed)
+  int *iwhere;                                   // [n]
+};
+
+LB_HD inline size_t work_doubles(int n) {
+  return (size_t)9 * n + (size_t)2 * M * n + 4 * M * M + M2 * M2 + 5 * M2 + n + (n + 1) / 2 + 4;
+}
+
+LB_HD inline void carve(Work &w, int n, double *base) {
+  w.n = n;
+  double *q = base;
+  w.x = q; q += n; w.l = q; q += n; w.u = q; q += n; w.g = q; q += n; w.z = q; q += n;
+  w.d = q; q += n; w.t = q; q += n; w.r = q; q += n; w.xp = q; q += n;
+  w.ws = q; q += M * n; w.wy = q; q += M * n;
+  w.sy = q; q += M * M; w.ss = q; q += M * M; w.wt = q; q += M * M; w.jinv = q; q += M * M;
+  w.wn = q; q += M2 * M2;
+  w.p = q; q += M2; w.c = q; q += M2; w.wbp = q; q += M2; w.v = q; q += M2; w.wv = q; q += M2;
+  w.tbrk = q; q += n;
+  w.iwhere = reinterpret_cast<int *>(q);
+}
+
+// ------------------------------------------------------------------------------------------------ small dense helpers
+// Cholesky of the leading n x n block of an upper-stored symmetric matrix A (ld = lda): R^T R = A, R overwrites the
+// upper triangle. Lane-parallel right-looking sweep executed by warp 0. Returns (uniformly, via smem flag) 0 / k+1.
+template <class T>
+LB_HD int chol_upper(T &tm, double *A, int lda, int n, int *flag) {
+  if (tm.w0) {
+    if (tm.lane == 0) *flag = 0;
+    tm.wsync();
+    for (int k = 0; k < n; ++k) {
+      double akk = A[k * lda + k];
+      if (!(akk > 0.0)) {
+        if (tm.lane == 0 && *flag == 0) *flag = k + 1;
+        akk = 1.0;
+      }
+      const double rkk = sqrt(akk);
+      tm.wsync();
+      if (tm.lane == 0) A[k * lda + k] = rkk;
+      for (int j = k + 1 + tm.lane; j < n; j += tm.nl) A[k * lda + j] /= rkk;
+      tm.wsync();
+      for (int j = k + 1 + tm.lane; j < n; j += tm.nl) {
+        const double rkj = A[k * lda + j];
+        for (int i = k + 1; i <= j; ++i) A[i * lda + j] -= A[k * lda + i] * rkj;
+      }
+      tm.wsync();
+    }
+  }
+  tm.sync();
+  return *flag;
+}
+
+// Solve with the upper-triangular R (ld = ldr, order n) in place on b: trans ? R^T x = b : R x = b. Warp 0 only
+// (callers synchronise the team afterwards).
+template <class T>
+LB_HD void tri_solve_w0(T &tm, const double *R, int ldr, int n, double *b, bool trans) {
+  if (!tm.w0) return;
+  if (trans) {
+    for (int j = 0; j < n; ++j) {
+      const double xj = b[j] / R[j * ldr + j];
+      tm.wsync();
+      if (tm.lane == 0) b[j] = xj;
+      for (int i = j + 1 + tm.lane; i < n; i += tm.nl) b[i] -= R[j * ldr + i] * xj;
+      tm.wsync();
+    }
+  } else {
+    for (int j = n - 1; j >= 0; --j) {
+      const double xj = b[j] / R[j * ldr + j];
+      tm.wsync();
+      if (tm.lane == 0) b[j] = xj;
+      for (int i = tm.lane; i < j; i += tm.nl) b[i] -= R[i * ldr + j] * xj;
+      tm.wsync();
+    }
+  }
+}
+
+// p = M v with the compact middle matrix (bmv of the reference implementation): v, p of length 2 col.
+template <class T>
+LB_HD void bmv(T &tm, const Work &w, int col, const double *v, double *p) {
+  if (col == 0) return;
+  if (tm.w0) {
+    // p2 = v2 + L D^-1 v1
+    for (int i = tm.lane; i < col; i += tm.nl) {
+      double s = 0.0;
+      for (int k = 0; k < i; ++k) s += w.sy[i * M + k] * v[k] / w.sy[k * M + k];
+      p[col + i] = v[col + i] + s;
+    }
+    tm.wsync();
+    tri_solve_w0(tm, w.wt, M, col, p + col, true);   // J p2 = ., J = wt^T
+    for (int i = tm.lane; i < col; i += tm.nl) p[i] = v[i] / sqrt(w.sy[i * M + i]);
+    tm.wsync();
+    tri_solve_w0(tm, w.wt, M, col, p + col, false);  // J^T p2 = p2
+    for (int i = tm.lane; i < col; i += tm.nl) {
+      double s = 0.0;
+      for (int k = i + 1; k < col; ++k) s += w.sy[k * M + i] * p[col + k] / w.sy[i * M + i];
+      p[i] = -p[i] / sqrt(w.sy[i * M + i]) + s;
+    }
+    tm.wsync();
+  }
+  tm.sync();
+}
+
+template <class T>
+LB_HD double dot(T &tm, const double *a, const double *b, int n) {
+  double s = 0.0;
+  for (int i = tm.tid; i < n; i += tm.nt) s += a[i] * b[i];
+  return tm.sum(s);
+}
+
+template <class T>
+LB_HD double projgr(T &tm, const Work &w) {
+  double sb = 0.0;
+  for (int i = tm.tid; i < w.n; i += tm.nt) {
+    double gi = w.g[i];
+    if (gi < 0.0) gi = fmax(w.x[i] - w.u[i], gi);
+    else gi = fmin(w.x[i] - w.l[i], gi);
+    sb = fmax(sb, fabs(gi));
+  }
+  return tm.max(sb);
+}
+
+// ------------------------------------------------------------------------------------------------ Cauchy point
+template <class T>
+LB_HD void cauchy(T &tm, Work &w, int col, double theta, double sbgnrm, int &nseg) {
+  const int n = w.n;
+  nseg = 0;
+  if (sbgnrm <= 0.0) {
+    for (int i = tm.tid; i < n; i += tm.nt) w.z[i] = w.x[i];
+    tm.sync();
+    return;
+  }
+  double f1 = 0.0;
+  double part[M2];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int j = 0; j < M2; ++j) part[j] = 0.0;
+  double nbrk_local = 0.0;
+  for (int i = tm.tid; i < n; i += tm.nt) {
+    const double neggi = -w.g[i];
+    const double tl = w.x[i] - w.l[i], tu = w.u[i] - w.x[i];
+    int iw = w.iwhere[i];
+    if (iw != 3 && iw != -1) {
+      iw = 0;
+      if (tl <= 0.0) { if (neggi <= 0.0) iw = 1; }
+      else if (tu <= 0.0) { if (neggi >= 0.0) iw = 2; }
+      else if (fabs(neggi) <= 0.0) iw = -3;
+      w.iwhere[i] = iw;
+    }
+    double tb = -1.0, di = 0.0;
+    if (iw == 0 || iw == -1) {
+      di = neggi;
+      f1 -= neggi * neggi;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+      for (int j = 0; j < M; ++j) {
+        if (j < col) {
+          part[j] += w.wy[j * n + i] * neggi;
+          part[M + j] += w.ws[j * n + i] * neggi;
+        }
+      }
+      if (neggi < 0.0) tb = tl / (-neggi);
+      else if (neggi > 0.0) tb = tu / neggi;
+      if (tb >= 0.0) nbrk_local += 1.0;
+    }
+    w.d[i] = di;
+    w.tbrk[i] = tb;
+    w.z[i] = w.x[i];
+  }
+  f1 = tm.sum(f1);
+  const int nbreak = (int)(tm.sum(nbrk_local) + 0.5);
+  tm.sum_n(part, M2);
+  if (tm.tid == 0) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int j = 0; j < M; ++j)
+      if (j < col) { w.p[j] = part[j]; w.p[col + j] = theta * part[M + j]; }
+    for (int j = 0; j < 2 * col; ++j) w.c[j] = 0.0;
+  }
+  tm.sync();
+  if (nbreak == 0) return;  // no variable can move: xcp = x (all boxed, so "nfree == n + 1" of the original holds)
+  double f2 = -theta * f1;
+  const double f2_org = f2;
+  if (col > 0) {
+    bmv(tm, w, col, w.p, w.v);
+    double s = 0.0;
+    for (int j = 0; j < 2 * col; ++j) s += w.v[j] * w.p[j];
+    f2 -= s;
+  }
+  double dtm = -f1 / f2;
+  double tsum = 0.0;
+  nseg = 1;
+  int nleft = nbreak;
+  double tj = 0.0;
+  bool all_fixed = false;
+  while (true) {
+    const double tj0 = tj;
+    double tmin = INFINITY;
+    int ibp = 0x7fffffff;
+    for (int i = tm.tid; i < n; i += tm.nt) {
+      const double tb = w.tbrk[i];
+      if (tb >= 0.0 && (tb < tmin || (tb == tmin && i < ibp))) { tmin = tb; ibp = i; }
+    }
+    tm.argmin(tmin, ibp);
+    tj = tmin;
+    const double dt = tj - tj0;
+    if (dtm < dt) break;
+    tsum += dt;
+    --nleft;
+    const double dibp = w.d[ibp];
+    const double xi = w.x[ibp];
+    double zibp;
+    tm.sync();
+    if (tm.tid == 0) {
+      w.d[ibp] = 0.0;
+      w.tbrk[ibp] = -1.0;
+      if (dibp > 0.0) { w.z[ibp] = w.u[ibp]; w.iwhere[ibp] = 2; }
+      else { w.z[ibp] = w.l[ibp]; w.iwhere[ibp] = 1; }
+    }
+    zibp = (dibp > 0.0) ? (w.u[ibp] - xi) : (w.l[ibp] - xi);
+    tm.sync();
+    if (nleft == 0 && nbreak == n) { dtm = dt; all_fixed = true; break; }
+    ++nseg;
+    const double dibp2 = dibp * dibp;
+    f1 = f1 + dt * f2 + dibp2 - theta * dibp * zibp;
+    f2 = f2 - theta * dibp2;
+    if (col > 0) {
+      for (int j = tm.tid; j < 2 * col; j += tm.nt) {
+        w.c[j] += dt * w.p[j];
+        w.wbp[j] = (j < col) ? w.wy[j * n + ibp] : theta * w.ws[(j - col) * n + ibp];
+      }
+      tm.sync();
+      bmv(tm, w, col, w.wbp, w.v);
+      double wmc = 0.0, wmp = 0.0, wmw = 0.0;
+      for (int j = 0; j < 2 * col; ++j) { wmc += w.c[j] * w.v[j]; wmp += w.p[j] * w.v[j]; wmw += w.wbp[j] * w.v[j]; }
+      tm.sync();
+      for (int j = tm.tid; j < 2 * col; j += tm.nt) w.p[j] -= dibp * w.wbp[j];
+      tm.sync();
+      f1 += dibp * wmc;
+      f2 += 2.0 * dibp * wmp - dibp2 * wmw;
+    }
+    f2 = fmax(EPSMCH * f2_org, f2);
+    if (nleft > 0) { dtm = -f1 / f2; continue; }
+    f1 = 0.0; f2 = 0.0; dtm = 0.0;   // all variables are bounded
+    break;
+  }
+  if (!all_fixed) {
+    if (dtm <= 0.0) dtm = 0.0;
+    tsum += dtm;
+    for (int i = tm.tid; i < n; i += tm.nt) w.z[i] += tsum * w.d[i];
+  }
+  if (col > 0)
+    for (int j = tm.tid; j < 2 * col; j += tm.nt) w.c[j] += dtm * w.p[j];
+  tm.sync();
+}
+
+// ------------------------------------------------------------------------------------------------ subspace minimisation
+// LEL^T factorisation of the indefinite K (formk). Free set: iwhere <= 0. Returns 0 or a failure code.
+template <class T>
+LB_HD int formk(T &tm, Work &w, int col, double theta, int *flag) {
+  const int n = w.n;
+  // raw inner products split over free (Z) and active (A) variables, one (i, j) entry per thread slot
+  // wn upper triangle layout (2 col x 2 col, ld M2):
+  //   (1,1): D + Y'ZZ'Y / theta ; (1,2): -L_a' + R_z' ; (2,2): theta S'AA'S
+  for (int e = tm.tid; e < 3 * col * col; e += tm.nt) {
+    const int blk = e / (col * col), rem = e % (col * col);
+    const int i = rem / col, j = rem % col;
+    if (blk == 0) {          // (1,1), i <= j
+      if (i > j) continue;
+      double s = 0.0;
+      for (int k = 0; k < n; ++k) if (w.iwhere[k] <= 0) s += w.wy[i * n + k] * w.wy[j * n + k];
+      w.wn[i * M2 + j] = s / theta + ((i == j) ? w.sy[i * M + i] : 0.0);
+    } else if (blk == 1) {   // (2,2), i <= j
+      if (i > j) continue;
+      double s = 0.0;
+      for (int k = 0; k < n; ++k) if (w.iwhere[k] > 0) s += w.ws[i * n + k] * w.ws[j * n + k];
+      w.wn[(col + i) * M2 + col + j] = s * theta;
+    } else {                 // (1,2): row jy = i (Y index), column col + iy, iy = j (S index)
+      const int jy = i, iy = j;
+      double s = 0.0;
+      if (jy < iy) {         // -L_a(iy, jy): active variables
+        for (int k = 0; k < n; ++k) if (w.iwhere[k] > 0) s += w.ws[iy * n + k] * w.wy[jy * n + k];
+        s = -s;
+      } else {               // R_z(iy, jy): free variables
+        for (int k = 0; k < n; ++k) if (w.iwhere[k] <= 0) s += w.ws[iy * n + k] * w.wy[jy * n + k];
+      }
+      w.wn[jy * M2 + col + iy] = s;
+    }
+  }
+  tm.sync();
+  int info = chol_upper(tm, w.wn, M2, col, flag);
+  if (info != 0) return -1;
+  // (1,2) <- L^-1 (1,2): one column per lane of warp 0 (each a forward substitution with R^T)
+  if (tm.w0) {
+    for (int js = tm.lane; js < col; js += tm.nl) {
+      double *b = w.wn + col + js;   // column, stride M2
+      for (int r = 0; r < col; ++r) {
+        double s = b[r * M2];
+        for (int k = 0; k < r; ++k) s -= w.wn[k * M2 + r] * b[k * M2];
+        b[r * M2] = s / w.wn[r * M2 + r];
+      }
+    }
+  }
+  tm.sync();
+  // (2,2) += (1,2)^T (1,2)
+  for (int e = tm.tid; e < col * col; e += tm.nt) {
+    const int is = e / col, js = e % col;
+    if (is > js) continue;
+    double s = 0.0;
+    for (int k = 0; k < col; ++k) s += w.wn[k * M2 + col + is] * w.wn[k * M2 + col + js];
+    w.wn[(col + is) * M2 + col + js] += s;
+  }
+  tm.sync();
+  info = chol_upper(tm, w.wn + col * M2 + col, M2, col, flag);
+  return info != 0 ? -2 : 0;
+}
+
+// r = -Z'(B(xcp - xk) + g) for the free variables (full-length array, active entries unused)
+template <class T>
+LB_HD void cmprlb(T &tm, Work &w, int col, double theta) {
+  const int n = w.n;
+  bmv(tm, w, col, w.c, w.p);  // p = M c (p is free for reuse after cauchy)
+  for (int i = tm.tid; i < n; i += tm.nt) {
+    double ri = 0.0;
+    if (w.iwhere[i] <= 0) {
+      ri = -theta * (w.z[i] - w.x[i]) - w.g[i];
+      for (int j = 0; j < col; ++j) ri += w.wy[j * n + i] * w.p[j] + w.ws[j * n + i] * (theta * w.p[col + j]);
+    }
+    w.r[i] = ri;
+  }
+  tm.sync();
+}
+
+// Subspace minimisation with the projected (Morales-Nocedal) safeguard. On entry w.z = xcp, w.r = reduced gradient;
+// on exit w.z holds the subspace minimiser. xk = w.x, gk = w.g.
+template <class T>
+LB_HD void subsm(T &tm, Work &w, int col, double theta) {
+  const int n = w.n;
+  double part[M2];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int j = 0; j < M2; ++j) part[j] = 0.0;
+  for (int i = tm.tid; i < n; i += tm.nt) {
+    if (w.iwhere[i] <= 0) {
+      const double di = w.r[i];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+      for (int j = 0; j < M; ++j)
+        if (j < col) { part[j] += w.wy[j * n + i] * di; part[M + j] += w.ws[j * n + i] * di; }
+    }
+  }
+  tm.sum_n(part, M2);
+  if (tm.tid == 0) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int j = 0; j < M; ++j)
+      if (j < col) { w.wv[j] = part[j]; w.wv[col + j] = theta * part[M + j]; }
+  }
+  tm.sync();
+  // wv <- K^-1 wv through the LEL^T factor
+  if (tm.w0) {
+    tri_solve_w0(tm, w.wn, M2, 2 * col, w.wv, true);
+    for (int j = tm.lane; j < col; j += tm.nl) w.wv[j] = -w.wv[j];
+    tm.wsync();
+    tri_solve_w0(tm, w.wn, M2, 2 * col, w.wv, false);
+  }
+  tm.sync();
+  // d = (1/theta) r + (1/theta^2) Z'W wv ; projected step; remember xcp in xp
+  double iword_l = 0.0;
+  for (int i = tm.tid; i < n; i += tm.nt) {
+    w.xp[i] = w.z[i];
+    if (w.iwhere[i] <= 0) {
+      double di = w.r[i];
+      for (int j = 0; j < col; ++j) di += w.wy[j * n + i] * w.wv[j] / theta + w.ws[j * n + i] * w.wv[col + j];
+      di *= 1.0 / theta;
+      w.r[i] = di;  // r now holds the Newton direction on the free variables
+      double xk = w.z[i] + di;
+      xk = fmax(w.l[i], xk);
+      xk = fmin(w.u[i], xk);
+      w.z[i] = xk;
+      if (xk == w.l[i] || xk == w.u[i]) iword_l = 1.0;
+    }
+  }
+  const double iword = tm.max(iword_l);
+  if (iword == 0.0) { tm.sync(); return; }
+  // sign of the directional derivative of the projected point
+  double ddp = 0.0;
+  for (int i = tm.tid; i < n; i += tm.nt) ddp += (w.z[i] - w.x[i]) * w.g[i];
+  ddp = tm.sum(ddp);
+  if (ddp > 0.0) {
+    // fall back to the truncated (backtracked) step along d from xcp
+    double alpha = 1.0;
+    int ibd = 0x7fffffff;
+    for (int i = tm.tid; i < n; i += tm.nt) {
+      if (w.iwhere[i] <= 0) {
+        const double dk = w.r[i];
+        double temp1 = 1.0;
+        bool cand = false;
+        if (dk < 0.0) {
+          const double temp2 = w.l[i] - w.xp[i];
+          if (temp2 >= 0.0) { temp1 = 0.0; cand = true; }
+          else if (dk * 1.0 < temp2) { temp1 = temp2 / dk; cand = true; }
+        } else if (dk > 0.0) {
+          const double temp2 = w.u[i] - w.xp[i];
+          if (temp2 <= 0.0) { temp1 = 0.0; cand = true; }
+          else if (dk * 1.0 > temp2) { temp1 = temp2 / dk; cand = true; }
+        }
+        if (cand && (temp1 < alpha || (temp1 == alpha && i < ibd))) { alpha = temp1; ibd = i; }
+      }
+    }
+    tm.argmin(alpha, ibd);
+    if (alpha > 1.0) alpha = 1.0;
+    tm.sync();
+    for (int i = tm.tid; i < n; i += tm.nt) {
+      double xi = w.xp[i];
+      if (w.iwhere[i] <= 0) {
+        const double dk = w.r[i];
+        if (alpha < 1.0 && i == ibd) xi = (dk > 0.0) ? w.u[i] : ((dk < 0.0) ? w.l[i] : xi);
+        else xi += alpha * dk;
+      }
+      w.z[i] = xi;
+    }
+  }
+  tm.sync();
+}
+
+// ------------------------------------------------------------------------------------------------ line search (dcsrch)
+struct LineSearch {
+  bool brackt;
+  int stage;
+  double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1;
+};
+
+LB_HD inline void dcstep(double &stx, double &fx, double &dx, double &sty, double &fy, double &dy, double &stp,
+                         double fp, double dp, bool &brackt, double stpmin, double stpmax) {
+  const double sgnd = dp * (dx / fabs(dx));
+  double stpf;
+  if (fp > fx) {
+    const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+    const double s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
+    double gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+    if (stp < stx) gamma = -gamma;
+    const double p = (gamma - dx) + theta, q = ((gamma - dx) + gamma) + dp, r = p / q;
+    const double stpc = stx + r * (stp - stx);
+    const double stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
+    stpf = (fabs(stpc - stx) < fabs(stpq - stx)) ? stpc : stpc + (stpq - stpc) / 2.0;
+    brackt = true;
+  } else if (sgnd < 0.0) {
+    const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+    const double s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
+    double gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+    if (stp > stx) gamma = -gamma;
+    const double p = (gamma - dp) + theta, q = ((gamma - dp) + gamma) + dx, r = p / q;
+    const double stpc = stp + r * (stx - stp);
+    const double stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    stpf = (fabs(stpc - stp) > fabs(stpq - stp)) ? stpc : stpq;
+    brackt = true;
+  } else if (fabs(dp) < fabs(dx)) {
+    const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+    const double s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
+    double gamma = s * sqrt(fmax(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
+    if (stp > stx) gamma = -gamma;
+    const double p = (gamma - dp) + theta, q = (gamma + (dx - dp)) + gamma, r = p / q;
+    double stpc;
+    if (r < 0.0 && gamma != 0.0) stpc = stp + r * (stx - stp);
+    else if (stp > stx) stpc = stpmax;
+    else stpc = stpmin;
+    const double stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    if (brackt) {
+      stpf = (fabs(stpc - stp) < fabs(stpq - stp)) ? stpc : stpq;
+      if (stp > stx) stpf = fmin(stp + 0.66 * (sty - stp), stpf);
+      else stpf = fmax(stp + 0.66 * (sty - stp), stpf);
+    } else {
+      stpf = (fabs(stpc - stp) > fabs(stpq - stp)) ? stpc : stpq;
+      stpf = fmin(stpmax, stpf);
+      stpf = fmax(stpmin, stpf);
+    }
+  } else {
+    if (brackt) {
+      const double theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
+      const double s = fmax(fabs(theta), fmax(fabs(dy), fabs(dp)));
+      double gamma = s * sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
+      if (stp > sty) gamma = -gamma;
+      const double p = (gamma - dp) + theta, q = ((gamma - dp) + gamma) + dy, r = p / q;
+      stpf = stp + r * (sty - stp);
+    } else if (stp > stx) stpf = stpmax;
+    else stpf = stpmin;
+  }
+  if (fp > fx) { sty = stp; fy = fp; dy = dp; }
+  else {
+    if (sgnd < 0.0) { sty = stx; fy = fx; dy = dx; }
+    stx = stp; fx = fp; dx = dp;
+  }
+  stp = stpf;
+}
+
+// returns 0: evaluate f,g at the new stp; 1: converged; 2: warning (treated like convergence by lnsrlb); <0 error
+LB_HD inline int dcsrch_start(LineSearch &ls, double f, double g, double &stp, double stpmax) {
+  if (stp < STPMIN || stp > stpmax || g >= 0.0) return -1;
+  ls.brackt = false;
+  ls.stage = 1;
+  ls.finit = f; ls.ginit = g; ls.gtest = FTOL_LS * g;
+  ls.width = stpmax - STPMIN; ls.width1 = ls.width / 0.5;
+  ls.stx = 0.0; ls.fx = f; ls.gx = g; ls.sty = 0.0; ls.fy = f; ls.gy = g;
+  ls.stmin = 0.0; ls.stmax = stp + 4.0 * stp;
+  return 0;
+}
+
+LB_HD inline int dcsrch_step(LineSearch &ls, double f, double g, double &stp, double stpmax) {
+  const double ftest = ls.finit + stp * ls.gtest;
+  if (ls.stage == 1 && f <= ftest && g >= 0.0) ls.stage = 2;
+  int res = 0;
+  if (ls.brackt && (stp <= ls.stmin || stp >= ls.stmax)) res = 2;
+  if (ls.brackt && ls.stmax - ls.stmin <= XTOL_LS * ls.stmax) res = 2;
+  if (stp == stpmax && f <= ftest && g <= ls.gtest) res = 2;
+  if (stp == STPMIN && (f > ftest || g >= ls.gtest)) res = 2;
+  if (f <= ftest && fabs(g) <= GTOL_LS * (-ls.ginit)) res = 1;
+  if (res != 0) return res;
+  if (ls.stage == 1 && f <= ls.fx && f > ftest) {
+    const double fm = f - stp * ls.gtest;
+    double fxm = ls.fx - ls.stx * ls.gtest, fym = ls.fy - ls.sty * ls.gtest;
+    const double gm = g - ls.gtest;
+    double gxm = ls.gx - ls.gtest, gym = ls.gy - ls.gtest;
+    dcstep(ls.stx, fxm, gxm, ls.sty, fym, gym, stp, fm, gm, ls.brackt, ls.stmin, ls.stmax);
+    ls.fx = fxm + ls.stx * ls.gtest; ls.fy = fym + ls.sty * ls.gtest;
+    ls.gx = gxm + ls.gtest; ls.gy = gym + ls.gtest;
+  } else {
+    dcstep(ls.stx, ls.fx, ls.gx, ls.sty, ls.fy, ls.gy, stp, f, g, ls.brackt, ls.stmin, ls.stmax);
+  }
+  if (ls.brackt) {
+    if (fabs(ls.sty - ls.stx) >= 0.66 * ls.width1) stp = ls.stx + 0.5 * (ls.sty - ls.stx);
+    ls.width1 = ls.width;
+    ls.width = fabs(ls.sty - ls.stx);
+  }
+  if (ls.brackt) { ls.stmin = fmin(ls.stx, ls.sty); ls.stmax = fmax(ls.stx, ls.sty); }
+  else { ls.stmin = stp + 1.1 * (stp - ls.stx); ls.stmax = stp + 4.0 * (stp - ls.stx); }
+  stp = fmax(stp, STPMIN);
+  stp = fmin(stp, stpmax);
+  if ((ls.brackt && (stp <= ls.stmin || stp >= ls.stmax)) || (ls.brackt && ls.stmax - ls.stmin <= XTOL_LS * ls.stmax))
+    stp = ls.stx;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ BFGS matrices
+// Append the pair (s = d, y = r) to the history (oldest first), update S'Y, S'S and theta (matupd), then form and
+// factor T = theta S'S + L D^-1 L' (formt). Returns 0 or -3 if T is not positive definite.
+template <class T>
+LB_HD int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, double dr, double stp, double dtd,
+                       int *flag) {
+  const int n = w.n;
+  if (col == M) {  // drop the oldest pair
+    for (int j = 0; j < M - 1; ++j) {
+      for (int i = tm.tid; i < n; i += tm.nt) { w.ws[j * n + i] = w.ws[(j + 1) * n + i]; w.wy[j * n + i] = w.wy[(j + 1) * n + i]; }
+      tm.sync();
+    }
+    if (tm.tid == 0) {
+      for (int i = 0; i < M - 1; ++i)
+        for (int j = 0; j < M - 1; ++j) { w.sy[i * M + j] = w.sy[(i + 1) * M + j + 1]; w.ss[i * M + j] = w.ss[(i + 1) * M + j + 1]; }
+    }
+    tm.sync();
+    col = M - 1;
+  }
+  const int c = col;
+  for (int i = tm.tid; i < n; i += tm.nt) { w.ws[c * n + i] = w.d[i]; w.wy[c * n + i] = w.r[i]; }
+  tm.sync();
+  theta = rr / dr;
+  // new row of S'Y (s_new . y_j) and new column of S'S (s_j . s_new)
+  double part[M2];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int j = 0; j < M2; ++j) part[j] = 0.0;
+  for (int i = tm.tid; i < n; i += tm.nt) {
+    const double di = w.d[i];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int j = 0; j < M; ++j)
+      if (j < c) { part[j] += di * w.wy[j * n + i]; part[M + j] += w.ws[j * n + i] * di; }
+  }
+  tm.sum_n(part, M2);
+  if (tm.tid == 0) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int j = 0; j < M; ++j)
+      if (j < c) { w.sy[c * M + j] = part[j]; w.ss[j * M + c] = part[M + j]; }
+    w.ss[c * M + c] = (stp == 1.0) ? dtd : stp * stp * dtd;
+    w.sy[c * M + c] = dr;
+  }
+  col = c + 1;
+  tm.sync();
+  // formt: upper triangle of T
+  for (int e = tm.tid; e < col * col; e += tm.nt) {
+    const int i = e / col, j = e % col;
+    if (i > j) continue;
+    double s = 0.0;
+    const int k1 = (i < j ? i : j);
+    for (int k = 0; k < k1; ++k) s += w.sy[i * M + k] * w.sy[j * M + k] / w.sy[k * M + k];
+    w.wt[i * M + j] = s + theta * w.ss[i * M + j];
+  }
+  tm.sync();
+  return chol_upper(tm, w.wt, M, col, flag) != 0 ? -3 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------ driver
+// Fn: functor  double operator()(Team&, const double* x, double* g)  -> f, fills g; called by the whole team.
+struct Result {
+  int status, nit, nfev;
+  double f;
+};
+
+template <class T, class Fn>
+LB_HD Result minimize(T &tm, Work &w, Fn &fn, int maxiter, double factr, double pgtol, int *flag) {
+  const int n = w.n;
+  Result res;
+  res.nit = 0; res.nfev = 0; res.status = RUNNING;
+  // project the start point, initialise iwhere
+  for (int i = tm.tid; i < n; i += tm.nt) {
+    double xi = w.x[i];
+    if (xi <= w.l[i]) xi = w.l[i];
+    else if (xi >= w.u[i]) xi = w.u[i];
+    w.x[i] = xi;
+    w.iwhere[i] = (w.u[i] - w.l[i] <= 0.0) ? 3 : 0;
+  }
+  tm.sync();
+  double f = fn(tm, w.x, w.g);
+  res.nfev = 1;
+  int col = 0;
+  double theta = 1.0;
+  bool updatd = false;
+  (void)updatd;
+  double sbgnrm = projgr(tm, w);
+  if (sbgnrm <= pgtol) { res.status = CONV_PGTOL; res.f = f; return res; }
+  int iter = 0;
+  while (true) {
+    int nseg;
+    cauchy(tm, w, col, theta, sbgnrm, nseg);
+    // free variables at the Cauchy point
+    double nfree_l = 0.0;
+    for (int i = tm.tid; i < n; i += tm.nt) nfree_l += (w.iwhere[i] <= 0) ? 1.0 : 0.0;
+    const int nfree = (int)(tm.sum(nfree_l) + 0.5);
+    if (nfree != 0 && col != 0) {
+      const int info = formk(tm, w, col, theta, flag);
+      if (info != 0) {  // refresh the memory and restart the iteration
+        col = 0; theta = 1.0; updatd = false;
+        continue;
+      }
+      cmprlb(tm, w, col, theta);
+      subsm(tm, w, col, theta);
+    }
+    // search direction and line search
+    double dtd_l = 0.0;
+    for (int i = tm.tid; i < n; i += tm.nt) {
+      const double di = w.z[i] - w.x[i];
+      w.d[i] = di;
+      dtd_l += di * di;
+    }
+    const double dtd = tm.sum(dtd_l);
+    const double dnorm = sqrt(dtd);
+    (void)dnorm;
+    double stpmx = BIG;
+    if (iter == 0) stpmx = 1.0;
+    else {
+      double smx = BIG;
+      for (int i = tm.tid; i < n; i += tm.nt) {
+        const double a1 = w.d[i];
+        if (a1 < 0.0) {
+          const double a2 = w.l[i] - w.x[i];
+          if (a2 >= 0.0) smx = 0.0;
+          else if (a1 * smx < a2) smx = a2 / a1;
+        } else if (a1 > 0.0) {
+          const double a2 = w.u[i] - w.x[i];
+          if (a2 <= 0.0) smx = 0.0;
+          else if (a1 * smx > a2) smx = a2 / a1;
+        }
+      }
+      stpmx = -tm.max(-smx);
+    }
+    double stp = 1.0;  // boxed problem: the first step is 1 as well
+    for (int i = tm.tid; i < n; i += tm.nt) { w.t[i] = w.x[i]; w.r[i] = w.g[i]; }
+    tm.sync();
+    const double fold = f;
+    int ifun = 0, iback = 0;
+    double gd = dot(tm, w.g, w.d, n);
+    const double gdold = gd;
+    LineSearch ls;
+    bool ls_failed = false;
+    if (gd >= 0.0) ls_failed = true;  // not a descent direction
+    else if (dcsrch_start(ls, f, gd, stp, stpmx) < 0) ls_failed = true;
+    if (!ls_failed) {
+      while (true) {
+        ++ifun; ++res.nfev; iback = ifun - 1;
+        if (stp == 1.0) { for (int i = tm.tid; i < n; i += tm.nt) w.x[i] = w.z[i]; }
+        else { for (int i = tm.tid; i < n; i += tm.nt) w.x[i] = stp * w.d[i] + w.t[i]; }
+        tm.sync();
+        f = fn(tm, w.x, w.g);
+        gd = dot(tm, w.g, w.d, n);
+        const int r = dcsrch_step(ls, f, gd, stp, stpmx);
+        if (r != 0) break;
+        if (iback + 1 >= MAXLS) { ls_failed = true; break; }
+      }
+    }
+    if (ls_failed) {
+      // restore the previous iterate
+      for (int i = tm.tid; i < n; i += tm.nt) { w.x[i] = w.t[i]; w.g[i] = w.r[i]; }
+      tm.sync();
+      f = fold;
+      if (col == 0) { res.status = ABNORMAL; break; }
+      col = 0; theta = 1.0; updatd = false;
+      continue;
+    }
+    ++iter;
+    sbgnrm = projgr(tm, w);
+    res.nit = iter;
+    if (iter >= maxiter) { res.status = STOP_MAXITER; break; }       // scipy driver stops at NEW_X before the tests
+    if (sbgnrm <= pgtol) { res.status = CONV_PGTOL; break; }
+    const double ddum0 = fmax(fabs(fold), fmax(fabs(f), 1.0));
+    if ((fold - f) <= EPSMCH * factr * ddum0) { res.status = CONV_FTOL; break; }
+    // BFGS update: r = g - g_old, d scaled by the accepted step
+    double rr_l = 0.0;
+    for (int i = tm.tid; i < n; i += tm.nt) {
+      const double ri = w.g[i] - w.r[i];
+      w.r[i] = ri;
+      rr_l += ri * ri;
+      if (stp != 1.0) w.d[i] *= stp;
+    }
+    const double rr = tm.sum(rr_l);
+    double dr, ddum;
+    if (stp == 1.0) { dr = gd - gdold; ddum = -gdold; }
+    else { dr = (gd - gdold) * stp; ddum = -gdold * stp; }
+    if (dr <= EPSMCH * ddum) { updatd = false; continue; }  // skip the update
+    updatd = true;
+    const int info = update_pairs(tm, w, col, theta, rr, dr, stp, dtd, flag);
+    if (info != 0) { col = 0; theta = 1.0; updatd = false; }
+  }
+  res.f = f;
+  return res;
+}
+
+}  // namespace lbfgsb

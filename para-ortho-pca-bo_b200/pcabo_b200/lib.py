@@ -8,7 +8,7 @@ _LIB = None
 EXPORTED_SYMBOLS = [
     "pcabo_abi_version", "pcabo_error_string", "pcabo_last_cuda_error",
     "pcabo_weights_pca_fit", "pcabo_inverse_map", "pcabo_gp_fit", "pcabo_gp_mll",
-    "pcabo_logei", "pcabo_argmax",
+    "pcabo_logei", "pcabo_argmax", "pcabo_lbfgsb_logei",
 ]
 
 
@@ -61,6 +61,8 @@ def load_library(build_if_missing: bool = False):
     lib.pcabo_gp_mll.argtypes = [ci, ci, ci] + [vp] * 6 + [vp]
     lib.pcabo_logei.restype = ci
     lib.pcabo_logei.argtypes = [ctypes.POINTER(GpModelStruct), ci, vp, vp, vp, vp, vp, vp]
+    lib.pcabo_lbfgsb_logei.restype = ci
+    lib.pcabo_lbfgsb_logei.argtypes = [ctypes.POINTER(GpModelStruct), ci, ci, ci, cd, cd] + [vp] * 8 + [vp]
     lib.pcabo_argmax.restype = ci
     lib.pcabo_argmax.argtypes = [ci, ci, vp, vp, vp, vp]
     _LIB = lib

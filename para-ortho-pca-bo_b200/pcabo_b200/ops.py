@@ -165,3 +165,29 @@ def argmax(v):
     bi = torch.empty(B, dtype=torch.int32, device=v.device)
     check(lib.pcabo_argmax(B, m, _d(v, "v"), _d(bv, "best_val"), _i(bi, "best_idx"), _stream()), "pcabo_argmax")
     return bv, bi
+
+
+LBFGSB_STATUS = {0: "CONVERGENCE: NORM OF PROJECTED GRADIENT <= PGTOL", 1: "CONVERGENCE: RELATIVE REDUCTION OF F <= FACTR*EPSMCH",
+                 2: "STOP: TOTAL NO. OF ITERATIONS REACHED LIMIT", 3: "ABNORMAL"}
+
+
+def lbfgsb_logei(buf: GPBuffers, ics, box_lo, box_hi, batch_limit=5, maxiter=200, factr=1e7, pgtol=1e-5, out=None):
+    """ics [B, num_restarts, kmax] -> dict(cand [B, R, kmax], fval/status/nit/nfev [B, nchunks]); one kernel launch."""
+    lib = load_library()
+    B, R, kmax = ics.shape
+    if B != buf.B or kmax != buf.kmax:
+        raise PcaboError("lbfgsb_logei: shape mismatch with the GP buffers")
+    nch = (R + batch_limit - 1) // batch_limit
+    dev = ics.device
+    if out is None:
+        out = dict(cand=torch.empty(B, R, kmax, dtype=torch.float64, device=dev),
+                   fval=torch.empty(B, nch, dtype=torch.float64, device=dev),
+                   status=torch.empty(B, nch, dtype=torch.int32, device=dev),
+                   nit=torch.empty(B, nch, dtype=torch.int32, device=dev),
+                   nfev=torch.empty(B, nch, dtype=torch.int32, device=dev))
+    m = model_struct(buf)
+    check(lib.pcabo_lbfgsb_logei(ctypes.byref(m), R, int(batch_limit), int(maxiter), float(factr), float(pgtol),
+                                 _d(ics, "ics"), _d(box_lo, "box_lo"), _d(box_hi, "box_hi"), _d(out["cand"], "cand"),
+                                 _d(out["fval"], "fval"), _i(out["status"], "status"), _i(out["nit"], "nit"),
+                                 _i(out["nfev"], "nfev"), _stream()), "pcabo_lbfgsb_logei")
+    return out

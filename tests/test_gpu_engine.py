@@ -103,3 +103,61 @@ def test_vanilla_engine_matches_oracle():
     rec = r.trace[0]
     assert np.max(np.abs(eng.last["z_new"][0] - rec["new_z"])) < 1e-6 * max(1.0, np.max(np.abs(rec["new_z"])))
     assert abs(eng.last["new_f"][0] - rec["new_f"]) < 1e-6 * max(1.0, abs(rec["new_f"]))
+
+
+def test_device_lbfgsb_matches_scipy_given_same_starts():
+    """The device-resident L-BFGS-B against scipy's L-BFGS-B driven by the same CUDA value+gradient kernel, from the
+    same initial conditions on the same GP: same optima (tolerance = L-BFGS-B's own stopping tolerance)."""
+    from pcabo_b200 import ops
+    from pcabo_b200.engine import BatchedBOEngine
+    from pcabo_b200.bbob import BatchedBBOB
+    fid, D = 15, 10
+    insts = [0, 1, 2, 3]
+    prob = BatchedBBOB([fid] * len(insts), insts, D, device="cuda")
+    eng = BatchedBOEngine(prob, D, prob.bounds, 10 * D + 50, 3 * D, [1000 * fid + 10 * D + i for i in insts])
+    eng.initial_design()
+    for _ in range(3):
+        eng.step()
+    eng._fit_models()
+    B = eng.B
+    k_host = eng.pca["k"].cpu().numpy().astype(np.int64)
+    box_lo, box_hi = eng.gp.box_lo.cpu(), eng.gp.box_hi.cpu()
+    ics = eng._initial_conditions(list(range(B)), k_host, box_lo, box_hi)
+    c_host, w_host = eng._optimize_scipy(list(range(B)), ics, k_host, box_lo, box_hi)
+    nit_host = dict(eng.last["nit"])
+    d_c, w_dev = eng._optimize_device(ics, k_host)
+    nit_dev = dict(eng.last["nit"])
+    vals_dev = ops.logei(eng.gp, d_c)["val"].cpu().numpy()
+    h_c = torch.zeros(B, eng.num_restarts, D, dtype=torch.float64)
+    for b in range(B):
+        h_c[b, :, :int(k_host[b])] = torch.from_numpy(c_host[b])
+    vals_host = ops.logei(eng.gp, h_c.cuda())["val"].cpu().numpy()
+    same_iters = 0
+    for b in range(B):
+        assert not w_dev[b] and not w_host[b]
+        # per chunk, the joint objective reached by both optimisers agrees to the solver tolerance
+        for c in range(2):
+            fh, fd = vals_host[b, 5 * c:5 * c + 5].sum(), vals_dev[b, 5 * c:5 * c + 5].sum()
+            assert abs(fh - fd) <= 1e-5 * max(1.0, abs(fh)), (b, c, fh, fd, nit_host[b], nit_dev[b])
+            same_iters += int(nit_host[b][c] == nit_dev[b][c])
+        assert abs(vals_host[b].max() - vals_dev[b].max()) <= 1e-6 * max(1.0, abs(vals_host[b].max()))
+    assert same_iters >= B   # most chunks follow scipy's iteration count exactly
+
+
+def test_engine_device_optimizer_trajectory():
+    """optimizer='device': first iterations of config C1 against the oracle (same tolerance as the scipy mode)."""
+    from pcabo_b200.engine import BatchedBOEngine
+    from pcabo_b200.bbob import BatchedBBOB
+    fid, D, inst, iters = 15, 10, 0, 3
+    prob = BatchedBBOB([fid], [inst], D, device="cuda")
+    eng = BatchedBOEngine(prob, D, prob.bounds, 10 * D + 50, 3 * D, [1000 * fid + 10 * D + inst], optimizer="device")
+    eng.initial_design()
+    r = _oracle_run(fid, D, inst, iters)
+    eng.step()
+    rec = r.trace[0]
+    assert int(eng.last["k"][0]) == rec["k"]
+    assert abs(eng.last["acq_val"][0] - rec["acq_value"]) < 1e-5 * max(1.0, abs(rec["acq_value"]))
+    assert np.max(np.abs(eng.last["z_new"][0, :rec["k"]] - rec["new_z"])) < 1e-4 * max(1.0, np.max(np.abs(rec["new_z"])))
+    for _ in range(iters - 1):
+        eng.step()
+    assert len(eng.f_evals[0]) == 3 * D + iters
