@@ -190,6 +190,8 @@ def run_ours(args):
     barrier()
     stats0 = dict(eng.stats)
     eng.kernel_events = []                          # CUDA-event pairs around every value+grad log-EI launch
+    if args.phases:
+        eng.phase_times = {}
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -230,7 +232,7 @@ def run_ours(args):
         tot_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
         tot_bytes = sum(nb for _, _, nb in evs)
         achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
-        roof = {"kernel": "logei_kernel<16,true> (value+grad, L-BFGS-B rounds)", "bound": "hbm",
+        roof = {"kernel": ("lbfgsb_logei_kernel<5> (device L-BFGS-B incl. log-EI value+grad)" if args.optimizer == "device" else "logei_kernel<16,true> (value+grad, L-BFGS-B rounds)"), "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
                 "traffic": None, "launches": len(evs), "avg_launch_us": 1e3 * tot_ms / len(evs),
@@ -249,6 +251,10 @@ def run_ours(args):
                                 "the timed region"},
                 "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
+    if args.phases and rank == 0:
+        tot = sum(eng.phase_times.values())
+        print(json.dumps({"phase_ms_per_step": {k: 1e3 * v / args.steps for k, v in eng.phase_times.items()},
+                          "sum_ms_per_step": 1e3 * tot / args.steps}), file=sys.stderr, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -259,10 +265,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--optimizer", default="scipy", choices=["scipy", "device"])
+    ap.add_argument("--optimizer", default="device", choices=["scipy", "device"])
     ap.add_argument("--n-start", type=int, default=N_DOE, help="fast-forward (untimed) until n points before warm-up")
     ap.add_argument("--cpu-steps", type=int, default=12, help="BO iterations per core of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--phases", action="store_true", help="print a host wall-time breakdown per phase (adds syncs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -166,6 +166,16 @@ class BatchedBBOB:
             out[sel] = self._eval_group(fid, sel, X[sel])
         return out + self.fopt
 
+    def eval_all(self, X: np.ndarray) -> np.ndarray:
+        """X [B, m, D] host array: m points per problem, one batched evaluation per function id -> [B, m]."""
+        Xt = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(self.device)
+        B, m, D = Xt.shape
+        out = torch.empty(B, m, dtype=torch.float64, device=self.device)
+        for fid, sel in self._groups.items():
+            rows = sel.repeat_interleave(m)
+            out[sel] = self._eval_group(fid, rows, Xt[sel].reshape(-1, D)).reshape(-1, m)
+        return (out + self.fopt[:, None]).cpu().numpy()
+
     def eval_many(self, b: int, X: np.ndarray) -> np.ndarray:
         """Rows of X [m, D] on problem b (host convenience for the DoE and the tests)."""
         Xt = torch.from_numpy(np.atleast_2d(np.asarray(X, dtype=np.float64))).to(self.device)

@@ -103,6 +103,7 @@ class BatchedBOEngine:
         self.timing_logs = {"pca": [], "SingleTaskGP": [], "optimize_acqf": []}
         self.stats = dict(kernel_launches=0, lbfgsb_rounds=0, h2d_bytes=0, d2h_bytes=0, retries=0)
         self.last = {}
+        self.phase_times = None     # set to {} to accumulate host wall time per phase (adds device syncs)
         self.kernel_events = None   # set to [] to record CUDA-event pairs around every value+grad log-EI launch
 
     # ------------------------------------------------------------------ bookkeeping (AbstractBayesianOptimizer.py:196-208)
@@ -117,17 +118,13 @@ class BatchedBOEngine:
     def initial_design(self):
         """AbstractBayesianOptimizer.__call__ (:142-168): LHS DoE, evaluation, best tracking."""
         B, D = self.B, self.D
+        designs = [rescale_lhs(lhs_center(self.np_rngs[b], D, self.n_doe), self.bounds) for b in range(B)]
+        if self.batched_problem is not None:
+            vals = self.batched_problem.eval_all(np.stack(designs))
         for b in range(B):
-            pts = rescale_lhs(lhs_center(self.np_rngs[b], D, self.n_doe), self.bounds)
-            if self.batched_problem is not None:
-                vals = self.batched_problem.eval_many(b, pts)
-                for p, v in zip(pts, vals):
-                    self.x_evals[b].append(p)
-                    self.f_evals[b].append(float(v))
-            else:
-                for p in pts:
-                    self.x_evals[b].append(p)
-                    self.f_evals[b].append(self._evaluate(b, p))
+            for j, p in enumerate(designs[b]):
+                self.x_evals[b].append(p)
+                self.f_evals[b].append(float(vals[b, j]) if self.batched_problem is not None else self._evaluate(b, p))
             self._assign_new_best(b)
         n0 = self.n_doe
         hx = torch.from_numpy(np.stack([np.stack(self.x_evals[b]) for b in range(B)]))
@@ -161,12 +158,23 @@ class BatchedBOEngine:
             torch.cuda.synchronize(self.device)
         return perf_counter()
 
+    def _phase(self, name, t0):
+        """Accumulate wall time since t0 under `name` when phase profiling is on; returns the new time origin."""
+        if self.phase_times is None:
+            return t0
+        torch.cuda.synchronize(self.device)
+        t1 = perf_counter()
+        self.phase_times[name] = self.phase_times.get(name, 0.0) + (t1 - t0)
+        return t1
+
     def _fit_models(self):
         B, D, n = self.B, self.D, self.n
         if self.algorithm == "pca":
+            tp = perf_counter()
             hv = self.h_noise[:B * n * D].view(B, n, D)
             for b in range(B):
                 hv[b] = torch.from_numpy(self.np_rngs[b].normal(0, 1e-8, size=(n, D)))     # PCA_BO.py:376
+            tp = self._phase("host_noise_rng", tp)
             dv = self.d_noise[:B * n * D].view(B, n, D)
             dv.copy_(hv, non_blocking=True)
             self.stats["h2d_bytes"] += hv.numel() * 8
@@ -185,6 +193,7 @@ class BatchedBOEngine:
             t2 = self._sync_time()
             self.stats["kernel_launches"] += 3
             self.timing_logs["SingleTaskGP"].append(t2 - t1)
+        self._phase("pca_gp_kernels", tp if self.algorithm == "pca" else perf_counter())
         # best_f as botorch stores it: torch.as_tensor(python float) -> float32
         bf = torch.tensor([float(torch.as_tensor(float(v))) for v in self.current_best], dtype=torch.float64)
         self.gp.best_f.copy_(bf)
@@ -198,13 +207,16 @@ class BatchedBOEngine:
         factor = 1
         while pending and factor < 5:
             nraw = self.raw_samples * factor
+            tp = perf_counter()
             h_raw = torch.zeros(B, nraw, D, dtype=torch.float64).pin_memory()
             for b in pending:
                 kb = int(k_host[b])
                 raw = scrambled_sobol(kb, nraw, self.torch_gens[b])
                 h_raw[b, :, :kb] = box_lo[b, :kb] + (box_hi[b, :kb] - box_lo[b, :kb]) * raw
+            tp = self._phase("host_sobol", tp)
             d_raw = h_raw.to(self.device, non_blocking=True)
             vals = ops.logei(self.gp, d_raw)["val"].cpu()
+            tp = self._phase("raw_logei_kernel", tp)
             self.stats["kernel_launches"] += 1
             self.stats["h2d_bytes"] += h_raw.numel() * 8
             self.stats["d2h_bytes"] += vals.numel() * 8
@@ -215,6 +227,7 @@ class BatchedBOEngine:
                 out[b] = h_raw[b, idcs, :kb].numpy().copy()
                 if bad:
                     still.append(b)
+            self._phase("host_multinomial", tp)
             pending = still
             factor += 1
         return out
@@ -337,7 +350,9 @@ class BatchedBOEngine:
             d_c = h_c.to(self.device, non_blocking=True)
             self.stats["h2d_bytes"] += h_c.numel() * 8
         else:
+            tp = perf_counter()
             d_c, warned = self._optimize_device(ics, k_host)
+            self._phase("lbfgsb_kernel", tp)
             retry = [b for b in runs if warned[b]]
             if retry:
                 self.stats["retries"] += len(retry)
@@ -362,6 +377,7 @@ class BatchedBOEngine:
         z_new, acq_val = self._propose()
         t1 = self._sync_time()
         self.timing_logs["optimize_acqf"].append(t1 - t0)
+        tp = perf_counter()
         if self.algorithm == "pca":
             im = ops.inverse_map(z_new, self.pca["k"], self.pca["V"], self.pca["m2"], self.pca["xbar"], self.lo, self.hi)
             self.stats["kernel_launches"] += 1
@@ -389,6 +405,7 @@ class BatchedBOEngine:
         self.last.update(z_new=z_host, x_new=x_new, new_f=new_f, oob=oob, acq_val=acq_val.cpu().numpy(),
                          k=self.k_host.copy())
         self.n = n + 1
+        self._phase("inverse_map_objective_bookkeeping", tp)
         return True
 
     def run(self, max_iterations=None):
