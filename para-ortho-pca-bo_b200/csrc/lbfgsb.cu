@@ -13,53 +13,29 @@ namespace {
 
 constexpr int LB_THREADS = logei::LE_THREADS;
 
-struct CudaTeam {
+enum Cmd { CMD_EVAL = 1, CMD_FORMK = 2, CMD_EXIT = 3 };
+
+// Block-level mailbox: warp 0 runs the optimiser and posts commands; warps 1..7 wait in a command loop and join the
+// block-wide phases (log-EI evaluation, the O(m^2 n) formk products). Everything else is warp-synchronous in warp 0.
+struct Mailbox {
+  int cmd, col;
+  double theta;
+};
+
+// The L-BFGS-B "team" on the device is ONE warp: reductions are shuffles, sync is __syncwarp (no block barriers).
+struct CudaWarpTeam {
   int tid, nt, lane, nl;
   bool w0;
-  double *red;  // [8][M2] + [16]
-  int *ired;    // [16]
-  __device__ void sync() { __syncthreads(); }
+  Mailbox *mb;
+  const lbfgsb::Work *wk;
+  __device__ void sync() { __syncwarp(); }
   __device__ void wsync() { __syncwarp(); }
-  __device__ double sum(double v) {
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) red[tid >> 5] = v;
-    __syncthreads();
-    double r = 0.0;
-#pragma unroll
-    for (int w = 0; w < LB_THREADS / 32; ++w) r += red[w];
-    return r;
-  }
-  __device__ double max(double v) {
-    v = warp_max(v);
-    __syncthreads();
-    if (lane == 0) red[tid >> 5] = v;
-    __syncthreads();
-    double r = red[0];
-#pragma unroll
-    for (int w = 1; w < LB_THREADS / 32; ++w) r = fmax(r, red[w]);
-    return r;
-  }
+  __device__ double sum(double v) { return warp_sum(v); }
+  __device__ double max(double v) { return warp_max(v); }
   __device__ void sum_n(double *vals, int cnt) {
 #pragma unroll
     for (int j = 0; j < lbfgsb::M2; ++j)
       if (j < cnt) vals[j] = warp_sum(vals[j]);
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-      for (int j = 0; j < lbfgsb::M2; ++j)
-        if (j < cnt) red[(tid >> 5) * lbfgsb::M2 + j] = vals[j];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < lbfgsb::M2; ++j) {
-      if (j < cnt) {
-        double r = 0.0;
-#pragma unroll
-        for (int w = 0; w < LB_THREADS / 32; ++w) r += red[w * lbfgsb::M2 + j];
-        vals[j] = r;
-      }
-    }
   }
   __device__ void argmin(double &val, int &idx) {
 #pragma unroll
@@ -68,17 +44,12 @@ struct CudaTeam {
       const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
       if (ov < val || (ov == val && oi < idx)) { val = ov; idx = oi; }
     }
+  }
+  __device__ void formk_products(const lbfgsb::Work &w, int col, double theta) {
+    if (lane == 0) { mb->cmd = CMD_FORMK; mb->col = col; mb->theta = theta; }
     __syncthreads();
-    if (lane == 0) { red[tid >> 5] = val; ired[tid >> 5] = idx; }
+    lbfgsb::formk_products_range(w, col, theta, threadIdx.x, LB_THREADS);
     __syncthreads();
-    val = red[0];
-    idx = ired[0];
-#pragma unroll
-    for (int w = 1; w < LB_THREADS / 32; ++w) {
-      const double ov = red[w];
-      const int oi = ired[w];
-      if (ov < val || (ov == val && oi < idx)) { val = ov; idx = oi; }
-    }
   }
 };
 
@@ -87,7 +58,14 @@ struct LogEiObjective {
   logei::Ctx ctx;
   int pcount, kk;
   double *vals;  // smem [PT]
-  __device__ double operator()(CudaTeam &, const double *x, double *g) {
+  // called by warp 0 (the team); posts the evaluation to the whole block
+  __device__ double operator()(CudaWarpTeam &tm, const double *x, double *g) {
+    if (tm.lane == 0) tm.mb->cmd = CMD_EVAL;
+    __syncthreads();
+    return run(x, g);
+  }
+  // executed by all LB_THREADS threads
+  __device__ double run(const double *x, double *g) {
     logei::eval_points<PT, true>(ctx, pcount, x, kk, vals, g, kk, kk, -1.0, nullptr, nullptr);
     double f = 0.0;
     for (int p = 0; p < pcount; ++p) f -= vals[p];
@@ -121,12 +99,9 @@ __global__ void __launch_bounds__(LB_THREADS, 2) lbfgsb_logei_kernel(LbArgs a) {
   lbfgsb::Work w;
   lbfgsb::carve(w, nvar, q);
   q += lbfgsb::work_doubles(nvar);
-  CudaTeam tm;
-  tm.tid = tid; tm.nt = LB_THREADS; tm.lane = tid & 31; tm.nl = 32; tm.w0 = tid < 32;
-  tm.red = q; q += 8 * lbfgsb::M2 + 16;
+  Mailbox *mb = reinterpret_cast<Mailbox *>(q); q += 2;
   obj.vals = q; q += 8;
-  tm.ired = reinterpret_cast<int *>(q); q += 8;
-  int *flag = tm.ired + 12;
+  int *flag = reinterpret_cast<int *>(q); q += 2;
   obj.pcount = pcount; obj.kk = kk;
 
   const double *ic = a.ics + ((size_t)b * a.num_restarts + p0) * kmax;
@@ -138,7 +113,27 @@ __global__ void __launch_bounds__(LB_THREADS, 2) lbfgsb_logei_kernel(LbArgs a) {
     w.x[i] = fmax(fmin(ic[(size_t)p * kmax + j], hi), lo);   // columnwise_clamp of the initial conditions
   }
   __syncthreads();
-  lbfgsb::Result r = lbfgsb::minimize(tm, w, obj, a.maxiter, a.factr, a.pgtol, flag);
+  lbfgsb::Result r;
+  if (tid < 32) {
+    CudaWarpTeam tm;
+    tm.tid = tid; tm.nt = 32; tm.lane = tid; tm.nl = 32; tm.w0 = true; tm.mb = mb; tm.wk = &w;
+    r = lbfgsb::minimize(tm, w, obj, a.maxiter, a.factr, a.pgtol, flag);
+    if (tid == 0) mb->cmd = CMD_EXIT;
+    __syncthreads();
+  } else {
+    for (;;) {
+      __syncthreads();
+      const int c = mb->cmd;
+      if (c == CMD_EVAL) {
+        obj.run(w.x, w.g);
+      } else if (c == CMD_FORMK) {
+        lbfgsb::formk_products_range(w, mb->col, mb->theta, tid, LB_THREADS);
+        __syncthreads();
+      } else {
+        break;
+      }
+    }
+  }
   __syncthreads();
   double *out = a.cand + ((size_t)b * a.num_restarts + p0) * kmax;
   for (int i = tid; i < pcount * kmax; i += LB_THREADS) {
@@ -156,7 +151,7 @@ int launch(const LbArgs &a, cudaStream_t st) {
   const int nchunks = (a.num_restarts + a.batch_limit - 1) / a.batch_limit;
   const int nvar_max = a.batch_limit * a.m.kmax;
   const size_t smem = (logei::scratch_doubles(PT, a.m.kmax, a.m.n, true) + lbfgsb::work_doubles(nvar_max) +
-                       8 * lbfgsb::M2 + 16 + 8 + 8 + 8) * sizeof(double);
+                       2 + 8 + 2 + 8) * sizeof(double);
   if (smem > 227 * 1024) return PCABO_E_UNSUPPORTED;
   PCABO_CUDA_CHECK(cudaFuncSetAttribute(lbfgsb_logei_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(nchunks, a.m.B);

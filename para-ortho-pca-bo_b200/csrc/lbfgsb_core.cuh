@@ -39,6 +39,7 @@ struct HostTeam {
   double max(double v) { return v; }
   void sum_n(double *, int) {}
   void argmin(double &, int &) {}
+  inline void formk_products(const struct Work &w, int col, double theta);
 };
 
 struct Work {
@@ -306,14 +307,12 @@ LB_HD void cauchy(T &tm, Work &w, int col, double theta, double sbgnrm, int &nse
 }
 
 // ------------------------------------------------------------------------------------------------ subspace minimisation
-// LEL^T factorisation of the indefinite K (formk). Free set: iwhere <= 0. Returns 0 or a failure code.
-template <class T>
-LB_HD int formk(T &tm, Work &w, int col, double theta, int *flag) {
+// Raw inner products of formk split over free (Z, iwhere <= 0) and active (A) variables; entries e = tid, tid + nt, ...
+// wn upper triangle layout (2 col x 2 col, ld M2):
+//   (1,1): D + Y'ZZ'Y / theta ; (1,2): -L_a' + R_z' ; (2,2): theta S'AA'S
+LB_HD inline void formk_products_range(const Work &w, int col, double theta, int tid, int nt) {
   const int n = w.n;
-  // raw inner products split over free (Z) and active (A) variables, one (i, j) entry per thread slot
-  // wn upper triangle layout (2 col x 2 col, ld M2):
-  //   (1,1): D + Y'ZZ'Y / theta ; (1,2): -L_a' + R_z' ; (2,2): theta S'AA'S
-  for (int e = tm.tid; e < 3 * col * col; e += tm.nt) {
+  for (int e = tid; e < 3 * col * col; e += nt) {
     const int blk = e / (col * col), rem = e % (col * col);
     const int i = rem / col, j = rem % col;
     if (blk == 0) {          // (1,1), i <= j
@@ -338,6 +337,14 @@ LB_HD int formk(T &tm, Work &w, int col, double theta, int *flag) {
       w.wn[jy * M2 + col + iy] = s;
     }
   }
+}
+
+inline void HostTeam::formk_products(const Work &w, int col, double theta) { formk_products_range(w, col, theta, 0, 1); }
+
+// LEL^T factorisation of the indefinite K (formk). Free set: iwhere <= 0. Returns 0 or a failure code.
+template <class T>
+LB_HD int formk(T &tm, Work &w, int col, double theta, int *flag) {
+  tm.formk_products(w, col, theta);   // the team may hand this O(m^2 n) part to more threads than itself
   tm.sync();
   int info = chol_upper(tm, w.wn, M2, col, flag);
   if (info != 0) return -1;

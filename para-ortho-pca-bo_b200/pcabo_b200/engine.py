@@ -8,6 +8,8 @@ ones in AbstractAlgorithm.py:310-328) and, in `optimizer="scipy"` mode, scipy's 
 communication with all runs' restart problems sharing one value+gradient kernel launch per round.
 """
 import math
+import os
+from concurrent.futures import ThreadPoolExecutor
 from time import perf_counter
 
 import numpy as np
@@ -46,7 +48,7 @@ class BatchedBOEngine:
     def __init__(self, problems, dim, bounds, budget, n_doe, seeds, algorithm="pca", var_threshold=0.95,
                  n_components=0, maximization=False, device="cuda:0", optimizer="scipy",
                  num_restarts=NUM_RESTARTS, raw_samples=RAW_SAMPLES, batch_limit=BATCH_LIMIT, maxiter=MAXITER,
-                 np_rngs=None, torch_gens=None, profile_timing=False, batch_objective=None):
+                 np_rngs=None, torch_gens=None, profile_timing=False, batch_objective=None, host_threads=None):
         if not torch.cuda.is_available():
             raise PcaboError("BatchedBOEngine needs a CUDA device: the PCA-BO hot path has no CPU fallback")
         if algorithm not in ("pca", "vanilla"):
@@ -93,6 +95,10 @@ class BatchedBOEngine:
         self.pca = None
         self.d_noise = torch.zeros(B * cap * D, **f64)
         self.h_noise = torch.zeros(B * cap * D, dtype=torch.float64).pin_memory()
+        self.h_raw = torch.zeros(B, self.raw_samples, D, dtype=torch.float64).pin_memory()
+        self.h_ics = torch.zeros(B, self.num_restarts, D, dtype=torch.float64).pin_memory()
+        # per-run host RNG work (numpy normal, torch randint / multinomial) releases the GIL: spread it over the cores
+        self.pool = ThreadPoolExecutor(max_workers=max(1, min(B, host_threads or (os.cpu_count() or 1))))
         self.n = 0
         self.x_evals = [[] for _ in range(B)]
         self.f_evals = [[] for _ in range(B)]
@@ -172,8 +178,12 @@ class BatchedBOEngine:
         if self.algorithm == "pca":
             tp = perf_counter()
             hv = self.h_noise[:B * n * D].view(B, n, D)
-            for b in range(B):
-                hv[b] = torch.from_numpy(self.np_rngs[b].normal(0, 1e-8, size=(n, D)))     # PCA_BO.py:376
+            hv_np = hv.numpy()
+
+            def _noise(b):
+                hv_np[b] = self.np_rngs[b].normal(0, 1e-8, size=(n, D))                  # PCA_BO.py:376
+
+            list(self.pool.map(_noise, range(B)))
             tp = self._phase("host_noise_rng", tp)
             dv = self.d_noise[:B * n * D].view(B, n, D)
             dv.copy_(hv, non_blocking=True)
@@ -208,11 +218,15 @@ class BatchedBOEngine:
         while pending and factor < 5:
             nraw = self.raw_samples * factor
             tp = perf_counter()
-            h_raw = torch.zeros(B, nraw, D, dtype=torch.float64).pin_memory()
-            for b in pending:
+            h_raw = self.h_raw if factor == 1 else torch.zeros(B, nraw, D, dtype=torch.float64).pin_memory()
+
+            def _sobol(b):
                 kb = int(k_host[b])
                 raw = scrambled_sobol(kb, nraw, self.torch_gens[b])
                 h_raw[b, :, :kb] = box_lo[b, :kb] + (box_hi[b, :kb] - box_lo[b, :kb]) * raw
+                h_raw[b, :, kb:] = 0.0
+
+            list(self.pool.map(_sobol, pending))
             tp = self._phase("host_sobol", tp)
             d_raw = h_raw.to(self.device, non_blocking=True)
             vals = ops.logei(self.gp, d_raw)["val"].cpu()
@@ -220,11 +234,14 @@ class BatchedBOEngine:
             self.stats["kernel_launches"] += 1
             self.stats["h2d_bytes"] += h_raw.numel() * 8
             self.stats["d2h_bytes"] += vals.numel() * 8
-            still = []
-            for b in pending:
+            def _pick(b):
                 kb = int(k_host[b])
                 idcs, bad = initialize_q_batch(vals[b], self.num_restarts, self.torch_gens[b])
-                out[b] = h_raw[b, idcs, :kb].numpy().copy()
+                return b, h_raw[b, idcs, :kb].numpy().copy(), bad
+
+            still = []
+            for b, ic, bad in self.pool.map(_pick, pending):
+                out[b] = ic
                 if bad:
                     still.append(b)
             self._phase("host_multinomial", tp)
@@ -297,7 +314,8 @@ class BatchedBOEngine:
 
         Returns (device tensor of clamped candidates [B, R, D], warned {b: bool})."""
         B, D, R = self.B, self.D, self.num_restarts
-        h_x = torch.zeros(B, R, D, dtype=torch.float64).pin_memory()
+        h_x = self.h_ics
+        h_x.zero_()
         for b in range(B):
             h_x[b, :, :int(k_host[b])] = torch.from_numpy(ics[b])
         d_x = h_x.to(self.device, non_blocking=True)
