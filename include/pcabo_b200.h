@@ -119,6 +119,17 @@ int pcabo_lbfgsb_logei(const pcabo_gp_model *m, int num_restarts, int batch_limi
                        double pgtol, const double *ics, const double *box_lo, const double *box_hi,
                        double *cand, double *fval, int *status, int *nit, int *nfev, void *stream);
 
+/* Scrambled Sobol raw samples scaled to the search box, generated on the device from host-drawn scramble bits
+ * (replaces botorch draw_sobol_samples / torch SobolEngine(k, scramble=True).draw(npts, float64) inside optimize_acqf,
+ * PCA_BO.py:607-614; bit-identical to torch).  shift [B][kmax] (30-bit), ltm_dots [B][kmax][30] (rows of the random
+ * lower-triangular matrices with unit diagonal, packed MSB-first), state0 [kmax][30] unscrambled direction numbers,
+ * box_lo / box_hi [B][kmax] -> X [B][npts][kmax] (columns >= k[b] zero).                                              */
+int pcabo_sobol_points(int B, int npts, int kmax, const int *k, const int *shift, const int *ltm_dots,
+                       const int *state0, const double *box_lo, const double *box_hi, double *X, void *stream);
+
+/* out[b][r][:] = X[b][idx[b][r]][:]  (selection of the initial conditions among the raw samples).                    */
+int pcabo_gather_rows(int B, int npts, int nsel, int kmax, const double *X, const int *idx, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,34 @@ def initialize_q_batch(acq_vals: torch.Tensor, n: int, generator: torch.Generato
     return idcs, False
 
 
+MAXBIT = 30
+_POW2_DESC = None
+_STATE0 = {}
+
+
+def sobol_state0(kmax: int) -> torch.Tensor:
+    """Unscrambled direction numbers of torch's SobolEngine for `kmax` dimensions, [kmax, 30] int32 (cached)."""
+    if kmax not in _STATE0:
+        _STATE0[kmax] = torch.quasirandom.SobolEngine(kmax, scramble=False).sobolstate.to(torch.int32).contiguous()
+    return _STATE0[kmax]
+
+
+def draw_scramble_bits(d: int, generator: torch.Generator, shift_out: torch.Tensor, dots_out: torch.Tensor):
+    """The two randint draws of SobolEngine._scramble for `d` dimensions from `generator`, reduced to what the device
+    kernel needs: shift_out[:d] (30-bit shift per dimension) and dots_out[:d, :30] (rows of the lower-triangular
+    matrices with unit diagonal packed MSB-first, ATen `cdot_pow2`). Consumes exactly the stream torch consumes."""
+    global _POW2_DESC
+    if _POW2_DESC is None:
+        _POW2_DESC = torch.pow(2, torch.arange(MAXBIT - 1, -1, -1))
+    shift_ints = torch.randint(2, (d, MAXBIT), generator=generator)
+    ltm = torch.randint(2, (d, MAXBIT, MAXBIT), generator=generator).tril_()
+    shift_out[:d] = torch.mv(shift_ints, torch.pow(2, torch.arange(0, MAXBIT)))
+    ltm.diagonal(0, -2, -1).fill_(1)
+    dots_out[:d] = (ltm * _POW2_DESC).sum(-1)
+    shift_out[d:] = 0
+    dots_out[d:] = 0
+
+
 class LbfgsbProblem:
     """One scipy L-BFGS-B minimisation driven by reverse communication (mirrors scipy _minimize_lbfgsb)."""
 

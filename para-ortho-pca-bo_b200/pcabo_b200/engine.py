@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .acq_host import LbfgsbProblem, initialize_q_batch, scrambled_sobol
+from .acq_host import LbfgsbProblem, draw_scramble_bits, initialize_q_batch, sobol_state0
 from .lib import PcaboError
 
 NUM_RESTARTS = 10      # PCA_BO.py:107
@@ -95,8 +95,11 @@ class BatchedBOEngine:
         self.pca = None
         self.d_noise = torch.zeros(B * cap * D, **f64)
         self.h_noise = torch.zeros(B * cap * D, dtype=torch.float64).pin_memory()
-        self.h_raw = torch.zeros(B, self.raw_samples, D, dtype=torch.float64).pin_memory()
-        self.h_ics = torch.zeros(B, self.num_restarts, D, dtype=torch.float64).pin_memory()
+        self.h_shift = torch.zeros(B, D, dtype=torch.int64)
+        self.h_dots = torch.zeros(B, D, 30, dtype=torch.int64)
+        self.h_idx = torch.zeros(B, self.num_restarts, dtype=torch.int64)
+        self.state0 = sobol_state0(D).to(self.device)
+        torch.set_num_threads(1)   # host-side torch is RNG plumbing on tiny tensors: intra-op threads only add contention
         # per-run host RNG work (numpy normal, torch randint / multinomial) releases the GIL: spread it over the cores
         self.pool = ThreadPoolExecutor(max_workers=max(1, min(B, host_threads or (os.cpu_count() or 1))))
         self.n = 0
@@ -209,51 +212,63 @@ class BatchedBOEngine:
         self.gp.best_f.copy_(bf)
         self.stats["h2d_bytes"] += B * 8
 
-    def _initial_conditions(self, runs, k_host, box_lo, box_hi):
-        """gen_batch_initial_conditions for the given runs: returns {b: ndarray [num_restarts, k_b]}."""
-        B, D = self.B, self.D
-        out = {}
+    def _initial_conditions(self, runs, k_host, d_ics=None):
+        """gen_batch_initial_conditions for the given runs.
+
+        Host: only the random bits (two torch.randint draws of the Sobol scramble, the Boltzmann multinomial) from each
+        run's own CPU generator. Device: Sobol points scaled to the box, log-EI of the raw samples, gather of the
+        selected rows. Returns the device tensor of initial conditions [B, num_restarts, D] (rows of `runs` updated)."""
+        B, D, R = self.B, self.D, self.num_restarts
+        if d_ics is None:
+            d_ics = torch.zeros(B, R, D, dtype=torch.float64, device=self.device)
         pending = list(runs)
         factor = 1
         while pending and factor < 5:
             nraw = self.raw_samples * factor
             tp = perf_counter()
-            h_raw = self.h_raw if factor == 1 else torch.zeros(B, nraw, D, dtype=torch.float64).pin_memory()
 
-            def _sobol(b):
-                kb = int(k_host[b])
-                raw = scrambled_sobol(kb, nraw, self.torch_gens[b])
-                h_raw[b, :, :kb] = box_lo[b, :kb] + (box_hi[b, :kb] - box_lo[b, :kb]) * raw
-                h_raw[b, :, kb:] = 0.0
+            def _bits(b):
+                draw_scramble_bits(int(k_host[b]), self.torch_gens[b], self.h_shift[b], self.h_dots[b])
 
-            list(self.pool.map(_sobol, pending))
-            tp = self._phase("host_sobol", tp)
-            d_raw = h_raw.to(self.device, non_blocking=True)
-            vals = ops.logei(self.gp, d_raw)["val"].cpu()
-            tp = self._phase("raw_logei_kernel", tp)
-            self.stats["kernel_launches"] += 1
-            self.stats["h2d_bytes"] += h_raw.numel() * 8
+            list(self.pool.map(_bits, pending))
+            tp = self._phase("host_sobol_bits", tp)
+            d_shift = self.h_shift.to(torch.int32).to(self.device, non_blocking=True)
+            d_dots = self.h_dots.to(torch.int32).to(self.device, non_blocking=True)
+            k_dev = self.pca["k"] if self.algorithm == "pca" else None
+            x_raw = ops.sobol_points(nraw, k_dev, d_shift, d_dots, self.state0, self.gp.box_lo, self.gp.box_hi)
+            vals = ops.logei(self.gp, x_raw)["val"].cpu()
+            self.stats["kernel_launches"] += 2
+            self.stats["h2d_bytes"] += d_shift.numel() * 4 + d_dots.numel() * 4
             self.stats["d2h_bytes"] += vals.numel() * 8
-            def _pick(b):
-                kb = int(k_host[b])
-                idcs, bad = initialize_q_batch(vals[b], self.num_restarts, self.torch_gens[b])
-                return b, h_raw[b, idcs, :kb].numpy().copy(), bad
+            tp = self._phase("sobol_raw_logei_kernels", tp)
 
-            still = []
-            for b, ic, bad in self.pool.map(_pick, pending):
-                out[b] = ic
-                if bad:
-                    still.append(b)
+            def _pick(b):
+                idcs, bad = initialize_q_batch(vals[b], R, self.torch_gens[b])
+                self.h_idx[b] = idcs
+                return b, bad
+
+            still = [b for b, bad in self.pool.map(_pick, pending) if bad]
+            d_idx = self.h_idx.to(torch.int32).to(self.device, non_blocking=True)
+            picked = ops.gather_rows(x_raw, d_idx)
+            if len(pending) == B:
+                d_ics.copy_(picked)
+            else:
+                sel = torch.tensor(pending, device=self.device)
+                d_ics[sel] = picked[sel]
+            self.stats["kernel_launches"] += 1
+            self.stats["h2d_bytes"] += d_idx.numel() * 4
             self._phase("host_multinomial", tp)
             pending = still
             factor += 1
-        return out
+        return d_ics
 
-    def _optimize_scipy(self, runs, ics, k_host, box_lo, box_hi):
+    def _optimize_scipy(self, runs, d_ics, k_host, box_lo, box_hi):
         """gen_candidates_scipy for every chunk of batch_limit restarts of every run, in lock-step.
 
         Returns (cands {b: [num_restarts, k_b]}, warned {b: bool})."""
         B, D, R = self.B, self.D, self.num_restarts
+        h_ics = d_ics.cpu().numpy()
+        ics = {b: h_ics[b, :, :int(k_host[b])] for b in runs}
         chunks = [(s, min(s + self.batch_limit, R)) for s in range(0, R, self.batch_limit)]
         probs = {}
         for b in runs:
@@ -309,16 +324,11 @@ class BatchedBOEngine:
             self.last.setdefault("nfev", {})[b] = [probs[(b, ci)].nfev for ci in range(len(chunks))]
         return cands, warned
 
-    def _optimize_device(self, ics, k_host):
+    def _optimize_device(self, d_x, k_host):
         """gen_candidates_scipy for all runs and chunks in ONE launch of the device-resident L-BFGS-B kernel.
 
         Returns (device tensor of clamped candidates [B, R, D], warned {b: bool})."""
         B, D, R = self.B, self.D, self.num_restarts
-        h_x = self.h_ics
-        h_x.zero_()
-        for b in range(B):
-            h_x[b, :, :int(k_host[b])] = torch.from_numpy(ics[b])
-        d_x = h_x.to(self.device, non_blocking=True)
         ev = None
         if self.kernel_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -338,7 +348,6 @@ class BatchedBOEngine:
             self.kernel_events.append((ev[0], ev[1], nbytes))
         self.stats["kernel_launches"] += 1
         self.stats["lbfgsb_rounds"] += int(nfev.max())
-        self.stats["h2d_bytes"] += h_x.numel() * 8
         self.stats["d2h_bytes"] += status.size * 12
         warned = {b: bool((status[b] == 3).any()) for b in range(B)}
         self.last["nit"] = {b: nit[b].tolist() for b in range(B)}
@@ -353,14 +362,14 @@ class BatchedBOEngine:
         box_lo, box_hi = self.gp.box_lo.cpu(), self.gp.box_hi.cpu()
         self.stats["d2h_bytes"] += B * 4 + 2 * B * D * 8
         runs = list(range(B))
-        ics = self._initial_conditions(runs, k_host, box_lo, box_hi)
+        ics = self._initial_conditions(runs, k_host)
         if self.optimizer == "scipy":
             cands, warned = self._optimize_scipy(runs, ics, k_host, box_lo, box_hi)
             retry = [b for b in runs if warned[b]]
             if retry:  # botorch retry_on_optimization_warning: new initial conditions, one more attempt
                 self.stats["retries"] += len(retry)
-                ics2 = self._initial_conditions(retry, k_host, box_lo, box_hi)
-                c2, _ = self._optimize_scipy(retry, ics2, k_host, box_lo, box_hi)
+                ics = self._initial_conditions(retry, k_host, ics)
+                c2, _ = self._optimize_scipy(retry, ics, k_host, box_lo, box_hi)
                 cands.update(c2)
             h_c = torch.zeros(B, R, D, dtype=torch.float64).pin_memory()
             for b in runs:
@@ -374,9 +383,9 @@ class BatchedBOEngine:
             retry = [b for b in runs if warned[b]]
             if retry:
                 self.stats["retries"] += len(retry)
-                ics2 = dict(ics)
-                ics2.update(self._initial_conditions(retry, k_host, box_lo, box_hi))
-                d_c2, _ = self._optimize_device(ics2, k_host)
+                ics = self._initial_conditions(retry, k_host, ics)
+                d_c = d_c.clone()
+                d_c2, _ = self._optimize_device(ics, k_host)
                 idx = torch.tensor(retry, device=self.device)
                 d_c[idx] = d_c2[idx]
         vals = ops.logei(self.gp, d_c)["val"]                        # final no-grad evaluation of the candidates

@@ -191,3 +191,27 @@ def lbfgsb_logei(buf: GPBuffers, ics, box_lo, box_hi, batch_limit=5, maxiter=200
                                  _d(out["fval"], "fval"), _i(out["status"], "status"), _i(out["nit"], "nit"),
                                  _i(out["nfev"], "nfev"), _stream()), "pcabo_lbfgsb_logei")
     return out
+
+
+def sobol_points(npts, k, shift, ltm_dots, state0, box_lo, box_hi, out=None):
+    """shift [B, kmax] int32, ltm_dots [B, kmax, 30] int32, state0 [kmax, 30] int32 -> X [B, npts, kmax] (device)."""
+    lib = load_library()
+    B, kmax = shift.shape
+    if out is None:
+        out = torch.empty(B, npts, kmax, dtype=torch.float64, device=shift.device)
+    check(lib.pcabo_sobol_points(B, int(npts), kmax, _i(k, "k"), _i(shift, "shift"), _i(ltm_dots, "ltm_dots"),
+                                 _i(state0, "state0"), _d(box_lo, "box_lo"), _d(box_hi, "box_hi"), _d(out, "X"),
+                                 _stream()), "pcabo_sobol_points")
+    return out
+
+
+def gather_rows(X, idx, out=None):
+    """X [B, npts, kmax], idx [B, nsel] int32 -> out [B, nsel, kmax]."""
+    lib = load_library()
+    B, npts, kmax = X.shape
+    nsel = idx.shape[1]
+    if out is None:
+        out = torch.empty(B, nsel, kmax, dtype=torch.float64, device=X.device)
+    check(lib.pcabo_gather_rows(B, npts, nsel, kmax, _d(X, "X"), _i(idx, "idx"), _d(out, "out"), _stream()),
+          "pcabo_gather_rows")
+    return out

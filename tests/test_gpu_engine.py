@@ -122,7 +122,7 @@ def test_device_lbfgsb_matches_scipy_given_same_starts():
     B = eng.B
     k_host = eng.pca["k"].cpu().numpy().astype(np.int64)
     box_lo, box_hi = eng.gp.box_lo.cpu(), eng.gp.box_hi.cpu()
-    ics = eng._initial_conditions(list(range(B)), k_host, box_lo, box_hi)
+    ics = eng._initial_conditions(list(range(B)), k_host)
     c_host, w_host = eng._optimize_scipy(list(range(B)), ics, k_host, box_lo, box_hi)
     nit_host = dict(eng.last["nit"])
     d_c, w_dev = eng._optimize_device(ics, k_host)
@@ -161,3 +161,35 @@ def test_engine_device_optimizer_trajectory():
     for _ in range(iters - 1):
         eng.step()
     assert len(eng.f_evals[0]) == 3 * D + iters
+
+
+def test_device_sobol_is_bit_identical_to_torch():
+    """pcabo_sobol_points from host-drawn scramble bits == SobolEngine(k, scramble=True).draw(n, float64) scaled to the box."""
+    from pcabo_b200 import ops
+    from pcabo_b200.acq_host import draw_scramble_bits, sobol_state0
+    from oracle import acqf
+    B, D, n = 3, 40, 512
+    ks = [31, 1, 40]
+    shift = torch.zeros(B, D, dtype=torch.int64)
+    dots = torch.zeros(B, D, 30, dtype=torch.int64)
+    lo = torch.randn(B, D, dtype=torch.float64)
+    hi = lo + torch.rand(B, D, dtype=torch.float64) * 3 + 0.1
+    refs = []
+    for b in range(B):
+        g1, g2 = torch.Generator(), torch.Generator()
+        g1.manual_seed(100 + b)
+        g2.manual_seed(100 + b)
+        draw_scramble_bits(ks[b], g1, shift[b], dots[b])
+        raw = acqf.scrambled_sobol(ks[b], n, g2)
+        refs.append(lo[b, :ks[b]] + (hi[b, :ks[b]] - lo[b, :ks[b]]) * raw)
+        assert g1.get_state().equal(g2.get_state())          # identical stream consumption
+    k = torch.tensor(ks, dtype=torch.int32).cuda()
+    X = ops.sobol_points(n, k, shift.to(torch.int32).cuda(), dots.to(torch.int32).cuda(), sobol_state0(D).cuda(),
+                         lo.cuda(), hi.cuda()).cpu()
+    for b in range(B):
+        assert torch.equal(X[b, :, :ks[b]], refs[b]), b
+        assert float(X[b, :, ks[b]:].abs().max()) == 0.0 if ks[b] < D else True
+    idx = torch.tensor([[5, 0, 511], [1, 1, 2], [100, 7, 3]], dtype=torch.int32)
+    got = ops.gather_rows(X.cuda(), idx.cuda()).cpu()
+    for b in range(B):
+        assert torch.equal(got[b], X[b, idx[b].long()])
