@@ -152,7 +152,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from pcabo_b200.bbob import BatchedBBOB
-    from pcabo_b200.engine import BatchedBOEngine
+    from pcabo_b200.engine import BatchedBOEngine, PipelinedEngines
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -173,25 +173,42 @@ def run_ours(args):
     fids = [f for f in FIDS for _ in range(RUNS_PER_FID)]
     insts = [RUNS_PER_FID * rank + i for _ in FIDS for i in range(RUNS_PER_FID)]
     seeds = [1000 * f + 10 * DIM + i for f, i in zip(fids, insts)]
-    prob = BatchedBBOB(fids, insts, DIM, device=dev)
-    eng = BatchedBOEngine(prob, DIM, prob.bounds, BUDGET, N_DOE, seeds, algorithm="pca", device=dev,
-                          optimizer=args.optimizer)
+    S = max(1, args.sub_batches)
+    subs = []
+    for s_ in range(S):
+        sel = list(range(s_, len(fids), S))
+        prob = BatchedBBOB([fids[i] for i in sel], [insts[i] for i in sel], DIM, device=dev)
+        subs.append(BatchedBOEngine(prob, DIM, prob.bounds, BUDGET, N_DOE, [seeds[i] for i in sel], algorithm="pca",
+                                    device=dev, optimizer=args.optimizer,
+                                    host_threads=max(1, (os.cpu_count() or 1) // (S * max(1, world)))))
+    eng = subs[0] if S == 1 else PipelinedEngines(subs)
     eng.initial_design()
-    for _ in range(args.n_start - N_DOE):          # optional fast-forward (untimed) to a later point of the runs
-        eng.step()
+    if args.n_start > N_DOE:                       # optional fast-forward (untimed) to a later point of the runs
+        if S == 1:
+            for _ in range(args.n_start - N_DOE):
+                eng.step()
+        else:
+            eng.run_steps(args.n_start - N_DOE)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        eng.step()
+    def advance(k):
+        if S == 1:
+            for _ in range(k):
+                eng.step()
+        else:
+            eng.run_steps(k)
+
+    advance(args.warmup)
     barrier()
     stats0 = dict(eng.stats)
-    eng.kernel_events = []                          # CUDA-event pairs around every value+grad log-EI launch
-    if args.phases:
-        eng.phase_times = {}
+    for e_ in subs:
+        e_.kernel_events = []                       # CUDA-event pairs around every optimiser-kernel launch
+        if args.phases:
+            e_.phase_times = {}
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -199,8 +216,7 @@ def run_ours(args):
     n_first = eng.n
     t0 = time.perf_counter()
     ev0.record()
-    for _ in range(args.steps):
-        eng.step()
+    advance(args.steps)
     ev1.record()
     barrier()
     wall = time.perf_counter() - t0
@@ -211,7 +227,7 @@ def run_ours(args):
         t = torch.tensor([secs], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         secs = float(t)
-    B = eng.B
+    B = sum(e_.B for e_ in subs)
     its = world * B * args.steps / secs
     stats1 = eng.stats
     launches = stats1["kernel_launches"] - stats0["kernel_launches"]
@@ -221,7 +237,7 @@ def run_ours(args):
     # roofline of the dominant kernel: the value+gradient log-EI launch of the L-BFGS-B rounds (HBM/L2 bound:
     # per run it streams the n x n lower-triangular FP64 cache L^-1 for 10 points, 2.5 flop/byte)
     roof = None
-    evs = getattr(eng, "kernel_events", [])
+    evs = [ev for e_ in subs for ev in (e_.kernel_events or [])]
     if evs:
         peaks = {}
         try:
@@ -236,7 +252,7 @@ def run_ours(args):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
                 "traffic": None, "launches": len(evs), "avg_launch_us": 1e3 * tot_ms / len(evs),
-                "share_of_step": tot_ms * 1e-3 / secs}
+                "share_of_step": tot_ms * 1e-3 / secs / S}
     if rank == 0:
         line = {"metric": METRIC, "value": its, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
@@ -244,7 +260,7 @@ def run_ours(args):
                 "config": workload_config(n_first - args.warmup, args.steps, args.warmup, args.optimizer,
                                           {"lbfgsb_rounds_per_step": (stats1["lbfgsb_rounds"] - stats0["lbfgsb_rounds"]) / args.steps,
                                            "retries": stats1["retries"] - stats0["retries"]}),
-                "roofline": roof, "cpu_baseline": cpu_base,
+                "roofline": roof, "cpu_baseline": cpu_base, "sub_batches": S,
                 "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "note": "every step is driven through the public engine API with host-generated RNG inputs "
                                 "(PCA noise, Sobol samples) copied in and proposals/objective values read back inside "
@@ -252,8 +268,12 @@ def run_ours(args):
                 "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if args.phases and rank == 0:
-        tot = sum(eng.phase_times.values())
-        print(json.dumps({"phase_ms_per_step": {k: 1e3 * v / args.steps for k, v in eng.phase_times.items()},
+        pt = {}
+        for e_ in subs:
+            for k_, v_ in e_.phase_times.items():
+                pt[k_] = pt.get(k_, 0.0) + v_
+        tot = sum(pt.values())
+        print(json.dumps({"phase_ms_per_step": {k: 1e3 * v / args.steps for k, v in pt.items()},
                           "sum_ms_per_step": 1e3 * tot / args.steps}), file=sys.stderr, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -269,6 +289,8 @@ def main():
     ap.add_argument("--n-start", type=int, default=N_DOE, help="fast-forward (untimed) until n points before warm-up")
     ap.add_argument("--cpu-steps", type=int, default=12, help="BO iterations per core of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sub-batches", type=int, default=1,
+                    help="split the per-GPU batch into S independently stepped sub-batches on S CUDA streams")
     ap.add_argument("--phases", action="store_true", help="print a host wall-time breakdown per phase (adds syncs)")
     args = ap.parse_args()
     if args.impl == "reference":

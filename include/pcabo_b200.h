@@ -127,6 +127,12 @@ int pcabo_lbfgsb_logei(const pcabo_gp_model *m, int num_restarts, int batch_limi
 int pcabo_sobol_points(int B, int npts, int kmax, const int *k, const int *shift, const int *ltm_dots,
                        const int *state0, const double *box_lo, const double *box_hi, double *X, void *stream);
 
+/* Device replay of the two torch.randint(2, ...) draws of SobolEngine._scramble (shapes (k, 30) and (k, 30, 30)) from
+ * each run's MT19937 state: mt_state [B][624] (uint32 words) and mt_pos [B] (index of the next word, 624 = regenerate
+ * first) are advanced in place exactly as torch's CPU generator would be; shift / ltm_dots as in pcabo_sobol_points. */
+int pcabo_sobol_scramble_bits(int B, int kmax, const int *k, unsigned *mt_state, int *mt_pos, int *shift,
+                              int *ltm_dots, void *stream);
+
 /* out[b][r][:] = X[b][idx[b][r]][:]  (selection of the initial conditions among the raw samples).                    */
 int pcabo_gather_rows(int B, int npts, int nsel, int kmax, const double *X, const int *idx, double *out, void *stream);
 

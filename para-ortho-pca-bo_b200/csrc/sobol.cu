@@ -58,6 +58,93 @@ __global__ void __launch_bounds__(256) sobol_kernel(int npts, int kmax, const in
   }
 }
 
+// ---------------------------------------------------------------------------------------------- MT19937 replay
+// torch.randint(2, size, generator=g) on the CPU consumes one 32-bit MT19937 output per element and keeps its lowest
+// bit (ATen uniform_int_from_to: random() % 2). The scramble of SobolEngine draws (k, 30) then (k, 30, 30) such bits.
+// This kernel replays the generator on the device: input = the generator's 624-word state + position, output = the
+// packed shift / lower-triangular rows the Sobol kernel needs and the advanced state, so the host generator can be
+// put exactly where torch would have left it.
+constexpr int MT_N = 624, MT_M = 397;
+
+__device__ __forceinline__ unsigned mt_twist(unsigned u, unsigned v) {
+  return (((u & 0x80000000u) | (v & 0x7fffffffu)) >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
+}
+
+__device__ void mt_regenerate(unsigned *st) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  // phase 1: i in [0, 227) uses old st[i], st[i+1], st[i+397]
+  for (int base = 0; base < MT_N - MT_M; base += nt) {
+    const int i = base + tid;
+    unsigned v = 0;
+    const bool on = i < MT_N - MT_M;
+    if (on) v = st[i + MT_M] ^ mt_twist(st[i], st[i + 1]);
+    __syncthreads();
+    if (on) st[i] = v;
+    __syncthreads();
+  }
+  // phases 2, 3: i in [227, 454) and [454, 623) use new st[i - 227], old st[i], st[i+1]
+  for (int lo = MT_N - MT_M; lo < MT_N - 1; lo += MT_N - MT_M) {
+    const int hi = min(lo + MT_N - MT_M, MT_N - 1);
+    for (int base = lo; base < hi; base += nt) {
+      const int i = base + tid;
+      unsigned v = 0;
+      const bool on = i < hi;
+      if (on) v = st[i - (MT_N - MT_M)] ^ mt_twist(st[i], st[i + 1]);
+      __syncthreads();
+      if (on) st[i] = v;
+      __syncthreads();
+    }
+  }
+  if (tid == 0) st[MT_N - 1] = st[MT_M - 1] ^ mt_twist(st[MT_N - 1], st[0]);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) mt_scramble_bits_kernel(int kmax, const int *k, unsigned *mt_state, int *mt_pos,
+                                                               int *shift, int *ltm_dots) {
+  __shared__ unsigned st[MT_N];
+  extern __shared__ int acc[];  // [kmax] shift + [kmax][30] dots
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int kk = k ? k[b] : kmax;
+  for (int i = tid; i < MT_N; i += nt) st[i] = mt_state[(size_t)b * MT_N + i];
+  for (int i = tid; i < kmax * (MAXBIT + 1); i += nt) acc[i] = 0;
+  int pos = mt_pos[b];
+  __syncthreads();
+  int *sh = acc, *dots = acc + kmax;
+  const int total = kk * MAXBIT + kk * MAXBIT * MAXBIT;
+  int done = 0;
+  while (done < total) {
+    if (pos >= MT_N) { mt_regenerate(st); pos = 0; }
+    const int take = min(MT_N - pos, total - done);
+    for (int t = tid; t < take; t += nt) {
+      unsigned y = st[pos + t];
+      y ^= y >> 11;
+      y ^= (y << 7) & 0x9d2c5680u;
+      y ^= (y << 15) & 0xefc60000u;
+      y ^= y >> 18;
+      if (y & 1u) {
+        const int e = done + t;
+        if (e < kk * MAXBIT) {
+          atomicOr(&sh[e / MAXBIT], 1 << (e % MAXBIT));                      // shift = sum bit_j 2^j
+        } else {
+          const int r = e - kk * MAXBIT;
+          const int d = r / (MAXBIT * MAXBIT), p = (r / MAXBIT) % MAXBIT, c = r % MAXBIT;
+          if (c < p) atomicOr(&dots[d * MAXBIT + p], 1 << (MAXBIT - 1 - c));   // tril, packed MSB-first
+        }
+      }
+    }
+    pos += take;
+    done += take;
+    __syncthreads();
+  }
+  for (int i = tid; i < kmax; i += nt) shift[(size_t)b * kmax + i] = (i < kk) ? sh[i] : 0;
+  for (int i = tid; i < kmax * MAXBIT; i += nt) {
+    const int d = i / MAXBIT, p = i % MAXBIT;
+    ltm_dots[(size_t)b * kmax * MAXBIT + i] = (d < kk) ? (dots[i] | (1 << (MAXBIT - 1 - p))) : 0;  // unit diagonal
+  }
+  for (int i = tid; i < MT_N; i += nt) mt_state[(size_t)b * MT_N + i] = st[i];
+  if (tid == 0) mt_pos[b] = pos;
+}
+
 __global__ void gather_rows_kernel(int npts, int nsel, int kmax, const double *X, const int *idx, double *out) {
   const int b = blockIdx.x;
   for (int e = threadIdx.x; e < nsel * kmax; e += blockDim.x) {
@@ -78,6 +165,16 @@ extern "C" int pcabo_sobol_points(int B, int npts, int kmax, const int *k, const
   if (smem > 48 * 1024)
     PCABO_CUDA_CHECK(cudaFuncSetAttribute(sobol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sobol_kernel<<<B, 256, smem, as_stream(stream)>>>(npts, kmax, k, shift, ltm_dots, state0, box_lo, box_hi, X);
+  PCABO_LAUNCH_CHECK();
+  return PCABO_OK;
+}
+
+extern "C" int pcabo_sobol_scramble_bits(int B, int kmax, const int *k, unsigned *mt_state, int *mt_pos, int *shift,
+                                        int *ltm_dots, void *stream) {
+  if (B <= 0 || kmax <= 0 || !mt_state || !mt_pos || !shift || !ltm_dots) return PCABO_E_INVALID;
+  if (kmax > 256) return PCABO_E_UNSUPPORTED;
+  const size_t smem = (size_t)kmax * (MAXBIT + 1) * sizeof(int);
+  mt_scramble_bits_kernel<<<B, 256, smem, as_stream(stream)>>>(kmax, k, mt_state, mt_pos, shift, ltm_dots);
   PCABO_LAUNCH_CHECK();
   return PCABO_OK;
 }

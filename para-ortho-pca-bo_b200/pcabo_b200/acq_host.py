@@ -58,6 +58,49 @@ def initialize_q_batch(acq_vals: torch.Tensor, n: int, generator: torch.Generato
     return idcs, False
 
 
+def select_initial_conditions(vals: torch.Tensor, n: int, gens, runs, q_buf=None, eta: float = 1.0):
+    """botorch initialize_q_batch for many runs at once: vals [B, nraw] (CPU) -> (idx [B, n] int64, bad [B] bool).
+
+    Boltzmann weights exp(eta (v - mean) / std) are computed batched; the sampling without replacement is torch's own
+    algorithm restated (ATen multinomial: q ~ Exp(1) drawn with `exponential_` from the run's generator, top-n of
+    weights / q), which consumes each generator exactly like torch.multinomial(weights, n, generator=g) and returns the
+    same indices; the arg-max of the raw values is forced in as the last pick when it was not drawn. Runs whose values
+    all coincide get a random permutation pick and are flagged `bad` (BadInitialCandidatesWarning in botorch)."""
+    B, nraw = vals.shape
+    idx = torch.zeros(B, n, dtype=torch.int64)
+    bad = [False] * B
+    if n >= nraw:
+        idx[:] = torch.arange(n)
+        return idx, bad
+    std = vals.std(dim=1)
+    mean = vals.mean(dim=1)
+    etaz = eta * (vals - mean[:, None]) / std[:, None]
+    w = torch.exp(etaz)
+    inf_rows = torch.isinf(w).any(dim=1)
+    while bool(inf_rows.any()):
+        etaz[inf_rows] *= 0.5
+        w[inf_rows] = torch.exp(etaz[inf_rows])
+        inf_rows = torch.isinf(w).any(dim=1)
+    q = q_buf if q_buf is not None and q_buf.shape == vals.shape else torch.empty_like(vals)
+    degenerate = ~(torch.isfinite(std) & (std != 0))
+    for b in runs:
+        if bool(degenerate[b]):
+            idx[b] = torch.randperm(nraw, generator=gens[b])[:n]
+            bad[b] = True
+            q[b] = 1.0
+            w[b] = 1.0
+        else:
+            q[b].exponential_(1, generator=gens[b])
+    top = torch.topk(w / q, n, dim=1).indices
+    amax = vals.argmax(dim=1)
+    missing = ~(top == amax[:, None]).any(dim=1)
+    top[missing, -1] = amax[missing]
+    for b in runs:
+        if not bad[b]:
+            idx[b] = top[b]
+    return idx, bad
+
+
 MAXBIT = 30
 _POW2_DESC = None
 _STATE0 = {}
@@ -84,6 +127,42 @@ def draw_scramble_bits(d: int, generator: torch.Generator, shift_out: torch.Tens
     dots_out[:d] = (ltm * _POW2_DESC).sum(-1)
     shift_out[d:] = 0
     dots_out[d:] = 0
+
+
+class GeneratorStateIO:
+    """Moves the MT19937 state of B torch CPU generators to / from packed arrays for the device replay kernel.
+
+    Layout of torch's CPU generator state (CPUGeneratorImplState, 5056 bytes): uint64 seed, int32 left, int32 seeded,
+    uint64 next, uint64 state[624] (32-bit words), normal-cache fields. `left`/`next` relate to a plain
+    "index of the next word" pos by pos = 624 if left == 1 else next, and back by next = pos, left = 625 - pos."""
+
+    def __init__(self, B: int):
+        self.B = B
+        self.buf = np.zeros((B, 5056), dtype=np.uint8)
+        self.tbuf = [torch.from_numpy(self.buf[b]) for b in range(B)]
+        self.left = self.buf[:, 8:12].view(np.int32)[:, 0]
+        self.next = self.buf[:, 16:24].view(np.uint64)[:, 0]
+        self.words = self.buf[:, 24:24 + 4992].view(np.uint64)
+        self.h_state = torch.zeros(B, 624, dtype=torch.int32)
+        self.h_pos = torch.zeros(B, dtype=torch.int32)
+        if torch.cuda.is_available():
+            self.h_state, self.h_pos = self.h_state.pin_memory(), self.h_pos.pin_memory()
+
+    def export(self, gens):
+        for b, g in enumerate(gens):
+            self.tbuf[b].copy_(g.get_state())
+        self.h_state.numpy().view(np.uint32)[:] = self.words.astype(np.uint32)
+        self.h_pos.numpy()[:] = np.where(self.left == 1, 624, self.next.astype(np.int64)).astype(np.int32)
+        return self.h_state, self.h_pos
+
+    def restore(self, gens, state: torch.Tensor, pos: torch.Tensor):
+        st = state.numpy().view(np.uint32)
+        ps = pos.numpy().astype(np.int64)
+        self.words[:] = st.astype(np.uint64)
+        self.left[:] = (625 - ps).astype(np.int32)
+        self.next[:] = ps.astype(np.uint64)
+        for b, g in enumerate(gens):
+            g.set_state(self.tbuf[b])
 
 
 class LbfgsbProblem:

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .acq_host import LbfgsbProblem, draw_scramble_bits, initialize_q_batch, sobol_state0
+from .acq_host import GeneratorStateIO, LbfgsbProblem, select_initial_conditions, sobol_state0
 from .lib import PcaboError
 
 NUM_RESTARTS = 10      # PCA_BO.py:107
@@ -95,10 +95,10 @@ class BatchedBOEngine:
         self.pca = None
         self.d_noise = torch.zeros(B * cap * D, **f64)
         self.h_noise = torch.zeros(B * cap * D, dtype=torch.float64).pin_memory()
-        self.h_shift = torch.zeros(B, D, dtype=torch.int64)
-        self.h_dots = torch.zeros(B, D, 30, dtype=torch.int64)
-        self.h_idx = torch.zeros(B, self.num_restarts, dtype=torch.int64)
+        self.gen_io = GeneratorStateIO(B)
+        self.h_q = torch.zeros(B, self.raw_samples, dtype=torch.float64)
         self.state0 = sobol_state0(D).to(self.device)
+        self.k_full = torch.full((B,), D, dtype=torch.int32, device=self.device)
         torch.set_num_threads(1)   # host-side torch is RNG plumbing on tiny tensors: intra-op threads only add contention
         # per-run host RNG work (numpy normal, torch randint / multinomial) releases the GIL: spread it over the cores
         self.pool = ThreadPoolExecutor(max_workers=max(1, min(B, host_threads or (os.cpu_count() or 1))))
@@ -226,29 +226,28 @@ class BatchedBOEngine:
         while pending and factor < 5:
             nraw = self.raw_samples * factor
             tp = perf_counter()
-
-            def _bits(b):
-                draw_scramble_bits(int(k_host[b]), self.torch_gens[b], self.h_shift[b], self.h_dots[b])
-
-            list(self.pool.map(_bits, pending))
-            tp = self._phase("host_sobol_bits", tp)
-            d_shift = self.h_shift.to(torch.int32).to(self.device, non_blocking=True)
-            d_dots = self.h_dots.to(torch.int32).to(self.device, non_blocking=True)
-            k_dev = self.pca["k"] if self.algorithm == "pca" else None
+            # the Sobol scramble bits: replay each run's torch CPU generator (MT19937) on the device
+            st, pos = self.gen_io.export(self.torch_gens)
+            d_state = st.to(self.device, non_blocking=True)
+            d_pos = pos.to(self.device, non_blocking=True)
+            if len(pending) == B:
+                k_dev = self.pca["k"] if self.algorithm == "pca" else self.k_full
+            else:  # runs that are not pending draw nothing (k = 0)
+                kk = torch.zeros(B, dtype=torch.int32)
+                kk[pending] = torch.from_numpy(k_host[pending].astype(np.int32))
+                k_dev = kk.to(self.device)
+            d_shift, d_dots = ops.sobol_scramble_bits(k_dev, d_state, d_pos, D)
             x_raw = ops.sobol_points(nraw, k_dev, d_shift, d_dots, self.state0, self.gp.box_lo, self.gp.box_hi)
-            vals = ops.logei(self.gp, x_raw)["val"].cpu()
-            self.stats["kernel_launches"] += 2
-            self.stats["h2d_bytes"] += d_shift.numel() * 4 + d_dots.numel() * 4
-            self.stats["d2h_bytes"] += vals.numel() * 8
-            tp = self._phase("sobol_raw_logei_kernels", tp)
-
-            def _pick(b):
-                idcs, bad = initialize_q_batch(vals[b], R, self.torch_gens[b])
-                self.h_idx[b] = idcs
-                return b, bad
-
-            still = [b for b, bad in self.pool.map(_pick, pending) if bad]
-            d_idx = self.h_idx.to(torch.int32).to(self.device, non_blocking=True)
+            vals_dev = ops.logei(self.gp, x_raw)["val"]
+            self.gen_io.restore(self.torch_gens, d_state.cpu(), d_pos.cpu())
+            vals = vals_dev.cpu()
+            self.stats["kernel_launches"] += 3
+            self.stats["h2d_bytes"] += st.numel() * 4 + pos.numel() * 4
+            self.stats["d2h_bytes"] += vals.numel() * 8 + st.numel() * 4 + pos.numel() * 4
+            tp = self._phase("sobol_bits_points_logei_kernels", tp)
+            idx, bad = select_initial_conditions(vals, R, self.torch_gens, pending, self.h_q if factor == 1 else None)
+            still = [b for b in pending if bad[b]]
+            d_idx = idx.to(torch.int32).to(self.device, non_blocking=True)
             picked = ops.gather_rows(x_raw, d_idx)
             if len(pending) == B:
                 d_ics.copy_(picked)
@@ -443,3 +442,54 @@ class BatchedBOEngine:
             self.step()
             it += 1
         return self
+
+
+class PipelinedEngines:
+    """S independent sub-batches of runs, each a BatchedBOEngine on its own CUDA stream driven by its own host thread.
+
+    Runs are independent, so splitting the per-GPU batch changes no result; it lets the host-side RNG work
+    of one sub-batch overlap the optimiser kernel of another (the kernel is latency bound: a sub-batch of 30 runs takes
+    as long as one of 90, and kernels of different streams share the SMs)."""
+
+    def __init__(self, engines):
+        self.engines = list(engines)
+        self.streams = [torch.cuda.Stream(device=e.device) for e in self.engines]
+        self.pool = ThreadPoolExecutor(max_workers=len(self.engines))
+        self.B = sum(e.B for e in self.engines)
+
+    def _on_stream(self, i, fn):
+        e, st = self.engines[i], self.streams[i]
+        torch.cuda.set_device(e.device)
+        with torch.cuda.stream(st):
+            out = fn(e)
+            st.synchronize()
+        return out
+
+    def initial_design(self):
+        for i in range(len(self.engines)):
+            self._on_stream(i, lambda e: e.initial_design())
+
+    def step(self):
+        futs = [self.pool.submit(self._on_stream, i, lambda e: e.step()) for i in range(len(self.engines))]
+        return all(f.result() for f in futs)
+
+    def run_steps(self, k):
+        """k steps of every sub-batch without a join between steps (sub-batches drift apart and overlap better)."""
+        def loop(e):
+            for _ in range(k):
+                e.step()
+        futs = [self.pool.submit(self._on_stream, i, loop) for i in range(len(self.engines))]
+        for f in futs:
+            f.result()
+
+    @property
+    def n(self):
+        return self.engines[0].n
+
+    @property
+    def stats(self):
+        out = {}
+        for e in self.engines:
+            for k, v in e.stats.items():
+                out[k] = out.get(k, 0) + v
+        return out

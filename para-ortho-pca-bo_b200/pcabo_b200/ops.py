@@ -215,3 +215,16 @@ def gather_rows(X, idx, out=None):
     check(lib.pcabo_gather_rows(B, npts, nsel, kmax, _d(X, "X"), _i(idx, "idx"), _d(out, "out"), _stream()),
           "pcabo_gather_rows")
     return out
+
+
+def sobol_scramble_bits(k, mt_state, mt_pos, kmax, out=None):
+    """mt_state [B, 624] int32 (uint32 words), mt_pos [B] int32, advanced in place -> (shift [B, kmax], dots [B, kmax, 30])."""
+    lib = load_library()
+    B = mt_state.shape[0]
+    dev = mt_state.device
+    if out is None:
+        out = (torch.empty(B, kmax, dtype=torch.int32, device=dev), torch.empty(B, kmax, 30, dtype=torch.int32, device=dev))
+    check(lib.pcabo_sobol_scramble_bits(B, kmax, _i(k, "k"), _i(mt_state, "mt_state"), _i(mt_pos, "mt_pos"),
+                                        _i(out[0], "shift"), _i(out[1], "ltm_dots"), _stream()),
+          "pcabo_sobol_scramble_bits")
+    return out

@@ -193,3 +193,38 @@ def test_device_sobol_is_bit_identical_to_torch():
     got = ops.gather_rows(X.cuda(), idx.cuda()).cpu()
     for b in range(B):
         assert torch.equal(got[b], X[b, idx[b].long()])
+
+
+def test_device_mt19937_replay_matches_torch_randint():
+    """pcabo_sobol_scramble_bits replays torch's CPU generator: same packed scramble bits as the two torch.randint
+    draws of SobolEngine._scramble, and the generator ends in the state torch would have left it in."""
+    from pcabo_b200 import ops
+    from pcabo_b200.acq_host import GeneratorStateIO, draw_scramble_bits
+    B, D = 5, 40
+    ks = [31, 1, 40, 0, 17]
+    g_dev = [torch.Generator() for _ in range(B)]
+    g_ref = [torch.Generator() for _ in range(B)]
+    for b in range(B):
+        g_dev[b].manual_seed(500 + b)
+        g_ref[b].manual_seed(500 + b)
+        pre = [0, 3, 624, 1000, 12345][b]          # different positions inside / across the 624-word state
+        if pre:
+            torch.randint(2, (pre,), generator=g_dev[b])
+            torch.randint(2, (pre,), generator=g_ref[b])
+    io = GeneratorStateIO(B)
+    for rep in range(2):                            # twice: the restored state must keep following torch
+        st, pos = io.export(g_dev)
+        d_state, d_pos = st.cuda(), pos.cuda()
+        k = torch.tensor(ks, dtype=torch.int32).cuda()
+        shift, dots = ops.sobol_scramble_bits(k, d_state, d_pos, D)
+        io.restore(g_dev, d_state.cpu(), d_pos.cpu())
+        for b in range(B):
+            sh_ref = torch.zeros(D, dtype=torch.int64)
+            dots_ref = torch.zeros(D, 30, dtype=torch.int64)
+            if ks[b] > 0:
+                draw_scramble_bits(ks[b], g_ref[b], sh_ref, dots_ref)
+            assert torch.equal(shift[b].cpu().long(), sh_ref), (rep, b)
+            assert torch.equal(dots[b].cpu().long(), dots_ref), (rep, b)
+            a = torch.rand(5, generator=g_dev[b], dtype=torch.float64)
+            r = torch.rand(5, generator=g_ref[b], dtype=torch.float64)
+            assert torch.equal(a, r), (rep, b)
