@@ -119,6 +119,14 @@ int pcabo_lbfgsb_logei(const pcabo_gp_model *m, int num_restarts, int batch_limi
                        double pgtol, const double *ics, const double *box_lo, const double *box_hi,
                        double *cand, double *fval, int *status, int *nit, int *nfev, void *stream);
 
+/* Same as pcabo_lbfgsb_logei with optional per-chunk cycle counters prof [B][nchunks][16] (clock64 ticks of the
+ * optimiser warp per phase: 1 cauchy, 2 formk, 3 cmprlb, 4 subsm, 5 line-search setup, 6 step to next point,
+ * 7 log-EI evaluation, 8 dcsrch, 9 update, 0 convergence tests); prof may be NULL. Tuning aid.                     */
+int pcabo_lbfgsb_logei_prof(const pcabo_gp_model *m, int num_restarts, int batch_limit, int maxiter, double factr,
+                            double pgtol, const double *ics, const double *box_lo, const double *box_hi,
+                            double *cand, double *fval, int *status, int *nit, int *nfev, long long *prof,
+                            void *stream);
+
 /* Scrambled Sobol raw samples scaled to the search box, generated on the device from host-drawn scramble bits
  * (replaces botorch draw_sobol_samples / torch SobolEngine(k, scramble=True).draw(npts, float64) inside optimize_acqf,
  * PCA_BO.py:607-614; bit-identical to torch).  shift [B][kmax] (30-bit), ltm_dots [B][kmax][30] (rows of the random

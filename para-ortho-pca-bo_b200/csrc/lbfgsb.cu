@@ -28,6 +28,15 @@ struct CudaWarpTeam {
   bool w0;
   Mailbox *mb;
   const lbfgsb::Work *wk;
+  long long *prof;      // optional [16] cycle counters of this block (lane 0), or nullptr
+  long long last;
+  // attribute the cycles since the previous tick to the phase that just ended (id = phase that STARTS now)
+  __device__ void tick(int id) {
+    if (prof == nullptr || lane != 0) return;
+    const long long t = clock64();
+    prof[id] += t - last;
+    last = t;
+  }
   __device__ void sync() { __syncwarp(); }
   __device__ void wsync() { __syncwarp(); }
   __device__ double sum(double v) { return warp_sum(v); }
@@ -80,6 +89,7 @@ struct LbArgs {
   const double *ics, *box_lo, *box_hi;
   double *cand, *fval;
   int *status, *nit, *nfev;
+  long long *prof;   // optional [B][nchunks][16] cycle counters
 };
 
 template <int PT>
@@ -117,6 +127,8 @@ __global__ void __launch_bounds__(LB_THREADS, 2) lbfgsb_logei_kernel(LbArgs a) {
   if (tid < 32) {
     CudaWarpTeam tm;
     tm.tid = tid; tm.nt = 32; tm.lane = tid; tm.nl = 32; tm.w0 = true; tm.mb = mb; tm.wk = &w;
+    tm.prof = a.prof ? a.prof + ((size_t)b * nchunks + chunk) * 16 : nullptr;
+    tm.last = clock64();
     r = lbfgsb::minimize(tm, w, obj, a.maxiter, a.factr, a.pgtol, flag);
     if (tid == 0) mb->cmd = CMD_EXIT;
     __syncthreads();
@@ -162,9 +174,22 @@ int launch(const LbArgs &a, cudaStream_t st) {
 
 }  // namespace
 
+extern "C" int pcabo_lbfgsb_logei_prof(const pcabo_gp_model *m, int num_restarts, int batch_limit, int maxiter,
+                                       double factr, double pgtol, const double *ics, const double *box_lo,
+                                       const double *box_hi, double *cand, double *fval, int *status, int *nit,
+                                       int *nfev, long long *prof, void *stream);
+
 extern "C" int pcabo_lbfgsb_logei(const pcabo_gp_model *m, int num_restarts, int batch_limit, int maxiter, double factr,
                                   double pgtol, const double *ics, const double *box_lo, const double *box_hi,
                                   double *cand, double *fval, int *status, int *nit, int *nfev, void *stream) {
+  return pcabo_lbfgsb_logei_prof(m, num_restarts, batch_limit, maxiter, factr, pgtol, ics, box_lo, box_hi, cand, fval,
+                                 status, nit, nfev, nullptr, stream);
+}
+
+extern "C" int pcabo_lbfgsb_logei_prof(const pcabo_gp_model *m, int num_restarts, int batch_limit, int maxiter,
+                                       double factr, double pgtol, const double *ics, const double *box_lo,
+                                       const double *box_hi, double *cand, double *fval, int *status, int *nit,
+                                       int *nfev, long long *prof, void *stream) {
   if (!m || num_restarts <= 0 || batch_limit <= 0 || maxiter <= 0 || !ics || !box_lo || !box_hi || !cand || !fval ||
       !status || !nit || !nfev || m->B <= 0 || m->n < 1 || m->ld_n < m->n || !m->norm_off || !m->norm_coef || !m->ZnT ||
       !m->alpha || !m->W || !m->ymean || !m->ystd || !m->best_f || !(m->lengthscale > 0.0))
@@ -173,7 +198,7 @@ extern "C" int pcabo_lbfgsb_logei(const pcabo_gp_model *m, int num_restarts, int
   LbArgs a;
   a.m = *m; a.num_restarts = num_restarts; a.batch_limit = batch_limit; a.maxiter = maxiter;
   a.factr = factr; a.pgtol = pgtol; a.ics = ics; a.box_lo = box_lo; a.box_hi = box_hi;
-  a.cand = cand; a.fval = fval; a.status = status; a.nit = nit; a.nfev = nfev;
+  a.cand = cand; a.fval = fval; a.status = status; a.nit = nit; a.nfev = nfev; a.prof = prof;
   cudaStream_t st = as_stream(stream);
   if (batch_limit <= 5) return launch<5>(a, st);
   return launch<8>(a, st);

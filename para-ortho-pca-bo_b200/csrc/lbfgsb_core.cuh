@@ -40,6 +40,7 @@ struct HostTeam {
   void sum_n(double *, int) {}
   void argmin(double &, int &) {}
   inline void formk_products(const struct Work &w, int col, double theta);
+  void tick(int) {}
 };
 
 struct Work {
@@ -696,7 +697,9 @@ LB_HD Result minimize(T &tm, Work &w, Fn &fn, int maxiter, double factr, double 
   int iter = 0;
   while (true) {
     int nseg;
+    tm.tick(0);
     cauchy(tm, w, col, theta, sbgnrm, nseg);
+    tm.tick(1);
     // free variables at the Cauchy point
     double nfree_l = 0.0;
     for (int i = tm.tid; i < n; i += tm.nt) nfree_l += (w.iwhere[i] <= 0) ? 1.0 : 0.0;
@@ -707,8 +710,11 @@ LB_HD Result minimize(T &tm, Work &w, Fn &fn, int maxiter, double factr, double 
         col = 0; theta = 1.0; updatd = false;
         continue;
       }
+      tm.tick(2);
       cmprlb(tm, w, col, theta);
+      tm.tick(3);
       subsm(tm, w, col, theta);
+      tm.tick(4);
     }
     // search direction and line search
     double dtd_l = 0.0;
@@ -749,13 +755,16 @@ LB_HD Result minimize(T &tm, Work &w, Fn &fn, int maxiter, double factr, double 
     bool ls_failed = false;
     if (gd >= 0.0) ls_failed = true;  // not a descent direction
     else if (dcsrch_start(ls, f, gd, stp, stpmx) < 0) ls_failed = true;
+    tm.tick(5);
     if (!ls_failed) {
       while (true) {
         ++ifun; ++res.nfev; iback = ifun - 1;
         if (stp == 1.0) { for (int i = tm.tid; i < n; i += tm.nt) w.x[i] = w.z[i]; }
         else { for (int i = tm.tid; i < n; i += tm.nt) w.x[i] = stp * w.d[i] + w.t[i]; }
         tm.sync();
+        tm.tick(6);
         f = fn(tm, w.x, w.g);
+        tm.tick(7);
         gd = dot(tm, w.g, w.d, n);
         const int r = dcsrch_step(ls, f, gd, stp, stpmx);
         if (r != 0) break;
@@ -771,6 +780,7 @@ LB_HD Result minimize(T &tm, Work &w, Fn &fn, int maxiter, double factr, double 
       col = 0; theta = 1.0; updatd = false;
       continue;
     }
+    tm.tick(8);
     ++iter;
     sbgnrm = projgr(tm, w);
     res.nit = iter;
@@ -793,6 +803,7 @@ LB_HD Result minimize(T &tm, Work &w, Fn &fn, int maxiter, double factr, double 
     if (dr <= EPSMCH * ddum) { updatd = false; continue; }  // skip the update
     updatd = true;
     const int info = update_pairs(tm, w, col, theta, rr, dr, stp, dtd, flag);
+    tm.tick(9);
     if (info != 0) { col = 0; theta = 1.0; updatd = false; }
   }
   res.f = f;

@@ -171,7 +171,8 @@ LBFGSB_STATUS = {0: "CONVERGENCE: NORM OF PROJECTED GRADIENT <= PGTOL", 1: "CONV
                  2: "STOP: TOTAL NO. OF ITERATIONS REACHED LIMIT", 3: "ABNORMAL"}
 
 
-def lbfgsb_logei(buf: GPBuffers, ics, box_lo, box_hi, batch_limit=5, maxiter=200, factr=1e7, pgtol=1e-5, out=None):
+def lbfgsb_logei(buf: GPBuffers, ics, box_lo, box_hi, batch_limit=5, maxiter=200, factr=1e7, pgtol=1e-5, out=None,
+                 prof=None):
     """ics [B, num_restarts, kmax] -> dict(cand [B, R, kmax], fval/status/nit/nfev [B, nchunks]); one kernel launch."""
     lib = load_library()
     B, R, kmax = ics.shape
@@ -186,10 +187,11 @@ def lbfgsb_logei(buf: GPBuffers, ics, box_lo, box_hi, batch_limit=5, maxiter=200
                    nit=torch.empty(B, nch, dtype=torch.int32, device=dev),
                    nfev=torch.empty(B, nch, dtype=torch.int32, device=dev))
     m = model_struct(buf)
-    check(lib.pcabo_lbfgsb_logei(ctypes.byref(m), R, int(batch_limit), int(maxiter), float(factr), float(pgtol),
-                                 _d(ics, "ics"), _d(box_lo, "box_lo"), _d(box_hi, "box_hi"), _d(out["cand"], "cand"),
-                                 _d(out["fval"], "fval"), _i(out["status"], "status"), _i(out["nit"], "nit"),
-                                 _i(out["nfev"], "nfev"), _stream()), "pcabo_lbfgsb_logei")
+    check(lib.pcabo_lbfgsb_logei_prof(ctypes.byref(m), R, int(batch_limit), int(maxiter), float(factr), float(pgtol),
+                                      _d(ics, "ics"), _d(box_lo, "box_lo"), _d(box_hi, "box_hi"),
+                                      _d(out["cand"], "cand"), _d(out["fval"], "fval"), _i(out["status"], "status"),
+                                      _i(out["nit"], "nit"), _i(out["nfev"], "nfev"),
+                                      _dev_ptr(prof, torch.int64, "prof"), _stream()), "pcabo_lbfgsb_logei")
     return out
 
 
