@@ -61,6 +61,8 @@ typedef struct pcabo_gp_model {
   const double *ymean;      /* [B] Standardize mean */
   const double *ystd;       /* [B] Standardize std  */
   const double *best_f;     /* [B] incumbent, already rounded to float32 as botorch stores it */
+  const double *WT;         /* [B][ld_n][ld_n] (L^-1)^T, upper triangular, row-major (column j of W contiguous) */
+  const double *Zn;         /* [B][ld_n][kmax] normalised training inputs, row-major */
 } pcabo_gp_model;
 
 /* Rank weights + weighted PCA + projection, one CTA per run.
@@ -86,15 +88,16 @@ int pcabo_inverse_map(int B, int D, const double *z, const int *k, const double 
  *   mode 0 (PCA_BO): Normalize bounds [zmin-0.1r, zmax+0.1r]; search box [zmin-0.5r, zmax+0.5r], min width 0.1
  *   mode 1 (Vanilla_BO): no input normalisation; search box = (fix_lo, fix_hi) [kmax]
  * outputs
- *   norm_off, norm_coef, box_lo, box_hi [B][kmax]; ymean, ystd [B]; ZnT [B][kmax][ld_n];
- *   L [B][ld_n][ld_n] (Cholesky factor of K + noise I, lower), W [B][ld_n][ld_n] (L^-1), alpha [B][ld_n],
+ *   norm_off, norm_coef, box_lo, box_hi [B][kmax]; ymean, ystd [B]; ZnT [B][kmax][ld_n], Zn [B][ld_n][kmax];
+ *   L [B][ld_n][ld_n] (Cholesky factor of K + noise I, lower), W [B][ld_n][ld_n] (L^-1), WT (its transpose),
+ *   alpha [B][ld_n],
  *   info [B] (0 ok, i > 0: non-positive pivot at row i -> caller should add jitter)                            */
 int pcabo_gp_fit(int B, int n, int kmax, int ld_n, int mode,
                  const double *Z, const int *k, const double *f, const double *fix_lo, const double *fix_hi,
                  double lengthscale, double noise,
                  double *norm_off, double *norm_coef, double *box_lo, double *box_hi,
-                 double *ymean, double *ystd, double *ZnT, double *L, double *W, double *alpha, int *info,
-                 void *stream);
+                 double *ymean, double *ystd, double *ZnT, double *Zn, double *L, double *W, double *WT,
+                 double *alpha, int *info, void *stream);
 
 /* Exact marginal log-likelihood of the standardised targets from the caches: mll [B]. ys = (f-ymean)/ystd. */
 int pcabo_gp_mll(int B, int n, int ld_n, const double *f, const double *ymean, const double *ystd,

@@ -30,7 +30,7 @@ struct PrepArgs {
   const double *Z;
   const int *k;
   const double *f, *fix_lo, *fix_hi;
-  double *norm_off, *norm_coef, *box_lo, *box_hi, *ymean, *ystd, *ZnT, *ys;
+  double *norm_off, *norm_coef, *box_lo, *box_hi, *ymean, *ystd, *ZnT, *Zn, *ys;
 };
 
 __global__ void __launch_bounds__(256) gp_prep_kernel(PrepArgs a) {
@@ -113,6 +113,11 @@ __global__ void __launch_bounds__(256) gp_prep_kernel(PrepArgs a) {
   for (int idx = tid; idx < kk * n; idx += nt) {
     const int c = idx / n, i = idx % n;
     ZnTb[(size_t)c * a.ld_n + i] = (Zb[(size_t)i * kmax + c] - off[c]) / coef[c];
+  }
+  double *Znb = a.Zn + (size_t)b * a.ld_n * kmax;
+  for (int idx = tid; idx < n * kmax; idx += nt) {
+    const int c = idx % kmax;
+    Znb[idx] = (c < kk) ? (Zb[idx] - off[c]) / coef[c] : 0.0;
   }
 }
 
@@ -266,7 +271,7 @@ __device__ __noinline__ void panel_gemm(Smem &s, double *Cp, long c_rs, long c_c
 
 struct CholArgs {
   int B, n, ld_n;
-  double *L, *W, *alpha;  // alpha holds y_s on entry
+  double *L, *W, *WT, *alpha;  // alpha holds y_s on entry
   int *info;
 };
 
@@ -399,6 +404,26 @@ __global__ void __launch_bounds__(CH_THREADS, 1) gp_chol_kernel(CholArgs a) {
       al[j] = acc;
     }
   }
+  // ---------------- WT = W^T (upper triangular, row-major): 32 x 32 tiles through shared memory, coalesced both ways
+  {
+    double *WT = a.WT + (size_t)b * ld * ld;
+    const int nb = (n + NB - 1) / NB;
+    for (int ti = 0; ti < nb; ++ti)
+      for (int tj = 0; tj <= ti; ++tj) {
+        __syncthreads();
+        for (int idx = tid; idx < NB * NB; idx += CH_THREADS) {
+          const int r = idx / NB, c = idx % NB;
+          const int i = ti * NB + r, j = tj * NB + c;
+          s.D[r][c] = (i < n && j <= i) ? W[(long)i * ld + j] : 0.0;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < NB * NB; idx += CH_THREADS) {
+          const int r = idx / NB, c = idx % NB;
+          const int j = tj * NB + r, i = ti * NB + c;   // WT[j][i] = W[i][j]
+          if (i < n && j < n && j <= i) WT[(long)j * ld + i] = s.D[c][r];
+        }
+      }
+  }
   if (tid == 0) a.info[b] = s.info;
 }
 
@@ -423,9 +448,10 @@ __global__ void gp_mll_kernel(int n, int ld_n, const double *f, const double *ym
 extern "C" int pcabo_gp_fit(int B, int n, int kmax, int ld_n, int mode, const double *Z, const int *k, const double *f,
                             const double *fix_lo, const double *fix_hi, double lengthscale, double noise,
                             double *norm_off, double *norm_coef, double *box_lo, double *box_hi, double *ymean,
-                            double *ystd, double *ZnT, double *L, double *W, double *alpha, int *info, void *stream) {
+                            double *ystd, double *ZnT, double *Zn, double *L, double *W, double *WT, double *alpha,
+                            int *info, void *stream) {
   if (B <= 0 || n < 1 || kmax < 1 || ld_n < n || !Z || !f || !norm_off || !norm_coef || !box_lo || !box_hi || !ymean ||
-      !ystd || !ZnT || !L || !W || !alpha || !info || !(lengthscale > 0.0))
+      !ystd || !ZnT || !Zn || !L || !W || !WT || !alpha || !info || !(lengthscale > 0.0))
     return PCABO_E_INVALID;
   if (mode != 0 && (!fix_lo || !fix_hi)) return PCABO_E_INVALID;
   if (kmax > 104 || n > 4096) return PCABO_E_UNSUPPORTED;
@@ -435,7 +461,7 @@ extern "C" int pcabo_gp_fit(int B, int n, int kmax, int ld_n, int mode, const do
     a.B = B; a.n = n; a.kmax = kmax; a.ld_n = ld_n; a.mode = mode;
     a.Z = Z; a.k = k; a.f = f; a.fix_lo = fix_lo; a.fix_hi = fix_hi;
     a.norm_off = norm_off; a.norm_coef = norm_coef; a.box_lo = box_lo; a.box_hi = box_hi;
-    a.ymean = ymean; a.ystd = ystd; a.ZnT = ZnT; a.ys = alpha;
+    a.ymean = ymean; a.ystd = ystd; a.ZnT = ZnT; a.Zn = Zn; a.ys = alpha;
     const int G = 256 / kmax > 0 ? 256 / kmax : 1;
     const size_t smem = (size_t)(2 * G * kmax + 2 * kmax + 34) * sizeof(double);
     gp_prep_kernel<<<B, 256, smem, st>>>(a);
@@ -449,7 +475,7 @@ extern "C" int pcabo_gp_fit(int B, int n, int kmax, int ld_n, int mode, const do
   }
   {
     CholArgs a;
-    a.B = B; a.n = n; a.ld_n = ld_n; a.L = L; a.W = W; a.alpha = alpha; a.info = info;
+    a.B = B; a.n = n; a.ld_n = ld_n; a.L = L; a.W = W; a.WT = WT; a.alpha = alpha; a.info = info;
     const size_t smem = sizeof(Smem) + (size_t)n * sizeof(double);
     PCABO_CUDA_CHECK(cudaFuncSetAttribute(gp_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gp_chol_kernel<<<B, CH_THREADS, smem, st>>>(a);

@@ -82,15 +82,15 @@ extern "C" int pcabo_logei(const pcabo_gp_model *m, int npts, const double *X, d
   LogEiArgs a;
   a.m = *m; a.npts = npts; a.X = X; a.val = val; a.grad = grad; a.mu = mu; a.sigma = sigma;
   cudaStream_t st = as_stream(stream);
-  const int np = (m->n + 1) & ~1;
+  auto fits = [&](int P, bool g) { return scratch_doubles(P, m->kmax, m->n, g) * sizeof(double) <= 200 * 1024; };
   if (grad) {
-    // 3 P np doubles of shared memory: pick the largest P that fits and does not over-pad small batches
-    if (npts > 8 && (size_t)3 * 16 * np * 8 + 16 * m->kmax * 8 < 200 * 1024) return launch_logei<16, true>(a, st);
-    if (npts > 4 && (size_t)3 * 8 * np * 8 + 8 * m->kmax * 8 < 200 * 1024) return launch_logei<8, true>(a, st);
+    // pick the largest P that fits shared memory and does not over-pad small batches
+    if (npts > 8 && fits(16, true)) return launch_logei<16, true>(a, st);
+    if (npts > 4 && fits(8, true)) return launch_logei<8, true>(a, st);
     return launch_logei<4, true>(a, st);
   }
-  if (npts > 8 && (size_t)16 * np * 8 + 16 * m->kmax * 8 < 200 * 1024) return launch_logei<16, false>(a, st);
-  if (npts > 4) return launch_logei<8, false>(a, st);
+  if (npts > 8 && fits(16, false)) return launch_logei<16, false>(a, st);
+  if (npts > 4 && fits(8, false)) return launch_logei<8, false>(a, st);
   return launch_logei<4, false>(a, st);
 }
 

@@ -46,26 +46,31 @@ __device__ __forceinline__ void log_h_and_grad(double u, double &lh, double &dlh
 // Per-block view of one run's GP caches plus the shared-memory scratch of the evaluation.
 struct Ctx {
   int n, kmax, ld, kk, np;
-  const double *ZnT, *W, *alpha, *off, *coef;
+  const double *ZnT, *Zn, *W, *WT, *alpha, *off, *coef;
   double inv_ell2, ymean, ystd, best_f, sgn;
-  double *xn;   // [P][kmax]
-  double *kst;  // [P][np]
-  double *tv;   // [P][np]  (GRAD)
-  double *gf;   // [P][np]  (GRAD)
-  double *red;  // [8][2P] + [4P]
+  double *xn;    // [P][kmax]
+  double *kst;   // [P][np]  k vector, later the gradient coefficients c_i
+  double *tv;    // [P][np]  t = W k
+  double *gf;    // [P][np]  d k / d(dist^2) factor (GRAD)
+  double *part;  // [256 P]  split-K partial sums
+  double *red;   // [8][2P] + [4P]
 };
+
+constexpr int RB = 64;               // row / column block of the triangular passes
+constexpr int NG = LE_THREADS / RB;  // split-K groups
 
 __host__ __device__ inline size_t scratch_doubles(int P, int kmax, int n, bool grad) {
   const int np = (n + 1) & ~1;
-  return (size_t)P * kmax + (size_t)(grad ? 3 : 1) * P * np + 8 * 2 * P + 4 * P + 8;
+  return (size_t)P * kmax + (size_t)(grad ? 3 : 2) * P * np + (size_t)LE_THREADS * P + 8 * 2 * P + 4 * P + 8;
 }
 
 __device__ inline void carve_ctx(Ctx &c, int P, bool grad, double *sm) {
   c.xn = sm;
   c.kst = c.xn + P * c.kmax;
   c.tv = c.kst + P * c.np;
-  c.gf = c.tv + (grad ? P * c.np : 0);
-  c.red = c.gf + (grad ? P * c.np : 0);
+  c.gf = c.tv + P * c.np;
+  c.part = c.gf + (grad ? P * c.np : 0);
+  c.red = c.part + LE_THREADS * P;
 }
 
 __device__ inline void load_ctx(Ctx &c, const pcabo_gp_model &m, int b) {
@@ -73,7 +78,9 @@ __device__ inline void load_ctx(Ctx &c, const pcabo_gp_model &m, int b) {
   c.kk = m.k ? m.k[b] : m.kmax;
   c.np = (m.n + 1) & ~1;
   c.ZnT = m.ZnT + (size_t)b * m.kmax * m.ld_n;
+  c.Zn = m.Zn + (size_t)b * m.ld_n * m.kmax;
   c.W = m.W + (size_t)b * m.ld_n * m.ld_n;
+  c.WT = m.WT + (size_t)b * m.ld_n * m.ld_n;
   c.alpha = m.alpha + (size_t)b * m.ld_n;
   c.off = m.norm_off + (size_t)b * m.kmax;
   c.coef = m.norm_coef + (size_t)b * m.kmax;
@@ -82,17 +89,45 @@ __device__ inline void load_ctx(Ctx &c, const pcabo_gp_model &m, int b) {
   c.sgn = m.maximize ? 1.0 : -1.0;
 }
 
+// acc[p] += sum_{j in [j0, j1)} M[j * ld + col] * v[p * np + j], loads issued eight at a time (the chain is latency bound)
+template <int P>
+__device__ __forceinline__ void strided_dot(double (&acc)[P], const double *__restrict__ M, long ld, int col, int j0,
+                                            int j1, const double *__restrict__ v, int np) {
+  int j = j0;
+  for (; j + 8 <= j1; j += 8) {
+    double w8[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) w8[u] = M[(long)(j + u) * ld + col];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int p = 0; p < P; ++p) acc[p] = fma(w8[u], v[p * np + j + u], acc[p]);
+  }
+  for (; j < j1; ++j) {
+    const double wv = M[(long)j * ld + col];
+#pragma unroll
+    for (int p = 0; p < P; ++p) acc[p] = fma(wv, v[p * np + j], acc[p]);
+  }
+}
+
 // Evaluate pcount <= P points. X: raw-space coordinates, point p at X + p * xstride (first kk entries used).
 // val[p] (p < pcount) <- log-EI; if GRAD: grad[p * gstride + j] <- gscale * d logEI / d x_j for j < kk and 0 for
 // kk <= j < gfill. mu / sigma optional. All LE_THREADS threads of the block must call; ends with __syncthreads().
+//
+// Every heavy phase is a thread-per-output loop over coalesced global loads with no cross-lane reduction:
+//   t = W k     : thread (g, r) owns row i of a 64-row block and the g-th quarter of j <= i, reading WT[j][i]
+//   s = W^T t   : thread (g, c) owns column j of a 64-column block and a quarter of i >= j, reading W[i][j]
+//   gradient    : thread (ig, j) owns dimension j and every IG-th training point, reading Zn[i][j]
+// the quarters are combined in a fixed order through shared memory (deterministic).
 template <int P, bool GRAD>
 __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstride, double *val, double *grad,
                             int gstride, int gfill, double gscale, double *mu_out, double *sigma_out) {
   const int tid = threadIdx.x;
-  const int n = c.n, kmax = c.kmax, ld = c.ld, kk = c.kk, np = c.np;
+  const int n = c.n, kmax = c.kmax, kk = c.kk, np = c.np;
+  const long ld = c.ld;
   const int warp = tid >> 5, lane = tid & 31, nw = LE_THREADS >> 5;
-  double *xn = c.xn, *kst = c.kst, *tv = c.tv, *gf = c.gf, *red = c.red;
-  const double *ZnT = c.ZnT, *W = c.W, *alpha = c.alpha;
+  double *xn = c.xn, *kst = c.kst, *tv = c.tv, *gf = c.gf, *part = c.part, *red = c.red;
+  const double *ZnT = c.ZnT, *alpha = c.alpha;
   const double inv_ell2 = c.inv_ell2;
 
   for (int idx = tid; idx < P * kmax; idx += LE_THREADS) {
@@ -108,7 +143,17 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
     double sq[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) sq[p] = 0.0;
-    for (int j = 0; j < kk; ++j) {
+    int j = 0;
+    for (; j + 4 <= kk; j += 4) {
+      double z4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) z4[u] = ZnT[(size_t)(j + u) * ld + i];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int p = 0; p < P; ++p) { const double d = z4[u] - xn[p * kmax + j + u]; sq[p] = fma(d, d, sq[p]); }
+    }
+    for (; j < kk; ++j) {
       const double z = ZnT[(size_t)j * ld + i];
 #pragma unroll
       for (int p = 0; p < P; ++p) { const double d = z - xn[p * kmax + j]; sq[p] = fma(d, d, sq[p]); }
@@ -126,32 +171,42 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
     }
   }
   __syncthreads();
-  // ---- t = W k (lower triangular), quadratic form v = |t|^2
+  // ---- t = W k (lower triangular): row blocks of RB, the j range of a block split over NG groups
+  const int g = tid / RB, r = tid % RB;
   double vpart[P];
 #pragma unroll
   for (int p = 0; p < P; ++p) vpart[p] = 0.0;
-  for (int i = warp; i < n; i += nw) {
+  for (int i0 = 0; i0 < n; i0 += RB) {
+    const int i = i0 + r;
+    const int span = (min(n, i0 + RB) + NG - 1) / NG;
     double acc[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) acc[p] = 0.0;
-    const double *wrow = W + (size_t)i * ld;
-    for (int j = lane; j <= i; j += 32) {
-      const double wv = wrow[j];
+    if (i < n) strided_dot<P>(acc, c.WT, ld, i, g * span, min(g * span + span, i + 1), kst, np);
 #pragma unroll
-      for (int p = 0; p < P; ++p) acc[p] = fma(wv, kst[p * np + j], acc[p]);
-    }
+    for (int p = 0; p < P; ++p) part[(g * P + p) * RB + r] = acc[p];
+    __syncthreads();
+    for (int idx = tid; idx < P * RB; idx += LE_THREADS) {
+      const int p = idx / RB, rr = idx % RB;
+      if (i0 + rr < n) {
+        double t = 0.0;
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-      const double t = warp_sum(acc[p]);
-      vpart[p] = fma(t, t, vpart[p]);
-      if (GRAD && lane == 0) tv[p * np + i] = t;
+        for (int gg = 0; gg < NG; ++gg) t += part[(gg * P + p) * RB + rr];
+        tv[p * np + i0 + rr] = t;
+      }
     }
+    __syncthreads();
   }
-  // ---- block reductions of the mean partials (per thread) and the variance partials (per warp, lanes equal)
+  for (int i = tid; i < n; i += LE_THREADS) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) { const double t = tv[p * np + i]; vpart[p] = fma(t, t, vpart[p]); }
+  }
+  // ---- block reductions of the mean and variance partials
 #pragma unroll
   for (int p = 0; p < P; ++p) {
     const double ms = warp_sum(mpart[p]);
-    if (lane == 0) { red[warp * 2 * P + p] = ms; red[warp * 2 * P + P + p] = vpart[p]; }
+    const double vs = warp_sum(vpart[p]);
+    if (lane == 0) { red[warp * 2 * P + p] = ms; red[warp * 2 * P + P + p] = vs; }
   }
   __syncthreads();
   double *res = red + nw * 2 * P;  // [2][P]: d logEI / d mu_s, d logEI / d var_s
@@ -182,34 +237,92 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
     }
   }
   __syncthreads();
-  if (!GRAD) return;
-  // ---- s = W^T t, then c_i = gf_i (A alpha_i - 2 B s_i)  (stored over the k vector)
-  for (int j = tid; j < n; j += LE_THREADS) {
+  if constexpr (GRAD) {
+  // ---- s = W^T t: column blocks of RB, the i range [j0, n) of a block split over NG groups;
+  //      then c_j = gf_j (A alpha_j - 2 B s_j) stored over the k vector
+  for (int j0 = 0; j0 < n; j0 += RB) {
+    const int j = j0 + r;
+    const int span = (n - j0 + NG - 1) / NG;
     double acc[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) acc[p] = 0.0;
-    for (int i = j; i < n; ++i) {
-      const double wv = W[(size_t)i * ld + j];
+    if (j < n) {
+      const int a0 = j0 + g * span;
+      // W[i][j] for i in [max(a0, j), min(a0 + span, n)): row-major W, consecutive j coalesce
+      int i = max(a0, j);
+      const int i1 = min(a0 + span, n);
+      for (; i + 8 <= i1; i += 8) {
+        double w8[8];
 #pragma unroll
-      for (int p = 0; p < P; ++p) acc[p] = fma(wv, tv[p * np + i], acc[p]);
+        for (int u = 0; u < 8; ++u) w8[u] = c.W[(long)(i + u) * ld + j];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int p = 0; p < P; ++p) acc[p] = fma(w8[u], tv[p * np + i + u], acc[p]);
+      }
+      for (; i < i1; ++i) {
+        const double wv = c.W[(long)i * ld + j];
+#pragma unroll
+        for (int p = 0; p < P; ++p) acc[p] = fma(wv, tv[p * np + i], acc[p]);
+      }
     }
-    const double al = alpha[j];
 #pragma unroll
-    for (int p = 0; p < P; ++p) kst[p * np + j] = gf[p * np + j] * (res[p] * al - 2.0 * res[P + p] * acc[p]);
+    for (int p = 0; p < P; ++p) part[(g * P + p) * RB + r] = acc[p];
+    __syncthreads();
+    for (int idx = tid; idx < P * RB; idx += LE_THREADS) {
+      const int p = idx / RB, rr = idx % RB;
+      const int jj = j0 + rr;
+      if (jj < n) {
+        double sv = 0.0;
+#pragma unroll
+        for (int gg = 0; gg < NG; ++gg) sv += part[(gg * P + p) * RB + rr];
+        kst[p * np + jj] = gf[p * np + jj] * (res[p] * alpha[jj] - 2.0 * res[P + p] * sv);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- grad[p][j] = gscale (1 / coef_j) sum_i c_i (xn_j - zn_ij): thread (ig, j), every IG-th training point
+  {
+    const int IG = LE_THREADS / kk;  // >= 2 for kk <= 104
+    const int ig = tid / kk, j = tid % kk;
+    double acc[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) acc[p] = 0.0;
+    if (ig < IG) {
+      double xj[P];
+#pragma unroll
+      for (int p = 0; p < P; ++p) xj[p] = xn[p * kmax + j];
+      int i = ig;
+      for (; i + 3 * IG < n; i += 4 * IG) {
+        double z4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) z4[u] = c.Zn[(size_t)(i + u * IG) * kmax + j];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int p = 0; p < P; ++p) acc[p] = fma(kst[p * np + i + u * IG], xj[p] - z4[u], acc[p]);
+      }
+      for (; i < n; i += IG) {
+        const double z = c.Zn[(size_t)i * kmax + j];
+#pragma unroll
+        for (int p = 0; p < P; ++p) acc[p] = fma(kst[p * np + i], xj[p] - z, acc[p]);
+      }
+#pragma unroll
+      for (int p = 0; p < P; ++p) part[(ig * P + p) * kk + j] = acc[p];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < pcount * gfill; idx += LE_THREADS) {
+      const int p = idx / gfill, jj = idx % gfill;
+      double sv = 0.0;
+      if (jj < kk) {
+        for (int q = 0; q < IG; ++q) sv += part[(q * P + p) * kk + jj];
+        sv = gscale * sv / c.coef[jj];
+      }
+      grad[(size_t)p * gstride + jj] = sv;
+    }
   }
   __syncthreads();
-  // ---- grad[p][j] = gscale (1 / coef_j) sum_i c_i (xn_j - zn_ij), warp per (p, j)
-  for (int pc = warp; pc < pcount * gfill; pc += nw) {
-    const int p = pc / gfill, j = pc % gfill;
-    double acc = 0.0;
-    if (j < kk) {
-      const double xc = xn[p * kmax + j];
-      for (int i = lane; i < n; i += 32) acc = fma(kst[p * np + i], xc - ZnT[(size_t)j * ld + i], acc);
-      acc = warp_sum(acc);
-    }
-    if (lane == 0) grad[(size_t)p * gstride + j] = (j < kk) ? gscale * acc / c.coef[j] : 0.0;
-  }
-  __syncthreads();
+  }  // GRAD
 }
 
 }  // namespace logei

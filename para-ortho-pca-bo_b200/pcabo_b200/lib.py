@@ -26,6 +26,7 @@ class GpModelStruct(ctypes.Structure):
         ("k", ctypes.c_void_p), ("norm_off", ctypes.c_void_p), ("norm_coef", ctypes.c_void_p),
         ("ZnT", ctypes.c_void_p), ("alpha", ctypes.c_void_p), ("W", ctypes.c_void_p),
         ("ymean", ctypes.c_void_p), ("ystd", ctypes.c_void_p), ("best_f", ctypes.c_void_p),
+        ("WT", ctypes.c_void_p), ("Zn", ctypes.c_void_p),
     ]
 
 
@@ -57,7 +58,7 @@ def load_library(build_if_missing: bool = False):
     lib.pcabo_inverse_map.restype = ci
     lib.pcabo_inverse_map.argtypes = [ci, ci] + [vp] * 9 + [vp]
     lib.pcabo_gp_fit.restype = ci
-    lib.pcabo_gp_fit.argtypes = [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, cd, cd] + [vp] * 11 + [vp]
+    lib.pcabo_gp_fit.argtypes = [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, cd, cd] + [vp] * 13 + [vp]
     lib.pcabo_gp_mll.restype = ci
     lib.pcabo_gp_mll.argtypes = [ci, ci, ci] + [vp] * 6 + [vp]
     lib.pcabo_logei.restype = ci

@@ -90,8 +90,10 @@ class GPBuffers:
         self.ymean = torch.zeros(B, **f64)
         self.ystd = torch.ones(B, **f64)
         self.ZnT = torch.zeros(B, kmax, ld_n, **f64)
+        self.Zn = torch.zeros(B, ld_n, kmax, **f64)
         self.L = torch.zeros(B, ld_n, ld_n, **f64)
         self.W = torch.zeros(B, ld_n, ld_n, **f64)
+        self.WT = torch.zeros(B, ld_n, ld_n, **f64)
         self.alpha = torch.zeros(B, ld_n, **f64)
         self.info = torch.zeros(B, dtype=torch.int32, device=device)
         self.best_f = torch.zeros(B, **f64)
@@ -111,7 +113,8 @@ def gp_fit(buf: GPBuffers, Z, k, f, n, mode=0, fix_lo=None, fix_hi=None, lengths
                            _d(fix_hi, "fix_hi"), float(lengthscale), float(noise),
                            _d(buf.norm_off, "norm_off"), _d(buf.norm_coef, "norm_coef"), _d(buf.box_lo, "box_lo"),
                            _d(buf.box_hi, "box_hi"), _d(buf.ymean, "ymean"), _d(buf.ystd, "ystd"), _d(buf.ZnT, "ZnT"),
-                           _d(buf.L, "L"), _d(buf.W, "W"), _d(buf.alpha, "alpha"), _i(buf.info, "info"), _stream()),
+                           _d(buf.Zn, "Zn"), _d(buf.L, "L"), _d(buf.W, "W"), _d(buf.WT, "WT"), _d(buf.alpha, "alpha"),
+                           _i(buf.info, "info"), _stream()),
           "pcabo_gp_fit")
     buf.n, buf.k, buf.lengthscale = n, k, lengthscale
     return buf
@@ -134,6 +137,7 @@ def model_struct(buf: GPBuffers) -> GpModelStruct:
     m.norm_off, m.norm_coef = _d(buf.norm_off, "norm_off"), _d(buf.norm_coef, "norm_coef")
     m.ZnT, m.alpha, m.W = _d(buf.ZnT, "ZnT"), _d(buf.alpha, "alpha"), _d(buf.W, "W")
     m.ymean, m.ystd, m.best_f = _d(buf.ymean, "ymean"), _d(buf.ystd, "ystd"), _d(buf.best_f, "best_f")
+    m.WT, m.Zn = _d(buf.WT, "WT"), _d(buf.Zn, "Zn")
     return m
 
 
