@@ -246,7 +246,7 @@ LB_HD void cauchy(T &tm, Work &w, int col, double theta, double sbgnrm, int &nse
   int nleft = nbreak;
   double tj = 0.0;
   bool all_fixed = false;
-  while (true) {
+  for (int guard = 0; guard <= nbreak; ++guard) {
     const double tj0 = tj;
     double tmin = INFINITY;
     int ibp = 0x7fffffff;
@@ -695,7 +695,10 @@ LB_HD Result minimize(T &tm, Work &w, Fn &fn, int maxiter, double factr, double 
   double sbgnrm = projgr(tm, w);
   if (sbgnrm <= pgtol) { res.status = CONV_PGTOL; res.f = f; return res; }
   int iter = 0;
+  int passes = 0;
   while (true) {
+    // every pass either completes an iteration or discards the BFGS memory once; the guard only fires on NaN storms
+    if (++passes > 3 * maxiter + 20) { res.status = ABNORMAL; break; }
     int nseg;
     tm.tick(0);
     cauchy(tm, w, col, theta, sbgnrm, nseg);

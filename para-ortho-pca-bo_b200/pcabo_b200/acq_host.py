@@ -77,7 +77,9 @@ def select_initial_conditions(vals: torch.Tensor, n: int, gens, runs, q_buf=None
     etaz = eta * (vals - mean[:, None]) / std[:, None]
     w = torch.exp(etaz)
     inf_rows = torch.isinf(w).any(dim=1)
-    while bool(inf_rows.any()):
+    for _ in range(64):        # botorch halves eta until the weights are finite; bounded here (inf input values)
+        if not bool(inf_rows.any()):
+            break
         etaz[inf_rows] *= 0.5
         w[inf_rows] = torch.exp(etaz[inf_rows])
         inf_rows = torch.isinf(w).any(dim=1)

@@ -22,8 +22,13 @@ def main():
     prob = BatchedBBOB(fids, insts, D, device="cuda")
     eng = BatchedBOEngine(prob, D, prob.bounds, 450, 120, [1000 * f + 400 + i for f, i in zip(fids, insts)], optimizer="device")
     eng.initial_design()
-    for _ in range(steps):
+    import time
+    t0 = time.time()
+    for s_ in range(steps):
         eng.step()
+        if s_ % 20 == 0:
+            print(f"step {s_} n={eng.n} t={time.time() - t0:.1f}s retries={eng.stats['retries']} "
+                  f"nfev_max={max(max(v) for v in eng.last['nfev'].values())}", file=sys.stderr, flush=True)
     eng._fit_models()
     k_host = eng.pca["k"].cpu().numpy().astype(np.int64)
     ics = eng._initial_conditions(list(range(eng.B)), k_host)
