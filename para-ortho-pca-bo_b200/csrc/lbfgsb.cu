@@ -24,6 +24,7 @@ struct Mailbox {
 
 // The L-BFGS-B "team" on the device is ONE warp: reductions are shuffles, sync is __syncwarp (no block barriers).
 struct CudaWarpTeam {
+  static constexpr bool kWarpRegs = true;
   int tid, nt, lane, nl;
   bool w0;
   Mailbox *mb;

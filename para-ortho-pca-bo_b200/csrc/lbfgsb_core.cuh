@@ -33,6 +33,7 @@ enum Status { CONV_PGTOL = 0, CONV_FTOL = 1, STOP_MAXITER = 2, ABNORMAL = 3, RUN
 struct HostTeam {
   static constexpr int tid = 0, nt = 1, lane = 0, nl = 1;
   static constexpr bool w0 = true;
+  static constexpr bool kWarpRegs = false;   // true: the team is one CUDA warp with register/shuffle small-matrix kernels
   void sync() {}
   void wsync() {}
   double sum(double v) { return v; }
@@ -52,6 +53,8 @@ struct Work {
   double *p, *c, *wbp, *v, *wv;                  // [M2]
   double *tbrk;                                  // [n] breakpoints (negative: none / consumed)
   int *iwhere;                                   // [n]
+  // reciprocals kept next to the factors (warp-register path): 1/sy_kk, 1/sqrt(sy_kk), 1/diag(wt), 1/diag(wn)
+  double *rsy, *rsq, *wt_rd, *wn_rd;
 };
 
 LB_HD inline size_t work_doubles(int n) {
@@ -65,11 +68,99 @@ LB_HD inline void carve(Work &w, int n, double *base) {
   w.d = q; q += n; w.t = q; q += n; w.r = q; q += n; w.xp = q; q += n;
   w.ws = q; q += M * n; w.wy = q; q += M * n;
   w.sy = q; q += M * M; w.ss = q; q += M * M; w.wt = q; q += M * M; w.jinv = q; q += M * M;
+  w.rsy = w.jinv; w.rsq = w.jinv + M; w.wt_rd = w.jinv + 2 * M; w.wn_rd = w.jinv + 3 * M;
   w.wn = q; q += M2 * M2;
   w.p = q; q += M2; w.c = q; q += M2; w.wbp = q; q += M2; w.v = q; q += M2; w.wv = q; q += M2;
   w.tbrk = q; q += n;
   w.iwhere = reinterpret_cast<int *>(q);
 }
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------ warp-register kernels
+// Small dense kernels for a team that is exactly one CUDA warp: matrices live in registers (lane j owns column j or row
+// j), pivots and right-hand sides travel by shuffles, divisions are replaced by stored reciprocal diagonals. The serial
+// chain per elimination step is one shuffle + one multiply + one FMA instead of shared-memory round trips.
+namespace dev {
+constexpr unsigned FULL = 0xffffffffu;
+__device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
+
+// Right-looking Cholesky R^T R = A of the leading n x n block (n <= N) of the upper-stored A (ld = lda); R overwrites A,
+// rdiag[j] = 1 / R[j][j]. For pivots k < nsplit the rows/columns >= nsplit receive +r_ki r_kj instead of -r_ki r_kj: with
+// nsplit = col on the 2 col x 2 col matrix of formk this is the LEL^T factorisation (Cholesky of the (1,1) block,
+// R12 = R11^-T A12, Cholesky of A22 + R12^T R12) in one sweep. Returns 0 or 1 + index of the first non-positive pivot.
+template <int N>
+__device__ int chol_upper_reg(double *A, int lda, int n, int nsplit, double *rdiag) {
+  const int lane = threadIdx.x & 31;
+  double a[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) a[i] = (lane < n && i <= lane) ? A[i * lda + lane] : 0.0;
+  int bad = 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    if (k < n) {
+      double piv = shfl(a[k], k);
+      if (!(piv > 0.0)) { if (bad == 0) bad = k + 1; piv = 1.0; }
+      const double rkk = sqrt(piv);
+      const double rinv = 1.0 / rkk;
+      if (lane == k) a[k] = rkk;
+      else if (lane > k) a[k] *= rinv;
+      const bool plus_k = k < nsplit;
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) {
+        const double rki = shfl(a[k], i);
+        if (i < n && lane >= i) {
+          const double prod = rki * a[k];
+          a[i] = (plus_k && i >= nsplit) ? a[i] + prod : a[i] - prod;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if (lane < n && i <= lane) A[i * lda + lane] = a[i];
+  double dj = 1.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if (i == lane) dj = a[i];
+  if (lane < n) rdiag[lane] = 1.0 / dj;
+  __syncwarp();
+  return bad;
+}
+
+// In place on b (shared memory, length n <= N): trans ? R^T x = b : R x = b, R upper triangular with reciprocal diagonal.
+template <int N>
+__device__ void tri_solve_reg(const double *R, int ldr, int n, double *b, const double *rdiag, bool trans) {
+  const int lane = threadIdx.x & 31;
+  double bi = (lane < n) ? b[lane] : 0.0;
+  double c[N];
+  if (trans) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) c[j] = (lane < n && j < lane) ? R[j * ldr + lane] : 0.0;      // column `lane`
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      if (j < n) {
+        const double xj = shfl(bi, j) * rdiag[j];
+        if (lane == j) bi = xj;
+        else if (lane > j) bi = fma(-c[j], xj, bi);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) c[j] = (lane < n && j > lane && j < n) ? R[lane * ldr + j] : 0.0;  // row `lane`
+#pragma unroll
+    for (int j = N - 1; j >= 0; --j) {
+      if (j < n) {
+        const double xj = shfl(bi, j) * rdiag[j];
+        if (lane == j) bi = xj;
+        else if (lane < j) bi = fma(-c[j], xj, bi);
+      }
+    }
+  }
+  if (lane < n) b[lane] = bi;
+  __syncwarp();
+}
+}  // namespace dev
+#endif  // __CUDACC__
 
 // ------------------------------------------------------------------------------------------------ small dense helpers
 // Cholesky of the leading n x n block of an upper-stored symmetric matrix A (ld = lda): R^T R = A, R overwrites the
@@ -129,6 +220,35 @@ LB_HD void tri_solve_w0(T &tm, const double *R, int ldr, int n, double *b, bool 
 template <class T>
 LB_HD void bmv(T &tm, const Work &w, int col, const double *v, double *p) {
   if (col == 0) return;
+#ifdef __CUDA_ARCH__
+  if constexpr (T::kWarpRegs) {
+    const int i = tm.lane;
+    const bool on = i < col;
+    const double v1 = on ? v[i] : 0.0, v2 = on ? v[col + i] : 0.0;
+    const double rsyi = on ? w.rsy[i] : 0.0, rsqi = on ? w.rsq[i] : 0.0;
+    const double u = v1 * rsyi;
+    double p2 = v2;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      const double uk = dev::shfl(u, k);
+      if (on && k < i) p2 = fma(w.sy[i * M + k], uk, p2);
+    }
+    if (on) p[col + i] = p2;
+    __syncwarp();
+    dev::tri_solve_reg<M>(w.wt, M, col, p + col, w.wt_rd, true);
+    dev::tri_solve_reg<M>(w.wt, M, col, p + col, w.wt_rd, false);
+    p2 = on ? p[col + i] : 0.0;
+    double sacc = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      const double pk = dev::shfl(p2, k);
+      if (on && k > i && k < col) sacc = fma(w.sy[k * M + i], pk, sacc);
+    }
+    if (on) p[i] = -(v1 * rsqi) * rsqi + sacc * rsyi;
+    __syncwarp();
+    return;
+  }
+#endif
   if (tm.w0) {
     // p2 = v2 + L D^-1 v1
     for (int i = tm.lane; i < col; i += tm.nl) {
@@ -347,6 +467,12 @@ template <class T>
 LB_HD int formk(T &tm, Work &w, int col, double theta, int *flag) {
   tm.formk_products(w, col, theta);   // the team may hand this O(m^2 n) part to more threads than itself
   tm.sync();
+#ifdef __CUDA_ARCH__
+  if constexpr (T::kWarpRegs) {
+    // Cholesky of (1,1), R12 = R11^-T A12 and Cholesky of A22 + R12^T R12 in one in-register sweep
+    return dev::chol_upper_reg<M2>(w.wn, M2, 2 * col, col, w.wn_rd) != 0 ? -1 : 0;
+  }
+#endif
   int info = chol_upper(tm, w.wn, M2, col, flag);
   if (info != 0) return -1;
   // (1,2) <- L^-1 (1,2): one column per lane of warp 0 (each a forward substitution with R^T)
@@ -420,6 +546,14 @@ LB_HD void subsm(T &tm, Work &w, int col, double theta) {
   }
   tm.sync();
   // wv <- K^-1 wv through the LEL^T factor
+#ifdef __CUDA_ARCH__
+  if constexpr (T::kWarpRegs) {
+    dev::tri_solve_reg<M2>(w.wn, M2, 2 * col, w.wv, w.wn_rd, true);
+    if (tm.lane < col) w.wv[tm.lane] = -w.wv[tm.lane];
+    __syncwarp();
+    dev::tri_solve_reg<M2>(w.wn, M2, 2 * col, w.wv, w.wn_rd, false);
+  } else
+#endif
   if (tm.w0) {
     tri_solve_w0(tm, w.wn, M2, 2 * col, w.wv, true);
     for (int j = tm.lane; j < col; j += tm.nl) w.wv[j] = -w.wv[j];
@@ -611,10 +745,9 @@ LB_HD int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, doubl
                        int *flag) {
   const int n = w.n;
   if (col == M) {  // drop the oldest pair
-    for (int j = 0; j < M - 1; ++j) {
-      for (int i = tm.tid; i < n; i += tm.nt) { w.ws[j * n + i] = w.ws[(j + 1) * n + i]; w.wy[j * n + i] = w.wy[(j + 1) * n + i]; }
-      tm.sync();
-    }
+    for (int i = tm.tid; i < n; i += tm.nt)   // each thread shifts its own columns: no synchronisation between pairs
+      for (int j = 0; j < M - 1; ++j) { w.ws[j * n + i] = w.ws[(j + 1) * n + i]; w.wy[j * n + i] = w.wy[(j + 1) * n + i]; }
+    tm.sync();
     if (tm.tid == 0) {
       for (int i = 0; i < M - 1; ++i)
         for (int j = 0; j < M - 1; ++j) { w.sy[i * M + j] = w.sy[(i + 1) * M + j + 1]; w.ss[i * M + j] = w.ss[(i + 1) * M + j + 1]; }
@@ -652,6 +785,8 @@ LB_HD int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, doubl
   }
   col = c + 1;
   tm.sync();
+  for (int k = tm.tid; k < col; k += tm.nt) { w.rsy[k] = 1.0 / w.sy[k * M + k]; w.rsq[k] = 1.0 / sqrt(w.sy[k * M + k]); }
+  tm.sync();
   // formt: upper triangle of T
   for (int e = tm.tid; e < col * col; e += tm.nt) {
     const int i = e / col, j = e % col;
@@ -662,6 +797,9 @@ LB_HD int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, doubl
     w.wt[i * M + j] = s + theta * w.ss[i * M + j];
   }
   tm.sync();
+#ifdef __CUDA_ARCH__
+  if constexpr (T::kWarpRegs) return dev::chol_upper_reg<M>(w.wt, M, col, col, w.wt_rd) != 0 ? -3 : 0;
+#endif
   return chol_upper(tm, w.wt, M, col, flag) != 0 ? -3 : 0;
 }
 
