@@ -351,6 +351,7 @@ LB_HD void cauchy(T &tm, Work &w, int col, double theta, double sbgnrm, int &nse
     for (int j = 0; j < 2 * col; ++j) w.c[j] = 0.0;
   }
   tm.sync();
+  tm.tick(11);
   if (nbreak == 0) return;  // no variable can move: xcp = x (all boxed, so "nfree == n + 1" of the original holds)
   double f2 = -theta * f1;
   const double f2_org = f2;
@@ -360,6 +361,7 @@ LB_HD void cauchy(T &tm, Work &w, int col, double theta, double sbgnrm, int &nse
     for (int j = 0; j < 2 * col; ++j) s += w.v[j] * w.p[j];
     f2 -= s;
   }
+  tm.tick(12);
   double dtm = -f1 / f2;
   double tsum = 0.0;
   nseg = 1;
@@ -467,6 +469,7 @@ template <class T>
 LB_HD int formk(T &tm, Work &w, int col, double theta, int *flag) {
   tm.formk_products(w, col, theta);   // the team may hand this O(m^2 n) part to more threads than itself
   tm.sync();
+  tm.tick(10);
 #ifdef __CUDA_ARCH__
   if constexpr (T::kWarpRegs) {
     // Cholesky of (1,1), R12 = R11^-T A12 and Cholesky of A22 + R12^T R12 in one in-register sweep
@@ -758,6 +761,7 @@ LB_HD int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, doubl
   const int c = col;
   for (int i = tm.tid; i < n; i += tm.nt) { w.ws[c * n + i] = w.d[i]; w.wy[c * n + i] = w.r[i]; }
   tm.sync();
+  tm.tick(13);
   theta = rr / dr;
   // new row of S'Y (s_new . y_j) and new column of S'S (s_j . s_new)
   double part[M2];
@@ -785,6 +789,7 @@ LB_HD int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, doubl
   }
   col = c + 1;
   tm.sync();
+  tm.tick(14);
   for (int k = tm.tid; k < col; k += tm.nt) { w.rsy[k] = 1.0 / w.sy[k * M + k]; w.rsq[k] = 1.0 / sqrt(w.sy[k * M + k]); }
   tm.sync();
   // formt: upper triangle of T

@@ -12,7 +12,8 @@ from pcabo_b200 import ops
 from pcabo_b200.bbob import BatchedBBOB
 from pcabo_b200.engine import BatchedBOEngine
 
-NAMES = ["tests", "cauchy", "formk", "cmprlb", "subsm", "ls_setup", "ls_step", "eval", "dcsrch", "update"]
+NAMES = ["tests", "cauchy_rest", "formk_chol", "cmprlb", "subsm", "ls_setup", "ls_step", "eval", "dcsrch", "update_formt_chol",
+         "formk_products", "cauchy_pass1", "cauchy_bmv", "update_shift", "update_products", "x15"]
 
 
 def main():
@@ -39,7 +40,7 @@ def main():
     out = ops.lbfgsb_logei(eng.gp, ics, eng.gp.box_lo, eng.gp.box_hi, prof=prof)
     e1.record()
     torch.cuda.synchronize()
-    p = prof.cpu().numpy().reshape(-1, 16)[:, :10].astype(np.float64)
+    p = prof.cpu().numpy().reshape(-1, 16).astype(np.float64)
     nit = out["nit"].cpu().numpy().reshape(-1)
     nfev = out["nfev"].cpu().numpy().reshape(-1)
     tot = p.sum(1)
