@@ -130,6 +130,18 @@ int pcabo_lbfgsb_logei_prof(const pcabo_gp_model *m, int num_restarts, int batch
                             double *cand, double *fval, int *status, int *nit, int *nfev, long long *prof,
                             void *stream);
 
+/* log-EI sweep with fused arg-max over `ncand` candidates against run `run` of the model (BASELINE config C4).
+ * Candidates: explicit X [ncand][kmax] (raw space), or X = NULL and generated in-kernel as scrambled Sobol points
+ * (global indices idx0 .. idx0 + ncand - 1; shift [kmax], sstate [kmax][30] = the engine's shift and SCRAMBLED direction
+ * numbers) scaled to [lo, hi] [kmax] exactly like pcabo_sobol_points. vals [ncand] optional (NULL: arg-max only).
+ * part_val / part_idx [nparts]: scratch for per-CTA partial maxima (nparts = number of CTAs to use, e.g. SM count).
+ * best_val / best_idx (device scalars): maximum log-EI and its GLOBAL candidate index (ties: lowest index).
+ * FP64 tensor cores (DMMA.8x8x4); needs n <= 512, even ld_n and kmax.                                                */
+int pcabo_ei_sweep(const pcabo_gp_model *m, int run, long long ncand, long long idx0, const double *X,
+                   const int *shift, const int *sstate, const double *lo, const double *hi, double *vals,
+                   double *part_val, long long *part_idx, int nparts, double *best_val, long long *best_idx,
+                   void *stream);
+
 /* Scrambled Sobol raw samples scaled to the search box, generated on the device from host-drawn scramble bits
  * (replaces botorch draw_sobol_samples / torch SobolEngine(k, scramble=True).draw(npts, float64) inside optimize_acqf,
  * PCA_BO.py:607-614; bit-identical to torch).  shift [B][kmax] (30-bit), ltm_dots [B][kmax][30] (rows of the random

@@ -94,14 +94,23 @@ template <int P>
 __device__ __forceinline__ void strided_dot(double (&acc)[P], const double *__restrict__ M, long ld, int col, int j0,
                                             int j1, const double *__restrict__ v, int np) {
   int j = j0;
-  for (; j + 8 <= j1; j += 8) {
-    double w8[8];
+  for (; j + 16 <= j1; j += 16) {
+    double w16[16];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) w8[u] = M[(long)(j + u) * ld + col];
+    for (int u = 0; u < 16; ++u) w16[u] = M[(long)(j + u) * ld + col];
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
+    for (int u = 0; u < 16; ++u)
 #pragma unroll
-      for (int p = 0; p < P; ++p) acc[p] = fma(w8[u], v[p * np + j + u], acc[p]);
+      for (int p = 0; p < P; ++p) acc[p] = fma(w16[u], v[p * np + j + u], acc[p]);
+  }
+  for (; j + 4 <= j1; j += 4) {
+    double w4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) w4[u] = M[(long)(j + u) * ld + col];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int p = 0; p < P; ++p) acc[p] = fma(w4[u], v[p * np + j + u], acc[p]);
   }
   for (; j < j1; ++j) {
     const double wv = M[(long)j * ld + col];
@@ -251,14 +260,23 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
       // W[i][j] for i in [max(a0, j), min(a0 + span, n)): row-major W, consecutive j coalesce
       int i = max(a0, j);
       const int i1 = min(a0 + span, n);
-      for (; i + 8 <= i1; i += 8) {
-        double w8[8];
+      for (; i + 16 <= i1; i += 16) {
+        double w16[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) w8[u] = c.W[(long)(i + u) * ld + j];
+        for (int u = 0; u < 16; ++u) w16[u] = c.W[(long)(i + u) * ld + j];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < 16; ++u)
 #pragma unroll
-          for (int p = 0; p < P; ++p) acc[p] = fma(w8[u], tv[p * np + i + u], acc[p]);
+          for (int p = 0; p < P; ++p) acc[p] = fma(w16[u], tv[p * np + i + u], acc[p]);
+      }
+      for (; i + 4 <= i1; i += 4) {
+        double w4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w4[u] = c.W[(long)(i + u) * ld + j];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int p = 0; p < P; ++p) acc[p] = fma(w4[u], tv[p * np + i + u], acc[p]);
       }
       for (; i < i1; ++i) {
         const double wv = c.W[(long)i * ld + j];

@@ -1,0 +1,351 @@
+// K6b/K7: log-EI sweep over a large candidate set against one fitted GP with a fused arg-max (BASELINE config C4:
+// n = 450 training points, r <= 40, 2^20 .. 2^26 scrambled-Sobol candidates in the 0.5-padded box).
+//
+// This is the raw-sample scoring pass of the reference's optimize_acqf (PCA_BO.py:607-614; botorch evaluates
+// LogExpectedImprovement on raw_samples = 512 Sobol points in chunks of batch_limit = 5) scaled to millions of
+// candidates, so unlike the 5-point evaluations of the BO loop it is a dense FP64 contraction and FP64-pipe bound:
+//     T = W K*      W = L^-1 (n x n lower triangular),  K*[j][c] = matern52(|zn_j - xn_c| / ell)   (n x N_cand)
+//     var_c = k** - sum_i T[i][c]^2 ,  mu_c = alpha . K*[:, c]  ->  log-EI_c  ->  arg-max
+// One CTA owns a tile of 32 candidates and keeps the whole n x 32 tile of T in registers as FP64 tensor-core
+// accumulators (mma.sync.aligned.m8n8k4.f64, the only FP64 MMA shape on sm_100: SASS DMMA.8x8x4). The k dimension is
+// streamed in panels of 16 training points: the W panel arrives by cp.async (double buffered, 16-byte copies), the K*
+// panel is computed on the fly from the staged training rows, so neither W nor K* is ever re-read per candidate and
+// candidates are generated in-kernel from the scrambled Sobol state (no HBM traffic for them at all).
+#include "logei_core.cuh"
+
+namespace {
+
+using logei::SQRT5;
+
+constexpr int SW_THREADS = 256;
+constexpr int NWARP = SW_THREADS / 32;
+constexpr int TC = 32;        // candidates per tile
+constexpr int CT = TC / 8;    // 8-wide column tiles
+constexpr int KB = 16;        // training points per k panel
+constexpr int WS_LD = 20;     // W panel row stride in doubles (bank-conflict free for the A fragments)
+constexpr int KS_LD = 36;     // K* panel row stride in doubles (bank-conflict free for the B fragments)
+constexpr int RT_MAX = 8;     // row tiles (of 8 rows) per warp: n <= 8 * 8 * 8 = 512
+constexpr int MAXBIT = 30;
+
+struct SweepArgs {
+  pcabo_gp_model m;
+  int b;                       // run (GP) of the batch to sweep against
+  long long ncand, idx0;       // candidates in this launch and global index of the first one
+  const double *X;             // optional explicit candidates [ncand][kmax] (raw space); nullptr -> Sobol
+  const int *shift, *sstate;   // Sobol: [kmax] shifts and [kmax][30] scrambled direction numbers
+  const double *lo, *hi;       // box [kmax]
+  double *vals;                // optional [ncand]
+  double *best_val;            // [gridDim.x]
+  long long *best_idx;         // [gridDim.x] global indices
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+struct Smem {
+  double *Ws[2];   // [rows8][WS_LD]
+  double *Ks[2];   // [KB][KS_LD]
+  double *Zs[2];   // [KB][kmax]
+  double *As[2];   // [KB] alpha
+  double *xn;      // [TC][kmax + 1]
+  double *red;     // [NWARP][TC] + [NWARP][TC]
+  int *sst;        // [kmax][MAXBIT]
+};
+
+__host__ __device__ inline size_t sweep_smem_bytes(int n, int kmax) {
+  const int rows8 = ((n + 7) / 8) * 8;
+  size_t d = 2 * (size_t)rows8 * WS_LD + 2 * KB * KS_LD + 2 * (size_t)KB * kmax + 2 * KB + (size_t)TC * (kmax + 1) +
+             2 * NWARP * TC + 8;
+  return d * sizeof(double) + (size_t)kmax * MAXBIT * sizeof(int);
+}
+
+__global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
+  extern __shared__ __align__(16) double smd[];
+  const pcabo_gp_model &m = a.m;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = m.n, kmax = m.kmax;
+  const long ld = m.ld_n;
+  const int b = a.b;
+  const int kk = m.k ? m.k[b] : kmax;
+  const int rows8 = ((n + 7) / 8) * 8;
+  const int nrt = rows8 / 8;  // row tiles
+  Smem s;
+  {
+    double *q = smd;
+    s.Ws[0] = q; q += (size_t)rows8 * WS_LD; s.Ws[1] = q; q += (size_t)rows8 * WS_LD;
+    s.Ks[0] = q; q += KB * KS_LD; s.Ks[1] = q; q += KB * KS_LD;
+    s.Zs[0] = q; q += KB * kmax; s.Zs[1] = q; q += KB * kmax;
+    s.As[0] = q; q += KB; s.As[1] = q; q += KB;
+    s.xn = q; q += TC * (kmax + 1);
+    s.red = q; q += 2 * NWARP * TC + 8;
+    s.sst = reinterpret_cast<int *>(q);
+  }
+  const double *W = m.W + (size_t)b * ld * ld;
+  const double *Zn = m.Zn + (size_t)b * ld * kmax;
+  const double *alpha = m.alpha + (size_t)b * ld;
+  const double *off = m.norm_off + (size_t)b * kmax, *coef = m.norm_coef + (size_t)b * kmax;
+  const double inv_ell2 = 1.0 / (m.lengthscale * m.lengthscale);
+  const double ystd = m.ystd[b], ymean = m.ymean[b], best_f = m.best_f[b], sgn = m.maximize ? 1.0 : -1.0;
+  const double d0 = 1e-15;
+  const double kss = (SQRT5 * d0 + 1.0 + (5.0 / 3.0) * (d0 * d0)) * exp(-SQRT5 * d0);
+
+  if (a.X == nullptr)
+    for (int i = tid; i < kk * MAXBIT; i += SW_THREADS) s.sst[i] = a.sstate[i];
+  double cta_best = -INFINITY;
+  long long cta_idx = 0x7fffffffffffffffLL;
+  const long long ntiles = (a.ncand + TC - 1) / TC;
+  const int nchunks = (n + KB - 1) / KB;
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long c0 = tile * TC;
+    __syncthreads();
+    // ---- candidate coordinates, normalised: xn[c][j]
+    for (int idx = tid; idx < TC * kk; idx += SW_THREADS) {
+      const int c = idx / kk, j = idx % kk;
+      const long long ci = c0 + c;
+      double x = 0.0;
+      if (ci < a.ncand) {
+        if (a.X != nullptr) {
+          x = a.X[(size_t)ci * kmax + j];
+        } else {
+          const unsigned long long g = (unsigned long long)(a.idx0 + ci);
+          const int sh = a.shift[j];
+          double raw;
+          if (g == 0) {
+            raw = (double)((float)sh) * (1.0 / 1073741824.0);
+          } else {
+            int q = sh;
+            unsigned gray = (unsigned)(g ^ (g >> 1));
+            while (gray) {
+              const int l = __ffs(gray) - 1;
+              q ^= s.sst[j * MAXBIT + l];
+              gray &= gray - 1;
+            }
+            raw = (double)q * (1.0 / 1073741824.0);
+          }
+          x = __dadd_rn(a.lo[j], __dmul_rn(__dsub_rn(a.hi[j], a.lo[j]), raw));
+        }
+      }
+      s.xn[c * (kmax + 1) + j] = (x - off[j]) / coef[j];
+    }
+    // ---- accumulators: warp owns row tiles rt = warp, warp + 8, ...; 4 column tiles each
+    double acc[RT_MAX][CT][2];
+#pragma unroll
+    for (int t = 0; t < RT_MAX; ++t)
+#pragma unroll
+      for (int c = 0; c < CT; ++c) { acc[t][c][0] = 0.0; acc[t][c][1] = 0.0; }
+    double mean_part = 0.0;  // thread owns K* entries (jj = tid / 16 .. , c = ...) -> partial of alpha . k for its c
+
+    auto issue_loads = [&](int chunk, int buf) {
+      const int j0 = chunk * KB;
+      const int i_lo = j0 & ~7;
+      // W panel: rows i_lo .. rows8-1 (clamped to n-1 for the padding rows), 16 columns as 8 x 16-byte copies per row
+      const int nrows = rows8 - i_lo;
+      for (int idx = tid; idx < nrows * (KB / 2); idx += SW_THREADS) {
+        const int r = idx / (KB / 2), h = idx % (KB / 2);
+        const int i = min(i_lo + r, n - 1);
+        const int jc = min(j0 + 2 * h, (n - 2) & ~1);   // stay inside the row; columns >= n meet zero rows of K*
+        cp_async16(&s.Ws[buf][(size_t)(i_lo + r) * WS_LD + 2 * h], &W[(size_t)i * ld + jc]);
+      }
+      // training rows j0 .. j0+15 (clamped) of Zn and alpha
+      for (int idx = tid; idx < KB * (kmax / 2); idx += SW_THREADS) {
+        const int r = idx / (kmax / 2), h = idx % (kmax / 2);
+        const int j = min(j0 + r, n - 1);
+        cp_async16(&s.Zs[buf][r * kmax + 2 * h], &Zn[(size_t)j * kmax + 2 * h]);
+      }
+      cp_async_commit();
+    };
+
+    issue_loads(0, 0);
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+      const int buf = chunk & 1;
+      const int j0 = chunk * KB;
+      cp_async_wait<0>();
+      __syncthreads();   // panel `chunk` has landed; every warp is past the MMAs of panel chunk - 1
+      if (chunk + 1 < nchunks) issue_loads(chunk + 1, buf ^ 1);
+      // ---- K* panel: Ks[jj][c] = matern52(|zn_{j0+jj} - xn_c|), 2 entries per thread; zero rows beyond n
+      {
+        const int c = tid % TC;
+        const double *xc = s.xn + c * (kmax + 1);
+#pragma unroll
+        for (int e = 0; e < KB * TC / SW_THREADS; ++e) {
+          const int jj = tid / TC + e * (SW_THREADS / TC);
+          const double *zr = s.Zs[buf] + jj * kmax;
+          double sq = 0.0;
+          for (int dmm = 0; dmm < kk; ++dmm) { const double dd = zr[dmm] - xc[dmm]; sq = fma(dd, dd, sq); }
+          const double s2 = sq * inv_ell2;
+          const double dist = sqrt(fmax(s2, 1e-30));
+          double kv = (SQRT5 * dist + 1.0 + (5.0 / 3.0) * (dist * dist)) * exp(-SQRT5 * dist);
+          if (j0 + jj >= n) kv = 0.0;
+          s.Ks[buf][jj * KS_LD + c] = kv;
+          if (j0 + jj < n) mean_part = fma(kv, alpha[j0 + jj], mean_part);
+        }
+      }
+      // entries of W above the diagonal inside this panel are not part of L^-1: zero them (rows j0 .. j0+15)
+      for (int idx = tid; idx < KB * KB; idx += SW_THREADS) {
+        const int r = idx / KB, jj = idx % KB;
+        const int i = j0 + r;
+        if (i < rows8 && j0 + jj > i) s.Ws[buf][(size_t)i * WS_LD + jj] = 0.0;
+      }
+      __syncthreads();
+      // ---- T += Wpanel (rows x 16) * Kspanel (16 x 32) on the FP64 tensor cores
+      {
+        const int ar = lane >> 2, ak = lane & 3;
+        const double *Wsb = s.Ws[buf];
+        const double *Ksb = s.Ks[buf];
+#pragma unroll
+        for (int k4 = 0; k4 < KB / 4; ++k4) {
+          double bf[CT];
+#pragma unroll
+          for (int c = 0; c < CT; ++c) bf[c] = Ksb[(k4 * 4 + ak) * KS_LD + c * 8 + ar];
+#pragma unroll
+          for (int t = 0; t < RT_MAX; ++t) {
+            const int rt = warp + t * NWARP;
+            if (rt < nrt && rt * 8 + 7 >= j0) {
+              const double af = (rt * 8 + ar < n) ? Wsb[(size_t)(rt * 8 + ar) * WS_LD + k4 * 4 + ak] : 0.0;
+#pragma unroll
+              for (int c = 0; c < CT; ++c) dmma_8x8x4(acc[t][c][0], acc[t][c][1], af, bf[c]);
+            }
+          }
+        }
+      }
+      // (the next iteration's __syncthreads after cp.async.wait protects the buffers)
+    }
+    // ---- variance partials: thread holds T[row = rt*8 + lane/4][col = c*8 + (lane%4)*2 + {0,1}]
+    double vpart[CT][2];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) { vpart[c][0] = 0.0; vpart[c][1] = 0.0; }
+#pragma unroll
+    for (int t = 0; t < RT_MAX; ++t)
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        vpart[c][0] = fma(acc[t][c][0], acc[t][c][0], vpart[c][0]);
+        vpart[c][1] = fma(acc[t][c][1], acc[t][c][1], vpart[c][1]);
+      }
+    // reduce over the 8 row groups of the warp (lanes with equal lane % 4): xor 4, 8, 16
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double v = vpart[c][h];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        vpart[c][h] = v;
+      }
+    __syncthreads();
+    if (lane < 4) {
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        s.red[warp * TC + c * 8 + lane * 2 + 0] = vpart[c][0];
+        s.red[warp * TC + c * 8 + lane * 2 + 1] = vpart[c][1];
+      }
+    }
+    // mean partials: thread (tid % TC = c) accumulated over its jj rows: 8 threads per candidate (tid / TC = 0..7)
+    s.red[NWARP * TC + (tid / TC) * TC + (tid % TC)] = mean_part;
+    __syncthreads();
+    if (tid < TC) {
+      const int c = tid;
+      double v = 0.0, ms = 0.0;
+#pragma unroll
+      for (int w8 = 0; w8 < NWARP; ++w8) { v += s.red[w8 * TC + c]; ms += s.red[NWARP * TC + w8 * TC + c]; }
+      const double mu = ymean + ystd * ms;
+      const double var_raw = ystd * ystd * (kss - v);
+      const double var = (var_raw >= 1e-10) ? var_raw : 1e-10;
+      const double sg = sqrt(var);
+      const double u = sgn * (mu - best_f) / sg;
+      double lh, dlh;
+      logei::log_h_and_grad(u, lh, dlh);
+      double val = lh + log(sg);
+      const long long ci = c0 + c;
+      if (ci < a.ncand) {
+        if (a.vals) a.vals[ci] = val;
+      } else {
+        val = -INFINITY;
+      }
+      // tile arg-max (first occurrence) over the 32 candidates of warp 0
+      long long gi = a.idx0 + ci;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, val, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, gi, o);
+        if (ov > val || (ov == val && oi < gi)) { val = ov; gi = oi; }
+      }
+      if (val > cta_best || (val == cta_best && gi < cta_idx)) { cta_best = val; cta_idx = gi; }
+    }
+  }
+  if (tid == 0) { a.best_val[blockIdx.x] = cta_best; a.best_idx[blockIdx.x] = cta_idx; }
+}
+
+__global__ void sweep_final_kernel(int nparts, const double *pv, const long long *pi, double *best_val,
+                                   long long *best_idx) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  double bv = -INFINITY;
+  long long bi = 0x7fffffffffffffffLL;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+    const double v = pv[i];
+    const long long g = pi[i];
+    if (v > bv || (v == bv && g < bi)) { bv = v; bi = g; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    bv = lane < nw ? sv[lane] : -INFINITY;
+    bi = lane < nw ? si[lane] : 0x7fffffffffffffffLL;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { *best_val = bv; *best_idx = bi; }
+  }
+}
+
+}  // namespace
+
+extern "C" int pcabo_ei_sweep(const pcabo_gp_model *m, int run, long long ncand, long long idx0, const double *X,
+                              const int *shift, const int *sstate, const double *lo, const double *hi, double *vals,
+                              double *part_val, long long *part_idx, int nparts, double *best_val,
+                              long long *best_idx, void *stream) {
+  if (!m || run < 0 || run >= m->B || ncand <= 0 || !part_val || !part_idx || nparts <= 0 || !best_val || !best_idx ||
+      !m->W || !m->Zn || !m->alpha || !m->norm_off || !m->norm_coef || !m->ymean || !m->ystd || !m->best_f)
+    return PCABO_E_INVALID;
+  if (X == nullptr && (!shift || !sstate || !lo || !hi)) return PCABO_E_INVALID;
+  // n <= 512 (accumulators of the whole T tile live in registers), even ld_n and kmax (16-byte cp.async copies)
+  if (m->n > 8 * NWARP * RT_MAX || m->n < 2 || (m->ld_n & 1) || (m->kmax & 1) || m->kmax > 104) return PCABO_E_UNSUPPORTED;
+  const size_t smem = sweep_smem_bytes(m->n, m->kmax);
+  if (smem > 227 * 1024) return PCABO_E_UNSUPPORTED;
+  PCABO_CUDA_CHECK(cudaFuncSetAttribute(ei_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SweepArgs a;
+  a.m = *m; a.b = run; a.ncand = ncand; a.idx0 = idx0; a.X = X; a.shift = shift; a.sstate = sstate; a.lo = lo; a.hi = hi;
+  a.vals = vals; a.best_val = part_val; a.best_idx = part_idx;
+  const long long ntiles = (ncand + TC - 1) / TC;
+  const int grid = (int)(ntiles < nparts ? ntiles : nparts);
+  cudaStream_t st = as_stream(stream);
+  ei_sweep_kernel<<<grid, SW_THREADS, smem, st>>>(a);
+  PCABO_LAUNCH_CHECK();
+  sweep_final_kernel<<<1, 256, 0, st>>>(grid, part_val, part_idx, best_val, best_idx);
+  PCABO_LAUNCH_CHECK();
+  return PCABO_OK;
+}

@@ -234,3 +234,34 @@ def sobol_scramble_bits(k, mt_state, mt_pos, kmax, out=None):
                                         _i(out[0], "shift"), _i(out[1], "ltm_dots"), _stream()),
           "pcabo_sobol_scramble_bits")
     return out
+
+
+class SweepWorkspace:
+    """Scratch and result buffers of pcabo_ei_sweep (allocate once, reuse)."""
+
+    def __init__(self, device, nparts=None):
+        if nparts is None:
+            nparts = torch.cuda.get_device_properties(device).multi_processor_count
+        self.nparts = int(nparts)
+        self.part_val = torch.empty(self.nparts, dtype=torch.float64, device=device)
+        self.part_idx = torch.empty(self.nparts, dtype=torch.int64, device=device)
+        self.best_val = torch.empty(1, dtype=torch.float64, device=device)
+        self.best_idx = torch.empty(1, dtype=torch.int64, device=device)
+
+
+def ei_sweep(buf: GPBuffers, ws: SweepWorkspace, ncand, idx0=0, run=0, X=None, sobol=None, vals=None):
+    """log-EI of `ncand` candidates against run `run` with a fused arg-max.
+
+    X: explicit candidates [ncand, kmax] (device) or None with sobol = (shift [kmax] int32, sstate [kmax, 30] int32,
+    lo [kmax], hi [kmax]) device tensors. Returns (best_val [1], best_idx [1]) device tensors (GLOBAL index)."""
+    lib = load_library()
+    m = model_struct(buf)
+    sh = st = lo = hi = None
+    if X is None:
+        sh, st, lo, hi = sobol
+    check(lib.pcabo_ei_sweep(ctypes.byref(m), int(run), int(ncand), int(idx0), _d(X, "X"), _i(sh, "shift"),
+                             _i(st, "sstate"), _d(lo, "lo"), _d(hi, "hi"), _d(vals, "vals"),
+                             _d(ws.part_val, "part_val"), _dev_ptr(ws.part_idx, torch.int64, "part_idx"), ws.nparts,
+                             _d(ws.best_val, "best_val"), _dev_ptr(ws.best_idx, torch.int64, "best_idx"), _stream()),
+          "pcabo_ei_sweep")
+    return ws.best_val, ws.best_idx
