@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       for (int idx = tid; idx < nrows * (KB / 2); idx += SW_THREADS) {
         const int r = idx / (KB / 2), h = idx % (KB / 2);
         const int i = min(i_lo + r, n - 1);
-        const int jc = min(j0 + 2 * h, (n - 2) & ~1);   // stay inside the row; columns >= n meet zero rows of K*
+        const int jc = min(j0 + 2 * h, (int)ld - 2);   // stay inside the (even) row; columns >= n meet zero rows of K*
         cp_async16(&s.Ws[buf][(size_t)(i_lo + r) * WS_LD + 2 * h], &W[(size_t)i * ld + jc]);
       }
       // training rows j0 .. j0+15 (clamped) of Zn and alpha
