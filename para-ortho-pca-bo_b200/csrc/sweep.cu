@@ -17,14 +17,14 @@ namespace {
 
 using logei::SQRT5;
 
-constexpr int SW_THREADS = 256;
-constexpr int NWARP = SW_THREADS / 32;
+constexpr int SW_THREADS = 512;
+constexpr int NWARP = SW_THREADS / 32;   // 16
 constexpr int TC = 32;        // candidates per tile
 constexpr int CT = TC / 8;    // 8-wide column tiles
 constexpr int KB = 16;        // training points per k panel
 constexpr int WS_LD = 20;     // W panel row stride in doubles (bank-conflict free for the A fragments)
 constexpr int KS_LD = 36;     // K* panel row stride in doubles (bank-conflict free for the B fragments)
-constexpr int RT_MAX = 8;     // row tiles (of 8 rows) per warp: n <= 8 * 8 * 8 = 512
+constexpr int RT_MAX = 4;     // row tiles (of 8 rows) per warp: n <= 16 * 4 * 8 = 512
 constexpr int MAXBIT = 30;
 
 struct SweepArgs {
@@ -54,19 +54,23 @@ __device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, dou
 }
 
 struct Smem {
-  double *Ws[2];   // [rows8][WS_LD]
-  double *Ks[2];   // [KB][KS_LD]
-  double *Zs[2];   // [KB][kmax]
-  double *As[2];   // [KB] alpha
-  double *xn;      // [TC][kmax + 1]
-  double *red;     // [NWARP][TC] + [NWARP][TC]
+  double *Ws[2];   // [rows8][WS_LD]      W panel
+  double *Ks[2];   // [KB][KS_LD]         K* panel
+  double *Zs[2];   // [KB][zld]           training rows of the panel
+  double *As[2];   // [KB]                alpha of the panel
+  double *xn;      // [TC][zld]           normalised candidates
+  double *xx;      // [TC]                |xn_c|^2
+  double *zz;      // [rows16]            |zn_j|^2
+  double *red;     // [NWARP][TC] + [8][TC]
   int *sst;        // [kmax][MAXBIT]
 };
 
+__host__ __device__ inline int sweep_zld(int kmax) { return ((kmax + 3) / 4) * 4 + 4; }
+
 __host__ __device__ inline size_t sweep_smem_bytes(int n, int kmax) {
-  const int rows8 = ((n + 7) / 8) * 8;
-  size_t d = 2 * (size_t)rows8 * WS_LD + 2 * KB * KS_LD + 2 * (size_t)KB * kmax + 2 * KB + (size_t)TC * (kmax + 1) +
-             2 * NWARP * TC + 8;
+  const int rows8 = ((n + 7) / 8) * 8, rows16 = ((n + 15) / 16) * 16, zld = sweep_zld(kmax);
+  size_t d = 2 * (size_t)rows8 * WS_LD + 2 * KB * KS_LD + 2 * (size_t)KB * zld + 2 * KB + (size_t)TC * zld + TC + rows16 +
+             (NWARP + 8) * TC + 8;
   return d * sizeof(double) + (size_t)kmax * MAXBIT * sizeof(int);
 }
 
@@ -78,17 +82,21 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
   const long ld = m.ld_n;
   const int b = a.b;
   const int kk = m.k ? m.k[b] : kmax;
-  const int rows8 = ((n + 7) / 8) * 8;
-  const int nrt = rows8 / 8;  // row tiles
+  const int kk4 = (kk + 3) / 4;               // k-steps of the distance MMA
+  const int zld = sweep_zld(kmax);
+  const int rows8 = ((n + 7) / 8) * 8, rows16 = ((n + 15) / 16) * 16;
+  const int nrt = rows8 / 8;
   Smem s;
   {
     double *q = smd;
     s.Ws[0] = q; q += (size_t)rows8 * WS_LD; s.Ws[1] = q; q += (size_t)rows8 * WS_LD;
     s.Ks[0] = q; q += KB * KS_LD; s.Ks[1] = q; q += KB * KS_LD;
-    s.Zs[0] = q; q += KB * kmax; s.Zs[1] = q; q += KB * kmax;
+    s.Zs[0] = q; q += KB * zld; s.Zs[1] = q; q += KB * zld;
     s.As[0] = q; q += KB; s.As[1] = q; q += KB;
-    s.xn = q; q += TC * (kmax + 1);
-    s.red = q; q += 2 * NWARP * TC + 8;
+    s.xn = q; q += TC * zld;
+    s.xx = q; q += TC;
+    s.zz = q; q += rows16;
+    s.red = q; q += (NWARP + 8) * TC + 8;
     s.sst = reinterpret_cast<int *>(q);
   }
   const double *W = m.W + (size_t)b * ld * ld;
@@ -102,10 +110,20 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
 
   if (a.X == nullptr)
     for (int i = tid; i < kk * MAXBIT; i += SW_THREADS) s.sst[i] = a.sstate[i];
+  // squared norms of the training rows (once per CTA) and zero padding of the staging buffers
+  for (int j = tid; j < rows16; j += SW_THREADS) {
+    double acc = 0.0;
+    if (j < n)
+      for (int dmm = 0; dmm < kk; ++dmm) { const double z = Zn[(size_t)j * kmax + dmm]; acc = fma(z, z, acc); }
+    s.zz[j] = acc;
+  }
+  for (int i = tid; i < 2 * KB * zld; i += SW_THREADS) s.Zs[0][i] = 0.0;   // Zs[0] and Zs[1] are contiguous
+  for (int i = tid; i < TC * zld; i += SW_THREADS) s.xn[i] = 0.0;
   double cta_best = -INFINITY;
   long long cta_idx = 0x7fffffffffffffffLL;
   const long long ntiles = (a.ncand + TC - 1) / TC;
   const int nchunks = (n + KB - 1) / KB;
+  const int ar = lane >> 2, ak = lane & 3;
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long c0 = tile * TC;
@@ -137,15 +155,21 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
           x = __dadd_rn(a.lo[j], __dmul_rn(__dsub_rn(a.hi[j], a.lo[j]), raw));
         }
       }
-      s.xn[c * (kmax + 1) + j] = (x - off[j]) / coef[j];
+      s.xn[c * zld + j] = (x - off[j]) / coef[j];
     }
-    // ---- accumulators: warp owns row tiles rt = warp, warp + 8, ...; 4 column tiles each
+    __syncthreads();
+    if (tid < TC) {
+      double acc = 0.0;
+      for (int dmm = 0; dmm < kk; ++dmm) { const double x = s.xn[tid * zld + dmm]; acc = fma(x, x, acc); }
+      s.xx[tid] = acc;
+    }
+    // ---- accumulators: warp owns row tiles rt = warp, warp + 16, ...; 4 column tiles each
     double acc[RT_MAX][CT][2];
 #pragma unroll
     for (int t = 0; t < RT_MAX; ++t)
 #pragma unroll
       for (int c = 0; c < CT; ++c) { acc[t][c][0] = 0.0; acc[t][c][1] = 0.0; }
-    double mean_part = 0.0;  // thread owns K* entries (jj = tid / 16 .. , c = ...) -> partial of alpha . k for its c
+    double mean_part[2] = {0.0, 0.0};  // warps 0..7: partial alpha . k of this thread's two candidates
 
     auto issue_loads = [&](int chunk, int buf) {
       const int j0 = chunk * KB;
@@ -158,11 +182,15 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
         const int jc = min(j0 + 2 * h, (int)ld - 2);   // stay inside the (even) row; columns >= n meet zero rows of K*
         cp_async16(&s.Ws[buf][(size_t)(i_lo + r) * WS_LD + 2 * h], &W[(size_t)i * ld + jc]);
       }
-      // training rows j0 .. j0+15 (clamped) of Zn and alpha
+      // training rows j0 .. j0+15 (clamped) of Zn, and alpha
       for (int idx = tid; idx < KB * (kmax / 2); idx += SW_THREADS) {
         const int r = idx / (kmax / 2), h = idx % (kmax / 2);
         const int j = min(j0 + r, n - 1);
-        cp_async16(&s.Zs[buf][r * kmax + 2 * h], &Zn[(size_t)j * kmax + 2 * h]);
+        cp_async16(&s.Zs[buf][r * zld + 2 * h], &Zn[(size_t)j * kmax + 2 * h]);
+      }
+      if (tid < KB / 2) {
+        const int j = min(j0 + 2 * tid, (int)ld - 2);
+        cp_async16(&s.As[buf][2 * tid], &alpha[j]);
       }
       cp_async_commit();
     };
@@ -174,34 +202,33 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       cp_async_wait<0>();
       __syncthreads();   // panel `chunk` has landed; every warp is past the MMAs of panel chunk - 1
       if (chunk + 1 < nchunks) issue_loads(chunk + 1, buf ^ 1);
-      // ---- K* panel: Ks[jj][c] = matern52(|zn_{j0+jj} - xn_c|), 2 entries per thread; zero rows beyond n
-      {
-        const int c = tid % TC;
-        const double *xc = s.xn + c * (kmax + 1);
+      // ---- K* panel (warps 0..7, one 8 x 8 tile each): dot = Zs (16 x kk) xn^T (kk x 32) on the tensor cores,
+      //      sq = |z|^2 + |x|^2 - 2 dot, Ks[jj][c] = matern52(sqrt(sq) / ell); rows beyond n are zero
+      if (warp < 2 * CT) {
+        const int tr = warp / CT, tc = warp % CT;     // tile row (8 training points), tile column (8 candidates)
+        double dt0 = 0.0, dt1 = 0.0;
+        const double *zrow = s.Zs[buf] + (tr * 8 + ar) * zld + ak;
+        const double *xrow = s.xn + (tc * 8 + ar) * zld + ak;
+        for (int k4 = 0; k4 < kk4; ++k4) dmma_8x8x4(dt0, dt1, zrow[k4 * 4], xrow[k4 * 4]);
+        const int jj = tr * 8 + ar;
+        const double zzj = s.zz[j0 + jj], aj = s.As[buf][jj];
+        const bool on = j0 + jj < n;
 #pragma unroll
-        for (int e = 0; e < KB * TC / SW_THREADS; ++e) {
-          const int jj = tid / TC + e * (SW_THREADS / TC);
-          const double *zr = s.Zs[buf] + jj * kmax;
-          double sq = 0.0;
-          for (int dmm = 0; dmm < kk; ++dmm) { const double dd = zr[dmm] - xc[dmm]; sq = fma(dd, dd, sq); }
+        for (int h = 0; h < 2; ++h) {
+          const int c = tc * 8 + ak * 2 + h;
+          const double dot = h ? dt1 : dt0;
+          const double sq = fmax((zzj + s.xx[c]) - 2.0 * dot, 0.0);
           const double s2 = sq * inv_ell2;
           const double dist = sqrt(fmax(s2, 1e-30));
           double kv = (SQRT5 * dist + 1.0 + (5.0 / 3.0) * (dist * dist)) * exp(-SQRT5 * dist);
-          if (j0 + jj >= n) kv = 0.0;
+          if (!on) kv = 0.0;
           s.Ks[buf][jj * KS_LD + c] = kv;
-          if (j0 + jj < n) mean_part = fma(kv, alpha[j0 + jj], mean_part);
+          if (on) mean_part[h] = fma(kv, aj, mean_part[h]);
         }
-      }
-      // entries of W above the diagonal inside this panel are not part of L^-1: zero them (rows j0 .. j0+15)
-      for (int idx = tid; idx < KB * KB; idx += SW_THREADS) {
-        const int r = idx / KB, jj = idx % KB;
-        const int i = j0 + r;
-        if (i < rows8 && j0 + jj > i) s.Ws[buf][(size_t)i * WS_LD + jj] = 0.0;
       }
       __syncthreads();
       // ---- T += Wpanel (rows x 16) * Kspanel (16 x 32) on the FP64 tensor cores
       {
-        const int ar = lane >> 2, ak = lane & 3;
         const double *Wsb = s.Ws[buf];
         const double *Ksb = s.Ks[buf];
 #pragma unroll
@@ -209,11 +236,14 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
           double bf[CT];
 #pragma unroll
           for (int c = 0; c < CT; ++c) bf[c] = Ksb[(k4 * 4 + ak) * KS_LD + c * 8 + ar];
+          const int jcol = j0 + k4 * 4 + ak;
 #pragma unroll
           for (int t = 0; t < RT_MAX; ++t) {
             const int rt = warp + t * NWARP;
             if (rt < nrt && rt * 8 + 7 >= j0) {
-              const double af = (rt * 8 + ar < n) ? Wsb[(size_t)(rt * 8 + ar) * WS_LD + k4 * 4 + ak] : 0.0;
+              const int row = rt * 8 + ar;
+              // entries above the diagonal and padding rows are not part of L^-1
+              const double af = (row < n && jcol <= row) ? Wsb[(size_t)row * WS_LD + k4 * 4 + ak] : 0.0;
 #pragma unroll
               for (int c = 0; c < CT; ++c) dmma_8x8x4(acc[t][c][0], acc[t][c][1], af, bf[c]);
             }
@@ -244,6 +274,17 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
         v += __shfl_xor_sync(0xffffffffu, v, 16);
         vpart[c][h] = v;
       }
+    // mean partials of warps 0..7: thread holds candidates tc*8 + ak*2 + {0,1} for training rows tr*8 + ar (all panels)
+    if (warp < 2 * CT) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double v = mean_part[h];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        mean_part[h] = v;
+      }
+    }
     __syncthreads();
     if (lane < 4) {
 #pragma unroll
@@ -251,15 +292,19 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
         s.red[warp * TC + c * 8 + lane * 2 + 0] = vpart[c][0];
         s.red[warp * TC + c * 8 + lane * 2 + 1] = vpart[c][1];
       }
+      if (warp < 2 * CT) {
+        const int tr = warp / CT, tc = warp % CT;
+        s.red[NWARP * TC + tr * TC + tc * 8 + lane * 2 + 0] = mean_part[0];
+        s.red[NWARP * TC + tr * TC + tc * 8 + lane * 2 + 1] = mean_part[1];
+      }
     }
-    // mean partials: thread (tid % TC = c) accumulated over its jj rows: 8 threads per candidate (tid / TC = 0..7)
-    s.red[NWARP * TC + (tid / TC) * TC + (tid % TC)] = mean_part;
     __syncthreads();
     if (tid < TC) {
       const int c = tid;
-      double v = 0.0, ms = 0.0;
+      double v = 0.0;
 #pragma unroll
-      for (int w8 = 0; w8 < NWARP; ++w8) { v += s.red[w8 * TC + c]; ms += s.red[NWARP * TC + w8 * TC + c]; }
+      for (int w8 = 0; w8 < NWARP; ++w8) v += s.red[w8 * TC + c];
+      const double ms = s.red[NWARP * TC + c] + s.red[NWARP * TC + TC + c];
       const double mu = ymean + ystd * ms;
       const double var_raw = ystd * ystd * (kss - v);
       const double var = (var_raw >= 1e-10) ? var_raw : 1e-10;
