@@ -56,8 +56,8 @@ __device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, dou
 struct Smem {
   double *Ws[2];   // [rows8][WS_LD]      W panel
   double *Ks[2];   // [KB][KS_LD]         K* panel
-  double *Zs[2];   // [KB][zld]           training rows of the panel
-  double *As[2];   // [KB]                alpha of the panel
+  double *Zs[3];   // [KB][zld]           training rows of the panel (loaded two panels ahead)
+  double *As[3];   // [KB]                alpha of the panel
   double *xn;      // [TC][zld]           normalised candidates
   double *xx;      // [TC]                |xn_c|^2
   double *zz;      // [rows16]            |zn_j|^2
@@ -69,8 +69,8 @@ __host__ __device__ inline int sweep_zld(int kmax) { return ((kmax + 3) / 4) * 4
 
 __host__ __device__ inline size_t sweep_smem_bytes(int n, int kmax) {
   const int rows8 = ((n + 7) / 8) * 8, rows16 = ((n + 15) / 16) * 16, zld = sweep_zld(kmax);
-  size_t d = 2 * (size_t)rows8 * WS_LD + 2 * KB * KS_LD + 2 * (size_t)KB * zld + 2 * KB + (size_t)TC * zld + TC + rows16 +
-             (NWARP + 8) * TC + 8;
+  size_t d = 2 * (size_t)rows8 * WS_LD + 2 * KB * KS_LD + 3 * (size_t)KB * zld + 3 * KB + (size_t)TC * zld + TC + rows16 +
+             2 * NWARP * TC + 8;
   return d * sizeof(double) + (size_t)kmax * MAXBIT * sizeof(int);
 }
 
@@ -91,12 +91,12 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
     double *q = smd;
     s.Ws[0] = q; q += (size_t)rows8 * WS_LD; s.Ws[1] = q; q += (size_t)rows8 * WS_LD;
     s.Ks[0] = q; q += KB * KS_LD; s.Ks[1] = q; q += KB * KS_LD;
-    s.Zs[0] = q; q += KB * zld; s.Zs[1] = q; q += KB * zld;
-    s.As[0] = q; q += KB; s.As[1] = q; q += KB;
+    s.Zs[0] = q; q += KB * zld; s.Zs[1] = q; q += KB * zld; s.Zs[2] = q; q += KB * zld;
+    s.As[0] = q; q += KB; s.As[1] = q; q += KB; s.As[2] = q; q += KB;
     s.xn = q; q += TC * zld;
     s.xx = q; q += TC;
     s.zz = q; q += rows16;
-    s.red = q; q += (NWARP + 8) * TC + 8;
+    s.red = q; q += 2 * NWARP * TC + 8;
     s.sst = reinterpret_cast<int *>(q);
   }
   const double *W = m.W + (size_t)b * ld * ld;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       for (int dmm = 0; dmm < kk; ++dmm) { const double z = Zn[(size_t)j * kmax + dmm]; acc = fma(z, z, acc); }
     s.zz[j] = acc;
   }
-  for (int i = tid; i < 2 * KB * zld; i += SW_THREADS) s.Zs[0][i] = 0.0;   // Zs[0] and Zs[1] are contiguous
+  for (int i = tid; i < 3 * KB * zld; i += SW_THREADS) s.Zs[0][i] = 0.0;   // the three Zs buffers are contiguous
   for (int i = tid; i < TC * zld; i += SW_THREADS) s.xn[i] = 0.0;
   double cta_best = -INFINITY;
   long long cta_idx = 0x7fffffffffffffffLL;
@@ -169,64 +169,76 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
     for (int t = 0; t < RT_MAX; ++t)
 #pragma unroll
       for (int c = 0; c < CT; ++c) { acc[t][c][0] = 0.0; acc[t][c][1] = 0.0; }
-    double mean_part[2] = {0.0, 0.0};  // warps 0..7: partial alpha . k of this thread's two candidates
+    double mean_part[2] = {0.0, 0.0};  // partial alpha . k of this thread's two candidates (its K* tiles)
 
-    auto issue_loads = [&](int chunk, int buf) {
-      const int j0 = chunk * KB;
+    // W panel `chunk` -> Ws[chunk & 1]; training rows / alpha of panel `chunk` -> Zs / As[chunk % 3]
+    auto issue_w = [&](int chunk) {
+      const int j0 = chunk * KB, buf = chunk & 1;
       const int i_lo = j0 & ~7;
-      // W panel: rows i_lo .. rows8-1 (clamped to n-1 for the padding rows), 16 columns as 8 x 16-byte copies per row
-      const int nrows = rows8 - i_lo;
+      const int nrows = rows8 - i_lo;   // rows above i_lo are entirely above the diagonal for this panel
       for (int idx = tid; idx < nrows * (KB / 2); idx += SW_THREADS) {
         const int r = idx / (KB / 2), h = idx % (KB / 2);
         const int i = min(i_lo + r, n - 1);
         const int jc = min(j0 + 2 * h, (int)ld - 2);   // stay inside the (even) row; columns >= n meet zero rows of K*
         cp_async16(&s.Ws[buf][(size_t)(i_lo + r) * WS_LD + 2 * h], &W[(size_t)i * ld + jc]);
       }
-      // training rows j0 .. j0+15 (clamped) of Zn, and alpha
+    };
+    auto issue_z = [&](int chunk) {
+      const int j0 = chunk * KB, zb = chunk % 3;
       for (int idx = tid; idx < KB * (kmax / 2); idx += SW_THREADS) {
         const int r = idx / (kmax / 2), h = idx % (kmax / 2);
         const int j = min(j0 + r, n - 1);
-        cp_async16(&s.Zs[buf][r * zld + 2 * h], &Zn[(size_t)j * kmax + 2 * h]);
+        cp_async16(&s.Zs[zb][r * zld + 2 * h], &Zn[(size_t)j * kmax + 2 * h]);
       }
       if (tid < KB / 2) {
         const int j = min(j0 + 2 * tid, (int)ld - 2);
-        cp_async16(&s.As[buf][2 * tid], &alpha[j]);
+        cp_async16(&s.As[zb][2 * tid], &alpha[j]);
       }
-      cp_async_commit();
+    };
+    // K* tile of panel `chunk` by this warp (tile id = warp / 2): dot = Zs (8 x kk) xn^T (kk x 8) on the tensor cores,
+    // sq = |z|^2 + |x|^2 - 2 dot, Ks[jj][c] = matern52(sqrt(sq) / ell); rows beyond n are zero
+    auto kstar_tile = [&](int chunk) {
+      const int j0 = chunk * KB, zb = chunk % 3, kb = chunk & 1;
+      const int id = warp >> 1, tr = id / CT, tc = id % CT;
+      double dt0 = 0.0, dt1 = 0.0;
+      const double *zrow = s.Zs[zb] + (tr * 8 + ar) * zld + ak;
+      const double *xrow = s.xn + (tc * 8 + ar) * zld + ak;
+      for (int k4 = 0; k4 < kk4; ++k4) dmma_8x8x4(dt0, dt1, zrow[k4 * 4], xrow[k4 * 4]);
+      const int jj = tr * 8 + ar;
+      const double zzj = s.zz[j0 + jj], aj = s.As[zb][jj];
+      const bool on = j0 + jj < n;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = tc * 8 + ak * 2 + h;
+        const double dot = h ? dt1 : dt0;
+        const double sq = fmax((zzj + s.xx[c]) - 2.0 * dot, 0.0);
+        const double s2 = sq * inv_ell2;
+        const double dist = sqrt(fmax(s2, 1e-30));
+        double kv = (SQRT5 * dist + 1.0 + (5.0 / 3.0) * (dist * dist)) * exp(-SQRT5 * dist);
+        if (!on) kv = 0.0;
+        s.Ks[kb][jj * KS_LD + c] = kv;
+        if (on) mean_part[h] = fma(kv, aj, mean_part[h]);
+      }
     };
 
-    issue_loads(0, 0);
+    // prologue: panel 0 (W, Z), Z of panel 1; K*(0)
+    issue_w(0);
+    issue_z(0);
+    if (nchunks > 1) issue_z(1);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if ((warp & 1) == 0) kstar_tile(0);
     for (int chunk = 0; chunk < nchunks; ++chunk) {
       const int buf = chunk & 1;
       const int j0 = chunk * KB;
       cp_async_wait<0>();
-      __syncthreads();   // panel `chunk` has landed; every warp is past the MMAs of panel chunk - 1
-      if (chunk + 1 < nchunks) issue_loads(chunk + 1, buf ^ 1);
-      // ---- K* panel (warps 0..7, one 8 x 8 tile each): dot = Zs (16 x kk) xn^T (kk x 32) on the tensor cores,
-      //      sq = |z|^2 + |x|^2 - 2 dot, Ks[jj][c] = matern52(sqrt(sq) / ell); rows beyond n are zero
-      if (warp < 2 * CT) {
-        const int tr = warp / CT, tc = warp % CT;     // tile row (8 training points), tile column (8 candidates)
-        double dt0 = 0.0, dt1 = 0.0;
-        const double *zrow = s.Zs[buf] + (tr * 8 + ar) * zld + ak;
-        const double *xrow = s.xn + (tc * 8 + ar) * zld + ak;
-        for (int k4 = 0; k4 < kk4; ++k4) dmma_8x8x4(dt0, dt1, zrow[k4 * 4], xrow[k4 * 4]);
-        const int jj = tr * 8 + ar;
-        const double zzj = s.zz[j0 + jj], aj = s.As[buf][jj];
-        const bool on = j0 + jj < n;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = tc * 8 + ak * 2 + h;
-          const double dot = h ? dt1 : dt0;
-          const double sq = fmax((zzj + s.xx[c]) - 2.0 * dot, 0.0);
-          const double s2 = sq * inv_ell2;
-          const double dist = sqrt(fmax(s2, 1e-30));
-          double kv = (SQRT5 * dist + 1.0 + (5.0 / 3.0) * (dist * dist)) * exp(-SQRT5 * dist);
-          if (!on) kv = 0.0;
-          s.Ks[buf][jj * KS_LD + c] = kv;
-          if (on) mean_part[h] = fma(kv, aj, mean_part[h]);
-        }
-      }
-      __syncthreads();
+      __syncthreads();   // K*(chunk), W(chunk), Z(chunk+1) are visible; every warp is past the MMAs of panel chunk - 1
+      if (chunk + 1 < nchunks) issue_w(chunk + 1);
+      if (chunk + 2 < nchunks) issue_z(chunk + 2);
+      cp_async_commit();
+      // the K* tile of the NEXT panel: warps alternate this duty so that others keep the tensor pipe busy meanwhile
+      if (chunk + 1 < nchunks && ((warp + chunk + 1) & 1) == 0) kstar_tile(chunk + 1);
       // ---- T += Wpanel (rows x 16) * Kspanel (16 x 32) on the FP64 tensor cores
       {
         const double *Wsb = s.Ws[buf];
@@ -250,7 +262,6 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
           }
         }
       }
-      // (the next iteration's __syncthreads after cp.async.wait protects the buffers)
     }
     // ---- variance partials: thread holds T[row = rt*8 + lane/4][col = c*8 + (lane%4)*2 + {0,1}]
     double vpart[CT][2];
@@ -274,8 +285,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
         v += __shfl_xor_sync(0xffffffffu, v, 16);
         vpart[c][h] = v;
       }
-    // mean partials of warps 0..7: thread holds candidates tc*8 + ak*2 + {0,1} for training rows tr*8 + ar (all panels)
-    if (warp < 2 * CT) {
+    // mean partials: thread holds candidates tc*8 + ak*2 + {0,1} for training rows tr*8 + ar of its panels
+    {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         double v = mean_part[h];
@@ -292,11 +303,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
         s.red[warp * TC + c * 8 + lane * 2 + 0] = vpart[c][0];
         s.red[warp * TC + c * 8 + lane * 2 + 1] = vpart[c][1];
       }
-      if (warp < 2 * CT) {
-        const int tr = warp / CT, tc = warp % CT;
-        s.red[NWARP * TC + tr * TC + tc * 8 + lane * 2 + 0] = mean_part[0];
-        s.red[NWARP * TC + tr * TC + tc * 8 + lane * 2 + 1] = mean_part[1];
-      }
+      s.red[NWARP * TC + warp * 8 + lane * 2 + 0] = mean_part[0];   // [warp][8 candidates of tile column (warp/2) % CT]
+      s.red[NWARP * TC + warp * 8 + lane * 2 + 1] = mean_part[1];
     }
     __syncthreads();
     if (tid < TC) {
@@ -304,7 +312,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       double v = 0.0;
 #pragma unroll
       for (int w8 = 0; w8 < NWARP; ++w8) v += s.red[w8 * TC + c];
-      const double ms = s.red[NWARP * TC + c] + s.red[NWARP * TC + TC + c];
+      double ms = 0.0;
+#pragma unroll
+      for (int w8 = 0; w8 < NWARP; ++w8)
+        if (((w8 >> 1) % CT) == c / 8) ms += s.red[NWARP * TC + w8 * 8 + (c & 7)];
       const double mu = ymean + ystd * ms;
       const double var_raw = ystd * ystd * (kss - v);
       const double var = (var_raw >= 1e-10) ? var_raw : 1e-10;
