@@ -53,17 +53,10 @@ __device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, dou
                : "d"(a), "d"(b));
 }
 
-struct Smem {
-  double *Ws[2];   // [rows8][WS_LD]      W panel
-  double *Ks[2];   // [KB][KS_LD]         K* panel
-  double *Zs[3];   // [KB][zld]           training rows of the panel (loaded two panels ahead)
-  double *As[3];   // [KB]                alpha of the panel
-  double *xn;      // [TC][zld]           normalised candidates
-  double *xx;      // [TC]                |xn_c|^2
-  double *zz;      // [rows16]            |zn_j|^2
-  double *red;     // [NWARP][TC] + [8][TC]
-  int *sst;        // [kmax][MAXBIT]
-};
+// Shared-memory carve-up (offsets in doubles from the dynamic shared base; buffers are addressed as base + offset so
+// that the compiler keeps them in the shared state space: LDS / STS, no generic loads):
+//   Ws[2][rows8][WS_LD] W panels | Ks[2][KB][KS_LD] K* panels | Zs[3][KB][zld] training rows (two panels ahead) |
+//   As[3][KB] alpha | xn[TC][zld] normalised candidates | xx[TC] |xn|^2 | zz[rows16] |zn|^2 | red | sst (ints)
 
 __host__ __device__ inline int sweep_zld(int kmax) { return ((kmax + 3) / 4) * 4 + 4; }
 
@@ -86,19 +79,16 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
   const int zld = sweep_zld(kmax);
   const int rows8 = ((n + 7) / 8) * 8, rows16 = ((n + 15) / 16) * 16;
   const int nrt = rows8 / 8;
-  Smem s;
-  {
-    double *q = smd;
-    s.Ws[0] = q; q += (size_t)rows8 * WS_LD; s.Ws[1] = q; q += (size_t)rows8 * WS_LD;
-    s.Ks[0] = q; q += KB * KS_LD; s.Ks[1] = q; q += KB * KS_LD;
-    s.Zs[0] = q; q += KB * zld; s.Zs[1] = q; q += KB * zld; s.Zs[2] = q; q += KB * zld;
-    s.As[0] = q; q += KB; s.As[1] = q; q += KB; s.As[2] = q; q += KB;
-    s.xn = q; q += TC * zld;
-    s.xx = q; q += TC;
-    s.zz = q; q += rows16;
-    s.red = q; q += 2 * NWARP * TC + 8;
-    s.sst = reinterpret_cast<int *>(q);
-  }
+  const int ws_sz = rows8 * WS_LD, ks_sz = KB * KS_LD, zs_sz = KB * zld;
+  double *const sWs = smd;
+  double *const sKs = sWs + 2 * ws_sz;
+  double *const sZs = sKs + 2 * ks_sz;
+  double *const sAs = sZs + 3 * zs_sz;
+  double *const sxn = sAs + 3 * KB;
+  double *const sxx = sxn + TC * zld;
+  double *const szz = sxx + TC;
+  double *const sred = szz + rows16;
+  int *const ssst = reinterpret_cast<int *>(sred + 2 * NWARP * TC + 8);
   const double *W = m.W + (size_t)b * ld * ld;
   const double *Zn = m.Zn + (size_t)b * ld * kmax;
   const double *alpha = m.alpha + (size_t)b * ld;
@@ -109,16 +99,16 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
   const double kss = (SQRT5 * d0 + 1.0 + (5.0 / 3.0) * (d0 * d0)) * exp(-SQRT5 * d0);
 
   if (a.X == nullptr)
-    for (int i = tid; i < kk * MAXBIT; i += SW_THREADS) s.sst[i] = a.sstate[i];
+    for (int i = tid; i < kk * MAXBIT; i += SW_THREADS) ssst[i] = a.sstate[i];
   // squared norms of the training rows (once per CTA) and zero padding of the staging buffers
   for (int j = tid; j < rows16; j += SW_THREADS) {
     double acc = 0.0;
     if (j < n)
       for (int dmm = 0; dmm < kk; ++dmm) { const double z = Zn[(size_t)j * kmax + dmm]; acc = fma(z, z, acc); }
-    s.zz[j] = acc;
+    szz[j] = acc;
   }
-  for (int i = tid; i < 3 * KB * zld; i += SW_THREADS) s.Zs[0][i] = 0.0;   // the three Zs buffers are contiguous
-  for (int i = tid; i < TC * zld; i += SW_THREADS) s.xn[i] = 0.0;
+  for (int i = tid; i < 3 * KB * zld; i += SW_THREADS) sZs[i] = 0.0;   // the three Zs buffers are contiguous
+  for (int i = tid; i < TC * zld; i += SW_THREADS) sxn[i] = 0.0;
   double cta_best = -INFINITY;
   long long cta_idx = 0x7fffffffffffffffLL;
   const long long ntiles = (a.ncand + TC - 1) / TC;
@@ -147,7 +137,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
             unsigned gray = (unsigned)(g ^ (g >> 1));
             while (gray) {
               const int l = __ffs(gray) - 1;
-              q ^= s.sst[j * MAXBIT + l];
+              q ^= ssst[j * MAXBIT + l];
               gray &= gray - 1;
             }
             raw = (double)q * (1.0 / 1073741824.0);
@@ -155,13 +145,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
           x = __dadd_rn(a.lo[j], __dmul_rn(__dsub_rn(a.hi[j], a.lo[j]), raw));
         }
       }
-      s.xn[c * zld + j] = (x - off[j]) / coef[j];
+      sxn[c * zld + j] = (x - off[j]) / coef[j];
     }
     __syncthreads();
     if (tid < TC) {
       double acc = 0.0;
-      for (int dmm = 0; dmm < kk; ++dmm) { const double x = s.xn[tid * zld + dmm]; acc = fma(x, x, acc); }
-      s.xx[tid] = acc;
+      for (int dmm = 0; dmm < kk; ++dmm) { const double x = sxn[tid * zld + dmm]; acc = fma(x, x, acc); }
+      sxx[tid] = acc;
     }
     // ---- accumulators: warp owns row tiles rt = warp, warp + 16, ...; 4 column tiles each
     double acc[RT_MAX][CT][2];
@@ -180,7 +170,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
         const int r = idx / (KB / 2), h = idx % (KB / 2);
         const int i = min(i_lo + r, n - 1);
         const int jc = min(j0 + 2 * h, (int)ld - 2);   // stay inside the (even) row; columns >= n meet zero rows of K*
-        cp_async16(&s.Ws[buf][(size_t)(i_lo + r) * WS_LD + 2 * h], &W[(size_t)i * ld + jc]);
+        cp_async16(&sWs[buf * ws_sz + (i_lo + r) * WS_LD + 2 * h], &W[(size_t)i * ld + jc]);
       }
     };
     auto issue_z = [&](int chunk) {
@@ -188,11 +178,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       for (int idx = tid; idx < KB * (kmax / 2); idx += SW_THREADS) {
         const int r = idx / (kmax / 2), h = idx % (kmax / 2);
         const int j = min(j0 + r, n - 1);
-        cp_async16(&s.Zs[zb][r * zld + 2 * h], &Zn[(size_t)j * kmax + 2 * h]);
+        cp_async16(&sZs[zb * zs_sz + r * zld + 2 * h], &Zn[(size_t)j * kmax + 2 * h]);
       }
       if (tid < KB / 2) {
         const int j = min(j0 + 2 * tid, (int)ld - 2);
-        cp_async16(&s.As[zb][2 * tid], &alpha[j]);
+        cp_async16(&sAs[zb * KB + 2 * tid], &alpha[j]);
       }
     };
     // K* tile of panel `chunk` by this warp (tile id = warp / 2): dot = Zs (8 x kk) xn^T (kk x 8) on the tensor cores,
@@ -201,22 +191,22 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       const int j0 = chunk * KB, zb = chunk % 3, kb = chunk & 1;
       const int id = warp >> 1, tr = id / CT, tc = id % CT;
       double dt0 = 0.0, dt1 = 0.0;
-      const double *zrow = s.Zs[zb] + (tr * 8 + ar) * zld + ak;
-      const double *xrow = s.xn + (tc * 8 + ar) * zld + ak;
+      const double *zrow = sZs + zb * zs_sz + (tr * 8 + ar) * zld + ak;
+      const double *xrow = sxn + (tc * 8 + ar) * zld + ak;
       for (int k4 = 0; k4 < kk4; ++k4) dmma_8x8x4(dt0, dt1, zrow[k4 * 4], xrow[k4 * 4]);
       const int jj = tr * 8 + ar;
-      const double zzj = s.zz[j0 + jj], aj = s.As[zb][jj];
+      const double zzj = szz[j0 + jj], aj = sAs[zb * KB + jj];
       const bool on = j0 + jj < n;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c = tc * 8 + ak * 2 + h;
         const double dot = h ? dt1 : dt0;
-        const double sq = fmax((zzj + s.xx[c]) - 2.0 * dot, 0.0);
+        const double sq = fmax((zzj + sxx[c]) - 2.0 * dot, 0.0);
         const double s2 = sq * inv_ell2;
         const double dist = sqrt(fmax(s2, 1e-30));
         double kv = (SQRT5 * dist + 1.0 + (5.0 / 3.0) * (dist * dist)) * exp(-SQRT5 * dist);
         if (!on) kv = 0.0;
-        s.Ks[kb][jj * KS_LD + c] = kv;
+        sKs[kb * ks_sz + jj * KS_LD + c] = kv;
         if (on) mean_part[h] = fma(kv, aj, mean_part[h]);
       }
     };
@@ -241,8 +231,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       if (chunk + 1 < nchunks && ((warp + chunk + 1) & 1) == 0) kstar_tile(chunk + 1);
       // ---- T += Wpanel (rows x 16) * Kspanel (16 x 32) on the FP64 tensor cores
       {
-        const double *Wsb = s.Ws[buf];
-        const double *Ksb = s.Ks[buf];
+        const double *Wsb = sWs + buf * ws_sz;
+        const double *Ksb = sKs + buf * ks_sz;
 #pragma unroll
         for (int k4 = 0; k4 < KB / 4; ++k4) {
           double bf[CT];
@@ -255,7 +245,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
             if (rt < nrt && rt * 8 + 7 >= j0) {
               const int row = rt * 8 + ar;
               // entries above the diagonal and padding rows are not part of L^-1
-              const double af = (row < n && jcol <= row) ? Wsb[(size_t)row * WS_LD + k4 * 4 + ak] : 0.0;
+              const double af = (row < n && jcol <= row) ? Wsb[row * WS_LD + k4 * 4 + ak] : 0.0;
 #pragma unroll
               for (int c = 0; c < CT; ++c) dmma_8x8x4(acc[t][c][0], acc[t][c][1], af, bf[c]);
             }
@@ -300,22 +290,22 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
     if (lane < 4) {
 #pragma unroll
       for (int c = 0; c < CT; ++c) {
-        s.red[warp * TC + c * 8 + lane * 2 + 0] = vpart[c][0];
-        s.red[warp * TC + c * 8 + lane * 2 + 1] = vpart[c][1];
+        sred[warp * TC + c * 8 + lane * 2 + 0] = vpart[c][0];
+        sred[warp * TC + c * 8 + lane * 2 + 1] = vpart[c][1];
       }
-      s.red[NWARP * TC + warp * 8 + lane * 2 + 0] = mean_part[0];   // [warp][8 candidates of tile column (warp/2) % CT]
-      s.red[NWARP * TC + warp * 8 + lane * 2 + 1] = mean_part[1];
+      sred[NWARP * TC + warp * 8 + lane * 2 + 0] = mean_part[0];   // [warp][8 candidates of tile column (warp/2) % CT]
+      sred[NWARP * TC + warp * 8 + lane * 2 + 1] = mean_part[1];
     }
     __syncthreads();
     if (tid < TC) {
       const int c = tid;
       double v = 0.0;
 #pragma unroll
-      for (int w8 = 0; w8 < NWARP; ++w8) v += s.red[w8 * TC + c];
+      for (int w8 = 0; w8 < NWARP; ++w8) v += sred[w8 * TC + c];
       double ms = 0.0;
 #pragma unroll
       for (int w8 = 0; w8 < NWARP; ++w8)
-        if (((w8 >> 1) % CT) == c / 8) ms += s.red[NWARP * TC + w8 * 8 + (c & 7)];
+        if (((w8 >> 1) % CT) == c / 8) ms += sred[NWARP * TC + w8 * 8 + (c & 7)];
       const double mu = ymean + ystd * ms;
       const double var_raw = ystd * ystd * (kss - v);
       const double var = (var_raw >= 1e-10) ? var_raw : 1e-10;
