@@ -24,7 +24,7 @@ FP64_PEAK_TFLOPS = 35.47   # cuBLAS DGEMM 8192^3 measured on this pool (tools/me
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--log2n", type=int, nargs="+", default=[20, 22, 24])
-    ap.add_argument("--r", type=int, nargs="+", default=[8, 16, 32, 40])
+    ap.add_argument("--dims", dest="r", type=int, nargs="+", default=[8, 16, 32, 40])
     ap.add_argument("--n", type=int, default=450)
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
