@@ -84,76 +84,53 @@ namespace dev {
 constexpr unsigned FULL = 0xffffffffu;
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
 
-// Right-looking Cholesky R^T R = A of the leading n x n block (n <= N) of the upper-stored A (ld = lda); R overwrites A,
-// rdiag[j] = 1 / R[j][j]. For pivots k < nsplit the rows/columns >= nsplit receive +r_ki r_kj instead of -r_ki r_kj: with
-// nsplit = col on the 2 col x 2 col matrix of formk this is the LEL^T factorisation (Cholesky of the (1,1) block,
-// R12 = R11^-T A12, Cholesky of A22 + R12^T R12) in one sweep. Returns 0 or 1 + index of the first non-positive pivot.
-template <int N>
-__device__ int chol_upper_reg(double *A, int lda, int n, int nsplit, double *rdiag) {
+// Right-looking Cholesky R^T R = A of the leading n x n block (n <= 32) of the upper-stored A (ld = lda) in shared
+// memory; R overwrites A, rdiag[j] = 1 / R[j][j]. Lane j owns column j. For pivots k < nsplit the rows/columns >= nsplit
+// receive +r_ki r_kj instead of -r_ki r_kj: with nsplit = col on the 2 col x 2 col matrix of formk this is the LEL^T
+// factorisation (Cholesky of the (1,1) block, R12 = R11^-T A12, Cholesky of A22 + R12^T R12) in one sweep.
+// Compact loops on purpose: the optimiser warp runs alone on its scheduler, so straight-line unrolled code only
+// thrashes the instruction cache. Returns 0 or 1 + index of the first non-positive pivot.
+__device__ inline int chol_upper_warp(double *A, int lda, int n, int nsplit, double *rdiag) {
   const int lane = threadIdx.x & 31;
-  double a[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) a[i] = (lane < n && i <= lane) ? A[i * lda + lane] : 0.0;
   int bad = 0;
-#pragma unroll
-  for (int k = 0; k < N; ++k) {
-    if (k < n) {
-      double piv = shfl(a[k], k);
-      if (!(piv > 0.0)) { if (bad == 0) bad = k + 1; piv = 1.0; }
-      const double rkk = sqrt(piv);
-      const double rinv = 1.0 / rkk;
-      if (lane == k) a[k] = rkk;
-      else if (lane > k) a[k] *= rinv;
+  for (int k = 0; k < n; ++k) {
+    double piv = A[k * lda + k];
+    if (!(piv > 0.0)) { if (bad == 0) bad = k + 1; piv = 1.0; }
+    const double rinv = rsqrt(piv);
+    const double rkj = (lane > k && lane < n) ? A[k * lda + lane] * rinv : 0.0;
+    __syncwarp();
+    if (lane == k) { A[k * lda + k] = piv * rinv; rdiag[k] = rinv; }
+    else if (lane > k && lane < n) A[k * lda + lane] = rkj;
+    __syncwarp();
+    if (lane > k && lane < n) {
       const bool plus_k = k < nsplit;
-#pragma unroll
-      for (int i = k + 1; i < N; ++i) {
-        const double rki = shfl(a[k], i);
-        if (i < n && lane >= i) {
-          const double prod = rki * a[k];
-          a[i] = (plus_k && i >= nsplit) ? a[i] + prod : a[i] - prod;
-        }
+      for (int i = k + 1; i <= lane; ++i) {
+        const double prod = A[k * lda + i] * rkj;
+        double *aij = A + i * lda + lane;
+        *aij = (plus_k && i >= nsplit) ? *aij + prod : *aij - prod;
       }
     }
+    __syncwarp();
   }
-#pragma unroll
-  for (int i = 0; i < N; ++i)
-    if (lane < n && i <= lane) A[i * lda + lane] = a[i];
-  double dj = 1.0;
-#pragma unroll
-  for (int i = 0; i < N; ++i)
-    if (i == lane) dj = a[i];
-  if (lane < n) rdiag[lane] = 1.0 / dj;
-  __syncwarp();
   return bad;
 }
 
-// In place on b (shared memory, length n <= N): trans ? R^T x = b : R x = b, R upper triangular with reciprocal diagonal.
-template <int N>
-__device__ void tri_solve_reg(const double *R, int ldr, int n, double *b, const double *rdiag, bool trans) {
+// In place on b (shared memory, length n <= 32): trans ? R^T x = b : R x = b, R upper triangular (shared memory) with
+// reciprocal diagonal; the right-hand side lives in one register per lane and travels by shuffles.
+__device__ inline void tri_solve_warp(const double *R, int ldr, int n, double *b, const double *rdiag, bool trans) {
   const int lane = threadIdx.x & 31;
   double bi = (lane < n) ? b[lane] : 0.0;
-  double c[N];
   if (trans) {
-#pragma unroll
-    for (int j = 0; j < N; ++j) c[j] = (lane < n && j < lane) ? R[j * ldr + lane] : 0.0;      // column `lane`
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      if (j < n) {
-        const double xj = shfl(bi, j) * rdiag[j];
-        if (lane == j) bi = xj;
-        else if (lane > j) bi = fma(-c[j], xj, bi);
-      }
+    for (int j = 0; j < n; ++j) {
+      const double rji = (lane > j && lane < n) ? R[j * ldr + lane] : 0.0;
+      const double xj = shfl(bi, j) * rdiag[j];
+      bi = (lane == j) ? xj : fma(-rji, xj, bi);
     }
   } else {
-#pragma unroll
-    for (int j = 0; j < N; ++j) c[j] = (lane < n && j > lane && j < n) ? R[lane * ldr + j] : 0.0;  // row `lane`
-#pragma unroll
-    for (int j = N - 1; j >= 0; --j) {
-      if (j < n) {
-        const double xj = shfl(bi, j) * rdiag[j];
-        if (lane == j) bi = xj;
-        else if (lane < j) bi = fma(-c[j], xj, bi);
-      }
+    for (int j = n - 1; j >= 0; --j) {
+      const double rij = (lane < j) ? R[lane * ldr + j] : 0.0;
+      const double xj = shfl(bi, j) * rdiag[j];
+      bi = (lane == j) ? xj : fma(-rij, xj, bi);
     }
   }
   if (lane < n) b[lane] = bi;
@@ -235,8 +212,8 @@ LB_HD void bmv(T &tm, const Work &w, int col, const double *v, double *p) {
     }
     if (on) p[col + i] = p2;
     __syncwarp();
-    dev::tri_solve_reg<M>(w.wt, M, col, p + col, w.wt_rd, true);
-    dev::tri_solve_reg<M>(w.wt, M, col, p + col, w.wt_rd, false);
+    dev::tri_solve_warp(w.wt, M, col, p + col, w.wt_rd, true);
+    dev::tri_solve_warp(w.wt, M, col, p + col, w.wt_rd, false);
     p2 = on ? p[col + i] : 0.0;
     double sacc = 0.0;
 #pragma unroll
@@ -473,7 +450,7 @@ LB_HD int formk(T &tm, Work &w, int col, double theta, int *flag) {
 #ifdef __CUDA_ARCH__
   if constexpr (T::kWarpRegs) {
     // Cholesky of (1,1), R12 = R11^-T A12 and Cholesky of A22 + R12^T R12 in one in-register sweep
-    return dev::chol_upper_reg<M2>(w.wn, M2, 2 * col, col, w.wn_rd) != 0 ? -1 : 0;
+    return dev::chol_upper_warp(w.wn, M2, 2 * col, col, w.wn_rd) != 0 ? -1 : 0;
   }
 #endif
   int info = chol_upper(tm, w.wn, M2, col, flag);
@@ -551,10 +528,10 @@ LB_HD void subsm(T &tm, Work &w, int col, double theta) {
   // wv <- K^-1 wv through the LEL^T factor
 #ifdef __CUDA_ARCH__
   if constexpr (T::kWarpRegs) {
-    dev::tri_solve_reg<M2>(w.wn, M2, 2 * col, w.wv, w.wn_rd, true);
+    dev::tri_solve_warp(w.wn, M2, 2 * col, w.wv, w.wn_rd, true);
     if (tm.lane < col) w.wv[tm.lane] = -w.wv[tm.lane];
     __syncwarp();
-    dev::tri_solve_reg<M2>(w.wn, M2, 2 * col, w.wv, w.wn_rd, false);
+    dev::tri_solve_warp(w.wn, M2, 2 * col, w.wv, w.wn_rd, false);
   } else
 #endif
   if (tm.w0) {
@@ -803,7 +780,7 @@ LB_HD int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, doubl
   }
   tm.sync();
 #ifdef __CUDA_ARCH__
-  if constexpr (T::kWarpRegs) return dev::chol_upper_reg<M>(w.wt, M, col, col, w.wt_rd) != 0 ? -3 : 0;
+  if constexpr (T::kWarpRegs) return dev::chol_upper_warp(w.wt, M, col, col, w.wt_rd) != 0 ? -3 : 0;
 #endif
   return chol_upper(tm, w.wt, M, col, flag) != 0 ? -3 : 0;
 }

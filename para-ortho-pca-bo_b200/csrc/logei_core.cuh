@@ -180,32 +180,30 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
     }
   }
   __syncthreads();
-  // ---- t = W k (lower triangular): row blocks of RB, the j range of a block split over NG groups
+  // ---- t = W k (lower triangular): every thread owns whole rows (no cross-thread combine, no barriers inside the
+  //      pass). Row blocks of RB rows are dealt to the NG thread groups longest-with-shortest so the triangular work
+  //      balances; within a group the RB lanes read WT[j][i0 .. i0 + RB) for one j: coalesced.
   const int g = tid / RB, r = tid % RB;
+  const int nblk = (n + RB - 1) / RB;
   double vpart[P];
 #pragma unroll
   for (int p = 0; p < P; ++p) vpart[p] = 0.0;
-  for (int i0 = 0; i0 < n; i0 += RB) {
-    const int i = i0 + r;
-    const int span = (min(n, i0 + RB) + NG - 1) / NG;
-    double acc[P];
+  for (int q = g; q < nblk; q += NG) {
+    // q-th block of this group: alternate between the long end and the short end of the triangle
+    const int round = q / NG;
+    const int blk = (round & 1) ? (round * NG + (NG - 1 - g)) : q;
+    if (blk >= nblk) continue;
+    const int i = blk * RB + r;
+    if (i < n) {
+      double acc[P];
 #pragma unroll
-    for (int p = 0; p < P; ++p) acc[p] = 0.0;
-    if (i < n) strided_dot<P>(acc, c.WT, ld, i, g * span, min(g * span + span, i + 1), kst, np);
+      for (int p = 0; p < P; ++p) acc[p] = 0.0;
+      strided_dot<P>(acc, c.WT, ld, i, 0, i + 1, kst, np);
 #pragma unroll
-    for (int p = 0; p < P; ++p) part[(g * P + p) * RB + r] = acc[p];
-    __syncthreads();
-    for (int idx = tid; idx < P * RB; idx += LE_THREADS) {
-      const int p = idx / RB, rr = idx % RB;
-      if (i0 + rr < n) {
-        double t = 0.0;
-#pragma unroll
-        for (int gg = 0; gg < NG; ++gg) t += part[(gg * P + p) * RB + rr];
-        tv[p * np + i0 + rr] = t;
-      }
+      for (int p = 0; p < P; ++p) tv[p * np + i] = acc[p];
     }
-    __syncthreads();
   }
+  __syncthreads();
   for (int i = tid; i < n; i += LE_THREADS) {
 #pragma unroll
     for (int p = 0; p < P; ++p) { const double t = tv[p * np + i]; vpart[p] = fma(t, t, vpart[p]); }
@@ -247,58 +245,24 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
   }
   __syncthreads();
   if constexpr (GRAD) {
-  // ---- s = W^T t: column blocks of RB, the i range [j0, n) of a block split over NG groups;
-  //      then c_j = gf_j (A alpha_j - 2 B s_j) stored over the k vector
-  for (int j0 = 0; j0 < n; j0 += RB) {
-    const int j = j0 + r;
-    const int span = (n - j0 + NG - 1) / NG;
-    double acc[P];
-#pragma unroll
-    for (int p = 0; p < P; ++p) acc[p] = 0.0;
+  // ---- s = W^T t: every thread owns whole columns (W[i][j], i >= j: consecutive j coalesce), blocks dealt like above
+  //      (column blocks get shorter towards the end); then c_j = gf_j (A alpha_j - 2 B s_j) stored over the k vector
+  for (int q = g; q < nblk; q += NG) {
+    const int round = q / NG;
+    const int blk = (round & 1) ? (round * NG + (NG - 1 - g)) : q;
+    if (blk >= nblk) continue;
+    const int j = blk * RB + r;
     if (j < n) {
-      const int a0 = j0 + g * span;
-      // W[i][j] for i in [max(a0, j), min(a0 + span, n)): row-major W, consecutive j coalesce
-      int i = max(a0, j);
-      const int i1 = min(a0 + span, n);
-      for (; i + 16 <= i1; i += 16) {
-        double w16[16];
+      double acc[P];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) w16[u] = c.W[(long)(i + u) * ld + j];
+      for (int p = 0; p < P; ++p) acc[p] = 0.0;
+      strided_dot<P>(acc, c.W + j, ld, 0, j, n, tv, np);   // rows i = j .. n-1 of column j
+      const double al = alpha[j];
 #pragma unroll
-        for (int u = 0; u < 16; ++u)
-#pragma unroll
-          for (int p = 0; p < P; ++p) acc[p] = fma(w16[u], tv[p * np + i + u], acc[p]);
-      }
-      for (; i + 4 <= i1; i += 4) {
-        double w4[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) w4[u] = c.W[(long)(i + u) * ld + j];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int p = 0; p < P; ++p) acc[p] = fma(w4[u], tv[p * np + i + u], acc[p]);
-      }
-      for (; i < i1; ++i) {
-        const double wv = c.W[(long)i * ld + j];
-#pragma unroll
-        for (int p = 0; p < P; ++p) acc[p] = fma(wv, tv[p * np + i], acc[p]);
-      }
+      for (int p = 0; p < P; ++p) kst[p * np + j] = gf[p * np + j] * (res[p] * al - 2.0 * res[P + p] * acc[p]);
     }
-#pragma unroll
-    for (int p = 0; p < P; ++p) part[(g * P + p) * RB + r] = acc[p];
-    __syncthreads();
-    for (int idx = tid; idx < P * RB; idx += LE_THREADS) {
-      const int p = idx / RB, rr = idx % RB;
-      const int jj = j0 + rr;
-      if (jj < n) {
-        double sv = 0.0;
-#pragma unroll
-        for (int gg = 0; gg < NG; ++gg) sv += part[(gg * P + p) * RB + rr];
-        kst[p * np + jj] = gf[p * np + jj] * (res[p] * alpha[jj] - 2.0 * res[P + p] * sv);
-      }
-    }
-    __syncthreads();
   }
+  __syncthreads();
   // ---- grad[p][j] = gscale (1 / coef_j) sum_i c_i (xn_j - zn_ij): thread (ig, j), every IG-th training point
   {
     const int IG = LE_THREADS / kk;  // >= 2 for kk <= 104
