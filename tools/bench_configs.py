@@ -1,0 +1,65 @@
+"""Throughput of the other BASELINE configs (C1, C2, C5) on one GPU: BO iterations/s over a few lock-step steps.
+
+C1: PCA-BO f15 D=10, 1 run (budget 150, n_doe 30)                       -- the reference's own CPU-runnable case
+C2: vanilla BO and PCA-BO on f15/f20 D=20, 30 runs each (budget 250, n_doe 60)
+C5: PCA-BO D=100, budget 1050, n_doe 300, 30 runs x 4 functions (f15-f17, f20: f21-f24 are not restated yet);
+    the device optimiser does not fit shared memory at this size, so C5 uses optimizer="scipy"
+Run on the GPU box: python tools/bench_configs.py [--steps 5]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "para-ortho-pca-bo_b200"))
+import torch
+
+
+def measure(name, fids, insts, D, algorithm, optimizer, steps, warmup=2, n_start=None):
+    from pcabo_b200.bbob import BatchedBBOB
+    from pcabo_b200.engine import BatchedBOEngine
+    prob = BatchedBBOB(fids, insts, D, device="cuda")
+    budget, ndoe = 10 * D + 50, 3 * D
+    eng = BatchedBOEngine(prob, D, prob.bounds, budget, ndoe, [1000 * f + 10 * D + i for f, i in zip(fids, insts)],
+                          algorithm=algorithm, optimizer=optimizer)
+    eng.initial_design()
+    for _ in range(warmup):
+        eng.step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out = {"config": name, "algorithm": algorithm, "optimizer": optimizer, "runs": eng.B, "dim": D, "n_points": eng.n,
+           "iterations_per_s": eng.B * steps / dt, "ms_per_step": 1e3 * dt / steps,
+           "lbfgsb_rounds_per_step": eng.stats["lbfgsb_rounds"] / (steps + warmup)}
+    print(json.dumps(out), flush=True)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    want = set(a.only.split(",")) if a.only else None
+    if not want or "C1" in want:
+        for opt in ("scipy", "device"):
+            measure("C1", [15], [0], 10, "pca", opt, a.steps)
+    if not want or "C2" in want:
+        fids = [f for f in (15, 20) for _ in range(30)]
+        insts = [i for _ in range(2) for i in range(30)]
+        for alg in ("vanilla", "pca"):
+            measure("C2", fids, insts, 20, alg, "device", a.steps)
+    if not want or "C5" in want:
+        fids = [f for f in (15, 16, 17, 20) for _ in range(30)]
+        insts = [i for _ in range(4) for i in range(30)]
+        measure("C5", fids, insts, 100, "pca", "scipy", max(2, a.steps // 2), warmup=1)
+
+
+if __name__ == "__main__":
+    main()
