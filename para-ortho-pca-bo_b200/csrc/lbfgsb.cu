@@ -15,6 +15,55 @@ constexpr int LB_THREADS = logei::LE_THREADS;
 
 enum Cmd { CMD_EVAL = 1, CMD_FORMK = 2, CMD_EXIT = 3 };
 
+// Raw inner products of formk (see lbfgsb::formk_products_range for the layout) by the whole block: 8 lanes share one
+// entry (k = seg, seg + 8, ...), 32 entries per pass, only the 2 col (col+1)/2 + col^2 entries that are used; the
+// free / active split is a 0/1 multiplier instead of a branch. Deterministic (fixed xor-shuffle tree).
+__device__ void formk_products_block(const lbfgsb::Work &w, int col, double theta) {
+  using lbfgsb::M;
+  using lbfgsb::M2;
+  const int n = w.n, tid = threadIdx.x, seg = tid & 7, slot = tid >> 3;
+  const int T = col * (col + 1) / 2, nent = 2 * T + col * col;
+  const double *__restrict__ wy = w.wy;
+  const double *__restrict__ ws = w.ws;
+  const int *__restrict__ iw = w.iwhere;
+  for (int e0 = 0; e0 < nent; e0 += LB_THREADS / 8) {
+    const int e = e0 + slot;
+    double s = 0.0;
+    int blk = 3, i = 0, j = 0;
+    if (e < nent) {
+      if (e < 2 * T) {
+        blk = e / T;
+        int t = e % T;
+        // upper-triangular index t -> (i, j), i <= j
+        j = 0;
+        while (t >= j + 1) { t -= j + 1; ++j; }
+        i = t;
+      } else {
+        blk = 2;
+        i = (e - 2 * T) / col;   // jy (Y index)
+        j = (e - 2 * T) % col;   // iy (S index)
+      }
+      const double *a, *b2;
+      bool want_free;
+      if (blk == 0) { a = wy + i * n; b2 = wy + j * n; want_free = true; }
+      else if (blk == 1) { a = ws + i * n; b2 = ws + j * n; want_free = false; }
+      else { a = ws + j * n; b2 = wy + i * n; want_free = !(i < j); }
+      for (int k = seg; k < n; k += 8) {
+        const double mk = ((iw[k] <= 0) == want_free) ? 1.0 : 0.0;
+        s = fma(a[k] * b2[k], mk, s);
+      }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (e < nent && seg == 0) {
+      if (blk == 0) w.wn[i * M2 + j] = s / theta + ((i == j) ? w.sy[i * M + i] : 0.0);
+      else if (blk == 1) w.wn[(col + i) * M2 + col + j] = s * theta;
+      else w.wn[i * M2 + col + j] = (i < j) ? -s : s;
+    }
+  }
+}
+
 // Block-level mailbox: warp 0 runs the optimiser and posts commands; warps 1..7 wait in a command loop and join the
 // block-wide phases (log-EI evaluation, the O(m^2 n) formk products). Everything else is warp-synchronous in warp 0.
 struct Mailbox {
@@ -43,9 +92,13 @@ struct CudaWarpTeam {
   __device__ double sum(double v) { return warp_sum(v); }
   __device__ double max(double v) { return warp_max(v); }
   __device__ void sum_n(double *vals, int cnt) {
+    // butterfly level by level over all values: 20 independent shuffles per level instead of 20 dependent chains
 #pragma unroll
-    for (int j = 0; j < lbfgsb::M2; ++j)
-      if (j < cnt) vals[j] = warp_sum(vals[j]);
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int j = 0; j < lbfgsb::M2; ++j) vals[j] += __shfl_xor_sync(0xffffffffu, vals[j], o);
+    }
+    (void)cnt;
   }
   __device__ void argmin(double &val, int &idx) {
 #pragma unroll
@@ -58,7 +111,7 @@ struct CudaWarpTeam {
   __device__ void formk_products(const lbfgsb::Work &w, int col, double theta) {
     if (lane == 0) { mb->cmd = CMD_FORMK; mb->col = col; mb->theta = theta; }
     __syncthreads();
-    lbfgsb::formk_products_range(w, col, theta, threadIdx.x, LB_THREADS);
+    formk_products_block(w, col, theta);
     __syncthreads();
   }
 };
@@ -140,7 +193,7 @@ __global__ void __launch_bounds__(LB_THREADS, 2) lbfgsb_logei_kernel(LbArgs a) {
       if (c == CMD_EVAL) {
         obj.run(w.x, w.g);
       } else if (c == CMD_FORMK) {
-        lbfgsb::formk_products_range(w, mb->col, mb->theta, tid, LB_THREADS);
+        formk_products_block(w, mb->col, mb->theta);
         __syncthreads();
       } else {
         break;

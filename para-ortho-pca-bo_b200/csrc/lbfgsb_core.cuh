@@ -20,6 +20,12 @@
 #define LB_HD
 #endif
 
+#if defined(__CUDACC__) || defined(__GNUC__)
+#define LB_RESTRICT __restrict__
+#else
+#define LB_RESTRICT
+#endif
+
 namespace lbfgsb {
 
 constexpr int M = 10;       // history pairs (scipy maxcor)
@@ -104,8 +110,20 @@ __device__ inline int chol_upper_warp(double *A, int lda, int n, int nsplit, dou
     __syncwarp();
     if (lane > k && lane < n) {
       const bool plus_k = k < nsplit;
-      for (int i = k + 1; i <= lane; ++i) {
-        const double prod = A[k * lda + i] * rkj;
+      const double *__restrict__ rk = A + k * lda;   // row k (final), read only below
+      int i = k + 1;
+      for (; i + 3 <= lane; i += 4) {                // own column, four rows at a time: loads, then stores
+        double r4[4], a4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { r4[u] = rk[i + u]; a4[u] = A[(i + u) * lda + lane]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double prod = r4[u] * rkj;
+          A[(i + u) * lda + lane] = (plus_k && i + u >= nsplit) ? a4[u] + prod : a4[u] - prod;
+        }
+      }
+      for (; i <= lane; ++i) {
+        const double prod = rk[i] * rkj;
         double *aij = A + i * lda + lane;
         *aij = (plus_k && i >= nsplit) ? *aij + prod : *aij - prod;
       }
@@ -284,37 +302,44 @@ LB_HD void cauchy(T &tm, Work &w, int col, double theta, double sbgnrm, int &nse
 #endif
   for (int j = 0; j < M2; ++j) part[j] = 0.0;
   double nbrk_local = 0.0;
-  for (int i = tm.tid; i < n; i += tm.nt) {
-    const double neggi = -w.g[i];
-    const double tl = w.x[i] - w.l[i], tu = w.u[i] - w.x[i];
-    int iw = w.iwhere[i];
-    if (iw != 3 && iw != -1) {
-      iw = 0;
-      if (tl <= 0.0) { if (neggi <= 0.0) iw = 1; }
-      else if (tu <= 0.0) { if (neggi >= 0.0) iw = 2; }
-      else if (fabs(neggi) <= 0.0) iw = -3;
-      w.iwhere[i] = iw;
-    }
-    double tb = -1.0, di = 0.0;
-    if (iw == 0 || iw == -1) {
-      di = neggi;
-      f1 -= neggi * neggi;
+  {
+    const double *LB_RESTRICT gx = w.g, *LB_RESTRICT xx = w.x, *LB_RESTRICT lx = w.l, *LB_RESTRICT ux = w.u;
+    const double *LB_RESTRICT wyx = w.wy, *LB_RESTRICT wsx = w.ws;
+    double *LB_RESTRICT dx = w.d, *LB_RESTRICT tb_ = w.tbrk, *LB_RESTRICT zx = w.z;
+    int *LB_RESTRICT iwx = w.iwhere;
+    for (int i = tm.tid; i < n; i += tm.nt) {
+      const double neggi = -gx[i];
+      const double xi = xx[i];
+      const double tl = xi - lx[i], tu = ux[i] - xi;
+      int iw = iwx[i];
+      if (iw != 3 && iw != -1) {
+        iw = 0;
+        if (tl <= 0.0) { if (neggi <= 0.0) iw = 1; }
+        else if (tu <= 0.0) { if (neggi >= 0.0) iw = 2; }
+        else if (fabs(neggi) <= 0.0) iw = -3;
+        iwx[i] = iw;
+      }
+      double tb = -1.0, di = 0.0;
+      if (iw == 0 || iw == -1) {
+        di = neggi;
+        f1 -= neggi * neggi;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-      for (int j = 0; j < M; ++j) {
-        if (j < col) {
-          part[j] += w.wy[j * n + i] * neggi;
-          part[M + j] += w.ws[j * n + i] * neggi;
+        for (int j = 0; j < M; ++j) {
+          if (j < col) {
+            part[j] += wyx[j * n + i] * neggi;
+            part[M + j] += wsx[j * n + i] * neggi;
+          }
         }
+        if (neggi < 0.0) tb = tl / (-neggi);
+        else if (neggi > 0.0) tb = tu / neggi;
+        if (tb >= 0.0) nbrk_local += 1.0;
       }
-      if (neggi < 0.0) tb = tl / (-neggi);
-      else if (neggi > 0.0) tb = tu / neggi;
-      if (tb >= 0.0) nbrk_local += 1.0;
+      dx[i] = di;
+      tb_[i] = tb;
+      zx[i] = xi;
     }
-    w.d[i] = di;
-    w.tbrk[i] = tb;
-    w.z[i] = w.x[i];
   }
   f1 = tm.sum(f1);
   const int nbreak = (int)(tm.sum(nbrk_local) + 0.5);
@@ -485,13 +510,19 @@ template <class T>
 LB_HD void cmprlb(T &tm, Work &w, int col, double theta) {
   const int n = w.n;
   bmv(tm, w, col, w.c, w.p);  // p = M c (p is free for reuse after cauchy)
-  for (int i = tm.tid; i < n; i += tm.nt) {
-    double ri = 0.0;
-    if (w.iwhere[i] <= 0) {
-      ri = -theta * (w.z[i] - w.x[i]) - w.g[i];
-      for (int j = 0; j < col; ++j) ri += w.wy[j * n + i] * w.p[j] + w.ws[j * n + i] * (theta * w.p[col + j]);
+  {
+    const double *LB_RESTRICT wyx = w.wy, *LB_RESTRICT wsx = w.ws, *LB_RESTRICT px = w.p;
+    const double *LB_RESTRICT zx = w.z, *LB_RESTRICT xx = w.x, *LB_RESTRICT gx = w.g;
+    const int *LB_RESTRICT iwx = w.iwhere;
+    double *LB_RESTRICT rx = w.r;
+    for (int i = tm.tid; i < n; i += tm.nt) {
+      double ri = 0.0;
+      if (iwx[i] <= 0) {
+        ri = -theta * (zx[i] - xx[i]) - gx[i];
+        for (int j = 0; j < col; ++j) ri += wyx[j * n + i] * px[j] + wsx[j * n + i] * (theta * px[col + j]);
+      }
+      rx[i] = ri;
     }
-    w.r[i] = ri;
   }
   tm.sync();
 }
@@ -725,8 +756,17 @@ LB_HD int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, doubl
                        int *flag) {
   const int n = w.n;
   if (col == M) {  // drop the oldest pair
-    for (int i = tm.tid; i < n; i += tm.nt)   // each thread shifts its own columns: no synchronisation between pairs
-      for (int j = 0; j < M - 1; ++j) { w.ws[j * n + i] = w.ws[(j + 1) * n + i]; w.wy[j * n + i] = w.wy[(j + 1) * n + i]; }
+    for (int i = tm.tid; i < n; i += tm.nt) {   // each thread shifts its own columns: loads first, then stores
+      double a[M - 1], b[M - 1];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+      for (int j = 0; j < M - 1; ++j) { a[j] = w.ws[(j + 1) * n + i]; b[j] = w.wy[(j + 1) * n + i]; }
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+      for (int j = 0; j < M - 1; ++j) { w.ws[j * n + i] = a[j]; w.wy[j * n + i] = b[j]; }
+    }
     tm.sync();
     if (tm.tid == 0) {
       for (int i = 0; i < M - 1; ++i)
