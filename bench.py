@@ -48,7 +48,7 @@ def workload_config(n_start, steps, warmup, optimizer, extra=None):
 
 # ------------------------------------------------------------------------------------------------ CPU oracle arm
 def _oracle_worker(args):
-    fid, inst, n_iter = args
+    fid, inst, n_iter, budget_s = args
     import torch
     torch.set_num_threads(1)
     from oracle import bbob, doe, loop
@@ -61,15 +61,36 @@ def _oracle_worker(args):
         s = time.perf_counter()
         r.iteration()
         times.append(time.perf_counter() - s)
+        if budget_s and time.perf_counter() - t0 > budget_s:
+            break
     return time.perf_counter() - t0, times
 
 
-def oracle_throughput(steps, warmup, cores=None):
-    """Reference CPU path: one oracle run per core (1 intra-op thread each, SURVEY B.8), `cores` runs in parallel,
-    each doing warmup+steps BO iterations from its DoE. Returns (iterations/s over the timed steps, cores, seconds)."""
+def _oracle_worker_primed(args):
+    """cpu_baseline sample: the oracle continues a run from a given history (x, f prefix) for n_iter BO iterations."""
+    fid, inst, X, f, n_iter = args
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    from oracle import bbob, doe, loop
+    p = bbob.BBOBProblem(fid, DIM, inst)
+    seed = doe.run_seed(fid, DIM, inst)
+    r = loop.OracleRun(p, DIM, p.bounds, BUDGET, N_DOE, seed)
+    np.random.seed(seed + len(f))
+    torch.manual_seed(seed + len(f))
+    r.x_evals = [np.asarray(x, dtype=np.float64) for x in X]
+    r.f_evals = [float(v) for v in f]
+    r.assign_new_best()
+    times = []
+    for _ in range(n_iter):
+        s = time.perf_counter()
+        r.iteration()
+        times.append(time.perf_counter() - s)
+    return times
+
+
+def _pool_map(fn, jobs, cores):
     import multiprocessing as mp
-    cores = cores or os.cpu_count() or 1
-    jobs = [(FIDS[j % len(FIDS)], j // len(FIDS), warmup + steps) for j in range(cores)]
     ctx = mp.get_context("spawn")
     # one BLAS/OpenMP thread per worker: with 16 processes x 16 library threads the tiny operands thrash (SURVEY B.8)
     saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS")}
@@ -77,33 +98,63 @@ def oracle_throughput(steps, warmup, cores=None):
         os.environ[k] = "1"
     try:
         with ctx.Pool(cores) as pool:
-            res = pool.map(_oracle_worker, jobs)
+            return pool.map(fn, jobs)
     finally:
         for k, v in saved.items():
             if v is None:
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
-    # per step, all workers run concurrently: the step time is the slowest worker's
+
+
+def oracle_sampled_throughput(histories, n_points, iters_per_point, cores=None):
+    """cpu_baseline of the GPU arm: `cores` oracle runs (one per host core, 1 thread each) continue the histories the
+    engine produced (histories[j] = (fid, inst, x_evals, f_evals)) from each n in n_points for iters_per_point BO
+    iterations (the first one of each segment is warm-up). Returns (iterations/s, cores, seconds, description)."""
+    cores = min(cores or os.cpu_count() or 1, len(histories))
+    total_it, total_s = 0, 0.0
+    for n0 in n_points:
+        jobs = [(fid, inst, X[:n0], f[:n0], iters_per_point) for fid, inst, X, f in histories[:cores]]
+        res = _pool_map(_oracle_worker_primed, jobs, cores)
+        total_s += max(sum(t[1:]) for t in res)          # workers run concurrently: the slowest one bounds the segment
+        total_it += cores * (iters_per_point - 1)
+    return total_it / total_s, cores, total_s
+
+
+def oracle_throughput(steps, warmup, cores=None, budget_s=None):
+    """Reference CPU path: one oracle run per core (1 intra-op thread each, SURVEY B.8), `cores` runs in parallel,
+    each doing warmup+steps BO iterations from its DoE (cut short after `budget_s` seconds of wall time).
+    Returns (iterations/s over the timed steps, cores, seconds, steps actually timed, per-step seconds)."""
+    cores = cores or os.cpu_count() or 1
+    steps = min(steps, BUDGET - N_DOE - warmup)
+    jobs = [(FIDS[j % len(FIDS)], j // len(FIDS), warmup + steps, budget_s) for j in range(cores)]
+    res = _pool_map(_oracle_worker, jobs, cores)
+    done = min(len(r[1]) for r in res)          # iterations every worker finished inside the budget
+    steps = max(1, done - warmup)
+    # the workers run concurrently and independently (no lock-step on the CPU): the job's wall time for the timed
+    # iterations is the slowest worker's total
+    timed = max(sum(r[1][warmup:warmup + steps]) for r in res)
     per_step = [max(r[1][i] for r in res) for i in range(warmup + steps)]
-    timed = sum(per_step[warmup:])
-    return cores * steps / timed, cores, timed
+    return cores * steps / timed, cores, timed, steps, per_step
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    its, cores, secs = oracle_throughput(args.steps, args.warmup)
+    its, cores, secs, steps, per_step = oracle_throughput(args.steps, args.warmup, budget_s=args.ref_budget_s)
     sample = (f"{cores} of the 90 runs (one per host core, 1 torch thread each), BO iterations "
-              f"{args.warmup}..{args.warmup + args.steps} from the DoE (n = {N_DOE + args.warmup}..)")
-    line = {"impl": "reference", "metric": METRIC, "value": its, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+              f"{args.warmup}..{args.warmup + steps} from the DoE (n = {N_DOE + args.warmup}..{N_DOE + args.warmup + steps})"
+              + ("" if steps == args.steps else f"; cut at the {args.ref_budget_s:.0f} s wall-time budget after {steps} of {args.steps} steps"))
+    line = {"impl": "reference", "metric": METRIC, "value": its, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (BBOB f15-f17 restated)",
-            "config": workload_config(N_DOE, args.steps, args.warmup, "scipy L-BFGS-B (CPU oracle)"),
+            "config": workload_config(N_DOE, steps, args.warmup, "scipy L-BFGS-B (CPU oracle)"),
             "cpu_baseline": {"value": its, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+    if args.trace:
+        json.dump({"n_first": N_DOE, "step_ms_max_over_workers": [1e3 * t for t in per_step]}, open(args.trace, "w"))
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -163,13 +214,6 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
 
-    cpu_base = None
-    if world == 1 and not args.no_cpu_baseline:
-        its, cores, secs = oracle_throughput(args.cpu_steps, 1)
-        cpu_base = {"value": its, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"{cores} of the 90 runs, one per host core (1 torch thread each), {args.cpu_steps} BO "
-                              f"iterations after 1 warm-up from the DoE (n = {N_DOE + 1}..), {secs:.1f} s of wall time"}
-
     fids = [f for f in FIDS for _ in range(RUNS_PER_FID)]
     insts = [RUNS_PER_FID * rank + i for _ in FIDS for i in range(RUNS_PER_FID)]
     seeds = [1000 * f + 10 * DIM + i for f, i in zip(fids, insts)]
@@ -202,6 +246,7 @@ def run_ours(args):
         else:
             eng.run_steps(k)
 
+    args.steps = max(1, min(args.steps, BUDGET - eng.n - args.warmup))
     advance(args.warmup)
     barrier()
     stats0 = dict(eng.stats)
@@ -216,7 +261,18 @@ def run_ours(args):
     n_first = eng.n
     t0 = time.perf_counter()
     ev0.record()
-    advance(args.steps)
+    step_ms, step_phases = [], []
+    if args.trace and S == 1:
+        for _ in range(args.steps):
+            ts = time.perf_counter()
+            p0 = dict(eng.phase_times) if args.phases else None
+            eng.step()
+            torch.cuda.synchronize()
+            step_ms.append(1e3 * (time.perf_counter() - ts))
+            if args.phases:
+                step_phases.append({k_: round(1e3 * (v_ - p0.get(k_, 0.0)), 3) for k_, v_ in eng.phase_times.items()})
+    else:
+        advance(args.steps)
     ev1.record()
     barrier()
     wall = time.perf_counter() - t0
@@ -253,6 +309,18 @@ def run_ours(args):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
                 "traffic": None, "launches": len(evs), "avg_launch_us": 1e3 * tot_ms / len(evs),
                 "share_of_step": tot_ms * 1e-3 / secs / S}
+    cpu_base = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline and S == 1:
+        # the CPU oracle continues the first `cores` runs from histories this run produced, at points spread over the
+        # n range that was timed (a bounded sample: ~10-30 s of host work)
+        n_lo, n_hi = n_first, eng.n
+        npts = [n_lo] if n_hi - n_lo < 30 else [n_lo, (n_lo + n_hi) // 2, max(n_lo, n_hi - args.cpu_steps)]
+        hist = [(fids[b], insts[b], eng.x_evals[b], eng.f_evals[b]) for b in range(0, B, max(1, B // (os.cpu_count() or 1)))]
+        cits, cores, csecs = oracle_sampled_throughput(hist, npts, args.cpu_steps)
+        cpu_base = {"value": cits, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{cores} of the 90 runs, one per host core (1 torch thread each), continuing this run's "
+                              f"histories at n = {npts} for {args.cpu_steps - 1} timed BO iterations each (+1 warm-up), "
+                              f"{csecs:.1f} s of wall time"}
     if rank == 0:
         line = {"metric": METRIC, "value": its, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
@@ -267,6 +335,10 @@ def run_ours(args):
                                 "the timed region"},
                 "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
+    if args.trace and rank == 0 and step_ms:
+        json.dump({"n_first": n_first, "step_ms": step_ms, "k_mean_last": float(subs[0].k_host.mean()),
+                   "step_phases_ms": step_phases},
+                  open(args.trace, "w"))
     if args.phases and rank == 0:
         pt = {}
         for e_ in subs:
@@ -282,15 +354,19 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=BUDGET - N_DOE - 3,
+                    help="timed BO iterations per run (default: the whole C3 run after the warm-up steps)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--optimizer", default="device", choices=["scipy", "device"])
     ap.add_argument("--n-start", type=int, default=N_DOE, help="fast-forward (untimed) until n points before warm-up")
-    ap.add_argument("--cpu-steps", type=int, default=12, help="BO iterations per core of the cpu_baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=6,
+                    help="BO iterations per core and sample point of the cpu_baseline leg (the first is warm-up)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sub-batches", type=int, default=1,
                     help="split the per-GPU batch into S independently stepped sub-batches on S CUDA streams")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="wall-time budget of the reference arm")
+    ap.add_argument("--trace", default=None, help="write per-step wall times (ms) to this JSON file (adds a sync per step)")
     ap.add_argument("--phases", action="store_true", help="print a host wall-time breakdown per phase (adds syncs)")
     args = ap.parse_args()
     if args.impl == "reference":

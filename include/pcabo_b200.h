@@ -122,13 +122,23 @@ int pcabo_lbfgsb_logei(const pcabo_gp_model *m, int num_restarts, int batch_limi
                        double pgtol, const double *ics, const double *box_lo, const double *box_hi,
                        double *cand, double *fval, int *status, int *nit, int *nfev, void *stream);
 
-/* Same as pcabo_lbfgsb_logei with optional per-chunk cycle counters prof [B][nchunks][16] (clock64 ticks of the
+/* Same as pcabo_lbfgsb_logei with optional per-chunk cycle counters prof [B][nchunks][32] (clock64 ticks of the
  * optimiser warp per phase: 1 cauchy, 2 formk, 3 cmprlb, 4 subsm, 5 line-search setup, 6 step to next point,
- * 7 log-EI evaluation, 8 dcsrch, 9 update, 0 convergence tests); prof may be NULL. Tuning aid.                     */
+ * 7 log-EI evaluation, 8 dcsrch, 9 update, 0 convergence tests, 10-14 sub-phases; 16-20 phases inside the log-EI
+ * evaluation: k vector, t = W k, posterior head, s = W^T t, gradient; 31 scratch); prof may be NULL. Tuning aid.                     */
 int pcabo_lbfgsb_logei_prof(const pcabo_gp_model *m, int num_restarts, int batch_limit, int maxiter, double factr,
                             double pgtol, const double *ics, const double *box_lo, const double *box_hi,
                             double *cand, double *fval, int *status, int *nit, int *nfev, long long *prof,
                             void *stream);
+
+/* General form: optimise only the runs listed in run_idx [nsel] (device ints; NULL = all runs, nsel = B) and size the
+ * per-block shared memory for k <= k_bound (0 = kmax; a run with k > k_bound gets status -1 and is left untouched).
+ * Outputs are indexed by RUN (not by position in run_idx), so a retry of a subset updates the same arrays in place:
+ * this is botorch's retry_on_optimization_warning (optimize_acqf re-optimises only the problem that warned).         */
+int pcabo_lbfgsb_logei_runs(const pcabo_gp_model *m, int nsel, const int *run_idx, int k_bound, int num_restarts,
+                            int batch_limit, int maxiter, double factr, double pgtol, const double *ics,
+                            const double *box_lo, const double *box_hi, double *cand, double *fval, int *status,
+                            int *nit, int *nfev, long long *prof, void *stream);
 
 /* log-EI sweep with fused arg-max over `ncand` candidates against run `run` of the model (BASELINE config C4).
  * Candidates: explicit X [ncand][kmax] (raw space), or X = NULL and generated in-kernel as scrambled Sobol points

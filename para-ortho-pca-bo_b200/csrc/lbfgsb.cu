@@ -143,13 +143,15 @@ struct LbArgs {
   const double *ics, *box_lo, *box_hi;
   double *cand, *fval;
   int *status, *nit, *nfev;
-  long long *prof;   // optional [B][nchunks][16] cycle counters
+  long long *prof;   // optional [B][nchunks][32] cycle counters
+  const int *run_idx;  // optional [gridDim.y] runs to optimise (nullptr: all runs, blockIdx.y)
+  int k_bound;         // shared memory was sized for k <= k_bound
 };
 
 template <int PT>
 __global__ void __launch_bounds__(LB_THREADS, 2) lbfgsb_logei_kernel(LbArgs a) {
   extern __shared__ __align__(16) double sm[];
-  const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int b = a.run_idx ? a.run_idx[blockIdx.y] : blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int nchunks = gridDim.x;
   const int p0 = chunk * a.batch_limit;
   const int pcount = min(a.batch_limit, a.num_restarts - p0);
@@ -157,6 +159,13 @@ __global__ void __launch_bounds__(LB_THREADS, 2) lbfgsb_logei_kernel(LbArgs a) {
   load_ctx(obj.ctx, a.m, b);
   const int kk = obj.ctx.kk, kmax = a.m.kmax;
   const int nvar = pcount * kk;
+  if (kk > a.k_bound) {   // the caller's bound on k was wrong: refuse (status -1) instead of overrunning shared memory
+    if (tid == 0) {
+      const size_t o = (size_t)b * nchunks + chunk;
+      a.status[o] = -1; a.nit[o] = 0; a.nfev[o] = 0; a.fval[o] = 0.0;
+    }
+    return;
+  }
   double *q = sm;
   carve_ctx(obj.ctx, PT, true, q);
   q += logei::scratch_doubles(PT, kmax, a.m.n, true);
@@ -167,6 +176,7 @@ __global__ void __launch_bounds__(LB_THREADS, 2) lbfgsb_logei_kernel(LbArgs a) {
   obj.vals = q; q += 8;
   int *flag = reinterpret_cast<int *>(q); q += 2;
   obj.pcount = pcount; obj.kk = kk;
+  if (a.prof) obj.ctx.prof = a.prof + ((size_t)b * nchunks + chunk) * 32;
 
   const double *ic = a.ics + ((size_t)b * a.num_restarts + p0) * kmax;
   const double *blo = a.box_lo + (size_t)b * kmax, *bhi = a.box_hi + (size_t)b * kmax;
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(LB_THREADS, 2) lbfgsb_logei_kernel(LbArgs a) {
   if (tid < 32) {
     CudaWarpTeam tm;
     tm.tid = tid; tm.nt = 32; tm.lane = tid; tm.nl = 32; tm.w0 = true; tm.mb = mb; tm.wk = &w;
-    tm.prof = a.prof ? a.prof + ((size_t)b * nchunks + chunk) * 16 : nullptr;
+    tm.prof = a.prof ? a.prof + ((size_t)b * nchunks + chunk) * 32 : nullptr;
     tm.last = clock64();
     r = lbfgsb::minimize(tm, w, obj, a.maxiter, a.factr, a.pgtol, flag);
     if (tid == 0) mb->cmd = CMD_EXIT;
@@ -213,14 +223,14 @@ __global__ void __launch_bounds__(LB_THREADS, 2) lbfgsb_logei_kernel(LbArgs a) {
 }
 
 template <int PT>
-int launch(const LbArgs &a, cudaStream_t st) {
+int launch(const LbArgs &a, int nsel, cudaStream_t st) {
   const int nchunks = (a.num_restarts + a.batch_limit - 1) / a.batch_limit;
-  const int nvar_max = a.batch_limit * a.m.kmax;
+  const int nvar_max = a.batch_limit * a.k_bound;
   const size_t smem = (logei::scratch_doubles(PT, a.m.kmax, a.m.n, true) + lbfgsb::work_doubles(nvar_max) +
                        2 + 8 + 2 + 8) * sizeof(double);
   if (smem > 227 * 1024) return PCABO_E_UNSUPPORTED;
   PCABO_CUDA_CHECK(cudaFuncSetAttribute(lbfgsb_logei_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(nchunks, a.m.B);
+  dim3 grid(nchunks, nsel);
   lbfgsb_logei_kernel<PT><<<grid, LB_THREADS, smem, st>>>(a);
   PCABO_LAUNCH_CHECK();
   return PCABO_OK;
@@ -228,32 +238,39 @@ int launch(const LbArgs &a, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" int pcabo_lbfgsb_logei_prof(const pcabo_gp_model *m, int num_restarts, int batch_limit, int maxiter,
-                                       double factr, double pgtol, const double *ics, const double *box_lo,
-                                       const double *box_hi, double *cand, double *fval, int *status, int *nit,
-                                       int *nfev, long long *prof, void *stream);
-
-extern "C" int pcabo_lbfgsb_logei(const pcabo_gp_model *m, int num_restarts, int batch_limit, int maxiter, double factr,
-                                  double pgtol, const double *ics, const double *box_lo, const double *box_hi,
-                                  double *cand, double *fval, int *status, int *nit, int *nfev, void *stream) {
-  return pcabo_lbfgsb_logei_prof(m, num_restarts, batch_limit, maxiter, factr, pgtol, ics, box_lo, box_hi, cand, fval,
-                                 status, nit, nfev, nullptr, stream);
+extern "C" int pcabo_lbfgsb_logei_runs(const pcabo_gp_model *m, int nsel, const int *run_idx, int k_bound,
+                                       int num_restarts, int batch_limit, int maxiter, double factr, double pgtol,
+                                       const double *ics, const double *box_lo, const double *box_hi, double *cand,
+                                       double *fval, int *status, int *nit, int *nfev, long long *prof, void *stream) {
+  if (!m || num_restarts <= 0 || batch_limit <= 0 || maxiter <= 0 || !ics || !box_lo || !box_hi || !cand || !fval ||
+      !status || !nit || !nfev || m->B <= 0 || m->n < 1 || m->ld_n < m->n || !m->norm_off || !m->norm_coef || !m->ZnT ||
+      !m->alpha || !m->W || !m->ymean || !m->ystd || !m->best_f || !(m->lengthscale > 0.0))
+    return PCABO_E_INVALID;
+  if (run_idx ? (nsel <= 0 || nsel > m->B) : (nsel != m->B)) return PCABO_E_INVALID;
+  if (k_bound <= 0 || k_bound > m->kmax) k_bound = m->kmax;
+  if (m->kmax > 104 || m->n > 4096 || batch_limit > 8) return PCABO_E_UNSUPPORTED;
+  LbArgs a;
+  a.m = *m; a.num_restarts = num_restarts; a.batch_limit = batch_limit; a.maxiter = maxiter;
+  a.factr = factr; a.pgtol = pgtol; a.ics = ics; a.box_lo = box_lo; a.box_hi = box_hi;
+  a.cand = cand; a.fval = fval; a.status = status; a.nit = nit; a.nfev = nfev; a.prof = prof;
+  a.run_idx = run_idx; a.k_bound = k_bound;
+  cudaStream_t st = as_stream(stream);
+  if (batch_limit <= 5) return launch<5>(a, nsel, st);
+  return launch<8>(a, nsel, st);
 }
 
 extern "C" int pcabo_lbfgsb_logei_prof(const pcabo_gp_model *m, int num_restarts, int batch_limit, int maxiter,
                                        double factr, double pgtol, const double *ics, const double *box_lo,
                                        const double *box_hi, double *cand, double *fval, int *status, int *nit,
                                        int *nfev, long long *prof, void *stream) {
-  if (!m || num_restarts <= 0 || batch_limit <= 0 || maxiter <= 0 || !ics || !box_lo || !box_hi || !cand || !fval ||
-      !status || !nit || !nfev || m->B <= 0 || m->n < 1 || m->ld_n < m->n || !m->norm_off || !m->norm_coef || !m->ZnT ||
-      !m->alpha || !m->W || !m->ymean || !m->ystd || !m->best_f || !(m->lengthscale > 0.0))
-    return PCABO_E_INVALID;
-  if (m->kmax > 104 || m->n > 4096 || batch_limit > 8) return PCABO_E_UNSUPPORTED;
-  LbArgs a;
-  a.m = *m; a.num_restarts = num_restarts; a.batch_limit = batch_limit; a.maxiter = maxiter;
-  a.factr = factr; a.pgtol = pgtol; a.ics = ics; a.box_lo = box_lo; a.box_hi = box_hi;
-  a.cand = cand; a.fval = fval; a.status = status; a.nit = nit; a.nfev = nfev; a.prof = prof;
-  cudaStream_t st = as_stream(stream);
-  if (batch_limit <= 5) return launch<5>(a, st);
-  return launch<8>(a, st);
+  if (!m) return PCABO_E_INVALID;
+  return pcabo_lbfgsb_logei_runs(m, m->B, nullptr, m->kmax, num_restarts, batch_limit, maxiter, factr, pgtol, ics,
+                                 box_lo, box_hi, cand, fval, status, nit, nfev, prof, stream);
+}
+
+extern "C" int pcabo_lbfgsb_logei(const pcabo_gp_model *m, int num_restarts, int batch_limit, int maxiter, double factr,
+                                  double pgtol, const double *ics, const double *box_lo, const double *box_hi,
+                                  double *cand, double *fval, int *status, int *nit, int *nfev, void *stream) {
+  return pcabo_lbfgsb_logei_prof(m, num_restarts, batch_limit, maxiter, factr, pgtol, ics, box_lo, box_hi, cand, fval,
+                                 status, nit, nfev, nullptr, stream);
 }

@@ -54,7 +54,17 @@ struct Ctx {
   double *gf;    // [P][np]  d k / d(dist^2) factor (GRAD)
   double *part;  // [256 P]  split-K partial sums
   double *red;   // [8][2P] + [4P]
+  long long *prof = nullptr;  // optional cycle counters of the evaluation phases (slots 16..22; slot 31 = last stamp)
 };
+
+// attribute the cycles since the previous stamp to evaluation phase `id` (thread 0 only; no-op without counters)
+__device__ __forceinline__ void ev_tick(const Ctx &c, int id) {
+  if (c.prof != nullptr && threadIdx.x == 0) {
+    const long long t = clock64();
+    if (id >= 0) c.prof[id] += t - c.prof[31];
+    c.prof[31] = t;
+  }
+}
 
 constexpr int RB = 64;               // row / column block of the triangular passes
 constexpr int NG = LE_THREADS / RB;  // split-K groups
@@ -139,6 +149,7 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
   const double *ZnT = c.ZnT, *alpha = c.alpha;
   const double inv_ell2 = c.inv_ell2;
 
+  ev_tick(c, -1);
   for (int idx = tid; idx < P * kmax; idx += LE_THREADS) {
     const int p = idx / kmax, j = idx % kmax;
     xn[idx] = (p < pcount && j < kk) ? (X[(size_t)p * xstride + j] - c.off[j]) / c.coef[j] : 0.0;
@@ -180,6 +191,7 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
     }
   }
   __syncthreads();
+  ev_tick(c, 16);
   // ---- t = W k (lower triangular): every thread owns whole rows (no cross-thread combine, no barriers inside the
   //      pass). Row blocks of RB rows are dealt to the NG thread groups longest-with-shortest so the triangular work
   //      balances; within a group the RB lanes read WT[j][i0 .. i0 + RB) for one j: coalesced.
@@ -188,10 +200,9 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
   double vpart[P];
 #pragma unroll
   for (int p = 0; p < P; ++p) vpart[p] = 0.0;
-  for (int q = g; q < nblk; q += NG) {
-    // q-th block of this group: alternate between the long end and the short end of the triangle
-    const int round = q / NG;
-    const int blk = (round & 1) ? (round * NG + (NG - 1 - g)) : q;
+  for (int base = 0, round = 0; base < nblk; base += NG, ++round) {
+    // this group's block of the round: alternate between the long end and the short end of the triangle
+    const int blk = base + ((round & 1) ? (NG - 1 - g) : g);
     if (blk >= nblk) continue;
     const int i = blk * RB + r;
     if (i < n) {
@@ -204,6 +215,7 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
     }
   }
   __syncthreads();
+  ev_tick(c, 17);
   for (int i = tid; i < n; i += LE_THREADS) {
 #pragma unroll
     for (int p = 0; p < P; ++p) { const double t = tv[p * np + i]; vpart[p] = fma(t, t, vpart[p]); }
@@ -244,12 +256,12 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
     }
   }
   __syncthreads();
+  ev_tick(c, 18);
   if constexpr (GRAD) {
   // ---- s = W^T t: every thread owns whole columns (W[i][j], i >= j: consecutive j coalesce), blocks dealt like above
   //      (column blocks get shorter towards the end); then c_j = gf_j (A alpha_j - 2 B s_j) stored over the k vector
-  for (int q = g; q < nblk; q += NG) {
-    const int round = q / NG;
-    const int blk = (round & 1) ? (round * NG + (NG - 1 - g)) : q;
+  for (int base = 0, round = 0; base < nblk; base += NG, ++round) {
+    const int blk = base + ((round & 1) ? (NG - 1 - g) : g);
     if (blk >= nblk) continue;
     const int j = blk * RB + r;
     if (j < n) {
@@ -263,6 +275,7 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
     }
   }
   __syncthreads();
+  ev_tick(c, 19);
   // ---- grad[p][j] = gscale (1 / coef_j) sum_i c_i (xn_j - zn_ij): thread (ig, j), every IG-th training point
   {
     const int IG = LE_THREADS / kk;  // >= 2 for kk <= 104
@@ -304,6 +317,7 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
     }
   }
   __syncthreads();
+  ev_tick(c, 20);
   }  // GRAD
 }
 

@@ -75,6 +75,9 @@ class BatchedBOEngine:
         self.batch_objective = batch_objective
         B, D, cap = self.B, self.D, self.budget
         self.cap = cap
+        # host RNG work may run ahead under the optimiser kernel only when the streams are the engine's own (the drop-in
+        # classes pass the process-global generators, which the user's objective may share)
+        self.owns_rngs = np_rngs is None
         self.np_rngs = np_rngs if np_rngs is not None else [np.random.RandomState(s) for s in self.seeds]
         if torch_gens is not None:
             self.torch_gens = torch_gens
@@ -112,6 +115,10 @@ class BatchedBOEngine:
         self.timing_logs = {"pca": [], "SingleTaskGP": [], "optimize_acqf": []}
         self.stats = dict(kernel_launches=0, lbfgsb_rounds=0, h2d_bytes=0, d2h_bytes=0, retries=0)
         self.last = {}
+        self.noise_ready_n = -1     # the pinned noise buffer holds the draw for the iteration with this many points
+        self.noise_copied = torch.cuda.Event()
+        self.overlap_hook = None
+        self.lb_out = None
         self.phase_times = None     # set to {} to accumulate host wall time per phase (adds device syncs)
         self.kernel_events = None   # set to [] to record CUDA-event pairs around every value+grad log-EI launch
 
@@ -176,20 +183,37 @@ class BatchedBOEngine:
         self.phase_times[name] = self.phase_times.get(name, 0.0) + (t1 - t0)
         return t1
 
+    def _draw_noise(self, n):
+        """The 1e-8 PCA noise of the iteration that fits n points, drawn from each run's numpy stream (PCA_BO.py:376)."""
+        B, D = self.B, self.D
+        hv_np = self.h_noise[:B * n * D].view(B, n, D).numpy()
+
+        def _noise(b):
+            hv_np[b] = self.np_rngs[b].normal(0, 1e-8, size=(n, D))
+
+        list(self.pool.map(_noise, range(B)))
+        self.noise_ready_n = n
+
+    def _prefetch_noise(self):
+        """Draw the NEXT iteration's noise while the optimiser kernel runs. The pinned buffer of this iteration has
+        been consumed (its H2D copy precedes the kernel on the stream) and the numpy streams are used for nothing else
+        between two iterations, so the draw order of every run is unchanged."""
+        if self.owns_rngs and self.algorithm == "pca" and self.n + 1 < self.budget:
+            self.noise_copied.synchronize()
+            self._draw_noise(self.n + 1)
+
     def _fit_models(self):
         B, D, n = self.B, self.D, self.n
         if self.algorithm == "pca":
             tp = perf_counter()
             hv = self.h_noise[:B * n * D].view(B, n, D)
-            hv_np = hv.numpy()
-
-            def _noise(b):
-                hv_np[b] = self.np_rngs[b].normal(0, 1e-8, size=(n, D))                  # PCA_BO.py:376
-
-            list(self.pool.map(_noise, range(B)))
+            if self.noise_ready_n != n:
+                self._draw_noise(n)
+            self.noise_ready_n = -1
             tp = self._phase("host_noise_rng", tp)
             dv = self.d_noise[:B * n * D].view(B, n, D)
             dv.copy_(hv, non_blocking=True)
+            self.noise_copied.record()
             self.stats["h2d_bytes"] += hv.numel() * 8
             t0 = self._sync_time()
             self.pca = ops.weights_pca_fit(self.X, self.f, dv, self.logtab, n, self.var_threshold,
@@ -323,35 +347,45 @@ class BatchedBOEngine:
             self.last.setdefault("nfev", {})[b] = [probs[(b, ci)].nfev for ci in range(len(chunks))]
         return cands, warned
 
-    def _optimize_device(self, d_x, k_host):
-        """gen_candidates_scipy for all runs and chunks in ONE launch of the device-resident L-BFGS-B kernel.
+    def _optimize_device(self, d_x, k_host, runs=None, out=None):
+        """gen_candidates_scipy for all (or the listed) runs and chunks in ONE launch of the device-resident L-BFGS-B
+        kernel; with `runs` the rows of those runs in `out` are re-optimised in place (botorch's retry).
 
-        Returns (device tensor of clamped candidates [B, R, D], warned {b: bool})."""
+        Returns (the output dict with the device tensor of clamped candidates cand [B, R, D], warned {b: bool})."""
         B, D, R = self.B, self.D, self.num_restarts
+        sel = list(range(B)) if runs is None else list(runs)
         ev = None
         if self.kernel_events is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        out = ops.lbfgsb_logei(self.gp, d_x, self.gp.box_lo, self.gp.box_hi, self.batch_limit, self.maxiter)
+        run_idx = None if runs is None else torch.tensor(sel, dtype=torch.int32).to(self.device, non_blocking=True)
+        out = ops.lbfgsb_logei(self.gp, d_x, self.gp.box_lo, self.gp.box_hi, self.batch_limit, self.maxiter, out=out,
+                               run_idx=run_idx, k_bound=int(max(k_host[b] for b in sel)))
         if ev is not None:
             ev[1].record()
+        if self.overlap_hook is not None:        # host work that does not depend on the result runs under the kernel
+            hook, self.overlap_hook = self.overlap_hook, None
+            hook()
         status = out["status"].cpu().numpy()
         nfev = out["nfev"].cpu().numpy()
         nit = out["nit"].cpu().numpy()
+        if (status[sel] < 0).any():
+            raise PcaboError("pcabo_lbfgsb_logei_runs: k_bound below a run's k")
         if ev is not None:
             n = self.n
             # algorithmic bytes of one value+gradient evaluation of one chunk: the n x n lower-triangular FP64 cache
             # L^-1 once (4 n^2), the training set and alpha (8 n k + 8 n); times the evaluations actually done
             nbytes = sum(int(nfev[b, c]) * (4 * n * n + 8 * n * int(k_host[b]) + 8 * n)
-                         for b in range(B) for c in range(nfev.shape[1]))
+                         for b in sel for c in range(nfev.shape[1]))
             self.kernel_events.append((ev[0], ev[1], nbytes))
         self.stats["kernel_launches"] += 1
-        self.stats["lbfgsb_rounds"] += int(nfev.max())
+        self.stats["lbfgsb_rounds"] += int(nfev[sel].max())
         self.stats["d2h_bytes"] += status.size * 12
-        warned = {b: bool((status[b] == 3).any()) for b in range(B)}
-        self.last["nit"] = {b: nit[b].tolist() for b in range(B)}
-        self.last["nfev"] = {b: nfev[b].tolist() for b in range(B)}
-        return out["cand"], warned
+        warned = {b: bool((status[b] == 3).any()) for b in sel}
+        for b in sel:
+            self.last.setdefault("nit", {})[b] = nit[b].tolist()
+            self.last.setdefault("nfev", {})[b] = nfev[b].tolist()
+        return out, warned
 
     def _propose(self):
         """optimize_acqf (PCA_BO.py:607-614): returns device tensor z_new [B, D] and its log-EI values [B]."""
@@ -377,16 +411,17 @@ class BatchedBOEngine:
             self.stats["h2d_bytes"] += h_c.numel() * 8
         else:
             tp = perf_counter()
-            d_c, warned = self._optimize_device(ics, k_host)
+            self.overlap_hook = self._prefetch_noise
+            self.lb_out, warned = self._optimize_device(ics, k_host, out=self.lb_out)
             self._phase("lbfgsb_kernel", tp)
             retry = [b for b in runs if warned[b]]
             if retry:
                 self.stats["retries"] += len(retry)
                 ics = self._initial_conditions(retry, k_host, ics)
-                d_c = d_c.clone()
-                d_c2, _ = self._optimize_device(ics, k_host)
-                idx = torch.tensor(retry, device=self.device)
-                d_c[idx] = d_c2[idx]
+                tp = perf_counter()
+                self.lb_out, _ = self._optimize_device(ics, k_host, runs=retry, out=self.lb_out)
+                self._phase("lbfgsb_kernel_retry", tp)
+            d_c = self.lb_out["cand"]
         vals = ops.logei(self.gp, d_c)["val"]                        # final no-grad evaluation of the candidates
         best_val, best_idx = ops.argmax(vals)                        # torch.argmax over the restarts
         z_new = d_c[torch.arange(B, device=self.device), best_idx.long()]

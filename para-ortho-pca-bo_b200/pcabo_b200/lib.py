@@ -8,7 +8,7 @@ _LIB = None
 EXPORTED_SYMBOLS = [
     "pcabo_abi_version", "pcabo_error_string", "pcabo_last_cuda_error",
     "pcabo_weights_pca_fit", "pcabo_inverse_map", "pcabo_gp_fit", "pcabo_gp_mll",
-    "pcabo_logei", "pcabo_argmax", "pcabo_lbfgsb_logei", "pcabo_lbfgsb_logei_prof", "pcabo_ei_sweep",
+    "pcabo_logei", "pcabo_argmax", "pcabo_lbfgsb_logei", "pcabo_lbfgsb_logei_prof", "pcabo_lbfgsb_logei_runs", "pcabo_ei_sweep",
     "pcabo_sobol_points", "pcabo_sobol_scramble_bits", "pcabo_gather_rows",
 ]
 
@@ -67,6 +67,8 @@ def load_library(build_if_missing: bool = False):
     lib.pcabo_lbfgsb_logei.argtypes = [ctypes.POINTER(GpModelStruct), ci, ci, ci, cd, cd] + [vp] * 8 + [vp]
     lib.pcabo_lbfgsb_logei_prof.restype = ci
     lib.pcabo_lbfgsb_logei_prof.argtypes = [ctypes.POINTER(GpModelStruct), ci, ci, ci, cd, cd] + [vp] * 9 + [vp]
+    lib.pcabo_lbfgsb_logei_runs.restype = ci
+    lib.pcabo_lbfgsb_logei_runs.argtypes = [ctypes.POINTER(GpModelStruct), ci, vp, ci, ci, ci, ci, cd, cd] + [vp] * 9 + [vp]
     lib.pcabo_ei_sweep.restype = ci
     lib.pcabo_ei_sweep.argtypes = [ctypes.POINTER(GpModelStruct), ci, ctypes.c_longlong, ctypes.c_longlong] + [vp] * 8 + \
                                   [ci, vp, vp, vp]

@@ -176,8 +176,11 @@ LBFGSB_STATUS = {0: "CONVERGENCE: NORM OF PROJECTED GRADIENT <= PGTOL", 1: "CONV
 
 
 def lbfgsb_logei(buf: GPBuffers, ics, box_lo, box_hi, batch_limit=5, maxiter=200, factr=1e7, pgtol=1e-5, out=None,
-                 prof=None):
-    """ics [B, num_restarts, kmax] -> dict(cand [B, R, kmax], fval/status/nit/nfev [B, nchunks]); one kernel launch."""
+                 prof=None, run_idx=None, k_bound=0):
+    """ics [B, num_restarts, kmax] -> dict(cand [B, R, kmax], fval/status/nit/nfev [B, nchunks]); one kernel launch.
+
+    run_idx (device int32 [nsel]): optimise only these runs, the rows of the other runs in `out` stay as they are.
+    k_bound: an upper bound of k over the runs optimised (sizes the shared memory; 0 = kmax)."""
     lib = load_library()
     B, R, kmax = ics.shape
     if B != buf.B or kmax != buf.kmax:
@@ -191,11 +194,13 @@ def lbfgsb_logei(buf: GPBuffers, ics, box_lo, box_hi, batch_limit=5, maxiter=200
                    nit=torch.empty(B, nch, dtype=torch.int32, device=dev),
                    nfev=torch.empty(B, nch, dtype=torch.int32, device=dev))
     m = model_struct(buf)
-    check(lib.pcabo_lbfgsb_logei_prof(ctypes.byref(m), R, int(batch_limit), int(maxiter), float(factr), float(pgtol),
+    nsel = B if run_idx is None else int(run_idx.numel())
+    check(lib.pcabo_lbfgsb_logei_runs(ctypes.byref(m), nsel, _i(run_idx, "run_idx"), int(k_bound), R, int(batch_limit),
+                                      int(maxiter), float(factr), float(pgtol),
                                       _d(ics, "ics"), _d(box_lo, "box_lo"), _d(box_hi, "box_hi"),
                                       _d(out["cand"], "cand"), _d(out["fval"], "fval"), _i(out["status"], "status"),
                                       _i(out["nit"], "nit"), _i(out["nfev"], "nfev"),
-                                      _dev_ptr(prof, torch.int64, "prof"), _stream()), "pcabo_lbfgsb_logei")
+                                      _dev_ptr(prof, torch.int64, "prof"), _stream()), "pcabo_lbfgsb_logei_runs")
     return out
 
 

@@ -125,7 +125,8 @@ def test_device_lbfgsb_matches_scipy_given_same_starts():
     ics = eng._initial_conditions(list(range(B)), k_host)
     c_host, w_host = eng._optimize_scipy(list(range(B)), ics, k_host, box_lo, box_hi)
     nit_host = dict(eng.last["nit"])
-    d_c, w_dev = eng._optimize_device(ics, k_host)
+    out_dev, w_dev = eng._optimize_device(ics, k_host)
+    d_c = out_dev["cand"]
     nit_dev = dict(eng.last["nit"])
     vals_dev = ops.logei(eng.gp, d_c)["val"].cpu().numpy()
     h_c = torch.zeros(B, eng.num_restarts, D, dtype=torch.float64)
@@ -142,6 +143,41 @@ def test_device_lbfgsb_matches_scipy_given_same_starts():
             same_iters += int(nit_host[b][c] == nit_dev[b][c])
         assert abs(vals_host[b].max() - vals_dev[b].max()) <= 1e-6 * max(1.0, abs(vals_host[b].max()))
     assert same_iters >= B   # most chunks follow scipy's iteration count exactly
+
+
+def test_device_lbfgsb_subset_retry_in_place():
+    """pcabo_lbfgsb_logei_runs: re-optimising a subset of runs (botorch's retry) with a tight k bound gives those runs
+    bit-identical results to a full launch and leaves the rows of the other runs untouched; a wrong bound is refused."""
+    from pcabo_b200 import ops
+    from pcabo_b200.engine import BatchedBOEngine
+    from pcabo_b200.bbob import BatchedBBOB
+    fid, D = 15, 10
+    insts = [0, 1, 2, 3, 4]
+    prob = BatchedBBOB([fid] * len(insts), insts, D, device="cuda")
+    eng = BatchedBOEngine(prob, D, prob.bounds, 10 * D + 50, 3 * D, [1000 * fid + 10 * D + i for i in insts])
+    eng.initial_design()
+    eng.step()
+    eng._fit_models()
+    B = eng.B
+    k_host = eng.pca["k"].cpu().numpy().astype(np.int64)
+    ics = eng._initial_conditions(list(range(B)), k_host)
+    full = ops.lbfgsb_logei(eng.gp, ics, eng.gp.box_lo, eng.gp.box_hi)
+    ref = {k: v.clone() for k, v in full.items()}
+    sel = [3, 1]
+    out = {k: torch.full_like(v, -7) for k, v in full.items()}
+    ops.lbfgsb_logei(eng.gp, ics, eng.gp.box_lo, eng.gp.box_hi, out=out,
+                     run_idx=torch.tensor(sel, dtype=torch.int32, device="cuda"), k_bound=int(k_host[sel].max()))
+    for key in ("cand", "fval", "status", "nit", "nfev"):
+        for b in range(B):
+            if b in sel:
+                assert torch.equal(out[key][b], ref[key][b]), (key, b)
+            else:
+                assert bool((out[key][b] == -7).all()), (key, b)
+    if int(k_host.max()) > 1:
+        bad = {k: torch.zeros_like(v) for k, v in full.items()}
+        ops.lbfgsb_logei(eng.gp, ics, eng.gp.box_lo, eng.gp.box_hi, out=bad, k_bound=int(k_host.max()) - 1)
+        st = bad["status"].cpu().numpy()
+        assert (st[k_host == k_host.max()] == -1).all()
 
 
 def test_engine_device_optimizer_trajectory():

@@ -129,7 +129,11 @@ def test_gp_fit(D, n):
         assert abs(mll[b] - model.mll()) < RTOL * abs(model.mll()), "marginal log-likelihood"
 
 
-@pytest.mark.parametrize("D,n,npts", [(5, 10, 7), (10, 77, 5), (20, 250, 16), (40, 120, 33), (40, 450, 10), (40, 450, 64)])
+# n values on both sides of every multiple of the 64-row block of the triangular passes, and block counts that are not
+# a multiple of the 4 thread groups (257..448 lost row blocks once: regression)
+@pytest.mark.parametrize("D,n,npts", [(5, 10, 7), (10, 77, 5), (20, 250, 16), (40, 120, 33), (40, 450, 10), (40, 450, 64),
+                                      (12, 64, 5), (12, 65, 5), (12, 129, 7), (20, 193, 5), (20, 256, 5), (20, 257, 5),
+                                      (40, 300, 5), (40, 330, 10), (40, 385, 6), (40, 448, 5), (40, 449, 5)])
 @pytest.mark.parametrize("maximization", [False, True])
 def test_logei_value_grad(D, n, npts, maximization):
     B = 2
