@@ -89,7 +89,9 @@ int pcabo_inverse_map(int B, int D, const double *z, const int *k, const double 
  *   mode 1 (Vanilla_BO): no input normalisation; search box = (fix_lo, fix_hi) [kmax]
  * outputs
  *   norm_off, norm_coef, box_lo, box_hi [B][kmax]; ymean, ystd [B]; ZnT [B][kmax][ld_n], Zn [B][ld_n][kmax];
- *   L [B][ld_n][ld_n] (Cholesky factor of K + noise I, lower), W [B][ld_n][ld_n] (L^-1), WT (its transpose),
+ *   L [B][ld_n][ld_n] (Cholesky factor of K + noise I, lower), W [B][ld_n][ld_n] (L^-1), WT (its transpose; inside
+ *   the diagonal 64 x 64 blocks the other triangle of W / WT is written as zero: pcabo_logei / pcabo_lbfgsb_logei
+ *   read those blocks whole),
  *   alpha [B][ld_n],
  *   info [B] (0 ok, i > 0: non-positive pivot at row i -> caller should add jitter)                            */
 int pcabo_gp_fit(int B, int n, int kmax, int ld_n, int mode,

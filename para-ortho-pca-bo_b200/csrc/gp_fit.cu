@@ -420,7 +420,22 @@ __global__ void __launch_bounds__(CH_THREADS, 1) gp_chol_kernel(CholArgs a) {
         for (int idx = tid; idx < NB * NB; idx += CH_THREADS) {
           const int r = idx / NB, c = idx % NB;
           const int j = tj * NB + r, i = ti * NB + c;   // WT[j][i] = W[i][j]
-          if (i < n && j < n && j <= i) WT[(long)j * ld + i] = s.D[c][r];
+          if (i < n && j < n) {
+            if (j <= i) WT[(long)j * ld + i] = s.D[c][r];
+            else WT[(long)j * ld + i] = 0.0;     // strict lower part of a diagonal tile
+          }
+        }
+      }
+    // The evaluation kernels read whole 64 x 64 diagonal blocks of W and WT (uniform trip counts, coalesced rows): the
+    // off-diagonal 32 x 32 tile of each such block that lies above W's / below WT's diagonal is written as zero here.
+    __syncthreads();
+    for (int ti = 0; ti + 1 < nb; ti += 2)
+      for (int idx = tid; idx < NB * NB; idx += CH_THREADS) {
+        const int r = idx / NB, c = idx % NB;
+        const int i = ti * NB + r, j = (ti + 1) * NB + c;   // i < j
+        if (j < n) {
+          W[(long)i * ld + j] = 0.0;
+          WT[(long)j * ld + i] = 0.0;
         }
       }
   }

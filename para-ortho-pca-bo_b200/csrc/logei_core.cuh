@@ -209,7 +209,9 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
       double acc[P];
 #pragma unroll
       for (int p = 0; p < P; ++p) acc[p] = 0.0;
-      strided_dot<P>(acc, c.WT, ld, i, 0, i + 1, kst, np);
+      // every lane runs to the end of its row block (WT is zero below its diagonal): uniform trip count, no tail
+      // divergence inside the warp
+      strided_dot<P>(acc, c.WT, ld, i, 0, min(blk * RB + RB, n), kst, np);
 #pragma unroll
       for (int p = 0; p < P; ++p) tv[p * np + i] = acc[p];
     }
@@ -268,7 +270,9 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
       double acc[P];
 #pragma unroll
       for (int p = 0; p < P; ++p) acc[p] = 0.0;
-      strided_dot<P>(acc, c.W + j, ld, 0, j, n, tv, np);   // rows i = j .. n-1 of column j
+      // rows i >= j of column j; every lane starts at the first row of the column block (W is zero above its
+      // diagonal) so that the lanes of a group read the same row of W in every step: coalesced 512-byte segments
+      strided_dot<P>(acc, c.W + j, ld, 0, blk * RB, n, tv, np);
       const double al = alpha[j];
 #pragma unroll
       for (int p = 0; p < P; ++p) kst[p * np + j] = gf[p * np + j] * (res[p] * al - 2.0 * res[P + p] * acc[p]);

@@ -242,3 +242,76 @@ def test_errors_are_loud():
         ops.argmax(torch.zeros(2, 3, dtype=torch.float64))
     with pytest.raises(PcaboError):
         ops.argmax(torch.zeros(2, 3, dtype=torch.float32, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------------ real late BO states
+@pytest.mark.parametrize("name", ["late_state_0.npz", "late_state_39.npz", "late_state_30.npz"])
+def test_late_trajectory_state_gp_and_logei(name):
+    """GP caches, posterior, log-EI value + gradient and the device L-BFGS-B on states taken from real C3 trajectories at
+    n = 330 (tests/golden/make_late_state_fixtures.py): 1000-penalties, clustered points, scales up to 1e12."""
+    import os
+    from oracle import gp, acqf
+    ops = _ops()
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+    Z, f, best, ics = d["Z"], d["f"], float(d["best"]), d["ics"]
+    n, k = Z.shape
+    kmax, cap = 40, 450
+    dev = torch.device("cuda")
+    Zd = torch.zeros(1, cap, kmax, dtype=torch.float64)
+    Zd[0, :n, :k] = torch.from_numpy(Z)
+    fd = torch.zeros(1, cap, dtype=torch.float64)
+    fd[0, :n] = torch.from_numpy(f)
+    kd = torch.tensor([k], dtype=torch.int32, device=dev)
+    buf = ops.GPBuffers(1, cap, kmax, dev)
+    ops.gp_fit(buf, Zd.to(dev), kd, fd.to(dev), n, mode=0)
+    buf.best_f[0] = gp.best_f_as_botorch(best)
+    model = gp.GPModel(Z, list(f), norm_bounds=acqf.normalize_box_pca(Z))
+    acq = gp.LogExpectedImprovement(model, best, maximize=False)
+    _, L, alpha, Linv = model.caches()
+    assert int(buf.info[0]) == 0
+    Lg = torch.tril(buf.L[0, :n, :n]).cpu().numpy()
+    assert np.max(np.abs(Lg - L.numpy())) < RTOL * np.max(np.abs(L.numpy())), "Cholesky factor"
+    Wg = torch.tril(buf.W[0, :n, :n]).cpu().numpy()
+    assert np.max(np.abs(Wg - Linv.numpy())) < RTOL * np.max(np.abs(Linv.numpy())), "L^-1"
+    # alpha = K^-1 y_s with cond(K) ~ 4e4: two backward-stable solvers agree to cond * eps, not to 1e-8 of each entry
+    ag = buf.alpha[0, :n].cpu().numpy()
+    assert np.max(np.abs(ag - alpha.numpy())) < 1e-8 * np.max(np.abs(alpha.numpy())), "alpha"
+    # points: the initial conditions of that iteration, some training points and points next to the incumbent
+    rng = np.random.RandomState(3)
+    pts = np.concatenate([ics, Z[rng.randint(n, size=3)], Z[int(np.argmin(f))][None] * (1 + 1e-9)], axis=0)
+    npts = pts.shape[0]
+    P = torch.zeros(1, npts, kmax, dtype=torch.float64)
+    P[0, :, :k] = torch.from_numpy(pts)
+    out = ops.logei(buf, P.to(dev), want_grad=True, want_posterior=True)
+    Xp = torch.from_numpy(pts)
+    mean, sigma = acq.mean_sigma(Xp)
+    vals, grad = acq.value_and_grad(Xp)
+    assert rel_err(out["mu"][0].cpu().numpy(), mean.numpy(), 1e-9) < RTOL, "posterior mean"
+    assert rel_err(out["sigma"][0].cpu().numpy(), sigma.numpy()) < 1e-7, "posterior sigma"
+    assert rel_err(out["val"][0].cpu().numpy(), vals.numpy(), 1e-6) < 1e-7, "logEI"
+    g = out["grad"][0, :, :k].cpu().numpy()
+    gr = grad.numpy()
+    scale = np.maximum(np.max(np.abs(gr), axis=1, keepdims=True), 1e-300)
+    assert np.max(np.abs(g - gr) / scale) < 1e-6, "logEI gradient (per-point max-norm relative)"
+    # the device optimiser from the iteration's own initial conditions: no abnormal termination, and the joint optimum
+    # of each chunk of 5 restarts matches scipy's L-BFGS-B on the oracle (the reference's gen_candidates_scipy)
+    box = acqf.search_box_pca(Z)
+    blo = torch.zeros(1, kmax, dtype=torch.float64)
+    bhi = torch.zeros(1, kmax, dtype=torch.float64)
+    blo[0, :k] = torch.from_numpy(np.asarray(box[0]))
+    bhi[0, :k] = torch.from_numpy(np.asarray(box[1]))
+    assert rel_err(buf.box_lo[0, :k].cpu().numpy(), blo[0, :k].numpy(), 1e-12) < 1e-12
+    I = torch.zeros(1, 10, kmax, dtype=torch.float64)
+    I[0, :, :k] = torch.from_numpy(ics)
+    res = ops.lbfgsb_logei(buf, I.to(dev), buf.box_lo, buf.box_hi, k_bound=k)
+    st = res["status"][0].cpu().numpy()
+    assert ((st >= 0) & (st <= 2)).all(), st
+    bounds = torch.tensor(np.stack([np.asarray(box[0]), np.asarray(box[1])]))
+    cand = res["cand"][0, :, :k].cpu()
+    for c in range(2):
+        cs, vs, warned = acqf.gen_candidates_scipy(torch.from_numpy(ics[5 * c:5 * c + 5]), acq, bounds)
+        assert not warned
+        with torch.no_grad():
+            vd = acq(cand[5 * c:5 * c + 5])
+        fs, fdv = float(vs.sum()), float(vd.sum())
+        assert abs(fs - fdv) <= 2e-4 * max(1.0, abs(fs)), (name, c, fs, fdv)
