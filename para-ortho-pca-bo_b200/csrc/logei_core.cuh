@@ -52,7 +52,7 @@ struct Ctx {
   double *kst;   // [P][np]  k vector, later the gradient coefficients c_i
   double *tv;    // [P][np]  t = W k
   double *gf;    // [P][np]  d k / d(dist^2) factor (GRAD)
-  double *part;  // [256 P]  split-K partial sums
+  double *part;  // [256 P]  split-K partial sums of the gradient pass (aliases tv)
   double *red;   // [8][2P] + [4P]
   long long *prof = nullptr;  // optional cycle counters of the evaluation phases (slots 16..22; slot 31 = last stamp)
 };
@@ -69,18 +69,24 @@ __device__ __forceinline__ void ev_tick(const Ctx &c, int id) {
 constexpr int RB = 64;               // row / column block of the triangular passes
 constexpr int NG = LE_THREADS / RB;  // split-K groups
 
+// tv (t = W k) is dead once s = W^T t is formed, so the split-K partials of the gradient pass share its storage.
+__host__ __device__ inline size_t tv_part_doubles(int P, int np, bool grad) {
+  const size_t tvd = (size_t)P * np, pd = grad ? (size_t)LE_THREADS * P : 0;
+  return tvd > pd ? tvd : pd;
+}
+
 __host__ __device__ inline size_t scratch_doubles(int P, int kmax, int n, bool grad) {
   const int np = (n + 1) & ~1;
-  return (size_t)P * kmax + (size_t)(grad ? 3 : 2) * P * np + (size_t)LE_THREADS * P + 8 * 2 * P + 4 * P + 8;
+  return (size_t)P * kmax + (size_t)(grad ? 2 : 1) * P * np + tv_part_doubles(P, np, grad) + 8 * 2 * P + 4 * P + 8;
 }
 
 __device__ inline void carve_ctx(Ctx &c, int P, bool grad, double *sm) {
   c.xn = sm;
   c.kst = c.xn + P * c.kmax;
-  c.tv = c.kst + P * c.np;
-  c.gf = c.tv + P * c.np;
-  c.part = c.gf + (grad ? P * c.np : 0);
-  c.red = c.part + LE_THREADS * P;
+  c.gf = c.kst + P * c.np;
+  c.tv = c.gf + (grad ? P * c.np : 0);
+  c.part = c.tv;
+  c.red = c.tv + tv_part_doubles(P, c.np, grad);
 }
 
 __device__ inline void load_ctx(Ctx &c, const pcabo_gp_model &m, int b) {
@@ -104,14 +110,37 @@ template <int P>
 __device__ __forceinline__ void strided_dot(double (&acc)[P], const double *__restrict__ M, long ld, int col, int j0,
                                             int j1, const double *__restrict__ v, int np) {
   int j = j0;
-  for (; j + 16 <= j1; j += 16) {
-    double w16[16];
+  if constexpr (P <= 8) {
+    if (j + 16 <= j1) {
+      // two accumulator sets: 2 P independent FMA chains per thread hide the FP64 pipe latency
+      double acc2[P];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) w16[u] = M[(long)(j + u) * ld + col];
+      for (int p = 0; p < P; ++p) acc2[p] = 0.0;
+      for (; j + 16 <= j1; j += 16) {
+        double w16[16];
 #pragma unroll
-    for (int u = 0; u < 16; ++u)
+        for (int u = 0; u < 16; ++u) w16[u] = M[(long)(j + u) * ld + col];
 #pragma unroll
-      for (int p = 0; p < P; ++p) acc[p] = fma(w16[u], v[p * np + j + u], acc[p]);
+        for (int u = 0; u < 16; u += 2)
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            acc[p] = fma(w16[u], v[p * np + j + u], acc[p]);
+            acc2[p] = fma(w16[u + 1], v[p * np + j + u + 1], acc2[p]);
+          }
+      }
+#pragma unroll
+      for (int p = 0; p < P; ++p) acc[p] += acc2[p];
+    }
+  } else {
+    for (; j + 16 <= j1; j += 16) {
+      double w16[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) w16[u] = M[(long)(j + u) * ld + col];
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+#pragma unroll
+        for (int p = 0; p < P; ++p) acc[p] = fma(w16[u], v[p * np + j + u], acc[p]);
+    }
   }
   for (; j + 4 <= j1; j += 4) {
     double w4[4];
@@ -230,6 +259,7 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
     if (lane == 0) { red[warp * 2 * P + p] = ms; red[warp * 2 * P + P + p] = vs; }
   }
   __syncthreads();
+  ev_tick(c, 21);
   double *res = red + nw * 2 * P;  // [2][P]: d logEI / d mu_s, d logEI / d var_s
   if (tid < P) {
     const int p = tid;
@@ -257,6 +287,7 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
       res[P + p] = clamped ? 0.0 : (1.0 - u * dlh) * ystd * ystd / (2.0 * var);  // d logEI / d var_s
     }
   }
+  ev_tick(c, 22);
   __syncthreads();
   ev_tick(c, 18);
   if constexpr (GRAD) {
