@@ -6,11 +6,20 @@
 // candidates, so unlike the 5-point evaluations of the BO loop it is a dense FP64 contraction and FP64-pipe bound:
 //     T = W K*      W = L^-1 (n x n lower triangular),  K*[j][c] = matern52(|zn_j - xn_c| / ell)   (n x N_cand)
 //     var_c = k** - sum_i T[i][c]^2 ,  mu_c = alpha . K*[:, c]  ->  log-EI_c  ->  arg-max
-// One CTA owns a tile of 32 candidates and keeps the whole n x 32 tile of T in registers as FP64 tensor-core
-// accumulators (mma.sync.aligned.m8n8k4.f64, the only FP64 MMA shape on sm_100: SASS DMMA.8x8x4). The k dimension is
-// streamed in panels of 16 training points: the W panel arrives by cp.async (double buffered, 16-byte copies), the K*
-// panel is computed on the fly from the staged training rows, so neither W nor K* is ever re-read per candidate and
-// candidates are generated in-kernel from the scrambled Sobol state (no HBM traffic for them at all).
+// One persistent CTA per SM owns tiles of 32 candidates and keeps the whole n x 32 tile of T in registers as FP64
+// tensor-core accumulators (mma.sync.aligned.m8n8k4.f64, the only FP64 MMA shape on sm_100: SASS DMMA.8x8x4). The k
+// dimension is streamed in panels of 16 training points.
+//
+// v5 pipeline (no block-wide barrier inside a tile):
+//   * K* panels travel through an 8-deep shared-memory ring guarded by mbarriers (full: 8 producer warps, empty: 16
+//     consumer warps). Every warp is a consumer of every panel and, on alternate panels, the producer of one 8 x 8 tile
+//     of the panel FOUR panels ahead (distances on the tensor cores from the training rows read straight from L2, then
+//     sqrt / exp on the FP64 pipe), so the Matern latency of one warp hides behind the DMMAs of the fifteen others and
+//     production runs across tile boundaries (the ring never drains).
+//   * W is staged per warp: a warp copies only the rows of its own row tiles (cp.async, double buffered, 16 B chunks)
+//     and synchronises with nobody else; panels entirely above the diagonal of a row tile are skipped.
+//   * candidates of the NEXT tile are generated (scrambled Sobol, bit-identical to pcabo_sobol_points) while the
+//     current tile is consumed; the only block barriers are the two around the per-tile epilogue.
 #include "logei_core.cuh"
 
 namespace {
@@ -22,9 +31,12 @@ constexpr int NWARP = SW_THREADS / 32;   // 16
 constexpr int TC = 32;        // candidates per tile
 constexpr int CT = TC / 8;    // 8-wide column tiles
 constexpr int KB = 16;        // training points per k panel
-constexpr int WS_LD = 20;     // W panel row stride in doubles (bank-conflict free for the A fragments)
+constexpr int WS_LD = 16;     // W panel row stride in doubles; columns are XOR-swizzled by 4 * (row & 3) so that the A
+                              // fragment loads (8 rows x 4 columns per warp) are bank-conflict free without padding
 constexpr int KS_LD = 36;     // K* panel row stride in doubles (bank-conflict free for the B fragments)
 constexpr int RT_MAX = 4;     // row tiles (of 8 rows) per warp: n <= 16 * 4 * 8 = 512
+constexpr int RING = 8;       // K* ring depth (panels)
+constexpr int AHEAD = 4;      // K* production distance (panels)
 constexpr int MAXBIT = 30;
 
 struct SweepArgs {
@@ -45,7 +57,7 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
@@ -53,17 +65,69 @@ __device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, dou
                : "d"(a), "d"(b));
 }
 
-// Shared-memory carve-up (offsets in doubles from the dynamic shared base; buffers are addressed as base + offset so
-// that the compiler keeps them in the shared state space: LDS / STS, no generic loads):
-//   Ws[2][rows8][WS_LD] W panels | Ks[2][KB][KS_LD] K* panels | Zs[3][KB][zld] training rows (two panels ahead) |
-//   As[3][KB] alpha | xn[TC][zld] normalised candidates | xx[TC] |xn|^2 | zz[rows16] |zn|^2 | red | sst (ints)
+// ---- mbarrier helpers (CTA scope, shared memory)
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(a) : "memory");
+}
+// arrival that publishes nothing (a consumer releasing a ring slot it has finished READING): relaxed, so that it
+// does not wait for this warp's outstanding cp.async copies the way the default release arrival does
+__device__ __forceinline__ void mbar_arrive_relaxed(unsigned long long *bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.relaxed.cta.shared::cta.b64 st, [%0];\n}\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra.uni WAIT_DONE;\n"
+      " bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(a), "r"(parity) : "memory");
+}
 
+// T[rows of this warp][32 candidates] += W panel (staged rows x 16) * K* panel (16 x 32) on the FP64 tensor cores.
+// T0: first row tile of the warp that reaches down to the panel (compile time -> no per-tile tests in the loop);
+// LAST: the panel may contain columns >= n (masked). No other masks: W holds explicit zeros above its diagonal inside
+// the diagonal 32 x 32 blocks (written by the fit) and padding rows are dropped in the epilogue.
+template <int T0, bool LAST>
+__device__ __forceinline__ void mma_panel(double (&acc)[RT_MAX][CT][2], const double *__restrict__ Wsb,
+                                          const double *__restrict__ Ksb, const int (&aoff)[KB / 4], int ntw,
+                                          int col0, int n) {
+#pragma unroll
+  for (int k4 = 0; k4 < KB / 4; ++k4) {
+    double bf[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) bf[c] = Ksb[k4 * 4 * KS_LD + c * 8];
+#pragma unroll
+    for (int t = T0; t < RT_MAX; ++t) {
+      if (t < ntw) {
+        double af = Wsb[t * 8 * WS_LD + aoff[k4]];
+        if (LAST && !(col0 + k4 * 4 < n)) af = 0.0;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) dmma_8x8x4(acc[t][c][0], acc[t][c][1], af, bf[c]);
+      }
+    }
+  }
+}
+
+// Shared-memory carve-up (offsets in doubles from the dynamic shared base):
+//   Ww[NWARP][2][RT_MAX * 8][WS_LD] per-warp W staging | Ks[RING][KB][KS_LD] K* ring | xn[2][TC][zld] normalised
+//   candidates of the current / next tile | xx[2][TC] |xn|^2 | zz[rows16] |zn|^2 | al[rows16] alpha | red | mbarriers |
+//   sst (ints)
 __host__ __device__ inline int sweep_zld(int kmax) { return ((kmax + 3) / 4) * 4 + 4; }
 
 __host__ __device__ inline size_t sweep_smem_bytes(int n, int kmax) {
-  const int rows8 = ((n + 7) / 8) * 8, rows16 = ((n + 15) / 16) * 16, zld = sweep_zld(kmax);
-  size_t d = 2 * (size_t)rows8 * WS_LD + 2 * KB * KS_LD + 3 * (size_t)KB * zld + 3 * KB + (size_t)TC * zld + TC + rows16 +
-             2 * NWARP * TC + 8;
+  const int rows16 = ((n + 15) / 16) * 16, zld = sweep_zld(kmax);
+  size_t d = (size_t)NWARP * 2 * RT_MAX * 8 * WS_LD + (size_t)RING * KB * KS_LD + 2 * (size_t)TC * zld + 2 * TC +
+             2 * (size_t)rows16 + 2 * NWARP * TC + 2 * RING + 8;
   return d * sizeof(double) + (size_t)kmax * MAXBIT * sizeof(int);
 }
 
@@ -79,16 +143,17 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
   const int zld = sweep_zld(kmax);
   const int rows8 = ((n + 7) / 8) * 8, rows16 = ((n + 15) / 16) * 16;
   const int nrt = rows8 / 8;
-  const int ws_sz = rows8 * WS_LD, ks_sz = KB * KS_LD, zs_sz = KB * zld;
-  double *const sWs = smd;
-  double *const sKs = sWs + 2 * ws_sz;
-  double *const sZs = sKs + 2 * ks_sz;
-  double *const sAs = sZs + 3 * zs_sz;
-  double *const sxn = sAs + 3 * KB;
-  double *const sxx = sxn + TC * zld;
-  double *const szz = sxx + TC;
-  double *const sred = szz + rows16;
-  int *const ssst = reinterpret_cast<int *>(sred + 2 * NWARP * TC + 8);
+  constexpr int ww_sz = RT_MAX * 8 * WS_LD, ks_sz = KB * KS_LD;
+  double *const sWw = smd + (size_t)warp * 2 * ww_sz;          // this warp's two W buffers
+  double *const sKs = smd + (size_t)NWARP * 2 * ww_sz;
+  double *const sxn = sKs + RING * ks_sz;
+  double *const sxx = sxn + 2 * TC * zld;
+  double *const szz = sxx + 2 * TC;
+  double *const sal = szz + rows16;
+  double *const sred = sal + rows16;
+  unsigned long long *const full_bar = reinterpret_cast<unsigned long long *>(sred + 2 * NWARP * TC);
+  unsigned long long *const empty_bar = full_bar + RING;
+  int *const ssst = reinterpret_cast<int *>(empty_bar + RING + 8);
   const double *W = m.W + (size_t)b * ld * ld;
   const double *Zn = m.Zn + (size_t)b * ld * kmax;
   const double *alpha = m.alpha + (size_t)b * ld;
@@ -100,25 +165,33 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
 
   if (a.X == nullptr)
     for (int i = tid; i < kk * MAXBIT; i += SW_THREADS) ssst[i] = a.sstate[i];
-  // squared norms of the training rows (once per CTA) and zero padding of the staging buffers
+  // squared norms of the training rows and alpha (once per CTA); zero padding of the candidate buffers
   for (int j = tid; j < rows16; j += SW_THREADS) {
     double acc = 0.0;
     if (j < n)
       for (int dmm = 0; dmm < kk; ++dmm) { const double z = Zn[(size_t)j * kmax + dmm]; acc = fma(z, z, acc); }
     szz[j] = acc;
+    sal[j] = (j < n) ? alpha[j] : 0.0;
   }
-  for (int i = tid; i < 3 * KB * zld; i += SW_THREADS) sZs[i] = 0.0;   // the three Zs buffers are contiguous
-  for (int i = tid; i < TC * zld; i += SW_THREADS) sxn[i] = 0.0;
+  for (int i = tid; i < 2 * TC * zld; i += SW_THREADS) sxn[i] = 0.0;
+  if (tid < RING) { mbar_init(&full_bar[tid], NWARP / 2); mbar_init(&empty_bar[tid], NWARP); }
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  __syncthreads();   // zero padding and barriers are in place before any thread fills the candidate buffers
+
   double cta_best = -INFINITY;
   long long cta_idx = 0x7fffffffffffffffLL;
   const long long ntiles = (a.ncand + TC - 1) / TC;
   const int nchunks = (n + KB - 1) / KB;
   const int ar = lane >> 2, ak = lane & 3;
+  // tiles of this CTA: blockIdx.x + k * gridDim.x, k = 0 .. ntk - 1
+  const long long ntk = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long npanels = ntk * nchunks;     // global panel sequence of this CTA
+  const int ahead = min(AHEAD, nchunks);       // production never runs further than into the next tile
 
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long c0 = tile * TC;
-    __syncthreads();
-    // ---- candidate coordinates, normalised: xn[c][j]
+  // ---- normalised candidates of local tile k -> xn buffer k & 1 (all threads; caller synchronises)
+  auto gen_candidates = [&](long long k) {
+    const long long c0 = ((long long)blockIdx.x + k * gridDim.x) * TC;
+    double *xb = sxn + (size_t)(k & 1) * TC * zld;
     for (int idx = tid; idx < TC * kk; idx += SW_THREADS) {
       const int c = idx / kk, j = idx % kk;
       const long long ci = c0 + c;
@@ -145,124 +218,205 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
           x = __dadd_rn(a.lo[j], __dmul_rn(__dsub_rn(a.hi[j], a.lo[j]), raw));
         }
       }
-      sxn[c * zld + j] = (x - off[j]) / coef[j];
+      xb[c * zld + j] = (x - off[j]) / coef[j];
     }
-    __syncthreads();
+  };
+  auto gen_norms = [&](long long k) {
     if (tid < TC) {
+      const double *xb = sxn + (size_t)(k & 1) * TC * zld;
       double acc = 0.0;
-      for (int dmm = 0; dmm < kk; ++dmm) { const double x = sxn[tid * zld + dmm]; acc = fma(x, x, acc); }
-      sxx[tid] = acc;
+      for (int dmm = 0; dmm < kk; ++dmm) { const double x = xb[tid * zld + dmm]; acc = fma(x, x, acc); }
+      sxx[(k & 1) * TC + tid] = acc;
     }
-    // ---- accumulators: warp owns row tiles rt = warp, warp + 16, ...; 4 column tiles each
+  };
+
+  // partial alpha . k of this thread's two candidates (its K* tiles), one set per tile parity
+  double mean_e0 = 0.0, mean_e1 = 0.0, mean_o0 = 0.0, mean_o1 = 0.0;   // even / odd tiles
+
+  // ---- per-lane constants of the hot loops
+  const int swz = ar & 3;
+  int aoff[KB / 4];                                  // A fragment offsets inside a staged row tile (swizzled columns)
+#pragma unroll
+  for (int k4 = 0; k4 < KB / 4; ++k4) aoff[k4] = ar * WS_LD + (((k4 ^ swz) << 2) | ak);
+  const int boff = ak * KS_LD + ar;                  // B fragment offset inside a K* panel
+  int ntw = 0;                                       // row tiles owned by this warp: rt = warp + t * 16 < nrt
+#pragma unroll
+  for (int t = 0; t < RT_MAX; ++t) ntw += (warp + t * NWARP < nrt) ? 1 : 0;
+  // W staging: lane copies chunk h (columns 2h, 2h+1) of rows r and r + 4 of each of its row tiles
+  const int cr = lane >> 3, ch = lane & 7;
+  const int wdst = cr * WS_LD + ((2 * ch) ^ (cr << 2));
+  const double *wsrc = W + (size_t)(warp * 8 + cr) * ld + 2 * ch;
+  const double *wlast = W + (size_t)(n - 1) * ld + 2 * ch;
+  const size_t wsrc_t = (size_t)NWARP * 8 * ld, wsrc_q = 4 * (size_t)ld;
+  unsigned rowok = 0;                                // bit 2 t + q: row (warp + 16 t) * 8 + cr + 4 q exists
+#pragma unroll
+  for (int t = 0; t < RT_MAX; ++t)
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if ((warp + t * NWARP) * 8 + cr + 4 * q < n) rowok |= 1u << (2 * t + q);
+  // first row tile of this warp that reaches down to column j0 (tiles entirely above the diagonal are skipped)
+  auto first_tile = [&](int j0) {
+    const int need = j0 - 7 - warp * 8;              // rt * 8 + 7 >= j0  <=>  t * 128 >= need
+    return need <= 0 ? 0 : (need + 127) >> 7;
+  };
+  // K* production only touches whole 4-column groups of the training rows when they exist in memory
+  const bool zfast = kk4 * 4 <= kmax;
+  const int id = warp >> 1, ptr_ = id / CT, ptc = id % CT;
+  const int pjj = ptr_ * 8 + ar;
+
+  // ---- producer: the 8 x 8 tile (ptr_, ptc) of K* panel `chunk` of the tile with parity `par` into ring slot `slot`
+  auto produce = [&](int chunk, int par, int slot, bool wait_empty, unsigned empty_parity) {
+    const int j0 = chunk * KB;
+    const int jrow = min(j0 + pjj, n - 1);
+    const bool on = j0 + pjj < n;
+    // distances on the tensor cores: two accumulator pairs (even / odd k-steps) halve the dependent DMMA chain
+    double da0 = 0.0, da1 = 0.0, db0 = 0.0, db1 = 0.0;
+    const double *zrow = Zn + (size_t)jrow * kmax + ak;
+    const double *xrow = sxn + (size_t)par * TC * zld + (ptc * 8 + ar) * zld + ak;
+    if (zfast) {
+      int k4 = 0;
+      for (; k4 + 4 <= kk4; k4 += 4) {
+        const double z0 = __ldg(zrow + k4 * 4), z1 = __ldg(zrow + k4 * 4 + 4), z2 = __ldg(zrow + k4 * 4 + 8),
+                     z3 = __ldg(zrow + k4 * 4 + 12);
+        dmma_8x8x4(da0, da1, z0, xrow[k4 * 4]);
+        dmma_8x8x4(db0, db1, z1, xrow[k4 * 4 + 4]);
+        dmma_8x8x4(da0, da1, z2, xrow[k4 * 4 + 8]);
+        dmma_8x8x4(db0, db1, z3, xrow[k4 * 4 + 12]);
+      }
+      for (; k4 < kk4; ++k4) dmma_8x8x4(da0, da1, __ldg(zrow + k4 * 4), xrow[k4 * 4]);
+    } else {
+      for (int k4 = 0; k4 < kk4; ++k4) {
+        const double z = (k4 * 4 + ak < kk) ? __ldg(zrow + k4 * 4) : 0.0;
+        dmma_8x8x4(da0, da1, z, xrow[k4 * 4]);
+      }
+    }
+    const double zzj = szz[j0 + pjj], aj = sal[j0 + pjj];
+    const double *xx = sxx + par * TC + ptc * 8 + ak * 2;
+    double kv[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const double dot = h ? (da1 + db1) : (da0 + db0);
+      const double sq = fmax((zzj + xx[h]) - 2.0 * dot, 0.0);
+      const double s2 = sq * inv_ell2;
+      const double dist = sqrt(fmax(s2, 1e-30));
+      const double v = (SQRT5 * dist + 1.0 + (5.0 / 3.0) * (dist * dist)) * exp(-SQRT5 * dist);
+      kv[h] = on ? v : 0.0;
+    }
+    if (par) { mean_o0 = fma(kv[0], aj, mean_o0); mean_o1 = fma(kv[1], aj, mean_o1); }
+    else { mean_e0 = fma(kv[0], aj, mean_e0); mean_e1 = fma(kv[1], aj, mean_e1); }
+    // the slot is free once all 16 warps consumed the panel that used it RING panels ago
+    if (wait_empty) mbar_wait(&empty_bar[slot], empty_parity);
+    double *ks = sKs + slot * ks_sz + pjj * KS_LD + ptc * 8 + ak * 2;
+    *reinterpret_cast<double2 *>(ks) = make_double2(kv[0], kv[1]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full_bar[slot]);
+  };
+
+  // ---- this warp's rows of W panel `chunk` -> its staging buffer `buf` (row tiles above the diagonal are skipped)
+  auto issue_w = [&](int chunk, int buf) {
+    const int j0 = chunk * KB;
+    double *dst = sWw + buf * ww_sz + wdst;
+    const int t0 = first_tile(j0);
+    // last panel of a matrix whose row is shorter than the panel: stay inside the (even) row; the clamped columns are
+    // >= n and are masked in the MMA loop of the last panel
+    const int jc = (j0 + KB <= (int)ld) ? j0 : min(j0 + 2 * ch, (int)ld - 2) - 2 * ch;
+    const double *src = wsrc + jc;
+    const double *slast = wlast + jc;               // padding rows of the last row tile re-read row n - 1 (never used)
+#pragma unroll
+    for (int t = 0; t < RT_MAX; ++t)
+      if (t >= t0 && t < ntw) {
+        cp_async16(dst + t * 8 * WS_LD, (rowok & (1u << (2 * t))) ? src + t * wsrc_t : slast);
+        cp_async16(dst + (t * 8 + 4) * WS_LD, (rowok & (2u << (2 * t))) ? src + t * wsrc_t + wsrc_q : slast);
+      }
+  };
+
+  // ---- prologue: candidates of tile 0, first `ahead` panels of K*, W panel 0
+  if (ntk > 0) gen_candidates(0);
+  __syncthreads();
+  if (ntk > 0) gen_norms(0);
+  __syncthreads();
+  const int npan = (int)npanels;
+  // producer cursor: panel pG = G + ahead of the global sequence, as (chunk, tile parity)
+  int pG = 0, pchunk = 0, ppar = 0;
+  auto advance_producer = [&]() {
+    ++pG;
+    if (++pchunk == nchunks) { pchunk = 0; ppar ^= 1; }
+  };
+  for (; pG < ahead && pG < npan; advance_producer())
+    if (((warp + pG) & 1) == 0) produce(pchunk, ppar, pG & (RING - 1), false, 0u);
+  if (npan > 0) issue_w(0, 0);
+  cp_async_commit();
+
+  int G = 0;
+  for (long long k = 0; k < ntk; ++k) {
+    const long long c0 = ((long long)blockIdx.x + k * gridDim.x) * TC;
+    // candidates of the next tile (its K* production starts `ahead` panels before this tile ends)
+    if (k + 1 < ntk) gen_candidates(k + 1);
+    __syncthreads();
+    if (k + 1 < ntk) gen_norms(k + 1);
+    __syncthreads();
+    // accumulators: warp owns row tiles rt = warp, warp + 16, ...; 4 column tiles each
     double acc[RT_MAX][CT][2];
 #pragma unroll
     for (int t = 0; t < RT_MAX; ++t)
 #pragma unroll
       for (int c = 0; c < CT; ++c) { acc[t][c][0] = 0.0; acc[t][c][1] = 0.0; }
-    double mean_part[2] = {0.0, 0.0};  // partial alpha . k of this thread's two candidates (its K* tiles)
 
-    // W panel `chunk` -> Ws[chunk & 1]; training rows / alpha of panel `chunk` -> Zs / As[chunk % 3]
-    auto issue_w = [&](int chunk) {
-      const int j0 = chunk * KB, buf = chunk & 1;
-      const int i_lo = j0 & ~7;
-      const int nrows = rows8 - i_lo;   // rows above i_lo are entirely above the diagonal for this panel
-      for (int idx = tid; idx < nrows * (KB / 2); idx += SW_THREADS) {
-        const int r = idx / (KB / 2), h = idx % (KB / 2);
-        const int i = min(i_lo + r, n - 1);
-        const int jc = min(j0 + 2 * h, (int)ld - 2);   // stay inside the (even) row; columns >= n meet zero rows of K*
-        cp_async16(&sWs[buf * ws_sz + (i_lo + r) * WS_LD + 2 * h], &W[(size_t)i * ld + jc]);
+    for (int chunk = 0; chunk < nchunks; ++chunk, ++G) {
+      const int wbuf = G & 1;
+      // K* tile of the panel `ahead` panels further on: warps alternate this duty. (Before the W prefetch: the release
+      // arrival at the end of produce() waits for this warp's outstanding cp.async copies.)
+      if (pG < npan) {
+        if (((warp + pG) & 1) == 0)
+          produce(pchunk, ppar, pG & (RING - 1), pG >= RING, (unsigned)(((pG / RING) - 1) & 1));
+        advance_producer();
       }
-    };
-    auto issue_z = [&](int chunk) {
-      const int j0 = chunk * KB, zb = chunk % 3;
-      for (int idx = tid; idx < KB * (kmax / 2); idx += SW_THREADS) {
-        const int r = idx / (kmax / 2), h = idx % (kmax / 2);
-        const int j = min(j0 + r, n - 1);
-        cp_async16(&sZs[zb * zs_sz + r * zld + 2 * h], &Zn[(size_t)j * kmax + 2 * h]);
-      }
-      if (tid < KB / 2) {
-        const int j = min(j0 + 2 * tid, (int)ld - 2);
-        cp_async16(&sAs[zb * KB + 2 * tid], &alpha[j]);
-      }
-    };
-    // K* tile of panel `chunk` by this warp (tile id = warp / 2): dot = Zs (8 x kk) xn^T (kk x 8) on the tensor cores,
-    // sq = |z|^2 + |x|^2 - 2 dot, Ks[jj][c] = matern52(sqrt(sq) / ell); rows beyond n are zero
-    auto kstar_tile = [&](int chunk) {
-      const int j0 = chunk * KB, zb = chunk % 3, kb = chunk & 1;
-      const int id = warp >> 1, tr = id / CT, tc = id % CT;
-      double dt0 = 0.0, dt1 = 0.0;
-      const double *zrow = sZs + zb * zs_sz + (tr * 8 + ar) * zld + ak;
-      const double *xrow = sxn + (tc * 8 + ar) * zld + ak;
-      for (int k4 = 0; k4 < kk4; ++k4) dmma_8x8x4(dt0, dt1, zrow[k4 * 4], xrow[k4 * 4]);
-      const int jj = tr * 8 + ar;
-      const double zzj = szz[j0 + jj], aj = sAs[zb * KB + jj];
-      const bool on = j0 + jj < n;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = tc * 8 + ak * 2 + h;
-        const double dot = h ? dt1 : dt0;
-        const double sq = fmax((zzj + sxx[c]) - 2.0 * dot, 0.0);
-        const double s2 = sq * inv_ell2;
-        const double dist = sqrt(fmax(s2, 1e-30));
-        double kv = (SQRT5 * dist + 1.0 + (5.0 / 3.0) * (dist * dist)) * exp(-SQRT5 * dist);
-        if (!on) kv = 0.0;
-        sKs[kb * ks_sz + jj * KS_LD + c] = kv;
-        if (on) mean_part[h] = fma(kv, aj, mean_part[h]);
-      }
-    };
-
-    // prologue: panel 0 (W, Z), Z of panel 1; K*(0)
-    issue_w(0);
-    issue_z(0);
-    if (nchunks > 1) issue_z(1);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    if ((warp & 1) == 0) kstar_tile(0);
-    for (int chunk = 0; chunk < nchunks; ++chunk) {
-      const int buf = chunk & 1;
-      const int j0 = chunk * KB;
-      cp_async_wait<0>();
-      __syncthreads();   // K*(chunk), W(chunk), Z(chunk+1) are visible; every warp is past the MMAs of panel chunk - 1
-      if (chunk + 1 < nchunks) issue_w(chunk + 1);
-      if (chunk + 2 < nchunks) issue_z(chunk + 2);
+      // W of the next panel of the sequence (wraps to panel 0 of the next tile)
+      if (G + 1 < npan) issue_w(chunk + 1 < nchunks ? chunk + 1 : 0, wbuf ^ 1);
       cp_async_commit();
-      // the K* tile of the NEXT panel: warps alternate this duty so that others keep the tensor pipe busy meanwhile
-      if (chunk + 1 < nchunks && ((warp + chunk + 1) & 1) == 0) kstar_tile(chunk + 1);
+      cp_async_wait<1>();
+      __syncwarp();
+      const int slot = G & (RING - 1);
+      mbar_wait(&full_bar[slot], (unsigned)((G / RING) & 1));
       // ---- T += Wpanel (rows x 16) * Kspanel (16 x 32) on the FP64 tensor cores
       {
-        const double *Wsb = sWs + buf * ws_sz;
-        const double *Ksb = sKs + buf * ks_sz;
-#pragma unroll
-        for (int k4 = 0; k4 < KB / 4; ++k4) {
-          double bf[CT];
-#pragma unroll
-          for (int c = 0; c < CT; ++c) bf[c] = Ksb[(k4 * 4 + ak) * KS_LD + c * 8 + ar];
-          const int jcol = j0 + k4 * 4 + ak;
-#pragma unroll
-          for (int t = 0; t < RT_MAX; ++t) {
-            const int rt = warp + t * NWARP;
-            if (rt < nrt && rt * 8 + 7 >= j0) {
-              const int row = rt * 8 + ar;
-              // entries above the diagonal and padding rows are not part of L^-1
-              const double af = (row < n && jcol <= row) ? Wsb[row * WS_LD + k4 * 4 + ak] : 0.0;
-#pragma unroll
-              for (int c = 0; c < CT; ++c) dmma_8x8x4(acc[t][c][0], acc[t][c][1], af, bf[c]);
-            }
+        const double *Wsb = sWw + wbuf * ww_sz;
+        const double *Ksb = sKs + slot * ks_sz + boff;
+        const int t0 = first_tile(chunk * KB);
+        if (chunk == nchunks - 1) {
+          const int col0 = chunk * KB + ak;
+          switch (t0) {
+            case 0: mma_panel<0, true>(acc, Wsb, Ksb, aoff, ntw, col0, n); break;
+            case 1: mma_panel<1, true>(acc, Wsb, Ksb, aoff, ntw, col0, n); break;
+            case 2: mma_panel<2, true>(acc, Wsb, Ksb, aoff, ntw, col0, n); break;
+            case 3: mma_panel<3, true>(acc, Wsb, Ksb, aoff, ntw, col0, n); break;
+            default: break;
+          }
+        } else {
+          switch (t0) {
+            case 0: mma_panel<0, false>(acc, Wsb, Ksb, aoff, ntw, 0, n); break;
+            case 1: mma_panel<1, false>(acc, Wsb, Ksb, aoff, ntw, 0, n); break;
+            case 2: mma_panel<2, false>(acc, Wsb, Ksb, aoff, ntw, 0, n); break;
+            case 3: mma_panel<3, false>(acc, Wsb, Ksb, aoff, ntw, 0, n); break;
+            default: break;
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_relaxed(&empty_bar[slot]);
     }
-    // ---- variance partials: thread holds T[row = rt*8 + lane/4][col = c*8 + (lane%4)*2 + {0,1}]
+    // ---- epilogue of the tile. Variance partials: thread holds T[row = rt*8 + lane/4][col = c*8 + (lane%4)*2 + {0,1}]
     double vpart[CT][2];
 #pragma unroll
     for (int c = 0; c < CT; ++c) { vpart[c][0] = 0.0; vpart[c][1] = 0.0; }
 #pragma unroll
     for (int t = 0; t < RT_MAX; ++t)
+      if ((warp + t * NWARP) * 8 + ar < n) {          // padding rows of the last row tile carry no L^-1 row
 #pragma unroll
-      for (int c = 0; c < CT; ++c) {
-        vpart[c][0] = fma(acc[t][c][0], acc[t][c][0], vpart[c][0]);
-        vpart[c][1] = fma(acc[t][c][1], acc[t][c][1], vpart[c][1]);
+        for (int c = 0; c < CT; ++c) {
+          vpart[c][0] = fma(acc[t][c][0], acc[t][c][0], vpart[c][0]);
+          vpart[c][1] = fma(acc[t][c][1], acc[t][c][1], vpart[c][1]);
+        }
       }
     // reduce over the 8 row groups of the warp (lanes with equal lane % 4): xor 4, 8, 16
 #pragma unroll
@@ -276,25 +430,25 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
         vpart[c][h] = v;
       }
     // mean partials: thread holds candidates tc*8 + ak*2 + {0,1} for training rows tr*8 + ar of its panels
-    {
+    double mp[2];
+    if (k & 1) { mp[0] = mean_o0; mp[1] = mean_o1; mean_o0 = 0.0; mean_o1 = 0.0; }
+    else { mp[0] = mean_e0; mp[1] = mean_e1; mean_e0 = 0.0; mean_e1 = 0.0; }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        double v = mean_part[h];
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        mean_part[h] = v;
-      }
+    for (int h = 0; h < 2; ++h) {
+      double v = mp[h];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      mp[h] = v;
     }
-    __syncthreads();
     if (lane < 4) {
 #pragma unroll
       for (int c = 0; c < CT; ++c) {
         sred[warp * TC + c * 8 + lane * 2 + 0] = vpart[c][0];
         sred[warp * TC + c * 8 + lane * 2 + 1] = vpart[c][1];
       }
-      sred[NWARP * TC + warp * 8 + lane * 2 + 0] = mean_part[0];   // [warp][8 candidates of tile column (warp/2) % CT]
-      sred[NWARP * TC + warp * 8 + lane * 2 + 1] = mean_part[1];
+      sred[NWARP * TC + warp * 8 + lane * 2 + 0] = mp[0];   // [warp][8 candidates of tile column (warp/2) % CT]
+      sred[NWARP * TC + warp * 8 + lane * 2 + 1] = mp[1];
     }
     __syncthreads();
     if (tid < TC) {
@@ -330,7 +484,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       }
       if (val > cta_best || (val == cta_best && gi < cta_idx)) { cta_best = val; cta_idx = gi; }
     }
+    // (sred is rewritten only after the two barriers at the top of the next tile)
   }
+  cp_async_wait<0>();
   if (tid == 0) { a.best_val[blockIdx.x] = cta_best; a.best_idx[blockIdx.x] = cta_idx; }
 }
 
