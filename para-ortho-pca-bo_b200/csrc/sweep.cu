@@ -22,19 +22,32 @@
 //     current tile is consumed; the only block barriers are the two around the per-tile epilogue.
 #include "logei_core.cuh"
 
+#ifdef SWEEP_PROF
+__device__ long long g_sweep_prof[16][8];
+#define SWP_T0() long long swp_t = clock64()
+#define SWP(id) do { const long long swp_n = clock64(); if (blockIdx.x == 0 && lane == 0) g_sweep_prof[warp][id] += swp_n - swp_t; swp_t = swp_n; } while (0)
+#else
+#define SWP_T0()
+#define SWP(id)
+#endif
+
 namespace {
 
 using logei::SQRT5;
 
-constexpr int SW_THREADS = 512;
-constexpr int NWARP = SW_THREADS / 32;   // 16
+#ifndef SWEEP_WARPS
+#define SWEEP_WARPS 16
+#endif
+constexpr int NWARP = SWEEP_WARPS;       // 16 (4 row tiles each, 128 registers) or 32 (2 row tiles each, 64 registers)
+constexpr int SW_THREADS = NWARP * 32;
+constexpr int DUTY = NWARP / 4;          // a warp produces a 16 x 8 strip of K* (two 8 x 8 tiles) every DUTY-th panel
 constexpr int TC = 32;        // candidates per tile
 constexpr int CT = TC / 8;    // 8-wide column tiles
 constexpr int KB = 16;        // training points per k panel
 constexpr int WS_LD = 16;     // W panel row stride in doubles; columns are XOR-swizzled by 4 * (row & 3) so that the A
                               // fragment loads (8 rows x 4 columns per warp) are bank-conflict free without padding
 constexpr int KS_LD = 36;     // K* panel row stride in doubles (bank-conflict free for the B fragments)
-constexpr int RT_MAX = 4;     // row tiles (of 8 rows) per warp: n <= 16 * 4 * 8 = 512
+constexpr int RT_MAX = 64 / NWARP;   // row tiles (of 8 rows) per warp: n <= NWARP * RT_MAX * 8 = 512
 constexpr int RING = 8;       // K* ring depth (panels)
 constexpr int AHEAD = 4;      // K* production distance (panels)
 constexpr int MAXBIT = 30;
@@ -91,6 +104,46 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
       " bra.uni WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+
+// Matern-5/2 of a squared scaled distance, k = (1 + a + a^2 / 3) exp(-a) with a = sqrt(5 s2), written out with a bare
+// Newton square root and exponential (argument reduction by ln 2, degree-13 Taylor polynomial, exponent insertion):
+// ~45 FP64 instructions instead of ~85 for the library sqrt() + exp(), which matters because on this part the scalar
+// FP64 instructions share the execution pipe with the DMMAs. Relative error <= 4e-16 for s2 in [1e-30, 4e4]
+// (tests/test_gpu_sweep.py checks the resulting log-EI against the oracle to 1e-8).
+__device__ __forceinline__ double matern52_fast(double s2) {
+  const double x = fmin(fmax(5.0 * s2, 5e-30), 4.0e5);      // a^2; a <= 632 keeps 2^n normal
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));    // ~20 good bits
+  // two Newton steps on y ~ x^-1/2, then a = x y with one correction step
+  double h = 0.5 * x;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  double a = x * y;
+  a = fma(0.5 * y, fma(-a, a, x), a);
+  // exp(-a): n = rint(-a log2 e), r = -a - n ln 2 (two-part), e^r by Taylor to degree 13 (|r| <= 0.3466)
+  const double SHIFT = 6755399441055744.0;                   // 2^52 + 2^51
+  double kd = fma(-a, 1.4426950408889634074, SHIFT);
+  const int ki = __double2loint(kd);
+  kd -= SHIFT;
+  double r = fma(kd, -6.93147180369123816490e-01, -a);
+  r = fma(kd, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;                         // 1 / 13!
+  p = fma(p, r, 2.08767569878681e-09);
+  p = fma(p, r, 2.505210838544172e-08);
+  p = fma(p, r, 2.755731922398589e-07);
+  p = fma(p, r, 2.7557319223985893e-06);
+  p = fma(p, r, 2.48015873015873e-05);
+  p = fma(p, r, 1.984126984126984e-04);
+  p = fma(p, r, 1.388888888888889e-03);
+  p = fma(p, r, 8.333333333333333e-03);
+  p = fma(p, r, 4.1666666666666664e-02);
+  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double e = __hiloint2double(__double2hiint(p) + (ki << 20), __double2loint(p));
+  return fma(a, fma(a, 1.0 / 3.0, 1.0), 1.0) * e;
 }
 
 // T[rows of this warp][32 candidates] += W panel (staged rows x 16) * K* panel (16 x 32) on the FP64 tensor cores.
@@ -174,7 +227,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
     sal[j] = (j < n) ? alpha[j] : 0.0;
   }
   for (int i = tid; i < 2 * TC * zld; i += SW_THREADS) sxn[i] = 0.0;
-  if (tid < RING) { mbar_init(&full_bar[tid], NWARP / 2); mbar_init(&empty_bar[tid], NWARP); }
+  if (tid < RING) { mbar_init(&full_bar[tid], 4); mbar_init(&empty_bar[tid], NWARP); }
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   __syncthreads();   // zero padding and barriers are in place before any thread fills the candidate buffers
 
@@ -256,58 +309,66 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       if ((warp + t * NWARP) * 8 + cr + 4 * q < n) rowok |= 1u << (2 * t + q);
   // first row tile of this warp that reaches down to column j0 (tiles entirely above the diagonal are skipped)
   auto first_tile = [&](int j0) {
-    const int need = j0 - 7 - warp * 8;              // rt * 8 + 7 >= j0  <=>  t * 128 >= need
-    return need <= 0 ? 0 : (need + 127) >> 7;
+    const int need = j0 - 7 - warp * 8;              // rt * 8 + 7 >= j0  <=>  t * (8 NWARP) >= need
+    return need <= 0 ? 0 : (need + 8 * NWARP - 1) / (8 * NWARP);
   };
   // K* production only touches whole 4-column groups of the training rows when they exist in memory
   const bool zfast = kk4 * 4 <= kmax;
-  const int id = warp >> 1, ptr_ = id / CT, ptc = id % CT;
-  const int pjj = ptr_ * 8 + ar;
+  const int ptc = warp / DUTY;                       // candidate column tile this warp produces (both row tiles)
 
-  // ---- producer: the 8 x 8 tile (ptr_, ptc) of K* panel `chunk` of the tile with parity `par` into ring slot `slot`
+  // ---- producer: the 16 x 8 strip (both row tiles, column tile ptc) of K* panel `chunk` of the tile with parity `par`
+  //      into ring slot `slot`. Four independent DMMA chains and four Matern evaluations per thread: the latency of
+  //      the FP64 chains (which share the pipe with the other warps' DMMAs) overlaps instead of adding up.
   auto produce = [&](int chunk, int par, int slot, bool wait_empty, unsigned empty_parity) {
     const int j0 = chunk * KB;
-    const int jrow = min(j0 + pjj, n - 1);
-    const bool on = j0 + pjj < n;
-    // distances on the tensor cores: two accumulator pairs (even / odd k-steps) halve the dependent DMMA chain
-    double da0 = 0.0, da1 = 0.0, db0 = 0.0, db1 = 0.0;
-    const double *zrow = Zn + (size_t)jrow * kmax + ak;
+    const int jr0 = min(j0 + ar, n - 1), jr1 = min(j0 + 8 + ar, n - 1);
+    const bool on0 = j0 + ar < n, on1 = j0 + 8 + ar < n;
+    double a00 = 0.0, a01 = 0.0, b00 = 0.0, b01 = 0.0;     // rows j0 + ar     : even / odd k-steps
+    double a10 = 0.0, a11 = 0.0, b10 = 0.0, b11 = 0.0;     // rows j0 + 8 + ar
+    const double *z0p = Zn + (size_t)jr0 * kmax + ak;
+    const double *z1p = Zn + (size_t)jr1 * kmax + ak;
     const double *xrow = sxn + (size_t)par * TC * zld + (ptc * 8 + ar) * zld + ak;
     if (zfast) {
       int k4 = 0;
-      for (; k4 + 4 <= kk4; k4 += 4) {
-        const double z0 = __ldg(zrow + k4 * 4), z1 = __ldg(zrow + k4 * 4 + 4), z2 = __ldg(zrow + k4 * 4 + 8),
-                     z3 = __ldg(zrow + k4 * 4 + 12);
-        dmma_8x8x4(da0, da1, z0, xrow[k4 * 4]);
-        dmma_8x8x4(db0, db1, z1, xrow[k4 * 4 + 4]);
-        dmma_8x8x4(da0, da1, z2, xrow[k4 * 4 + 8]);
-        dmma_8x8x4(db0, db1, z3, xrow[k4 * 4 + 12]);
+      for (; k4 + 2 <= kk4; k4 += 2) {
+        const double u0 = __ldg(z0p + k4 * 4), u1 = __ldg(z0p + k4 * 4 + 4);
+        const double v0 = __ldg(z1p + k4 * 4), v1 = __ldg(z1p + k4 * 4 + 4);
+        const double x0 = xrow[k4 * 4], x1 = xrow[k4 * 4 + 4];
+        dmma_8x8x4(a00, a01, u0, x0);
+        dmma_8x8x4(a10, a11, v0, x0);
+        dmma_8x8x4(b00, b01, u1, x1);
+        dmma_8x8x4(b10, b11, v1, x1);
       }
-      for (; k4 < kk4; ++k4) dmma_8x8x4(da0, da1, __ldg(zrow + k4 * 4), xrow[k4 * 4]);
+      if (k4 < kk4) {
+        const double x0 = xrow[k4 * 4];
+        dmma_8x8x4(a00, a01, __ldg(z0p + k4 * 4), x0);
+        dmma_8x8x4(a10, a11, __ldg(z1p + k4 * 4), x0);
+      }
     } else {
       for (int k4 = 0; k4 < kk4; ++k4) {
-        const double z = (k4 * 4 + ak < kk) ? __ldg(zrow + k4 * 4) : 0.0;
-        dmma_8x8x4(da0, da1, z, xrow[k4 * 4]);
+        const bool cin = k4 * 4 + ak < kk;
+        const double x0 = xrow[k4 * 4];
+        dmma_8x8x4(a00, a01, cin ? __ldg(z0p + k4 * 4) : 0.0, x0);
+        dmma_8x8x4(a10, a11, cin ? __ldg(z1p + k4 * 4) : 0.0, x0);
       }
     }
-    const double zzj = szz[j0 + pjj], aj = sal[j0 + pjj];
+    const double zz0 = szz[j0 + ar], zz1 = szz[j0 + 8 + ar];
+    const double al0 = sal[j0 + ar], al1 = sal[j0 + 8 + ar];
     const double *xx = sxx + par * TC + ptc * 8 + ak * 2;
-    double kv[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const double dot = h ? (da1 + db1) : (da0 + db0);
-      const double sq = fmax((zzj + xx[h]) - 2.0 * dot, 0.0);
-      const double s2 = sq * inv_ell2;
-      const double dist = sqrt(fmax(s2, 1e-30));
-      const double v = (SQRT5 * dist + 1.0 + (5.0 / 3.0) * (dist * dist)) * exp(-SQRT5 * dist);
-      kv[h] = on ? v : 0.0;
-    }
-    if (par) { mean_o0 = fma(kv[0], aj, mean_o0); mean_o1 = fma(kv[1], aj, mean_o1); }
-    else { mean_e0 = fma(kv[0], aj, mean_e0); mean_e1 = fma(kv[1], aj, mean_e1); }
-    // the slot is free once all 16 warps consumed the panel that used it RING panels ago
+    const double xx0 = xx[0], xx1 = xx[1];
+    double k00 = matern52_fast(fmax((zz0 + xx0) - 2.0 * (a00 + b00), 0.0) * inv_ell2);
+    double k01 = matern52_fast(fmax((zz0 + xx1) - 2.0 * (a01 + b01), 0.0) * inv_ell2);
+    double k10 = matern52_fast(fmax((zz1 + xx0) - 2.0 * (a10 + b10), 0.0) * inv_ell2);
+    double k11 = matern52_fast(fmax((zz1 + xx1) - 2.0 * (a11 + b11), 0.0) * inv_ell2);
+    if (!on0) { k00 = 0.0; k01 = 0.0; }
+    if (!on1) { k10 = 0.0; k11 = 0.0; }
+    if (par) { mean_o0 = fma(k00, al0, fma(k10, al1, mean_o0)); mean_o1 = fma(k01, al0, fma(k11, al1, mean_o1)); }
+    else { mean_e0 = fma(k00, al0, fma(k10, al1, mean_e0)); mean_e1 = fma(k01, al0, fma(k11, al1, mean_e1)); }
+    // the slot is free once all warps consumed the panel that used it RING panels ago
     if (wait_empty) mbar_wait(&empty_bar[slot], empty_parity);
-    double *ks = sKs + slot * ks_sz + pjj * KS_LD + ptc * 8 + ak * 2;
-    *reinterpret_cast<double2 *>(ks) = make_double2(kv[0], kv[1]);
+    double *ks = sKs + slot * ks_sz + ar * KS_LD + ptc * 8 + ak * 2;
+    *reinterpret_cast<double2 *>(ks) = make_double2(k00, k01);
+    *reinterpret_cast<double2 *>(ks + 8 * KS_LD) = make_double2(k10, k11);
     __syncwarp();
     if (lane == 0) mbar_arrive(&full_bar[slot]);
   };
@@ -343,11 +404,12 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
     if (++pchunk == nchunks) { pchunk = 0; ppar ^= 1; }
   };
   for (; pG < ahead && pG < npan; advance_producer())
-    if (((warp + pG) & 1) == 0) produce(pchunk, ppar, pG & (RING - 1), false, 0u);
+    if (((warp + pG) % DUTY) == 0) produce(pchunk, ppar, pG & (RING - 1), false, 0u);
   if (npan > 0) issue_w(0, 0);
   cp_async_commit();
 
   int G = 0;
+  SWP_T0();
   for (long long k = 0; k < ntk; ++k) {
     const long long c0 = ((long long)blockIdx.x + k * gridDim.x) * TC;
     // candidates of the next tile (its K* production starts `ahead` panels before this tile ends)
@@ -364,20 +426,25 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
 
     for (int chunk = 0; chunk < nchunks; ++chunk, ++G) {
       const int wbuf = G & 1;
+      SWP(0);
       // K* tile of the panel `ahead` panels further on: warps alternate this duty. (Before the W prefetch: the release
       // arrival at the end of produce() waits for this warp's outstanding cp.async copies.)
       if (pG < npan) {
-        if (((warp + pG) & 1) == 0)
+        if (((warp + pG) % DUTY) == 0)
           produce(pchunk, ppar, pG & (RING - 1), pG >= RING, (unsigned)(((pG / RING) - 1) & 1));
         advance_producer();
       }
+      SWP(1);
       // W of the next panel of the sequence (wraps to panel 0 of the next tile)
       if (G + 1 < npan) issue_w(chunk + 1 < nchunks ? chunk + 1 : 0, wbuf ^ 1);
       cp_async_commit();
+      SWP(2);
       cp_async_wait<1>();
       __syncwarp();
+      SWP(3);
       const int slot = G & (RING - 1);
       mbar_wait(&full_bar[slot], (unsigned)((G / RING) & 1));
+      SWP(4);
       // ---- T += Wpanel (rows x 16) * Kspanel (16 x 32) on the FP64 tensor cores
       {
         const double *Wsb = sWw + wbuf * ww_sz;
@@ -385,26 +452,22 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
         const int t0 = first_tile(chunk * KB);
         if (chunk == nchunks - 1) {
           const int col0 = chunk * KB + ak;
-          switch (t0) {
-            case 0: mma_panel<0, true>(acc, Wsb, Ksb, aoff, ntw, col0, n); break;
-            case 1: mma_panel<1, true>(acc, Wsb, Ksb, aoff, ntw, col0, n); break;
-            case 2: mma_panel<2, true>(acc, Wsb, Ksb, aoff, ntw, col0, n); break;
-            case 3: mma_panel<3, true>(acc, Wsb, Ksb, aoff, ntw, col0, n); break;
-            default: break;
-          }
+          if (t0 == 0) mma_panel<0, true>(acc, Wsb, Ksb, aoff, ntw, col0, n);
+          else if (t0 == 1) mma_panel<1 % RT_MAX, true>(acc, Wsb, Ksb, aoff, ntw, col0, n);
+          else if (RT_MAX > 2 && t0 == 2) mma_panel<2 % RT_MAX, true>(acc, Wsb, Ksb, aoff, ntw, col0, n);
+          else if (RT_MAX > 3 && t0 == 3) mma_panel<3 % RT_MAX, true>(acc, Wsb, Ksb, aoff, ntw, col0, n);
         } else {
-          switch (t0) {
-            case 0: mma_panel<0, false>(acc, Wsb, Ksb, aoff, ntw, 0, n); break;
-            case 1: mma_panel<1, false>(acc, Wsb, Ksb, aoff, ntw, 0, n); break;
-            case 2: mma_panel<2, false>(acc, Wsb, Ksb, aoff, ntw, 0, n); break;
-            case 3: mma_panel<3, false>(acc, Wsb, Ksb, aoff, ntw, 0, n); break;
-            default: break;
-          }
+          if (t0 == 0) mma_panel<0, false>(acc, Wsb, Ksb, aoff, ntw, 0, n);
+          else if (t0 == 1) mma_panel<1 % RT_MAX, false>(acc, Wsb, Ksb, aoff, ntw, 0, n);
+          else if (RT_MAX > 2 && t0 == 2) mma_panel<2 % RT_MAX, false>(acc, Wsb, Ksb, aoff, ntw, 0, n);
+          else if (RT_MAX > 3 && t0 == 3) mma_panel<3 % RT_MAX, false>(acc, Wsb, Ksb, aoff, ntw, 0, n);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed(&empty_bar[slot]);
+      SWP(5);
     }
+    SWP(0);
     // ---- epilogue of the tile. Variance partials: thread holds T[row = rt*8 + lane/4][col = c*8 + (lane%4)*2 + {0,1}]
     double vpart[CT][2];
 #pragma unroll
@@ -447,7 +510,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
         sred[warp * TC + c * 8 + lane * 2 + 0] = vpart[c][0];
         sred[warp * TC + c * 8 + lane * 2 + 1] = vpart[c][1];
       }
-      sred[NWARP * TC + warp * 8 + lane * 2 + 0] = mp[0];   // [warp][8 candidates of tile column (warp/2) % CT]
+      sred[NWARP * TC + warp * 8 + lane * 2 + 0] = mp[0];   // [warp][8 candidates of tile column warp / DUTY]
       sred[NWARP * TC + warp * 8 + lane * 2 + 1] = mp[1];
     }
     __syncthreads();
@@ -459,7 +522,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       double ms = 0.0;
 #pragma unroll
       for (int w8 = 0; w8 < NWARP; ++w8)
-        if (((w8 >> 1) % CT) == c / 8) ms += sred[NWARP * TC + w8 * 8 + (c & 7)];
+        if (w8 / DUTY == c / 8) ms += sred[NWARP * TC + w8 * 8 + (c & 7)];
       const double mu = ymean + ystd * ms;
       const double var_raw = ystd * ystd * (kss - v);
       const double var = (var_raw >= 1e-10) ? var_raw : 1e-10;
@@ -485,6 +548,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       if (val > cta_best || (val == cta_best && gi < cta_idx)) { cta_best = val; cta_idx = gi; }
     }
     // (sred is rewritten only after the two barriers at the top of the next tile)
+    SWP(6);
   }
   cp_async_wait<0>();
   if (tid == 0) { a.best_val[blockIdx.x] = cta_best; a.best_idx[blockIdx.x] = cta_idx; }
@@ -525,6 +589,12 @@ __global__ void sweep_final_kernel(int nparts, const double *pv, const long long
 }
 
 }  // namespace
+
+#ifdef SWEEP_PROF
+extern "C" int pcabo_sweep_prof_read(long long *out) {
+  return cudaMemcpyFromSymbol(out, g_sweep_prof, sizeof(long long) * 16 * 8) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 extern "C" int pcabo_ei_sweep(const pcabo_gp_model *m, int run, long long ncand, long long idx0, const double *X,
                               const int *shift, const int *sstate, const double *lo, const double *hi, double *vals,

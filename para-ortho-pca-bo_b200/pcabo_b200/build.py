@@ -29,6 +29,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("PCABO_NVCC_EXTRA", "").split()      # e.g. -DSWEEP_PROF for tools/profile_sweep.py
     objs = []
     build_dir = os.path.join(HERE, "..", "build")
     os.makedirs(build_dir, exist_ok=True)
