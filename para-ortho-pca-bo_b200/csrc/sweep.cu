@@ -11,15 +11,16 @@
 // dimension is streamed in panels of 16 training points.
 //
 // v5 pipeline (no block-wide barrier inside a tile):
-//   * K* panels travel through an 8-deep shared-memory ring guarded by mbarriers (full: 8 producer warps, empty: 16
+//   * K* panels travel through an 8-deep shared-memory ring guarded by mbarriers (full: 4 producer warps, empty: 16
 //     consumer warps). Every warp is a consumer of every panel and, on alternate panels, the producer of one 8 x 8 tile
 //     of the panel FOUR panels ahead (distances on the tensor cores from the training rows read straight from L2, then
 //     sqrt / exp on the FP64 pipe), so the Matern latency of one warp hides behind the DMMAs of the fifteen others and
 //     production runs across tile boundaries (the ring never drains).
 //   * W is staged per warp: a warp copies only the rows of its own row tiles (cp.async, double buffered, 16 B chunks)
 //     and synchronises with nobody else; panels entirely above the diagonal of a row tile are skipped.
-//   * candidates of the NEXT tile are generated (scrambled Sobol, bit-identical to pcabo_sobol_points) while the
-//     current tile is consumed; the only block barriers are the two around the per-tile epilogue.
+//   * candidates of the NEXT tile are generated warp by warp (scrambled Sobol, bit-identical to pcabo_sobol_points)
+//     while the current tile is consumed, and the per-tile epilogue (variance / mean reduction, log-EI, arg-max) is
+//     done by one warp on rotating duty behind an mbarrier: there is no block-wide barrier in the steady state.
 #include "logei_core.cuh"
 
 #ifdef SWEEP_PROF
@@ -180,7 +181,7 @@ __host__ __device__ inline int sweep_zld(int kmax) { return ((kmax + 3) / 4) * 4
 __host__ __device__ inline size_t sweep_smem_bytes(int n, int kmax) {
   const int rows16 = ((n + 15) / 16) * 16, zld = sweep_zld(kmax);
   size_t d = (size_t)NWARP * 2 * RT_MAX * 8 * WS_LD + (size_t)RING * KB * KS_LD + 2 * (size_t)TC * zld + 2 * TC +
-             2 * (size_t)rows16 + 2 * NWARP * TC + 2 * RING + 8;
+             2 * (size_t)rows16 + 4 * NWARP * TC + 2 * RING + 8;
   return d * sizeof(double) + (size_t)kmax * MAXBIT * sizeof(int);
 }
 
@@ -204,8 +205,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
   double *const szz = sxx + 2 * TC;
   double *const sal = szz + rows16;
   double *const sred = sal + rows16;
-  unsigned long long *const full_bar = reinterpret_cast<unsigned long long *>(sred + 2 * NWARP * TC);
+  unsigned long long *const full_bar = reinterpret_cast<unsigned long long *>(sred + 4 * NWARP * TC);
   unsigned long long *const empty_bar = full_bar + RING;
+  unsigned long long *const xn_bar = empty_bar + RING;        // [2] candidates of the even / odd tile are in place
+  unsigned long long *const red_bar = xn_bar + 2;             // [2] partial sums of the even / odd tile are in place
   int *const ssst = reinterpret_cast<int *>(empty_bar + RING + 8);
   const double *W = m.W + (size_t)b * ld * ld;
   const double *Zn = m.Zn + (size_t)b * ld * kmax;
@@ -228,6 +231,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
   }
   for (int i = tid; i < 2 * TC * zld; i += SW_THREADS) sxn[i] = 0.0;
   if (tid < RING) { mbar_init(&full_bar[tid], 4); mbar_init(&empty_bar[tid], NWARP); }
+  if (tid < 2) { mbar_init(&xn_bar[tid], NWARP); mbar_init(&red_bar[tid], NWARP); }
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   __syncthreads();   // zero padding and barriers are in place before any thread fills the candidate buffers
 
@@ -241,46 +245,49 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
   const long long npanels = ntk * nchunks;     // global panel sequence of this CTA
   const int ahead = min(AHEAD, nchunks);       // production never runs further than into the next tile
 
-  // ---- normalised candidates of local tile k -> xn buffer k & 1 (all threads; caller synchronises)
+  // ---- this warp's share (TC / NWARP candidates) of the normalised candidates of local tile k -> xn buffer k & 1,
+  //      their squared norms, then one arrival on the tile-parity barrier: no block-wide barrier per tile
   auto gen_candidates = [&](long long k) {
     const long long c0 = ((long long)blockIdx.x + k * gridDim.x) * TC;
-    double *xb = sxn + (size_t)(k & 1) * TC * zld;
-    for (int idx = tid; idx < TC * kk; idx += SW_THREADS) {
-      const int c = idx / kk, j = idx % kk;
+    const int par = (int)(k & 1);
+    double *xb = sxn + (size_t)par * TC * zld;
+    for (int cc = 0; cc < TC / NWARP; ++cc) {
+      const int c = warp * (TC / NWARP) + cc;
       const long long ci = c0 + c;
-      double x = 0.0;
-      if (ci < a.ncand) {
-        if (a.X != nullptr) {
-          x = a.X[(size_t)ci * kmax + j];
-        } else {
-          const unsigned long long g = (unsigned long long)(a.idx0 + ci);
-          const int sh = a.shift[j];
-          double raw;
-          if (g == 0) {
-            raw = (double)((float)sh) * (1.0 / 1073741824.0);
+      double ss = 0.0;
+      for (int j = lane; j < kk; j += 32) {
+        double x = 0.0;
+        if (ci < a.ncand) {
+          if (a.X != nullptr) {
+            x = a.X[(size_t)ci * kmax + j];
           } else {
-            int q = sh;
-            unsigned gray = (unsigned)(g ^ (g >> 1));
-            while (gray) {
-              const int l = __ffs(gray) - 1;
-              q ^= ssst[j * MAXBIT + l];
-              gray &= gray - 1;
+            const unsigned long long g = (unsigned long long)(a.idx0 + ci);
+            const int sh = a.shift[j];
+            double raw;
+            if (g == 0) {
+              raw = (double)((float)sh) * (1.0 / 1073741824.0);
+            } else {
+              int q = sh;
+              unsigned gray = (unsigned)(g ^ (g >> 1));
+              while (gray) {
+                const int l = __ffs(gray) - 1;
+                q ^= ssst[j * MAXBIT + l];
+                gray &= gray - 1;
+              }
+              raw = (double)q * (1.0 / 1073741824.0);
             }
-            raw = (double)q * (1.0 / 1073741824.0);
+            x = __dadd_rn(a.lo[j], __dmul_rn(__dsub_rn(a.hi[j], a.lo[j]), raw));
           }
-          x = __dadd_rn(a.lo[j], __dmul_rn(__dsub_rn(a.hi[j], a.lo[j]), raw));
         }
+        const double xv = (x - off[j]) / coef[j];
+        xb[c * zld + j] = xv;
+        ss = fma(xv, xv, ss);
       }
-      xb[c * zld + j] = (x - off[j]) / coef[j];
+      ss = warp_sum(ss);
+      if (lane == 0) sxx[par * TC + c] = ss;
     }
-  };
-  auto gen_norms = [&](long long k) {
-    if (tid < TC) {
-      const double *xb = sxn + (size_t)(k & 1) * TC * zld;
-      double acc = 0.0;
-      for (int dmm = 0; dmm < kk; ++dmm) { const double x = xb[tid * zld + dmm]; acc = fma(x, x, acc); }
-      sxx[(k & 1) * TC + tid] = acc;
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&xn_bar[par]);
   };
 
   // partial alpha . k of this thread's two candidates (its K* tiles), one set per tile parity
@@ -319,8 +326,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
   // ---- producer: the 16 x 8 strip (both row tiles, column tile ptc) of K* panel `chunk` of the tile with parity `par`
   //      into ring slot `slot`. Four independent DMMA chains and four Matern evaluations per thread: the latency of
   //      the FP64 chains (which share the pipe with the other warps' DMMAs) overlaps instead of adding up.
-  auto produce = [&](int chunk, int par, int slot, bool wait_empty, unsigned empty_parity) {
+  auto produce = [&](int chunk, int par, int slot, bool wait_empty, unsigned empty_parity, unsigned xn_parity) {
     const int j0 = chunk * KB;
+    mbar_wait(&xn_bar[par], xn_parity);               // complete long ago except right after the prologue
     const int jr0 = min(j0 + ar, n - 1), jr1 = min(j0 + 8 + ar, n - 1);
     const bool on0 = j0 + ar < n, on1 = j0 + 8 + ar < n;
     double a00 = 0.0, a01 = 0.0, b00 = 0.0, b01 = 0.0;     // rows j0 + ar     : even / odd k-steps
@@ -393,18 +401,15 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
 
   // ---- prologue: candidates of tile 0, first `ahead` panels of K*, W panel 0
   if (ntk > 0) gen_candidates(0);
-  __syncthreads();
-  if (ntk > 0) gen_norms(0);
-  __syncthreads();
   const int npan = (int)npanels;
   // producer cursor: panel pG = G + ahead of the global sequence, as (chunk, tile parity)
-  int pG = 0, pchunk = 0, ppar = 0;
+  int pG = 0, pchunk = 0, ptile = 0;
   auto advance_producer = [&]() {
     ++pG;
-    if (++pchunk == nchunks) { pchunk = 0; ppar ^= 1; }
+    if (++pchunk == nchunks) { pchunk = 0; ++ptile; }
   };
   for (; pG < ahead && pG < npan; advance_producer())
-    if (((warp + pG) % DUTY) == 0) produce(pchunk, ppar, pG & (RING - 1), false, 0u);
+    if (((warp + pG) % DUTY) == 0) produce(pchunk, ptile & 1, pG & (RING - 1), false, 0u, (unsigned)((ptile >> 1) & 1));
   if (npan > 0) issue_w(0, 0);
   cp_async_commit();
 
@@ -414,9 +419,6 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
     const long long c0 = ((long long)blockIdx.x + k * gridDim.x) * TC;
     // candidates of the next tile (its K* production starts `ahead` panels before this tile ends)
     if (k + 1 < ntk) gen_candidates(k + 1);
-    __syncthreads();
-    if (k + 1 < ntk) gen_norms(k + 1);
-    __syncthreads();
     // accumulators: warp owns row tiles rt = warp, warp + 16, ...; 4 column tiles each
     double acc[RT_MAX][CT][2];
 #pragma unroll
@@ -431,7 +433,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       // arrival at the end of produce() waits for this warp's outstanding cp.async copies.)
       if (pG < npan) {
         if (((warp + pG) % DUTY) == 0)
-          produce(pchunk, ppar, pG & (RING - 1), pG >= RING, (unsigned)(((pG / RING) - 1) & 1));
+          produce(pchunk, ptile & 1, pG & (RING - 1), pG >= RING, (unsigned)(((pG / RING) - 1) & 1),
+                  (unsigned)((ptile >> 1) & 1));
         advance_producer();
       }
       SWP(1);
@@ -504,25 +507,31 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       v += __shfl_xor_sync(0xffffffffu, v, 16);
       mp[h] = v;
     }
+    // partial sums of this tile -> buffer of its parity; one arrival per warp. The warp on epilogue duty (they rotate)
+    // waits for all sixteen, everybody else goes straight on to the next tile.
+    const int epar = (int)(k & 1);
+    double *rb = sred + (size_t)epar * 2 * NWARP * TC;
     if (lane < 4) {
 #pragma unroll
       for (int c = 0; c < CT; ++c) {
-        sred[warp * TC + c * 8 + lane * 2 + 0] = vpart[c][0];
-        sred[warp * TC + c * 8 + lane * 2 + 1] = vpart[c][1];
+        rb[warp * TC + c * 8 + lane * 2 + 0] = vpart[c][0];
+        rb[warp * TC + c * 8 + lane * 2 + 1] = vpart[c][1];
       }
-      sred[NWARP * TC + warp * 8 + lane * 2 + 0] = mp[0];   // [warp][8 candidates of tile column warp / DUTY]
-      sred[NWARP * TC + warp * 8 + lane * 2 + 1] = mp[1];
+      rb[NWARP * TC + warp * 8 + lane * 2 + 0] = mp[0];   // [warp][8 candidates of tile column warp / DUTY]
+      rb[NWARP * TC + warp * 8 + lane * 2 + 1] = mp[1];
     }
-    __syncthreads();
-    if (tid < TC) {
-      const int c = tid;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&red_bar[epar]);
+    if (warp == (int)(k % NWARP)) {
+      mbar_wait(&red_bar[epar], (unsigned)((k >> 1) & 1));
+      const int c = lane;
       double v = 0.0;
 #pragma unroll
-      for (int w8 = 0; w8 < NWARP; ++w8) v += sred[w8 * TC + c];
+      for (int w8 = 0; w8 < NWARP; ++w8) v += rb[w8 * TC + c];
       double ms = 0.0;
 #pragma unroll
       for (int w8 = 0; w8 < NWARP; ++w8)
-        if (w8 / DUTY == c / 8) ms += sred[NWARP * TC + w8 * 8 + (c & 7)];
+        if (w8 / DUTY == c / 8) ms += rb[NWARP * TC + w8 * 8 + (c & 7)];
       const double mu = ymean + ystd * ms;
       const double var_raw = ystd * ystd * (kss - v);
       const double var = (var_raw >= 1e-10) ? var_raw : 1e-10;
@@ -537,7 +546,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       } else {
         val = -INFINITY;
       }
-      // tile arg-max (first occurrence) over the 32 candidates of warp 0
+      // tile arg-max (first occurrence) over the 32 candidates
       long long gi = a.idx0 + ci;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -547,11 +556,25 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       }
       if (val > cta_best || (val == cta_best && gi < cta_idx)) { cta_best = val; cta_idx = gi; }
     }
-    // (sred is rewritten only after the two barriers at the top of the next tile)
+    // (the buffer of this parity is rewritten two tiles later, which nobody reaches before the duty warp, in program
+    // order behind this epilogue, has consumed the panels in between)
     SWP(6);
   }
   cp_async_wait<0>();
-  if (tid == 0) { a.best_val[blockIdx.x] = cta_best; a.best_idx[blockIdx.x] = cta_idx; }
+  // every warp carries the best of the tiles it closed: combine
+  __syncthreads();
+  double *fin_v = sred;
+  long long *fin_i = reinterpret_cast<long long *>(sred + NWARP);
+  if (lane == 0) { fin_v[warp] = cta_best; fin_i[warp] = cta_idx; }
+  __syncthreads();
+  if (tid == 0) {
+    double bv = -INFINITY;
+    long long bi = 0x7fffffffffffffffLL;
+    for (int w8 = 0; w8 < NWARP; ++w8)
+      if (fin_v[w8] > bv || (fin_v[w8] == bv && fin_i[w8] < bi)) { bv = fin_v[w8]; bi = fin_i[w8]; }
+    a.best_val[blockIdx.x] = bv;
+    a.best_idx[blockIdx.x] = bi;
+  }
 }
 
 __global__ void sweep_final_kernel(int nparts, const double *pv, const long long *pi, double *best_val,
