@@ -16,8 +16,12 @@
 
 #ifdef __CUDACC__
 #define LB_HD __host__ __device__
+// (the big phases stay inlined: as separate functions they take the Work / Ctx structs by reference through local
+// memory, which measured 50 % slower on the B200)
+#define LB_PHASE __host__ __device__
 #else
 #define LB_HD
+#define LB_PHASE
 #endif
 
 #if defined(__CUDACC__) || defined(__GNUC__)
@@ -96,6 +100,9 @@ __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(F
 // factorisation (Cholesky of the (1,1) block, R12 = R11^-T A12, Cholesky of A22 + R12^T R12) in one sweep.
 // Compact loops on purpose: the optimiser warp runs alone on its scheduler, so straight-line unrolled code only
 // thrashes the instruction cache. Returns 0 or 1 + index of the first non-positive pivot.
+// Row k is published through shared memory (three warp barriers per pivot) and every lane only loops over the rows of
+// its own column; a variant that broadcasts row k by shuffles instead was slower for the 2m x 2m matrix (n - k - 1
+// broadcasts per pivot on every lane: 18.8 k -> 29 k cycles on B200).
 __device__ inline int chol_upper_warp(double *A, int lda, int n, int nsplit, double *rdiag) {
   const int lane = threadIdx.x & 31;
   int bad = 0;
@@ -287,7 +294,7 @@ LB_HD double projgr(T &tm, const Work &w) {
 
 // ------------------------------------------------------------------------------------------------ Cauchy point
 template <class T>
-LB_HD void cauchy(T &tm, Work &w, int col, double theta, double sbgnrm, int &nseg) {
+LB_PHASE void cauchy(T &tm, Work &w, int col, double theta, double sbgnrm, int &nseg) {
   const int n = w.n;
   nseg = 0;
   if (sbgnrm <= 0.0) {
@@ -468,7 +475,7 @@ inline void HostTeam::formk_products(const Work &w, int col, double theta) { for
 
 // LEL^T factorisation of the indefinite K (formk). Free set: iwhere <= 0. Returns 0 or a failure code.
 template <class T>
-LB_HD int formk(T &tm, Work &w, int col, double theta, int *flag) {
+LB_PHASE int formk(T &tm, Work &w, int col, double theta, int *flag) {
   tm.formk_products(w, col, theta);   // the team may hand this O(m^2 n) part to more threads than itself
   tm.sync();
   tm.tick(10);
@@ -507,7 +514,7 @@ LB_HD int formk(T &tm, Work &w, int col, double theta, int *flag) {
 
 // r = -Z'(B(xcp - xk) + g) for the free variables (full-length array, active entries unused)
 template <class T>
-LB_HD void cmprlb(T &tm, Work &w, int col, double theta) {
+LB_PHASE void cmprlb(T &tm, Work &w, int col, double theta) {
   const int n = w.n;
   bmv(tm, w, col, w.c, w.p);  // p = M c (p is free for reuse after cauchy)
   {
@@ -530,7 +537,7 @@ LB_HD void cmprlb(T &tm, Work &w, int col, double theta) {
 // Subspace minimisation with the projected (Morales-Nocedal) safeguard. On entry w.z = xcp, w.r = reduced gradient;
 // on exit w.z holds the subspace minimiser. xk = w.x, gk = w.g.
 template <class T>
-LB_HD void subsm(T &tm, Work &w, int col, double theta) {
+LB_PHASE void subsm(T &tm, Work &w, int col, double theta) {
   const int n = w.n;
   double part[M2];
 #ifdef __CUDA_ARCH__
@@ -574,12 +581,13 @@ LB_HD void subsm(T &tm, Work &w, int col, double theta) {
   tm.sync();
   // d = (1/theta) r + (1/theta^2) Z'W wv ; projected step; remember xcp in xp
   double iword_l = 0.0;
+  const double rtheta = 1.0 / theta;   // one reciprocal instead of a division per (variable, pair)
   for (int i = tm.tid; i < n; i += tm.nt) {
     w.xp[i] = w.z[i];
     if (w.iwhere[i] <= 0) {
       double di = w.r[i];
-      for (int j = 0; j < col; ++j) di += w.wy[j * n + i] * w.wv[j] / theta + w.ws[j * n + i] * w.wv[col + j];
-      di *= 1.0 / theta;
+      for (int j = 0; j < col; ++j) di += w.wy[j * n + i] * w.wv[j] * rtheta + w.ws[j * n + i] * w.wv[col + j];
+      di *= rtheta;
       w.r[i] = di;  // r now holds the Newton direction on the free variables
       double xk = w.z[i] + di;
       xk = fmax(w.l[i], xk);
@@ -752,7 +760,7 @@ LB_HD inline int dcsrch_step(LineSearch &ls, double f, double g, double &stp, do
 // Append the pair (s = d, y = r) to the history (oldest first), update S'Y, S'S and theta (matupd), then form and
 // factor T = theta S'S + L D^-1 L' (formt). Returns 0 or -3 if T is not positive definite.
 template <class T>
-LB_HD int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, double dr, double stp, double dtd,
+LB_PHASE int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, double dr, double stp, double dtd,
                        int *flag) {
   const int n = w.n;
   if (col == M) {  // drop the oldest pair
@@ -768,6 +776,20 @@ LB_HD int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, doubl
       for (int j = 0; j < M - 1; ++j) { w.ws[j * n + i] = a[j]; w.wy[j * n + i] = b[j]; }
     }
     tm.sync();
+#ifdef __CUDA_ARCH__
+    if constexpr (T::kWarpRegs) {
+      // S'Y and S'S move up-left by one, row by row (row i is rewritten from row i + 1 before row i + 1 is): lanes
+      // 0..8 carry S'Y, lanes 16..24 carry S'S, one element of the row each
+      const int j = tm.lane & 15;
+      double *mat = (tm.lane < 16) ? w.sy : w.ss;
+      for (int i = 0; i < M - 1; ++i) {
+        double v = 0.0;
+        if (j < M - 1) v = mat[(i + 1) * M + j + 1];
+        tm.wsync();
+        if (j < M - 1) mat[i * M + j] = v;
+      }
+    } else
+#endif
     if (tm.tid == 0) {
       for (int i = 0; i < M - 1; ++i)
         for (int j = 0; j < M - 1; ++j) { w.sy[i * M + j] = w.sy[(i + 1) * M + j + 1]; w.ss[i * M + j] = w.ss[(i + 1) * M + j + 1]; }
@@ -815,7 +837,7 @@ LB_HD int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, doubl
     if (i > j) continue;
     double s = 0.0;
     const int k1 = (i < j ? i : j);
-    for (int k = 0; k < k1; ++k) s += w.sy[i * M + k] * w.sy[j * M + k] / w.sy[k * M + k];
+    for (int k = 0; k < k1; ++k) s += w.sy[i * M + k] * w.sy[j * M + k] * w.rsy[k];   // rsy = 1 / diag(S'Y)
     w.wt[i * M + j] = s + theta * w.ss[i * M + j];
   }
   tm.sync();

@@ -110,37 +110,14 @@ template <int P>
 __device__ __forceinline__ void strided_dot(double (&acc)[P], const double *__restrict__ M, long ld, int col, int j0,
                                             int j1, const double *__restrict__ v, int np) {
   int j = j0;
-  if constexpr (P <= 8) {
-    if (j + 16 <= j1) {
-      // two accumulator sets: 2 P independent FMA chains per thread hide the FP64 pipe latency
-      double acc2[P];
+  for (; j + 16 <= j1; j += 16) {
+    double w16[16];
 #pragma unroll
-      for (int p = 0; p < P; ++p) acc2[p] = 0.0;
-      for (; j + 16 <= j1; j += 16) {
-        double w16[16];
+    for (int u = 0; u < 16; ++u) w16[u] = M[(long)(j + u) * ld + col];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) w16[u] = M[(long)(j + u) * ld + col];
+    for (int u = 0; u < 16; ++u)
 #pragma unroll
-        for (int u = 0; u < 16; u += 2)
-#pragma unroll
-          for (int p = 0; p < P; ++p) {
-            acc[p] = fma(w16[u], v[p * np + j + u], acc[p]);
-            acc2[p] = fma(w16[u + 1], v[p * np + j + u + 1], acc2[p]);
-          }
-      }
-#pragma unroll
-      for (int p = 0; p < P; ++p) acc[p] += acc2[p];
-    }
-  } else {
-    for (; j + 16 <= j1; j += 16) {
-      double w16[16];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) w16[u] = M[(long)(j + u) * ld + col];
-#pragma unroll
-      for (int u = 0; u < 16; ++u)
-#pragma unroll
-        for (int p = 0; p < P; ++p) acc[p] = fma(w16[u], v[p * np + j + u], acc[p]);
-    }
+      for (int p = 0; p < P; ++p) acc[p] = fma(w16[u], v[p * np + j + u], acc[p]);
   }
   for (; j + 4 <= j1; j += 4) {
     double w4[4];

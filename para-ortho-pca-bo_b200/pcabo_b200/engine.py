@@ -128,6 +128,16 @@ class BatchedBOEngine:
         self.current_best[b] = max(fe) if self.maximization else min(fe)
         self.current_best_index[b] = fe.index(self.current_best[b], self.current_best_index[b])
 
+    def _update_best_with_last(self, b):
+        """_assign_new_best after ONE appended value, without rescanning the history: a strictly better value is new and
+        sits at the last index; otherwise min / max and `index(best, previous index)` are unchanged (ties keep the
+        earlier position) -- identical to AbstractBayesianOptimizer.assign_new_best (:196-208)."""
+        fe = self.f_evals[b]
+        v = fe[-1]
+        if (v > self.current_best[b]) if self.maximization else (v < self.current_best[b]):
+            self.current_best[b] = v
+            self.current_best_index[b] = len(fe) - 1
+
     def _evaluate(self, b, x):
         return float(self.problems[b](x))
 
@@ -392,8 +402,11 @@ class BatchedBOEngine:
         B, D, R = self.B, self.D, self.num_restarts
         k_host = self.pca["k"].cpu().numpy().astype(np.int64) if self.algorithm == "pca" else np.full(B, D, np.int64)
         self.k_host = k_host
-        box_lo, box_hi = self.gp.box_lo.cpu(), self.gp.box_hi.cpu()
-        self.stats["d2h_bytes"] += B * 4 + 2 * B * D * 8
+        box_lo = box_hi = None
+        self.stats["d2h_bytes"] += B * 4
+        if self.optimizer == "scipy":              # the host optimiser needs the search box; the device one reads it in HBM
+            box_lo, box_hi = self.gp.box_lo.cpu(), self.gp.box_hi.cpu()
+            self.stats["d2h_bytes"] += 2 * B * D * 8
         runs = list(range(B))
         ics = self._initial_conditions(runs, k_host)
         if self.optimizer == "scipy":
@@ -459,7 +472,7 @@ class BatchedBOEngine:
                 new_f[b] = f_dev[b] if f_dev is not None else self._evaluate(b, x_new[b])
             self.x_evals[b].append(x_new[b].copy())
             self.f_evals[b].append(float(new_f[b]))
-            self._assign_new_best(b)
+            self._update_best_with_last(b)
         self.X[:, n].copy_(torch.from_numpy(x_new))
         self.f[:, n].copy_(torch.from_numpy(new_f))
         self.stats["h2d_bytes"] += B * D * 8 + B * 8

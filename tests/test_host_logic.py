@@ -151,3 +151,28 @@ def test_world_size_2_gloo_sharding_and_argmax():
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
     assert "argmax ok" in outs[0]
+
+
+def test_incremental_best_tracking_equals_rescan():
+    """BatchedBOEngine._update_best_with_last == AbstractBayesianOptimizer.assign_new_best (:196-208) on sequences with
+    ties, penalties and both optimisation senses (host logic only: no engine is constructed)."""
+    from pcabo_b200.engine import BatchedBOEngine
+    rng = np.random.RandomState(0)
+    for maximization in (False, True):
+        for trial in range(20):
+            vals = rng.choice([1000.0, -1000.0, 3.5, 3.5, 7.25, -2.0, 0.0], size=60).tolist()
+            vals += rng.randn(20).tolist()
+            rng.shuffle(vals)
+            a = BatchedBOEngine.__new__(BatchedBOEngine)
+            b = BatchedBOEngine.__new__(BatchedBOEngine)
+            for e in (a, b):
+                e.maximization = maximization
+                e.f_evals = [list(vals[:5])]
+                e.current_best, e.current_best_index = [0.0], [0]
+                BatchedBOEngine._assign_new_best(e, 0)
+            for v in vals[5:]:
+                a.f_evals[0].append(v)
+                b.f_evals[0].append(v)
+                a._assign_new_best(0)
+                b._update_best_with_last(0)
+                assert (a.current_best, a.current_best_index) == (b.current_best, b.current_best_index)
