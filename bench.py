@@ -224,7 +224,7 @@ def run_ours(args):
         prob = BatchedBBOB([fids[i] for i in sel], [insts[i] for i in sel], DIM, device=dev)
         subs.append(BatchedBOEngine(prob, DIM, prob.bounds, BUDGET, N_DOE, [seeds[i] for i in sel], algorithm="pca",
                                     device=dev, optimizer=args.optimizer,
-                                    host_threads=max(1, (os.cpu_count() or 1) // (S * max(1, world)))))
+                                    host_threads=max(1, (os.cpu_count() or 1) // max(1, world))))
     eng = subs[0] if S == 1 else PipelinedEngines(subs)
     eng.initial_design()
     if args.n_start > N_DOE:                       # optional fast-forward (untimed) to a later point of the runs
@@ -315,12 +315,15 @@ def run_ours(args):
                 "launches": len(evs), "avg_launch_us": 1e3 * tot_ms / len(evs),
                 "share_of_step": tot_ms * 1e-3 / secs / S}
     cpu_base = None
-    if world == 1 and rank == 0 and not args.no_cpu_baseline and S == 1:
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
         # the CPU oracle continues the first `cores` runs from histories this run produced, at points spread over the
         # n range that was timed (a bounded sample: ~10-30 s of host work)
         n_lo, n_hi = n_first, eng.n
         npts = [n_lo] if n_hi - n_lo < 30 else [n_lo, (n_lo + n_hi) // 2, max(n_lo, n_hi - args.cpu_steps)]
-        hist = [(fids[b], insts[b], eng.x_evals[b], eng.f_evals[b]) for b in range(0, B, max(1, B // (os.cpu_count() or 1)))]
+        allh = []
+        for s_, e_ in enumerate(subs):            # sub-batch s_ holds runs s_, s_ + S, ... of the rank's list
+            allh += [(fids[s_ + S * j], insts[s_ + S * j], e_.x_evals[j], e_.f_evals[j]) for j in range(e_.B)]
+        hist = allh[::max(1, B // (os.cpu_count() or 1))]
         cits, cores, csecs = oracle_sampled_throughput(hist, npts, args.cpu_steps)
         cpu_base = {"value": cits, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"{cores} of the 90 runs, one per host core (1 torch thread each), continuing this run's "
@@ -369,7 +372,8 @@ def main():
                     help="BO iterations per core and sample point of the cpu_baseline leg (the first is warm-up)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sub-batches", type=int, default=1,
-                    help="split the per-GPU batch into S independently stepped sub-batches on S CUDA streams")
+                    help="split the per-GPU batch into S sub-batches on S CUDA streams, software-pipelined by one host "
+                         "thread (the optimiser kernel of one overlaps the host work of the next)")
     ap.add_argument("--ref-budget-s", type=float, default=240.0, help="wall-time budget of the reference arm")
     ap.add_argument("--trace", default=None, help="write per-step wall times (ms) to this JSON file (adds a sync per step)")
     ap.add_argument("--phases", action="store_true", help="print a host wall-time breakdown per phase (adds syncs)")

@@ -119,6 +119,8 @@ class BatchedBOEngine:
         self.noise_copied = torch.cuda.Event()
         self.overlap_hook = None
         self.lb_out = None
+        self.h_status = self.h_nfev = self.h_nit = None
+        self.pending = None         # state of a step between step_begin() and step_end()
         self.phase_times = None     # set to {} to accumulate host wall time per phase (adds device syncs)
         self.kernel_events = None   # set to [] to record CUDA-event pairs around every value+grad log-EI launch
 
@@ -357,12 +359,12 @@ class BatchedBOEngine:
             self.last.setdefault("nfev", {})[b] = [probs[(b, ci)].nfev for ci in range(len(chunks))]
         return cands, warned
 
-    def _optimize_device(self, d_x, k_host, runs=None, out=None):
-        """gen_candidates_scipy for all (or the listed) runs and chunks in ONE launch of the device-resident L-BFGS-B
-        kernel; with `runs` the rows of those runs in `out` are re-optimised in place (botorch's retry).
-
-        Returns (the output dict with the device tensor of clamped candidates cand [B, R, D], warned {b: bool})."""
-        B, D, R = self.B, self.D, self.num_restarts
+    def _launch_device(self, d_x, k_host, runs=None, out=None):
+        """Enqueue gen_candidates_scipy for all (or the listed) runs and chunks: ONE launch of the device-resident
+        L-BFGS-B kernel, then the asynchronous read-back of the per-chunk status words into pinned memory. With `runs`
+        the rows of those runs in `out` are re-optimised in place (botorch's retry). Returns a handle for
+        _finish_device; the host is free until then."""
+        B = self.B
         sel = list(range(B)) if runs is None else list(runs)
         ev = None
         if self.kernel_events is not None:
@@ -373,12 +375,25 @@ class BatchedBOEngine:
                                run_idx=run_idx, k_bound=int(max(k_host[b] for b in sel)))
         if ev is not None:
             ev[1].record()
+        if self.h_status is None or self.h_status.shape != out["status"].shape:
+            self.h_status = torch.zeros(out["status"].shape, dtype=torch.int32).pin_memory()
+            self.h_nfev, self.h_nit = torch.zeros_like(self.h_status).pin_memory(), torch.zeros_like(self.h_status).pin_memory()
+        self.h_status.copy_(out["status"], non_blocking=True)
+        self.h_nfev.copy_(out["nfev"], non_blocking=True)
+        self.h_nit.copy_(out["nit"], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
         if self.overlap_hook is not None:        # host work that does not depend on the result runs under the kernel
             hook, self.overlap_hook = self.overlap_hook, None
             hook()
-        status = out["status"].cpu().numpy()
-        nfev = out["nfev"].cpu().numpy()
-        nit = out["nit"].cpu().numpy()
+        return dict(out=out, sel=sel, ev=ev, done=done, k_host=k_host)
+
+    def _finish_device(self, h):
+        """Wait for the optimiser kernel of `h`. Returns (the output dict with the device tensor of clamped candidates
+        cand [B, R, D], warned {b: bool})."""
+        h["done"].synchronize()
+        out, sel, ev, k_host = h["out"], h["sel"], h["ev"], h["k_host"]
+        status, nfev, nit = self.h_status.numpy(), self.h_nfev.numpy(), self.h_nit.numpy()
         if (status[sel] < 0).any():
             raise PcaboError("pcabo_lbfgsb_logei_runs: k_bound below a run's k")
         if ev is not None:
@@ -397,19 +412,33 @@ class BatchedBOEngine:
             self.last.setdefault("nfev", {})[b] = nfev[b].tolist()
         return out, warned
 
-    def _propose(self):
-        """optimize_acqf (PCA_BO.py:607-614): returns device tensor z_new [B, D] and its log-EI values [B]."""
-        B, D, R = self.B, self.D, self.num_restarts
+    def _optimize_device(self, d_x, k_host, runs=None, out=None):
+        """_launch_device + _finish_device (blocking)."""
+        return self._finish_device(self._launch_device(d_x, k_host, runs=runs, out=out))
+
+    def _propose_begin(self):
+        """optimize_acqf (PCA_BO.py:607-614) up to the point where the optimiser kernel is in flight (device mode)."""
+        B, D = self.B, self.D
         k_host = self.pca["k"].cpu().numpy().astype(np.int64) if self.algorithm == "pca" else np.full(B, D, np.int64)
         self.k_host = k_host
-        box_lo = box_hi = None
         self.stats["d2h_bytes"] += B * 4
-        if self.optimizer == "scipy":              # the host optimiser needs the search box; the device one reads it in HBM
-            box_lo, box_hi = self.gp.box_lo.cpu(), self.gp.box_hi.cpu()
-            self.stats["d2h_bytes"] += 2 * B * D * 8
         runs = list(range(B))
         ics = self._initial_conditions(runs, k_host)
+        st = dict(k_host=k_host, runs=runs, ics=ics, handle=None)
+        if self.optimizer == "device":
+            st["t_launch"] = perf_counter()
+            self.overlap_hook = self._prefetch_noise
+            st["handle"] = self._launch_device(ics, k_host, out=self.lb_out)
+        return st
+
+    def _propose_end(self, st):
+        """The rest of optimize_acqf: returns device tensor z_new [B, D] and its log-EI values [B]."""
+        B, D, R = self.B, self.D, self.num_restarts
+        k_host, runs, ics = st["k_host"], st["runs"], st["ics"]
         if self.optimizer == "scipy":
+            # the host optimiser needs the search box; the device one reads it in HBM
+            box_lo, box_hi = self.gp.box_lo.cpu(), self.gp.box_hi.cpu()
+            self.stats["d2h_bytes"] += 2 * B * D * 8
             cands, warned = self._optimize_scipy(runs, ics, k_host, box_lo, box_hi)
             retry = [b for b in runs if warned[b]]
             if retry:  # botorch retry_on_optimization_warning: new initial conditions, one more attempt
@@ -423,10 +452,8 @@ class BatchedBOEngine:
             d_c = h_c.to(self.device, non_blocking=True)
             self.stats["h2d_bytes"] += h_c.numel() * 8
         else:
-            tp = perf_counter()
-            self.overlap_hook = self._prefetch_noise
-            self.lb_out, warned = self._optimize_device(ics, k_host, out=self.lb_out)
-            self._phase("lbfgsb_kernel", tp)
+            self.lb_out, warned = self._finish_device(st["handle"])
+            self._phase("lbfgsb_kernel", st["t_launch"])
             retry = [b for b in runs if warned[b]]
             if retry:
                 self.stats["retries"] += len(retry)
@@ -441,16 +468,27 @@ class BatchedBOEngine:
         self.stats["kernel_launches"] += 2
         return z_new.contiguous(), best_val
 
-    def step(self):
-        """One BO iteration for all runs (PCA_BO.py:178-281)."""
+    def step_begin(self):
+        """First half of a BO iteration: model fit, raw samples, initial conditions, optimiser kernel launched. The
+        call returns while the kernel runs (device mode), so a caller can interleave several engines on different
+        streams; step_end() completes the iteration. Returns False when the budget is exhausted."""
         if self.n >= self.budget:
+            self.pending = None
             return False
-        B, D, n = self.B, self.D, self.n
         self._fit_models()
         t0 = self._sync_time()
-        z_new, acq_val = self._propose()
+        self.pending = dict(t0=t0, st=self._propose_begin())
+        return True
+
+    def step_end(self):
+        """Second half of a BO iteration (PCA_BO.py:239-281): candidates, inverse map, objective, bookkeeping."""
+        if self.pending is None:
+            return False
+        B, D, n = self.B, self.D, self.n
+        z_new, acq_val = self._propose_end(self.pending["st"])
         t1 = self._sync_time()
-        self.timing_logs["optimize_acqf"].append(t1 - t0)
+        self.timing_logs["optimize_acqf"].append(t1 - self.pending["t0"])
+        self.pending = None
         tp = perf_counter()
         if self.algorithm == "pca":
             im = ops.inverse_map(z_new, self.pca["k"], self.pca["V"], self.pca["m2"], self.pca["xbar"], self.lo, self.hi)
@@ -482,6 +520,13 @@ class BatchedBOEngine:
         self._phase("inverse_map_objective_bookkeeping", tp)
         return True
 
+
+    def step(self):
+        """One BO iteration for all runs (PCA_BO.py:178-281)."""
+        if not self.step_begin():
+            return False
+        return self.step_end()
+
     def run(self, max_iterations=None):
         if self.n == 0:
             self.initial_design()
@@ -493,42 +538,43 @@ class BatchedBOEngine:
 
 
 class PipelinedEngines:
-    """S independent sub-batches of runs, each a BatchedBOEngine on its own CUDA stream driven by its own host thread.
+    """S independent sub-batches of runs, each a BatchedBOEngine on its own CUDA stream, interleaved by ONE host thread.
 
-    Runs are independent, so splitting the per-GPU batch changes no result; it lets the host-side RNG work
-    of one sub-batch overlap the optimiser kernel of another (the kernel is latency bound: a sub-batch of 30 runs takes
-    as long as one of 90, and kernels of different streams share the SMs)."""
+    Runs are independent, so splitting the per-GPU batch changes no result. The optimiser kernel is latency
+    bound (a sub-batch of 30 runs takes as long as one of 90, and kernels of different streams share the SMs), so while
+    the kernel of one sub-batch is in flight the host prepares the next sub-batch (model fit, raw samples, multinomial)
+    and launches its kernel too: step_begin() of every engine returns with its kernel running, step_end() collects."""
 
     def __init__(self, engines):
         self.engines = list(engines)
         self.streams = [torch.cuda.Stream(device=e.device) for e in self.engines]
-        self.pool = ThreadPoolExecutor(max_workers=len(self.engines))
         self.B = sum(e.B for e in self.engines)
 
-    def _on_stream(self, i, fn):
-        e, st = self.engines[i], self.streams[i]
-        torch.cuda.set_device(e.device)
-        with torch.cuda.stream(st):
-            out = fn(e)
-            st.synchronize()
-        return out
-
     def initial_design(self):
-        for i in range(len(self.engines)):
-            self._on_stream(i, lambda e: e.initial_design())
-
-    def step(self):
-        futs = [self.pool.submit(self._on_stream, i, lambda e: e.step()) for i in range(len(self.engines))]
-        return all(f.result() for f in futs)
+        for e, st in zip(self.engines, self.streams):
+            with torch.cuda.stream(st):
+                e.initial_design()
+        torch.cuda.synchronize(self.engines[0].device)
 
     def run_steps(self, k):
-        """k steps of every sub-batch without a join between steps (sub-batches drift apart and overlap better)."""
-        def loop(e):
-            for _ in range(k):
-                e.step()
-        futs = [self.pool.submit(self._on_stream, i, loop) for i in range(len(self.engines))]
-        for f in futs:
-            f.result()
+        """k lock-step iterations of every sub-batch, software-pipelined across the sub-batches."""
+        if k <= 0:
+            return
+        for e, st in zip(self.engines, self.streams):
+            with torch.cuda.stream(st):
+                e.step_begin()
+        for it in range(k):
+            for e, st in zip(self.engines, self.streams):
+                with torch.cuda.stream(st):
+                    e.step_end()
+                    if it + 1 < k:
+                        e.step_begin()
+        for st in self.streams:
+            st.synchronize()
+
+    def step(self):
+        self.run_steps(1)
+        return self.engines[0].n < self.engines[0].budget
 
     @property
     def n(self):

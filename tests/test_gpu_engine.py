@@ -264,3 +264,42 @@ def test_device_mt19937_replay_matches_torch_randint():
             a = torch.rand(5, generator=g_dev[b], dtype=torch.float64)
             r = torch.rand(5, generator=g_ref[b], dtype=torch.float64)
             assert torch.equal(a, r), (rep, b)
+
+
+def test_pipelined_sub_batches_equal_one_batch():
+    """PipelinedEngines (sub-batches on separate streams, step_begin / step_end interleaved by one host thread) gives
+    every run the trajectory it has inside one big lock-step batch: runs are independent and the kernels treat them
+    independently. (The batched objective goes through cuBLAS, whose kernel choice depends on the batch size, so f can
+    differ in the last bits: compared to 1e-9 over the first iterations, before L-BFGS-B amplifies such bits.)"""
+    from pcabo_b200.engine import BatchedBOEngine, PipelinedEngines
+    from pcabo_b200.bbob import BatchedBBOB
+    D, budget, ndoe, steps = 10, 150, 30, 2
+    fids = [15, 15, 16, 16, 17, 17]
+    insts = [0, 1, 0, 1, 0, 1]
+    seeds = [1000 * f + 10 * D + i for f, i in zip(fids, insts)]
+
+    def make(sel):
+        prob = BatchedBBOB([fids[i] for i in sel], [insts[i] for i in sel], D, device="cuda")
+        return BatchedBOEngine(prob, D, prob.bounds, budget, ndoe, [seeds[i] for i in sel], optimizer="device")
+
+    whole = make(list(range(6)))
+    whole.initial_design()
+    for _ in range(steps):
+        whole.step()
+    S = 3
+    subs = [make(list(range(s, 6, S))) for s in range(S)]
+    pipe = PipelinedEngines(subs)
+    pipe.initial_design()
+    pipe.run_steps(steps)
+    torch.cuda.synchronize()
+    assert pipe.n == whole.n == ndoe + steps
+    same = 0
+    for s, e in enumerate(subs):
+        for j in range(e.B):
+            b = s + S * j
+            fa, fb = np.array(e.f_evals[j]), np.array(whole.f_evals[b])
+            xa, xb = np.array(e.x_evals[j]), np.array(whole.x_evals[b])
+            assert np.allclose(fa[:ndoe + 1], fb[:ndoe + 1], rtol=1e-9, atol=1e-9), (s, j)
+            assert np.allclose(xa[:ndoe + 1], xb[:ndoe + 1], rtol=1e-9, atol=1e-9), (s, j)
+            same += int(np.allclose(xa, xb, rtol=1e-6, atol=1e-6))
+    assert same >= 5
