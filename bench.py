@@ -39,6 +39,8 @@ def workload_config(n_start, steps, warmup, optimizer, extra=None):
            "runs_per_gpu": len(FIDS) * RUNS_PER_FID, "dim": DIM, "budget": BUDGET, "n_doe": N_DOE,
            "n_points_range": [n_start + warmup, n_start + warmup + steps],
            "optimizer": optimizer,
+           "sub_batches": "the 90 runs of a GPU advance as S lock-step sub-batches on S CUDA streams, software-pipelined by "
+                          "one host thread (S in the `sub_batches` key; results do not depend on S)",
            "l2_policy": "per-step inputs exceed L2: every step refits PCA/GP from new data and streams "
                         "90 x n^2/2 FP64 cache matrices; no result is reused between steps"}
     if extra:
@@ -371,7 +373,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=6,
                     help="BO iterations per core and sample point of the cpu_baseline leg (the first is warm-up)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sub-batches", type=int, default=1,
+    ap.add_argument("--sub-batches", type=int, default=3,
                     help="split the per-GPU batch into S sub-batches on S CUDA streams, software-pipelined by one host "
                          "thread (the optimiser kernel of one overlaps the host work of the next)")
     ap.add_argument("--ref-budget-s", type=float, default=240.0, help="wall-time budget of the reference arm")

@@ -120,6 +120,7 @@ class BatchedBOEngine:
         self.overlap_hook = None
         self.lb_out = None
         self.h_status = self.h_nfev = self.h_nit = None
+        self.h_vals = self.h_state_back = self.h_pos_back = self.h_k = None
         self.pending = None         # state of a step between step_begin() and step_end()
         self.phase_times = None     # set to {} to accumulate host wall time per phase (adds device syncs)
         self.kernel_events = None   # set to [] to record CUDA-event pairs around every value+grad log-EI launch
@@ -248,52 +249,82 @@ class BatchedBOEngine:
         self.gp.best_f.copy_(bf)
         self.stats["h2d_bytes"] += B * 8
 
-    def _initial_conditions(self, runs, k_host, d_ics=None):
+    def _ic_launch(self, pending, k_host, factor):
+        """Enqueue the device part of gen_batch_initial_conditions for the `pending` runs: Sobol scramble bits (each
+        run's torch CPU generator, MT19937, replayed on the device), Sobol points scaled to the box, log-EI of the raw
+        samples, and the asynchronous read-back of the values and generator states into pinned memory."""
+        B, D = self.B, self.D
+        nraw = self.raw_samples * factor
+        st, pos = self.gen_io.export(self.torch_gens)
+        d_state = st.to(self.device, non_blocking=True)
+        d_pos = pos.to(self.device, non_blocking=True)
+        if len(pending) == B:
+            k_dev = self.pca["k"] if self.algorithm == "pca" else self.k_full
+        else:  # runs that are not pending draw nothing (k = 0)
+            kk = torch.zeros(B, dtype=torch.int32)
+            kk[pending] = torch.from_numpy(k_host[pending].astype(np.int32))
+            k_dev = kk.to(self.device)
+        d_shift, d_dots = ops.sobol_scramble_bits(k_dev, d_state, d_pos, D)
+        x_raw = ops.sobol_points(nraw, k_dev, d_shift, d_dots, self.state0, self.gp.box_lo, self.gp.box_hi)
+        vals_dev = ops.logei(self.gp, x_raw)["val"]
+        if self.h_vals is None or self.h_vals.shape != vals_dev.shape:
+            self.h_vals = torch.zeros(vals_dev.shape, dtype=torch.float64).pin_memory()
+        if self.h_state_back is None:
+            self.h_state_back = torch.zeros(B, 624, dtype=torch.int32).pin_memory()
+            self.h_pos_back = torch.zeros(B, dtype=torch.int32).pin_memory()
+            self.h_k = torch.zeros(B, dtype=torch.int32).pin_memory()
+        self.h_state_back.copy_(d_state, non_blocking=True)
+        self.h_pos_back.copy_(d_pos, non_blocking=True)
+        self.h_vals.copy_(vals_dev, non_blocking=True)
+        if self.algorithm == "pca":
+            self.h_k.copy_(self.pca["k"], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        self.stats["kernel_launches"] += 3
+        self.stats["h2d_bytes"] += st.numel() * 4 + pos.numel() * 4
+        self.stats["d2h_bytes"] += vals_dev.numel() * 8 + st.numel() * 4 + pos.numel() * 4
+        return dict(pending=list(pending), factor=factor, x_raw=x_raw, done=done)
+
+    def _ic_finish(self, h, d_ics):
+        """Host part: generator states back, Boltzmann multinomial per run, gather of the selected rows into d_ics.
+        Returns the runs whose raw values were degenerate (botorch retries those with more raw samples)."""
+        B, R = self.B, self.num_restarts
+        pending = h["pending"]
+        h["done"].synchronize()
+        self.gen_io.restore(self.torch_gens, self.h_state_back, self.h_pos_back)
+        idx, bad = select_initial_conditions(self.h_vals, R, self.torch_gens, pending,
+                                             self.h_q if h["factor"] == 1 else None)
+        d_idx = idx.to(torch.int32).to(self.device, non_blocking=True)
+        picked = ops.gather_rows(h["x_raw"], d_idx)
+        if len(pending) == B:
+            d_ics.copy_(picked)
+        else:
+            sel = torch.tensor(pending, device=self.device)
+            d_ics[sel] = picked[sel]
+        self.stats["kernel_launches"] += 1
+        self.stats["h2d_bytes"] += d_idx.numel() * 4
+        return [b for b in pending if bad[b]]
+
+    def _initial_conditions(self, runs, k_host, d_ics=None, first=None):
         """gen_batch_initial_conditions for the given runs.
 
-        Host: only the random bits (two torch.randint draws of the Sobol scramble, the Boltzmann multinomial) from each
-        run's own CPU generator. Device: Sobol points scaled to the box, log-EI of the raw samples, gather of the
-        selected rows. Returns the device tensor of initial conditions [B, num_restarts, D] (rows of `runs` updated)."""
+        Host: only the Boltzmann multinomial from each run's own CPU generator. Device: scramble bits, Sobol points
+        scaled to the box, log-EI of the raw samples, gather of the selected rows. `first`: an already launched
+        _ic_launch handle for (runs, factor 1). Returns the device tensor of initial conditions [B, num_restarts, D]
+        (rows of `runs` updated)."""
         B, D, R = self.B, self.D, self.num_restarts
         if d_ics is None:
             d_ics = torch.zeros(B, R, D, dtype=torch.float64, device=self.device)
         pending = list(runs)
         factor = 1
         while pending and factor < 5:
-            nraw = self.raw_samples * factor
             tp = perf_counter()
-            # the Sobol scramble bits: replay each run's torch CPU generator (MT19937) on the device
-            st, pos = self.gen_io.export(self.torch_gens)
-            d_state = st.to(self.device, non_blocking=True)
-            d_pos = pos.to(self.device, non_blocking=True)
-            if len(pending) == B:
-                k_dev = self.pca["k"] if self.algorithm == "pca" else self.k_full
-            else:  # runs that are not pending draw nothing (k = 0)
-                kk = torch.zeros(B, dtype=torch.int32)
-                kk[pending] = torch.from_numpy(k_host[pending].astype(np.int32))
-                k_dev = kk.to(self.device)
-            d_shift, d_dots = ops.sobol_scramble_bits(k_dev, d_state, d_pos, D)
-            x_raw = ops.sobol_points(nraw, k_dev, d_shift, d_dots, self.state0, self.gp.box_lo, self.gp.box_hi)
-            vals_dev = ops.logei(self.gp, x_raw)["val"]
-            self.gen_io.restore(self.torch_gens, d_state.cpu(), d_pos.cpu())
-            vals = vals_dev.cpu()
-            self.stats["kernel_launches"] += 3
-            self.stats["h2d_bytes"] += st.numel() * 4 + pos.numel() * 4
-            self.stats["d2h_bytes"] += vals.numel() * 8 + st.numel() * 4 + pos.numel() * 4
+            h = first if (first is not None and factor == 1) else self._ic_launch(pending, k_host, factor)
+            if self.phase_times is not None:
+                h["done"].synchronize()
             tp = self._phase("sobol_bits_points_logei_kernels", tp)
-            idx, bad = select_initial_conditions(vals, R, self.torch_gens, pending, self.h_q if factor == 1 else None)
-            still = [b for b in pending if bad[b]]
-            d_idx = idx.to(torch.int32).to(self.device, non_blocking=True)
-            picked = ops.gather_rows(x_raw, d_idx)
-            if len(pending) == B:
-                d_ics.copy_(picked)
-            else:
-                sel = torch.tensor(pending, device=self.device)
-                d_ics[sel] = picked[sel]
-            self.stats["kernel_launches"] += 1
-            self.stats["h2d_bytes"] += d_idx.numel() * 4
+            pending = self._ic_finish(h, d_ics)
             self._phase("host_multinomial", tp)
-            pending = still
             factor += 1
         return d_ics
 
@@ -416,15 +447,20 @@ class BatchedBOEngine:
         """_launch_device + _finish_device (blocking)."""
         return self._finish_device(self._launch_device(d_x, k_host, runs=runs, out=out))
 
-    def _propose_begin(self):
-        """optimize_acqf (PCA_BO.py:607-614) up to the point where the optimiser kernel is in flight (device mode)."""
+    def _propose_launch(self):
+        """optimize_acqf (PCA_BO.py:607-614), phase A: raw samples and their log-EI enqueued, nothing awaited."""
+        runs = list(range(self.B))
+        return dict(runs=runs, ic=self._ic_launch(runs, None, 1), handle=None)
+
+    def _propose_begin(self, st):
+        """Phase B: initial conditions selected (host multinomial), optimiser kernel in flight (device mode)."""
         B, D = self.B, self.D
-        k_host = self.pca["k"].cpu().numpy().astype(np.int64) if self.algorithm == "pca" else np.full(B, D, np.int64)
+        st["ic"]["done"].synchronize()
+        k_host = self.h_k.numpy().astype(np.int64) if self.algorithm == "pca" else np.full(B, D, np.int64)
         self.k_host = k_host
         self.stats["d2h_bytes"] += B * 4
-        runs = list(range(B))
-        ics = self._initial_conditions(runs, k_host)
-        st = dict(k_host=k_host, runs=runs, ics=ics, handle=None)
+        ics = self._initial_conditions(st["runs"], k_host, first=st["ic"])
+        st.update(k_host=k_host, ics=ics)
         if self.optimizer == "device":
             st["t_launch"] = perf_counter()
             self.overlap_hook = self._prefetch_noise
@@ -468,22 +504,42 @@ class BatchedBOEngine:
         self.stats["kernel_launches"] += 2
         return z_new.contiguous(), best_val
 
-    def step_begin(self):
-        """First half of a BO iteration: model fit, raw samples, initial conditions, optimiser kernel launched. The
-        call returns while the kernel runs (device mode), so a caller can interleave several engines on different
-        streams; step_end() completes the iteration. Returns False when the budget is exhausted."""
+    def step_launch(self):
+        """Phase A of a BO iteration: model fit and raw-sample scoring enqueued; returns without waiting for the GPU.
+        Returns False when the budget is exhausted."""
         if self.n >= self.budget:
             self.pending = None
             return False
         self._fit_models()
         t0 = self._sync_time()
-        self.pending = dict(t0=t0, st=self._propose_begin())
+        self.pending = dict(t0=t0, st=self._propose_launch(), phase="A")
         return True
 
+    def step_begin(self):
+        """Phases A + B: everything up to the optimiser kernel in flight (device mode). step_end() completes the
+        iteration; a caller can interleave several engines on different streams in between."""
+        if self.pending is None or self.pending.get("phase") != "A":
+            if not self.step_launch():
+                return False
+        self._propose_begin(self.pending["st"])
+        self.pending["phase"] = "B"
+        return True
+
+    def wait_event(self):
+        """The CUDA event the next phase of the pending iteration will block on (None if nothing is pending)."""
+        if self.pending is None:
+            return None
+        st = self.pending["st"]
+        if self.pending["phase"] == "A":
+            return st["ic"]["done"]
+        return st["handle"]["done"] if st.get("handle") is not None else None
+
     def step_end(self):
-        """Second half of a BO iteration (PCA_BO.py:239-281): candidates, inverse map, objective, bookkeeping."""
+        """Last phase of a BO iteration (PCA_BO.py:239-281): candidates, inverse map, objective, bookkeeping."""
         if self.pending is None:
             return False
+        if self.pending.get("phase") == "A":
+            self.step_begin()
         B, D, n = self.B, self.D, self.n
         z_new, acq_val = self._propose_end(self.pending["st"])
         t1 = self._sync_time()
@@ -557,7 +613,11 @@ class PipelinedEngines:
         torch.cuda.synchronize(self.engines[0].device)
 
     def run_steps(self, k):
-        """k lock-step iterations of every sub-batch, software-pipelined across the sub-batches."""
+        """k lock-step iterations of every sub-batch, software-pipelined across the sub-batches: after the optimiser
+        kernel of one sub-batch is launched (step_begin) the host turns to the next sub-batch, and comes back to collect
+        (step_end) one round later. A finer, event-driven schedule (run the next phase of whichever engine's CUDA event
+        has completed) was measured and is worse: it lets the optimiser kernels of all sub-batches start together, after
+        which the host has nothing to overlap with them."""
         if k <= 0:
             return
         for e, st in zip(self.engines, self.streams):
