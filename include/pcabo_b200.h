@@ -37,6 +37,8 @@ extern "C" {
 #define PCABO_OK 0
 #define PCABO_E_INVALID (-1)      /* bad argument (null pointer, n < 2, ...) */
 #define PCABO_E_UNSUPPORTED (-2)  /* size outside what the kernels support (D > 104, n > 2048, k > 104) */
+#define PCABO_ACQ_LOG_EI 0
+#define PCABO_ACQ_PI 1
 #define PCABO_E_CUDA (-3)         /* a CUDA runtime call failed; see pcabo_last_cuda_error() */
 
 int pcabo_abi_version(void);
@@ -49,8 +51,9 @@ typedef struct pcabo_gp_model {
   int n;            /* training points per run */
   int kmax;         /* column capacity of per-run z arrays (= D) */
   int ld_n;         /* row capacity */
-  int maximize;     /* LogExpectedImprovement(maximize=...) */
-  int pad_;
+  int maximize;     /* acquisition(maximize=...) */
+  int acq;          /* PCABO_ACQ_LOG_EI (0): botorch LogExpectedImprovement, the reference's "expected_improvement"
+                       (PCA_BO.py:681-682); PCABO_ACQ_PI (1): ProbabilityOfImprovement (PCA_BO.py:683-684) */
   double lengthscale;       /* Matern-5/2 lengthscale (reference: softplus(0) = ln 2) */
   const int *k;             /* [B] active dimensions per run */
   const double *norm_off;   /* [B][kmax]  Normalize offset  (lo)        */

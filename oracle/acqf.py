@@ -108,6 +108,40 @@ def initialize_q_batch(X: torch.Tensor, acq_vals: torch.Tensor, n: int, eta: flo
     return X[idcs], acq_vals[idcs]
 
 
+def initialize_q_batch_nonneg(X: torch.Tensor, acq_vals: torch.Tensor, n: int, eta: float = 1.0, alpha: float = 1e-4,
+                              generator=None):
+    """botorch.optim.initializers.initialize_q_batch_nonneg [3P-mem] (used for acquisition functions botorch registers
+    as non-negative: EI, PI, ...)."""
+    n_samples = X.shape[0]
+    if n > n_samples:
+        raise RuntimeError("n cannot be larger than the number of provided samples")
+    if n == n_samples:
+        return X, acq_vals
+    max_val, max_idx = torch.max(acq_vals, dim=0)
+    if torch.any(max_val <= 0):
+        warnings.warn("All acquisition values for raw sampled points are nonpositive, so initial conditions are being "
+                      "selected randomly.", BadInitialCandidatesWarning)
+        perm = torch.randperm(n_samples, generator=generator)[:n]
+        return X[perm], acq_vals[perm]
+    pos = acq_vals > 0
+    num_pos = int(pos.sum())
+    if num_pos < n:
+        remaining = (~pos).nonzero(as_tuple=False).view(-1)
+        rand = torch.randperm(remaining.shape[0], generator=generator)
+        pos[remaining[rand[: n - num_pos]]] = 1
+        return X[pos], acq_vals[pos]
+    alpha_pos = acq_vals >= alpha * max_val
+    while alpha_pos.sum() < n:
+        alpha = 0.1 * alpha
+        alpha_pos = acq_vals >= alpha * max_val
+    alpha_pos_idcs = torch.arange(len(acq_vals))[alpha_pos]
+    weights = torch.exp(eta * (acq_vals[alpha_pos] / max_val - 1))
+    idcs = alpha_pos_idcs[torch.multinomial(weights, n, generator=generator)]
+    if max_idx not in idcs:
+        idcs[-1] = max_idx
+    return X[idcs], acq_vals[idcs]
+
+
 def gen_batch_initial_conditions(acq, bounds: torch.Tensor, num_restarts=NUM_RESTARTS, raw_samples=RAW_SAMPLES,
                                  batch_limit=BATCH_LIMIT, generator=None, trace=None):
     """botorch.optim.initializers.gen_batch_initial_conditions (q=1, no constraints)."""
@@ -122,7 +156,8 @@ def gen_batch_initial_conditions(acq, bounds: torch.Tensor, num_restarts=NUM_RES
                 acq_vals = torch.cat([acq(x_) for x_ in X_rnd.split(batch_limit, dim=0)], dim=0)
             if trace is not None:
                 trace.append(dict(kind="raw", X=X_rnd.clone(), vals=acq_vals.clone()))
-            ics, _ = initialize_q_batch(X_rnd, acq_vals, num_restarts, generator=generator)
+            init = initialize_q_batch_nonneg if getattr(acq, "nonnegative", False) else initialize_q_batch
+            ics, _ = init(X_rnd, acq_vals, num_restarts, generator=generator)
             if not any(issubclass(w.category, BadInitialCandidatesWarning) for w in ws):
                 return ics
             if factor < max_factor:

@@ -204,6 +204,21 @@ class LogExpectedImprovement:
         return vals.detach(), grad
 
 
+class ProbabilityOfImprovement(LogExpectedImprovement):
+    """botorch ProbabilityOfImprovement(model, best_f, maximize): Phi(u) (the reference's
+    "probability_of_improvement", PCA_BO.py:683-684). Registered as non-negative in botorch, which makes
+    gen_batch_initial_conditions use initialize_q_batch_nonneg for it."""
+
+    nonnegative = True
+
+    def __call__(self, X):
+        X = X.reshape(-1, self.model.k) if X.dim() == 3 else X
+        mean, sigma = self.mean_sigma(X)
+        u = (mean - self.best_f) / sigma
+        u = u if self.maximize else -u
+        return _Phi(u)
+
+
 class ExpectedImprovement(LogExpectedImprovement):
     """exp(logEI) -- imported but unused by the reference (PCA_BO.py:13); kept for the EI sweep (config C4)."""
 

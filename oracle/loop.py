@@ -17,11 +17,14 @@ from . import doe, weights_pca, gp, acqf
 class OracleRun:
     def __init__(self, problem, dim, bounds, budget, n_doe, seed, algorithm="pca", var_threshold=0.95,
                  n_components=0, maximization=False, num_restarts=acqf.NUM_RESTARTS,
-                 raw_samples=acqf.RAW_SAMPLES, keep_trace=False):
+                 raw_samples=acqf.RAW_SAMPLES, keep_trace=False, acquisition="expected_improvement"):
         self.problem, self.dim, self.bounds = problem, dim, np.asarray(bounds, dtype=np.float64)
         self.budget, self.n_doe, self.seed = budget, n_doe if n_doe > 0 else dim, seed
         self.algorithm, self.var_threshold, self.n_components = algorithm, var_threshold, n_components
         self.maximization = maximization
+        # PCA_BO.py:679-686: name -> botorch class ("expected_improvement" is LogExpectedImprovement)
+        self.acq_class = {"expected_improvement": gp.LogExpectedImprovement,
+                          "probability_of_improvement": gp.ProbabilityOfImprovement}[acquisition]
         self.num_restarts, self.raw_samples = num_restarts, raw_samples
         self.x_evals, self.f_evals, self.z_evals = [], [], []
         self.current_best, self.current_best_index = (-np.inf if maximization else np.inf), 0
@@ -67,7 +70,7 @@ class OracleRun:
             model = gp.GPModel(X, self.f_evals, norm_bounds=None)
             self.timing["SingleTaskGP"].append(perf_counter() - t0)
             box = self.bounds.transpose().copy()
-        acq = gp.LogExpectedImprovement(model, best_f=self.current_best, maximize=self.maximization)
+        acq = self.acq_class(model, best_f=self.current_best, maximize=self.maximization)
         t0 = perf_counter()
         cand, val = acqf.optimize_acqf(acq, box, self.num_restarts, self.raw_samples, trace=inner)
         self.timing["optimize_acqf"].append(perf_counter() - t0)

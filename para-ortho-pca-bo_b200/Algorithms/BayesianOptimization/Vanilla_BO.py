@@ -39,8 +39,10 @@ class Vanilla_BO(AbstractBayesianOptimizer):
 
     def __call__(self, problem: Callable, dim: Optional[int] = -1, bounds: Optional[np.ndarray] = None, **kwargs) -> None:
         from pcabo_b200.engine import BatchedBOEngine
-        if self.acquisition_function_name != "expected_improvement":
-            raise NotImplementedError(f"acquisition '{self.acquisition_function_name}' is not on the accelerated path yet")
+        if self.acquisition_function_name == "upper_confidence_bound":
+            # the reference builds acquisition_function_class(model=..., best_f=..., maximize=...) for every choice
+            # (PCA_BO.py:199-203); botorch's UpperConfidenceBound has no best_f argument, so this choice fails there too
+            raise TypeError("UpperConfidenceBound.__init__() got an unexpected keyword argument 'best_f'")
         original_stdout = None
         if self._pbar is not None:
             from ..utils.tqdm_write_stream import redirect_stdout_to_tqdm
@@ -54,7 +56,7 @@ class Vanilla_BO(AbstractBayesianOptimizer):
                               num_restarts=self.__torch_config["NUM_RESTARTS"],
                               raw_samples=self.__torch_config["RAW_SAMPLES"],
                               np_rngs=[np.random.mtrand._rand], torch_gens=[torch.default_generator],
-                              profile_timing=True)
+                              profile_timing=True, acquisition=self.acquisition_function_name)
         eng.attach_history([self.x_evals], [self.f_evals])
         self._engine = eng
         for _ in range(self.budget - self.n_DoE):

@@ -40,8 +40,9 @@ class LogExpectedImprovement(AnalyticAcquisitionFunction):
         return ops.logei(eng.gp, pts.to(eng.device))["val"][0].cpu()
 
 
-class ProbabilityOfImprovement(AnalyticAcquisitionFunction):
-    pass
+class ProbabilityOfImprovement(LogExpectedImprovement):
+    """Handle to the device-resident probability of improvement Phi(u) (botorch ProbabilityOfImprovement, the
+    reference's "probability_of_improvement", PCA_BO.py:683-684); evaluated by the same kernel with acq = PCABO_ACQ_PI."""
 
 
 class UpperConfidenceBound(AnalyticAcquisitionFunction):

@@ -38,6 +38,18 @@ class ExperimentRunner:
         self.rank, self.world_size = rank, world_size
         self.results = []
 
+    def _acquisition_long_name(self):
+        """The runner hands `acquisition_function` to the optimiser classes (reference ExperimentRunner.py:154-170), whose
+        setter accepts the shorthands "EI" / "PI" / "UCB" (PCA_BO.py:653-677)."""
+        from ..BayesianOptimization._acquisition_names import (ALLOWED_ACQUISITION_FUNCTION_STRINGS,
+                                                                ALLOWED_SHORTHAND_ACQUISITION_FUNCTION_STRINGS)
+        name = ALLOWED_SHORTHAND_ACQUISITION_FUNCTION_STRINGS.get(self.acquisition_function, self.acquisition_function)
+        if name not in ALLOWED_ACQUISITION_FUNCTION_STRINGS:
+            raise ValueError("Oddly defined name")
+        if name == "upper_confidence_bound":
+            raise TypeError("UpperConfidenceBound.__init__() got an unexpected keyword argument 'best_f'")
+        return name
+
     def shard(self, instances):
         """Run-level data parallelism: instances round-robin over ranks, no collective."""
         return [i for j, i in enumerate(instances) if j % self.world_size == self.rank]
@@ -63,7 +75,7 @@ class ExperimentRunner:
                     eng = BatchedBOEngine(prob, dim, prob.bounds, budget, n_doe, seeds, algorithm=algorithm,
                                           var_threshold=self.var_threshold, n_components=self.pca_components or 0,
                                           maximization=False, device=self.device, optimizer=self.optimizer_backend,
-                                          profile_timing=True)
+                                          profile_timing=True, acquisition=self._acquisition_long_name())
                     t0 = time()
                     eng.run()
                     wall = time() - t0

@@ -45,7 +45,7 @@ __device__ __forceinline__ void log_h_and_grad(double u, double &lh, double &dlh
 
 // Per-block view of one run's GP caches plus the shared-memory scratch of the evaluation.
 struct Ctx {
-  int n, kmax, ld, kk, np;
+  int n, kmax, ld, kk, np, acq;
   const double *ZnT, *Zn, *W, *WT, *alpha, *off, *coef;
   double inv_ell2, ymean, ystd, best_f, sgn;
   double *xn;    // [P][kmax]
@@ -90,7 +90,7 @@ __device__ inline void carve_ctx(Ctx &c, int P, bool grad, double *sm) {
 }
 
 __device__ inline void load_ctx(Ctx &c, const pcabo_gp_model &m, int b) {
-  c.n = m.n; c.kmax = m.kmax; c.ld = m.ld_n;
+  c.n = m.n; c.kmax = m.kmax; c.ld = m.ld_n; c.acq = m.acq;
   c.kk = m.k ? m.k[b] : m.kmax;
   c.np = (m.n + 1) & ~1;
   c.ZnT = m.ZnT + (size_t)b * m.kmax * m.ld_n;
@@ -252,16 +252,28 @@ __device__ void eval_points(const Ctx &c, int pcount, const double *X, int xstri
     const double var = clamped ? 1e-10 : var_raw;
     const double sg = sqrt(var);
     const double u = c.sgn * (mu - c.best_f) / sg;
-    double lh, dlh;
-    log_h_and_grad(u, lh, dlh);
+    double value, dmu, dvar;   // acquisition value, d value / d mu_s, d value / d var_s
+    if (c.acq == PCABO_ACQ_PI) {
+      // botorch ProbabilityOfImprovement: Phi(u); d/du = phi(u); du/dmu = sgn/sigma, du/dvar = -u / (2 var)
+      value = 0.5 * erfc(-INV_SQRT2 * u);
+      const double phi = INV_SQRT_2PI * exp(-0.5 * u * u);
+      dmu = phi * c.sgn * ystd / sg;
+      dvar = clamped ? 0.0 : -phi * u * ystd * ystd / (2.0 * var);
+    } else {
+      double lh, dlh;
+      log_h_and_grad(u, lh, dlh);
+      value = lh + log(sg);
+      dmu = dlh * c.sgn * ystd / sg;
+      dvar = clamped ? 0.0 : (1.0 - u * dlh) * ystd * ystd / (2.0 * var);
+    }
     if (p < pcount) {
-      val[p] = lh + log(sg);
+      val[p] = value;
       if (mu_out) mu_out[p] = mu;
       if (sigma_out) sigma_out[p] = sg;
     }
     if (GRAD) {
-      res[p] = dlh * c.sgn * ystd / sg;                                          // d logEI / d mu_s
-      res[P + p] = clamped ? 0.0 : (1.0 - u * dlh) * ystd * ystd / (2.0 * var);  // d logEI / d var_s
+      res[p] = dmu;
+      res[P + p] = dvar;
     }
   }
   ev_tick(c, 22);

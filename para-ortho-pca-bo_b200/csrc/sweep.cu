@@ -627,6 +627,7 @@ extern "C" int pcabo_ei_sweep(const pcabo_gp_model *m, int run, long long ncand,
       !m->W || !m->Zn || !m->alpha || !m->norm_off || !m->norm_coef || !m->ymean || !m->ystd || !m->best_f)
     return PCABO_E_INVALID;
   if (X == nullptr && (!shift || !sstate || !lo || !hi)) return PCABO_E_INVALID;
+  if (m->acq != PCABO_ACQ_LOG_EI) return PCABO_E_UNSUPPORTED;   // the sweep scores log-EI (BASELINE config C4)
   // n <= 512 (accumulators of the whole T tile live in registers), even ld_n and kmax (16-byte cp.async copies)
   if (m->n > 8 * NWARP * RT_MAX || m->n < 2 || (m->ld_n & 1) || (m->kmax & 1) || m->kmax > 104) return PCABO_E_UNSUPPORTED;
   const size_t smem = sweep_smem_bytes(m->n, m->kmax);

@@ -103,6 +103,50 @@ def select_initial_conditions(vals: torch.Tensor, n: int, gens, runs, q_buf=None
     return idx, bad
 
 
+def select_initial_conditions_nonneg(vals: torch.Tensor, n: int, gens, runs, eta: float = 1.0, alpha: float = 1e-4):
+    """botorch initialize_q_batch_nonneg, which gen_batch_initial_conditions uses for acquisition functions registered
+    as non-negative (ProbabilityOfImprovement among them), per run: vals [B, nraw] (CPU) -> (idx [B, n], bad [B]).
+
+    max <= 0: random permutation pick + BadInitialCandidatesWarning (flagged `bad`, botorch retries with more raw
+    samples); fewer than n positive values: all of them plus randomly chosen others (in index order, as boolean
+    masking returns them); otherwise Boltzmann weights exp(eta (v / max - 1)) over the points within alpha of the
+    maximum (alpha shrinking by 10 until there are n), multinomial without replacement, arg-max forced in last.
+    Every random draw comes from the run's own generator, in botorch's order."""
+    B, nraw = vals.shape
+    idx = torch.zeros(B, n, dtype=torch.int64)
+    bad = [False] * B
+    if n >= nraw:
+        idx[:] = torch.arange(n)
+        return idx, bad
+    for b in runs:
+        v = vals[b]
+        max_val, max_idx = torch.max(v, dim=0)
+        if bool(max_val <= 0):
+            idx[b] = torch.randperm(nraw, generator=gens[b])[:n]
+            bad[b] = True
+            continue
+        pos = v > 0
+        num_pos = int(pos.sum())
+        if num_pos < n:
+            remaining = (~pos).nonzero(as_tuple=False).view(-1)
+            rand = torch.randperm(remaining.shape[0], generator=gens[b])
+            pos[remaining[rand[: n - num_pos]]] = True
+            idx[b] = pos.nonzero(as_tuple=False).view(-1)
+            continue
+        a = alpha
+        alpha_pos = v >= a * max_val
+        while int(alpha_pos.sum()) < n:
+            a = 0.1 * a
+            alpha_pos = v >= a * max_val
+        alpha_idcs = torch.arange(nraw)[alpha_pos]
+        weights = torch.exp(eta * (v[alpha_pos] / max_val - 1))
+        pick = alpha_idcs[torch.multinomial(weights, n, generator=gens[b])]
+        if int(max_idx) not in pick.tolist():
+            pick[-1] = max_idx
+        idx[b] = pick
+    return idx, bad
+
+
 MAXBIT = 30
 _POW2_DESC = None
 _STATE0 = {}

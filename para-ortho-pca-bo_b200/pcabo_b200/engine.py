@@ -16,7 +16,8 @@ import numpy as np
 import torch
 
 from . import ops
-from .acq_host import GeneratorStateIO, LbfgsbProblem, select_initial_conditions, sobol_state0
+from .acq_host import (GeneratorStateIO, LbfgsbProblem, select_initial_conditions,
+                       select_initial_conditions_nonneg, sobol_state0)
 from .lib import PcaboError
 
 NUM_RESTARTS = 10      # PCA_BO.py:107
@@ -48,13 +49,20 @@ class BatchedBOEngine:
     def __init__(self, problems, dim, bounds, budget, n_doe, seeds, algorithm="pca", var_threshold=0.95,
                  n_components=0, maximization=False, device="cuda:0", optimizer="scipy",
                  num_restarts=NUM_RESTARTS, raw_samples=RAW_SAMPLES, batch_limit=BATCH_LIMIT, maxiter=MAXITER,
-                 np_rngs=None, torch_gens=None, profile_timing=False, batch_objective=None, host_threads=None):
+                 np_rngs=None, torch_gens=None, profile_timing=False, batch_objective=None, host_threads=None,
+                 acquisition="expected_improvement"):
         if not torch.cuda.is_available():
             raise PcaboError("BatchedBOEngine needs a CUDA device: the PCA-BO hot path has no CPU fallback")
         if algorithm not in ("pca", "vanilla"):
             raise ValueError(f"Invalid algorithm name: '{algorithm}'")
         if optimizer not in ("scipy", "device"):
             raise ValueError(f"Invalid optimizer: '{optimizer}'")
+        if acquisition not in ops.ACQ_KINDS:
+            # "upper_confidence_bound" cannot run in the reference either: it builds UpperConfidenceBound(model=...,
+            # best_f=..., maximize=...) (PCA_BO.py:199-203) and botorch's class has no best_f argument
+            raise ValueError(f"acquisition '{acquisition}' is not available on the accelerated path "
+                             f"(one of {sorted(ops.ACQ_KINDS)})")
+        self.acquisition = acquisition
         # `problems`: a list of B callables p(x) -> float, or one batched objective (e.g. pcabo_b200.bbob.BatchedBBOB)
         # exposing B, eval_many(b, X[m, D]) -> ndarray and __call__(X[B, D] device tensor) -> [B] device tensor
         self.batched_problem = problems if hasattr(problems, "eval_many") else None
@@ -95,6 +103,7 @@ class BatchedBOEngine:
         self.hi = torch.from_numpy(self.bounds[:, 1].copy()).to(self.device)
         self.gp = ops.GPBuffers(B, cap, D, self.device)
         self.gp.maximize = self.maximization
+        self.gp.acq = ops.ACQ_KINDS[acquisition]
         self.pca = None
         self.d_noise = torch.zeros(B * cap * D, **f64)
         self.h_noise = torch.zeros(B * cap * D, dtype=torch.float64).pin_memory()
@@ -292,8 +301,11 @@ class BatchedBOEngine:
         pending = h["pending"]
         h["done"].synchronize()
         self.gen_io.restore(self.torch_gens, self.h_state_back, self.h_pos_back)
-        idx, bad = select_initial_conditions(self.h_vals, R, self.torch_gens, pending,
-                                             self.h_q if h["factor"] == 1 else None)
+        if self.gp.acq == ops.ACQ_PI:      # botorch picks initialize_q_batch_nonneg for non-negative acquisitions
+            idx, bad = select_initial_conditions_nonneg(self.h_vals, R, self.torch_gens, pending)
+        else:
+            idx, bad = select_initial_conditions(self.h_vals, R, self.torch_gens, pending,
+                                                 self.h_q if h["factor"] == 1 else None)
         d_idx = idx.to(torch.int32).to(self.device, non_blocking=True)
         picked = ops.gather_rows(h["x_raw"], d_idx)
         if len(pending) == B:

@@ -21,7 +21,7 @@ class GpModelStruct(ctypes.Structure):
     """struct pcabo_gp_model (include/pcabo_b200.h)."""
     _fields_ = [
         ("B", ctypes.c_int), ("n", ctypes.c_int), ("kmax", ctypes.c_int), ("ld_n", ctypes.c_int),
-        ("maximize", ctypes.c_int), ("pad_", ctypes.c_int),
+        ("maximize", ctypes.c_int), ("acq", ctypes.c_int),
         ("lengthscale", ctypes.c_double),
         ("k", ctypes.c_void_p), ("norm_off", ctypes.c_void_p), ("norm_coef", ctypes.c_void_p),
         ("ZnT", ctypes.c_void_p), ("alpha", ctypes.c_void_p), ("W", ctypes.c_void_p),

@@ -77,6 +77,10 @@ def inverse_map(z, k, V, m2, xbar, lo, hi, out=None):
     return out
 
 
+ACQ_LOG_EI, ACQ_PI = 0, 1
+ACQ_KINDS = {"expected_improvement": ACQ_LOG_EI, "probability_of_improvement": ACQ_PI}
+
+
 class GPBuffers:
     """Device storage for the batched GP caches (allocated once per engine, reused every iteration)."""
 
@@ -100,6 +104,7 @@ class GPBuffers:
         self.n = 0
         self.k = None
         self.maximize = False
+        self.acq = ACQ_LOG_EI       # PCABO_ACQ_LOG_EI / PCABO_ACQ_PI (include/pcabo_b200.h)
         self.lengthscale = LENGTHSCALE
 
 
@@ -132,6 +137,7 @@ def model_struct(buf: GPBuffers) -> GpModelStruct:
     m = GpModelStruct()
     m.B, m.n, m.kmax, m.ld_n = buf.B, buf.n, buf.kmax, buf.ld_n
     m.maximize = int(bool(buf.maximize))
+    m.acq = int(buf.acq)
     m.lengthscale = float(buf.lengthscale)
     m.k = _i(buf.k, "k") if buf.k is not None else None
     m.norm_off, m.norm_coef = _d(buf.norm_off, "norm_off"), _d(buf.norm_coef, "norm_coef")

@@ -303,3 +303,32 @@ def test_pipelined_sub_batches_equal_one_batch():
             assert np.allclose(xa[:ndoe + 1], xb[:ndoe + 1], rtol=1e-9, atol=1e-9), (s, j)
             same += int(np.allclose(xa, xb, rtol=1e-6, atol=1e-6))
     assert same >= 5
+
+
+def test_engine_probability_of_improvement_matches_oracle():
+    """acquisition="probability_of_improvement": first iterations against the oracle loop (non-negative initialiser,
+    Phi(u) values and gradients in the device optimiser)."""
+    from pcabo_b200.engine import BatchedBOEngine
+    from pcabo_b200.bbob import BatchedBBOB
+    from oracle import bbob, doe, loop
+    fid, D, inst, iters = 15, 10, 0, 3
+    budget, ndoe = doe.budget_and_ndoe(D)
+    torch.set_num_threads(1)
+    p = bbob.BBOBProblem(fid, D, inst)
+    r = loop.OracleRun(p, D, p.bounds, budget, ndoe, doe.run_seed(fid, D, inst), keep_trace=True,
+                       acquisition="probability_of_improvement")
+    r.run(max_iterations=iters)
+    for optimizer in ("scipy", "device"):
+        prob = BatchedBBOB([fid], [inst], D, device="cuda")
+        eng = BatchedBOEngine(prob, D, prob.bounds, budget, ndoe, [1000 * fid + 10 * D + inst], optimizer=optimizer,
+                              acquisition="probability_of_improvement")
+        eng.initial_design()
+        eng.step()
+        rec = r.trace[0]
+        assert int(eng.last["k"][0]) == rec["k"]
+        tol = 1e-6 if optimizer == "scipy" else 1e-4
+        assert abs(eng.last["acq_val"][0] - rec["acq_value"]) < tol * max(1.0, abs(rec["acq_value"])), optimizer
+        assert np.max(np.abs(eng.last["z_new"][0, :rec["k"]] - rec["new_z"])) < \
+            100 * tol * max(1.0, np.max(np.abs(rec["new_z"]))), optimizer
+    with pytest.raises(ValueError):
+        BatchedBOEngine(prob, D, prob.bounds, budget, ndoe, [1], acquisition="upper_confidence_bound")

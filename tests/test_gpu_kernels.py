@@ -315,3 +315,42 @@ def test_late_trajectory_state_gp_and_logei(name):
             vd = acq(cand[5 * c:5 * c + 5])
         fs, fdv = float(vs.sum()), float(vd.sum())
         assert abs(fs - fdv) <= 2e-4 * max(1.0, abs(fs)), (name, c, fs, fdv)
+
+
+@pytest.mark.parametrize("D,n,npts", [(5, 10, 7), (20, 250, 9), (40, 330, 10), (40, 450, 12)])
+@pytest.mark.parametrize("maximization", [False, True])
+def test_probability_of_improvement_value_grad(D, n, npts, maximization):
+    """acq = PCABO_ACQ_PI: botorch ProbabilityOfImprovement (the reference's "probability_of_improvement",
+    PCA_BO.py:683-684), value and autograd gradient against the oracle."""
+    B = 2
+    ops, hist, X, f, pca, buf = _fit_gp_batch(D, n, B, maximization, seed0=77)
+    from oracle import gp, acqf
+    rng = np.random.RandomState(6)
+    pts = torch.zeros(B, npts, D, dtype=torch.float64)
+    models = []
+    for b in range(B):
+        k = int(pca["k"][b])
+        Z = pca["Z"][b, :n, :k].cpu().numpy()
+        fb = hist[b][1]
+        model = gp.GPModel(Z, fb, norm_bounds=acqf.normalize_box_pca(Z))
+        best = float(np.max(fb) if maximization else np.min(fb))
+        models.append((k, gp.ProbabilityOfImprovement(model, best, maximize=maximization)))
+        box = acqf.search_box_pca(Z)
+        P = box[0] + (box[1] - box[0]) * rng.rand(npts, k)
+        P[0] = Z[int(np.argmin(fb))] + 1e-3 * rng.randn(k)
+        P[1] = 0.5 * (Z[rng.randint(n)] + Z[rng.randint(n)])
+        pts[b, :, :k] = torch.from_numpy(P)
+        buf.best_f[b] = gp.best_f_as_botorch(best)
+    buf.maximize = maximization
+    buf.acq = ops.ACQ_PI
+    out = ops.logei(buf, pts.cuda(), want_grad=True)
+    torch.cuda.synchronize()
+    for b in range(B):
+        k, acq = models[b]
+        vals, grad = acq.value_and_grad(pts[b, :, :k])
+        v = out["val"][b].cpu().numpy()
+        assert np.max(np.abs(v - vals.numpy())) < 1e-9 * max(1.0, float(vals.abs().max())), "PI"
+        g = out["grad"][b, :, :k].cpu().numpy()
+        gr = grad.numpy()
+        scale = np.maximum(np.max(np.abs(gr), axis=1, keepdims=True), 1e-12)
+        assert np.max(np.abs(g - gr) / scale) < 1e-7, "PI gradient (per-point max-norm relative)"

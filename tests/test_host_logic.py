@@ -176,3 +176,45 @@ def test_incremental_best_tracking_equals_rescan():
                 a._assign_new_best(0)
                 b._update_best_with_last(0)
                 assert (a.current_best, a.current_best_index) == (b.current_best, b.current_best_index)
+
+
+def test_initialize_q_batch_nonneg_matches_oracle():
+    """The per-run non-negative initialiser (ProbabilityOfImprovement) against the oracle's restatement of botorch's
+    initialize_q_batch_nonneg on the three branches: enough positive values, too few, none."""
+    from pcabo_b200.acq_host import select_initial_conditions_nonneg
+    from oracle import acqf
+    rng = np.random.RandomState(4)
+    cases = [np.abs(rng.randn(64)) * 0.3,                                  # all positive: alpha window + multinomial
+             np.where(rng.rand(64) < 0.08, rng.rand(64), 0.0),             # fewer than n positive
+             np.zeros(64)]                                                 # max <= 0: random pick, flagged bad
+    cases[1][5] = 0.7
+    X = torch.arange(64, dtype=torch.float64).reshape(64, 1)
+    for ci, v in enumerate(cases):
+        vals = torch.from_numpy(v)
+        g1, g2 = torch.Generator(), torch.Generator()
+        g1.manual_seed(11 + ci)
+        g2.manual_seed(11 + ci)
+        idx, bad = select_initial_conditions_nonneg(vals.reshape(1, -1).clone(), 10, [g1], [0])
+        import warnings
+        with warnings.catch_warnings(record=True) as ws:
+            warnings.simplefilter("always")
+            Xo, _ = acqf.initialize_q_batch_nonneg(X, vals.clone(), 10, generator=g2)
+        assert torch.equal(X[idx[0]], Xo), ci
+        assert bad[0] == any(issubclass(w.category, acqf.BadInitialCandidatesWarning) for w in ws)
+        assert torch.equal(g1.get_state(), g2.get_state())                # same draws consumed
+
+
+def test_dropin_acquisition_choices():
+    """"probability_of_improvement" is accepted; "upper_confidence_bound" fails exactly where the reference fails
+    (acquisition_function_class(model=, best_f=, maximize=) on a class without best_f, PCA_BO.py:199-203)."""
+    from Algorithms import PCA_BO, Vanilla_BO, ExperimentRunner
+    f = lambda x: float(np.sum(x * x))
+    for cls in (PCA_BO, Vanilla_BO):
+        opt = cls(budget=12, n_DoE=4, acquisition_function="UCB", verbose=False)
+        with pytest.raises(TypeError):
+            opt(f, dim=2, bounds=np.array([[-1.0, 1.0], [-1.0, 1.0]]))
+        assert cls(budget=12, acquisition_function="PI").acquisition_function_name == "probability_of_improvement"
+    with pytest.raises(TypeError):
+        ExperimentRunner(["pca"], [5], [15], num_runs=1, acquisition_function="UCB")._acquisition_long_name()
+    assert ExperimentRunner(["pca"], [5], [15], num_runs=1, acquisition_function="PI")._acquisition_long_name() == \
+        "probability_of_improvement"
