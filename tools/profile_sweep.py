@@ -14,10 +14,10 @@ import numpy as np
 NAMES = ["tile_top+loop", "produce", "issue_w", "wait_w", "wait_full", "mma", "epilogue", "-"]
 
 if __name__ == "__main__":
-    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_sweep.py"), "--log2n", "22", "--dims", "40", "--reps", "1"])
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_sweep.py"), "--log2n", "22", "--dims", os.environ.get("SWEEP_R", "40"), "--reps", "1"])
     # same process is needed to read the symbol: rerun in-process
     import runpy
-    sys.argv = ["bench_sweep.py", "--log2n", "20", "--dims", "40", "--reps", "1"]
+    sys.argv = ["bench_sweep.py", "--log2n", "20", "--dims", os.environ.get("SWEEP_R", "40"), "--reps", "1"]
     from pcabo_b200.lib import load_library
     lib = load_library()
     buf = (ctypes.c_longlong * 128)()
