@@ -64,11 +64,11 @@ def main():
         shutil.copy(j("launches_%s_final.csv" % tag), os.path.join(PROF, f"{tag}_launches_bench_steps3.csv"))
         launch_summary(j("launches_%s_final.csv" % tag), os.path.join(PROF, f"{tag}_launch_summary.csv"),
                        "ncu launch list summary (ncu --metrics gpu__time_duration.sum --clock-control none, "
-                       "bench.py --steps 3 --warmup 1 --no-cpu-baseline, device optimizer, n = 120..123); per-launch "
+                       "bench.py --steps 3 --warmup 1 --no-cpu-baseline --sub-batches 1, device optimizer, n = 120..123); per-launch "
                        "times are cold-cache and serialised: compare SHARES with bench.py's roofline.share_of_step")
     for rep, dst, hd in [
         (f"prof_lbfgsb_{tag}_final.ncu-rep", f"{tag}_lbfgsb_ncu_raw_summary.csv",
-         "ncu --set full, lbfgsb_logei_kernel<5>, bench.py --steps 3 --warmup 1, n = 122, 90 runs x 2 chunks"),
+         "ncu --set full, lbfgsb_logei_kernel<5>, bench.py --steps 3 --warmup 1 --sub-batches 1, n = 122, 90 runs x 2 chunks"),
         (f"prof_lbfgsb_{tag}_n390.ncu-rep", f"{tag}_lbfgsb_n390_ncu_raw_summary.csv",
          "ncu --set full, lbfgsb_logei_kernel<5> at n ~ 390 (tools/profile_lbfgsb.py 280, launch 271), before the "
          "uniform-trip-count / dual-accumulator changes"),
