@@ -340,7 +340,10 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (BBOB f15-f17 restated)",
                 "config": workload_config(n_first - args.warmup, args.steps, args.warmup, args.optimizer,
                                           {"lbfgsb_rounds_per_step": (stats1["lbfgsb_rounds"] - stats0["lbfgsb_rounds"]) / args.steps,
-                                           "retries": stats1["retries"] - stats0["retries"]}),
+                                           "retries": stats1["retries"] - stats0["retries"],
+                                           "host_blocked_ms_per_step": {
+                                               "optimiser_kernel": 1e3 * (stats1["wait_opt_s"] - stats0["wait_opt_s"]) / args.steps,
+                                               "fit_and_raw_samples": 1e3 * (stats1["wait_ic_s"] - stats0["wait_ic_s"]) / args.steps}}),
                 "roofline": roof, "cpu_baseline": cpu_base, "sub_batches": S,
                 "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "note": "every step is driven through the public engine API with host-generated RNG inputs "

@@ -174,6 +174,16 @@ int pcabo_sobol_scramble_bits(int B, int kmax, const int *k, unsigned *mt_state,
 /* out[b][r][:] = X[b][idx[b][r]][:]  (selection of the initial conditions among the raw samples).                    */
 int pcabo_gather_rows(int B, int npts, int nsel, int kmax, const double *X, const int *idx, double *out, void *stream);
 
+/* Batched BBOB objectives f15 / f16 / f17 / f20 (the synthetic workloads of BASELINE configs C1-C3), one block per
+ * (problem, point): replaces the per-iteration host call problem(x) of the reference (PCA_BO.py:263,
+ * AbstractBayesianOptimizer.py:163; ioh's C++ objective) when the runs of a batch are BBOB problems.
+ *   fid [B] (15, 16, 17, 20), xopt [B][D], R / M [B][D][D] (first rotation / second linear map), sign [B][D] (f20),
+ *   fopt [B], lam [D] = sqrt(10)^(i/(D-1)), f0 = the Weierstrass constant: instance data built on the host like ioh / COCO.
+ *   X [B][m][D] (m points per problem) -> out [B][m] = f(x) (f_opt included, like ioh's problem(x)).           */
+int pcabo_bbob_eval(int B, int m, int D, const int *fid, const double *xopt, const double *R, const double *M,
+                    const double *sign, const double *fopt, const double *lam, double f0, const double *X,
+                    double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

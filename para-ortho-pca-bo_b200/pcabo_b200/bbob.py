@@ -130,6 +130,7 @@ class BatchedBBOB:
         self.f0 = float(np.sum(np.power(0.5, k) * np.cos(2.0 * math.pi * np.power(3.0, k) * 0.5)))
         self.bounds = np.tile(np.array([[-5.0, 5.0]]), (D, 1))
         self.device = torch.device(device)
+        self._fid32 = None
         self._groups = {fid: torch.tensor([b for b in range(self.B) if fids[b] == fid], device=device)
                         for fid in sorted(set(fids))}
 
@@ -159,8 +160,18 @@ class BatchedBBOB:
         r = (s.pow(0.25) * (1.0 + torch.sin(50.0 * s.pow(0.1)) ** 2)).sum(-1)
         return (r / (D - 1.0)).pow(2) + 10.0 * pen
 
+    def _kernel(self, X3: torch.Tensor) -> torch.Tensor:
+        """X3 [B, m, D] on the GPU -> [B, m] through the hand-written kernel (pcabo_bbob_eval): one launch."""
+        from . import ops
+        if self._fid32 is None:
+            self._fid32 = self.fid_t.to(torch.int32)
+        return ops.bbob_eval(self._fid32, self.xopt, self.R, self.M, self.sign, self.fopt, self.lam, self.f0,
+                             X3.contiguous())
+
     def __call__(self, X: torch.Tensor) -> torch.Tensor:
         """X [B, D] (one point per problem) -> objective values [B] (with f_opt added, like ioh's `problem(x)`)."""
+        if X.is_cuda:
+            return self._kernel(X.reshape(self.B, 1, self.D)).reshape(self.B)
         out = torch.empty(self.B, dtype=torch.float64, device=X.device)
         for fid, sel in self._groups.items():
             out[sel] = self._eval_group(fid, sel, X[sel])
@@ -170,6 +181,8 @@ class BatchedBBOB:
         """X [B, m, D] host array: m points per problem, one batched evaluation per function id -> [B, m]."""
         Xt = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(self.device)
         B, m, D = Xt.shape
+        if Xt.is_cuda:
+            return self._kernel(Xt).cpu().numpy()
         out = torch.empty(B, m, dtype=torch.float64, device=self.device)
         for fid, sel in self._groups.items():
             rows = sel.repeat_interleave(m)

@@ -122,7 +122,8 @@ class BatchedBOEngine:
         self.current_best_index = [0] * B
         self.k_host = np.full(B, D, dtype=np.int64)
         self.timing_logs = {"pca": [], "SingleTaskGP": [], "optimize_acqf": []}
-        self.stats = dict(kernel_launches=0, lbfgsb_rounds=0, h2d_bytes=0, d2h_bytes=0, retries=0)
+        self.stats = dict(kernel_launches=0, lbfgsb_rounds=0, h2d_bytes=0, d2h_bytes=0, retries=0,
+                          wait_opt_s=0.0, wait_ic_s=0.0)   # host time blocked on the optimiser / raw-sample events
         self.last = {}
         self.noise_ready_n = -1     # the pinned noise buffer holds the draw for the iteration with this many points
         self.noise_copied = torch.cuda.Event()
@@ -434,7 +435,9 @@ class BatchedBOEngine:
     def _finish_device(self, h):
         """Wait for the optimiser kernel of `h`. Returns (the output dict with the device tensor of clamped candidates
         cand [B, R, D], warned {b: bool})."""
+        tw = perf_counter()
         h["done"].synchronize()
+        self.stats["wait_opt_s"] += perf_counter() - tw
         out, sel, ev, k_host = h["out"], h["sel"], h["ev"], h["k_host"]
         status, nfev, nit = self.h_status.numpy(), self.h_nfev.numpy(), self.h_nit.numpy()
         if (status[sel] < 0).any():
@@ -467,7 +470,9 @@ class BatchedBOEngine:
     def _propose_begin(self, st):
         """Phase B: initial conditions selected (host multinomial), optimiser kernel in flight (device mode)."""
         B, D = self.B, self.D
+        tw = perf_counter()
         st["ic"]["done"].synchronize()
+        self.stats["wait_ic_s"] += perf_counter() - tw
         k_host = self.h_k.numpy().astype(np.int64) if self.algorithm == "pca" else np.full(B, D, np.int64)
         self.k_host = k_host
         self.stats["d2h_bytes"] += B * 4

@@ -354,3 +354,26 @@ def test_probability_of_improvement_value_grad(D, n, npts, maximization):
         gr = grad.numpy()
         scale = np.maximum(np.max(np.abs(gr), axis=1, keepdims=True), 1e-12)
         assert np.max(np.abs(g - gr) / scale) < 1e-7, "PI gradient (per-point max-norm relative)"
+
+
+@pytest.mark.parametrize("D", [2, 5, 10, 40])
+def test_bbob_kernel_matches_oracle(D):
+    """pcabo_bbob_eval (f15, f16, f17, f20; several instances) against the CPU oracle's BBOB restatement, on points
+    inside and outside the box (boundary penalty), one point per problem and many points per problem."""
+    from pcabo_b200.bbob import BatchedBBOB
+    from oracle import bbob
+    fids = [15, 16, 17, 20, 15, 16, 17, 20]
+    insts = [0, 0, 0, 0, 3, 7, 11, 29]
+    prob = BatchedBBOB(fids, insts, D, device="cuda")
+    rng = np.random.RandomState(D)
+    m = 9
+    X = rng.uniform(-5, 5, size=(len(fids), m, D))
+    X[:, 0] = rng.uniform(-7, 7, size=(len(fids), D))          # outside the box
+    X[:, 1] = 0.0
+    got_many = prob.eval_all(X)
+    got_one = prob(torch.from_numpy(np.ascontiguousarray(X[:, 2])).cuda()).cpu().numpy()
+    for b, (fid, inst) in enumerate(zip(fids, insts)):
+        p = bbob.BBOBProblem(fid, D, inst)
+        ref = np.array([p(X[b, j]) for j in range(m)])
+        assert np.max(np.abs(got_many[b] - ref) / np.maximum(1.0, np.abs(ref))) < 1e-11, (fid, inst)
+        assert abs(got_one[b] - ref[2]) <= 1e-11 * max(1.0, abs(ref[2]))
