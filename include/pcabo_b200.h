@@ -174,6 +174,16 @@ int pcabo_sobol_scramble_bits(int B, int kmax, const int *k, unsigned *mt_state,
 /* out[b][r][:] = X[b][idx[b][r]][:]  (selection of the initial conditions among the raw samples).                    */
 int pcabo_gather_rows(int B, int npts, int nsel, int kmax, const double *X, const int *idx, double *out, void *stream);
 
+/* botorch initialize_q_batch (the Boltzmann pick of the num_restarts initial conditions inside optimize_acqf,
+ * PCA_BO.py:607-614) on the device, one run per block: weights exp(eta (v - mean) / std) of the raw-sample values
+ * vals [B][nraw], torch.multinomial without replacement replayed from each run's torch CPU generator (MT19937 state
+ * mt_state [B][624] + position mt_pos [B], advanced in place exactly as torch advances it), arg-max forced in last.
+ * Outputs: ics [B][nsel][kmax] = the picked rows of X [B][nraw][kmax], idx [B][nsel], flag [B] (1: degenerate values,
+ * nothing drawn and nothing written for that run -- botorch takes a random permutation and warns; host path).   */
+int pcabo_select_initial_conditions(int B, int nraw, int nsel, int kmax, double eta, const double *vals,
+                                    unsigned *mt_state, int *mt_pos, const double *X, double *ics, int *idx,
+                                    int *flag, void *stream);
+
 /* Batched BBOB objectives f15 / f16 / f17 / f20 (the synthetic workloads of BASELINE configs C1-C3), one block per
  * (problem, point): replaces the per-iteration host call problem(x) of the reference (PCA_BO.py:263,
  * AbstractBayesianOptimizer.py:163; ioh's C++ objective) when the runs of a batch are BBOB problems.

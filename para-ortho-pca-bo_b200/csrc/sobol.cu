@@ -145,6 +145,143 @@ __global__ void __launch_bounds__(256) mt_scramble_bits_kernel(int kmax, const i
   if (tid == 0) mt_pos[b] = pos;
 }
 
+// ---------------------------------------------------------------------------------------------- initial conditions
+// botorch initialize_q_batch (optim/initializers.py) for one run per block, entirely on the device:
+//   Boltzmann weights w = exp(eta (v - mean) / std) of the raw-sample values (eta halved while a weight overflows),
+//   torch.multinomial(w, nsel) without replacement = top-nsel of w / q with q ~ Exp(1), where torch's CPU exponential_
+//   draws q_i = -log1p(-u_i), u_i = 53 low bits of random64() * 2^-53, random64() = two consecutive MT19937 outputs
+//   (high word first) of the run's generator -- replayed here from the device-resident generator state --, the arg-max of
+//   the values forced in as the last pick when it was not drawn, and the gather of the picked rows.
+// Runs whose values are degenerate (std zero or not finite: botorch picks a random permutation and warns) are only
+// flagged, their generator is left untouched, and the host path handles them.
+__global__ void __launch_bounds__(256) ic_select_kernel(int nraw, int nsel, int kmax, double eta, const double *vals,
+                                                        unsigned *mt_state, int *mt_pos, const double *X, double *ics,
+                                                        int *idx_out, int *flag) {
+  __shared__ unsigned st[MT_N];
+  __shared__ double red[34];
+  __shared__ int ired[34];
+  __shared__ int picks[32];
+  extern __shared__ double dyn[];            // score [nraw] | raw words [2 nraw] (as unsigned)
+  double *score = dyn;
+  unsigned *words = reinterpret_cast<unsigned *>(dyn + nraw);
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const double *v = vals + (size_t)b * nraw;
+  // mean and unbiased standard deviation (two passes)
+  double s = 0.0;
+  for (int i = tid; i < nraw; i += nt) s += v[i];
+  const double mean = block_sum(s, red) / nraw;
+  double q2 = 0.0;
+  for (int i = tid; i < nraw; i += nt) { const double d = v[i] - mean; q2 = fma(d, d, q2); }
+  const double sd = sqrt(block_sum(q2, red) / (nraw - 1));
+  if (!(isfinite(sd) && sd != 0.0)) {
+    if (tid == 0) flag[b] = 1;
+    return;
+  }
+  if (tid == 0) flag[b] = 0;
+  // Boltzmann weights; botorch: while isinf(weights).any(): etaZ *= 0.5
+  double scale = eta / sd;
+  for (int iter = 0; iter < 64; ++iter) {
+    int inf = 0;
+    for (int i = tid; i < nraw; i += nt) {
+      const double w = exp(scale * (v[i] - mean));
+      score[i] = w;
+      inf |= isinf(w) ? 1 : 0;
+    }
+    if (!__syncthreads_or(inf)) break;
+    scale *= 0.5;
+  }
+  // 2 nraw tempered MT19937 outputs from the run's generator
+  for (int i = tid; i < MT_N; i += nt) st[i] = mt_state[(size_t)b * MT_N + i];
+  int pos = mt_pos[b];
+  __syncthreads();
+  const int total = 2 * nraw;
+  int done = 0;
+  while (done < total) {
+    if (pos >= MT_N) { mt_regenerate(st); pos = 0; }
+    const int take = min(MT_N - pos, total - done);
+    for (int t = tid; t < take; t += nt) {
+      unsigned y = st[pos + t];
+      y ^= y >> 11;
+      y ^= (y << 7) & 0x9d2c5680u;
+      y ^= (y << 15) & 0xefc60000u;
+      y ^= y >> 18;
+      words[done + t] = y;
+    }
+    pos += take;
+    done += take;
+    __syncthreads();
+  }
+  for (int i = tid; i < MT_N; i += nt) mt_state[(size_t)b * MT_N + i] = st[i];
+  if (tid == 0) mt_pos[b] = pos;
+  // score = w / q
+  for (int i = tid; i < nraw; i += nt) {
+    const unsigned long long x = ((unsigned long long)words[2 * i] << 32) | words[2 * i + 1];
+    const double u = (double)(x & ((1ULL << 53) - 1)) * (1.0 / 9007199254740992.0);
+    const double q = -log1p(-u);
+    score[i] = score[i] / q;
+  }
+  __syncthreads();
+  // arg-max of the raw values (first occurrence)
+  const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  int amax;
+  {
+    double bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < nraw; i += nt)
+      if (v[i] > bv || (v[i] == bv && i < bi)) { bv = v[i]; bi = i; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { red[wid] = bv; ired[wid] = bi; }
+    __syncthreads();
+    bv = red[0]; bi = ired[0];
+    for (int w8 = 1; w8 < nw; ++w8)
+      if (red[w8] > bv || (red[w8] == bv && ired[w8] < bi)) { bv = red[w8]; bi = ired[w8]; }
+    amax = bi;
+    __syncthreads();
+  }
+  // top-nsel of the scores (descending; a taken entry is retired)
+  for (int r = 0; r < nsel; ++r) {
+    double bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < nraw; i += nt) {
+      const double sc = score[i];
+      if (sc > bv || (sc == bv && i < bi)) { bv = sc; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { red[wid] = bv; ired[wid] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      bv = red[0]; bi = ired[0];
+      for (int w8 = 1; w8 < nw; ++w8)
+        if (red[w8] > bv || (red[w8] == bv && ired[w8] < bi)) { bv = red[w8]; bi = ired[w8]; }
+      if (bi == 0x7fffffff) bi = r;            // only NaN scores left: any index
+      picks[r] = bi;
+      score[bi] = -INFINITY;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    bool have = false;
+    for (int r = 0; r < nsel; ++r) have = have || picks[r] == amax;
+    if (!have) picks[nsel - 1] = amax;
+  }
+  __syncthreads();
+  for (int r = tid; r < nsel; r += nt) idx_out[(size_t)b * nsel + r] = picks[r];
+  for (int e = tid; e < nsel * kmax; e += nt) {
+    const int r = e / kmax, c = e % kmax;
+    ics[((size_t)b * nsel + r) * kmax + c] = X[((size_t)b * nraw + picks[r]) * kmax + c];
+  }
+}
+
 __global__ void gather_rows_kernel(int npts, int nsel, int kmax, const double *X, const int *idx, double *out) {
   const int b = blockIdx.x;
   for (int e = threadIdx.x; e < nsel * kmax; e += blockDim.x) {
@@ -175,6 +312,19 @@ extern "C" int pcabo_sobol_scramble_bits(int B, int kmax, const int *k, unsigned
   if (kmax > 256) return PCABO_E_UNSUPPORTED;
   const size_t smem = (size_t)kmax * (MAXBIT + 1) * sizeof(int);
   mt_scramble_bits_kernel<<<B, 256, smem, as_stream(stream)>>>(kmax, k, mt_state, mt_pos, shift, ltm_dots);
+  PCABO_LAUNCH_CHECK();
+  return PCABO_OK;
+}
+
+extern "C" int pcabo_select_initial_conditions(int B, int nraw, int nsel, int kmax, double eta, const double *vals,
+                                               unsigned *mt_state, int *mt_pos, const double *X, double *ics,
+                                               int *idx, int *flag, void *stream) {
+  if (B <= 0 || nraw < 2 || nsel <= 0 || nsel > 32 || nsel >= nraw || kmax <= 0 || !vals || !mt_state || !mt_pos || !X ||
+      !ics || !idx || !flag)
+    return PCABO_E_INVALID;
+  const size_t smem = (size_t)nraw * sizeof(double) + 2 * (size_t)nraw * sizeof(unsigned);
+  if (smem > 40 * 1024) return PCABO_E_UNSUPPORTED;
+  ic_select_kernel<<<B, 256, smem, as_stream(stream)>>>(nraw, nsel, kmax, eta, vals, mt_state, mt_pos, X, ics, idx, flag);
   PCABO_LAUNCH_CHECK();
   return PCABO_OK;
 }

@@ -130,7 +130,10 @@ class BatchedBOEngine:
         self.overlap_hook = None
         self.lb_out = None
         self.h_status = self.h_nfev = self.h_nit = None
-        self.h_vals = self.h_state_back = self.h_pos_back = self.h_k = None
+        self.h_vals = self.h_state_back = self.h_pos_back = self.h_k = self.h_flag = None
+        self.d_mt_state = self.d_mt_pos = self.ic_out = None
+        self.gens_on_host = True       # False: the device-resident MT19937 states are ahead of the torch CPU generators
+        self.force_host_ic = False     # tests: always take the host path for the Boltzmann pick
         self.pending = None         # state of a step between step_begin() and step_end()
         self.phase_times = None     # set to {} to accumulate host wall time per phase (adds device syncs)
         self.kernel_events = None   # set to [] to record CUDA-event pairs around every value+grad log-EI launch
@@ -259,11 +262,49 @@ class BatchedBOEngine:
         self.gp.best_f.copy_(bf)
         self.stats["h2d_bytes"] += B * 8
 
+    def _gens_to_host(self):
+        """Bring the torch CPU generators up to date with the device-resident MT19937 states (fast path)."""
+        if not self.gens_on_host:
+            self.gen_io.restore(self.torch_gens, self.d_mt_state.cpu(), self.d_mt_pos.cpu())
+            self.gens_on_host = True
+
+    def _ic_launch_fast(self):
+        """_ic_launch for the common case (all runs, 512 raw samples, log-EI, generators owned by the engine): the
+        Boltzmann pick itself runs on the device too (pcabo_select_initial_conditions replays torch.multinomial from
+        the device-resident generator states), so nothing but a per-run flag and k comes back to the host."""
+        B, D, R = self.B, self.D, self.num_restarts
+        if self.gens_on_host:
+            st, pos = self.gen_io.export(self.torch_gens)
+            self.d_mt_state = st.to(self.device, non_blocking=True)
+            self.d_mt_pos = pos.to(self.device, non_blocking=True)
+            self.gens_on_host = False
+            self.stats["h2d_bytes"] += st.numel() * 4 + pos.numel() * 4
+        k_dev = self.pca["k"] if self.algorithm == "pca" else self.k_full
+        d_shift, d_dots = ops.sobol_scramble_bits(k_dev, self.d_mt_state, self.d_mt_pos, D)
+        x_raw = ops.sobol_points(self.raw_samples, k_dev, d_shift, d_dots, self.state0, self.gp.box_lo, self.gp.box_hi)
+        vals_dev = ops.logei(self.gp, x_raw)["val"]
+        self.ic_out = ops.select_initial_conditions(vals_dev, self.d_mt_state, self.d_mt_pos, x_raw, R, out=self.ic_out)
+        if self.h_flag is None:
+            self.h_flag = torch.zeros(B, dtype=torch.int32).pin_memory()
+            self.h_k = torch.zeros(B, dtype=torch.int32).pin_memory()
+        self.h_flag.copy_(self.ic_out["flag"], non_blocking=True)
+        if self.algorithm == "pca":
+            self.h_k.copy_(self.pca["k"], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        self.stats["kernel_launches"] += 4
+        self.stats["d2h_bytes"] += 8 * B
+        return dict(pending=list(range(B)), factor=1, x_raw=x_raw, vals_dev=vals_dev, done=done, fast=True)
+
     def _ic_launch(self, pending, k_host, factor):
         """Enqueue the device part of gen_batch_initial_conditions for the `pending` runs: Sobol scramble bits (each
         run's torch CPU generator, MT19937, replayed on the device), Sobol points scaled to the box, log-EI of the raw
         samples, and the asynchronous read-back of the values and generator states into pinned memory."""
         B, D = self.B, self.D
+        if (factor == 1 and len(pending) == B and self.owns_rngs and self.gp.acq == ops.ACQ_LOG_EI
+                and self.num_restarts <= 32 and self.raw_samples <= 1024 and not self.force_host_ic):
+            return self._ic_launch_fast()
+        self._gens_to_host()
         nraw = self.raw_samples * factor
         st, pos = self.gen_io.export(self.torch_gens)
         d_state = st.to(self.device, non_blocking=True)
@@ -301,6 +342,21 @@ class BatchedBOEngine:
         B, R = self.B, self.num_restarts
         pending = h["pending"]
         h["done"].synchronize()
+        if h.get("fast"):
+            d_ics.copy_(self.ic_out["ics"])
+            flagged = [b for b in pending if int(self.h_flag[b]) != 0]
+            if not flagged:
+                return []
+            # degenerate raw values (botorch: random permutation pick + warning, then more raw samples): host path for
+            # those runs, from the generator states the device left them in
+            self._gens_to_host()
+            vals = h["vals_dev"].cpu()
+            idx, bad = select_initial_conditions(vals, R, self.torch_gens, flagged, None)
+            d_idx = idx.to(torch.int32).to(self.device)
+            picked = ops.gather_rows(h["x_raw"], d_idx)
+            sel = torch.tensor(flagged, device=self.device)
+            d_ics[sel] = picked[sel]
+            return [b for b in flagged if bad[b]]
         self.gen_io.restore(self.torch_gens, self.h_state_back, self.h_pos_back)
         if self.gp.acq == ops.ACQ_PI:      # botorch picks initialize_q_batch_nonneg for non-negative acquisitions
             idx, bad = select_initial_conditions_nonneg(self.h_vals, R, self.torch_gens, pending)

@@ -9,7 +9,7 @@ EXPORTED_SYMBOLS = [
     "pcabo_abi_version", "pcabo_error_string", "pcabo_last_cuda_error",
     "pcabo_weights_pca_fit", "pcabo_inverse_map", "pcabo_gp_fit", "pcabo_gp_mll",
     "pcabo_logei", "pcabo_argmax", "pcabo_lbfgsb_logei", "pcabo_lbfgsb_logei_prof", "pcabo_lbfgsb_logei_runs", "pcabo_ei_sweep",
-    "pcabo_sobol_points", "pcabo_sobol_scramble_bits", "pcabo_gather_rows", "pcabo_bbob_eval",
+    "pcabo_sobol_points", "pcabo_sobol_scramble_bits", "pcabo_gather_rows", "pcabo_bbob_eval", "pcabo_select_initial_conditions",
 ]
 
 
@@ -78,6 +78,8 @@ def load_library(build_if_missing: bool = False):
     lib.pcabo_sobol_scramble_bits.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp]
     lib.pcabo_gather_rows.restype = ci
     lib.pcabo_gather_rows.argtypes = [ci, ci, ci, ci, vp, vp, vp, vp]
+    lib.pcabo_select_initial_conditions.restype = ci
+    lib.pcabo_select_initial_conditions.argtypes = [ci, ci, ci, ci, cd] + [vp] * 7 + [vp]
     lib.pcabo_bbob_eval.restype = ci
     lib.pcabo_bbob_eval.argtypes = [ci, ci, ci] + [vp] * 7 + [cd, vp, vp, vp]
     lib.pcabo_argmax.restype = ci

@@ -288,3 +288,20 @@ def bbob_eval(fid, xopt, R, M, sign, fopt, lam, f0, X, out=None):
                               _d(fopt, "fopt"), _d(lam, "lam"), float(f0), _d(X, "X"), _d(out, "out"), _stream()),
           "pcabo_bbob_eval")
     return out
+
+
+def select_initial_conditions(vals, mt_state, mt_pos, X, nsel, eta=1.0, out=None):
+    """vals [B, nraw], X [B, nraw, kmax], mt_state [B, 624] int32 / mt_pos [B] int32 (advanced in place) ->
+    dict(ics [B, nsel, kmax], idx [B, nsel] int32, flag [B] int32)."""
+    lib = load_library()
+    B, nraw, kmax = X.shape
+    dev = X.device
+    if out is None:
+        out = dict(ics=torch.zeros(B, nsel, kmax, dtype=torch.float64, device=dev),
+                   idx=torch.zeros(B, nsel, dtype=torch.int32, device=dev),
+                   flag=torch.zeros(B, dtype=torch.int32, device=dev))
+    check(lib.pcabo_select_initial_conditions(B, nraw, int(nsel), kmax, float(eta), _d(vals, "vals"),
+                                              _i(mt_state, "mt_state"), _i(mt_pos, "mt_pos"), _d(X, "X"),
+                                              _d(out["ics"], "ics"), _i(out["idx"], "idx"), _i(out["flag"], "flag"),
+                                              _stream()), "pcabo_select_initial_conditions")
+    return out

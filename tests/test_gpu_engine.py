@@ -332,3 +332,69 @@ def test_engine_probability_of_improvement_matches_oracle():
             100 * tol * max(1.0, np.max(np.abs(rec["new_z"]))), optimizer
     with pytest.raises(ValueError):
         BatchedBOEngine(prob, D, prob.bounds, budget, ndoe, [1], acquisition="upper_confidence_bound")
+
+
+def test_device_initial_condition_selection_equals_torch_multinomial():
+    """pcabo_select_initial_conditions against the host restatement of botorch's initialize_q_batch (which uses
+    torch's own exponential_ / topk on the run's CPU generator): same picks, same generator state afterwards; runs with
+    degenerate values are flagged and left untouched."""
+    from pcabo_b200 import ops
+    from pcabo_b200.acq_host import GeneratorStateIO, select_initial_conditions
+    B, nraw, kmax, R = 6, 512, 8, 10
+    rng = np.random.RandomState(2)
+    vals = torch.from_numpy(rng.randn(B, nraw) * np.array([1.0, 5.0, 40.0, 300.0, 1e-3, 1.0])[:, None])
+    vals[5] = 0.25                                   # degenerate: all values equal
+    vals[3, 7] = 2000.0                              # weights overflow: eta is halved
+    X = torch.from_numpy(rng.rand(B, nraw, kmax))
+    gens_a, gens_b = [], []
+    for b in range(B):
+        for gl in (gens_a, gens_b):
+            g = torch.Generator()
+            g.manual_seed(100 + b)
+            _ = torch.randint(2, (b * 37 + 5,), generator=g)      # move every generator to a different position
+            gl.append(g)
+    io = GeneratorStateIO(B)
+    st, pos = io.export(gens_a)
+    d_st, d_pos = st.cuda(), pos.cuda()
+    out = ops.select_initial_conditions(vals.cuda(), d_st, d_pos, X.cuda(), R)
+    torch.cuda.synchronize()
+    io.restore(gens_a, d_st.cpu(), d_pos.cpu())
+    idx_h, bad = select_initial_conditions(vals.clone(), R, gens_b, list(range(B - 1)))
+    flag = out["flag"].cpu().numpy()
+    assert flag.tolist() == [0, 0, 0, 0, 0, 1] and not any(bad[:5])
+    idx_d = out["idx"].cpu().numpy()
+    for b in range(B - 1):
+        assert sorted(idx_d[b].tolist()) == sorted(idx_h[b].tolist()), b
+        assert idx_d[b, -1] == idx_h[b, -1] or int(torch.argmax(vals[b])) in idx_d[b].tolist()
+        assert torch.equal(gens_a[b].get_state(), gens_b[b].get_state()), b
+        picked = out["ics"][b].cpu()
+        assert torch.equal(picked, X[b][torch.from_numpy(idx_d[b]).long()])
+    g5 = torch.Generator()
+    g5.manual_seed(105)
+    _ = torch.randint(2, (5 * 37 + 5,), generator=g5)
+    assert torch.equal(gens_a[5].get_state(), g5.get_state())     # flagged run: generator untouched
+
+
+def test_engine_device_and_host_initial_conditions_agree():
+    """The same runs with the Boltzmann pick on the device (default) and on the host (force_host_ic): identical first
+    iterations (same picks from the same generator streams)."""
+    from pcabo_b200.engine import BatchedBOEngine
+    from pcabo_b200.bbob import BatchedBBOB
+    D, budget, ndoe = 10, 150, 30
+    fids, insts = [15, 16, 17, 15], [0, 1, 2, 3]
+    seeds = [1000 * f + 10 * D + i for f, i in zip(fids, insts)]
+    engs = []
+    for force in (False, True):
+        prob = BatchedBBOB(fids, insts, D, device="cuda")
+        e = BatchedBOEngine(prob, D, prob.bounds, budget, ndoe, seeds, optimizer="device")
+        e.force_host_ic = force
+        e.initial_design()
+        for _ in range(3):
+            e.step()
+        engs.append(e)
+    a, b = engs
+    for r in range(len(fids)):
+        assert np.allclose(np.array(a.x_evals[r]), np.array(b.x_evals[r]), rtol=1e-9, atol=1e-9), r
+    a._gens_to_host()
+    for r in range(len(fids)):
+        assert torch.equal(a.torch_gens[r].get_state(), b.torch_gens[r].get_state()), r
