@@ -127,6 +127,7 @@ class BatchedBOEngine:
         self.last = {}
         self.noise_ready_n = -1     # the pinned noise buffer holds the draw for the iteration with this many points
         self.noise_copied = torch.cuda.Event()
+        self.noise_futs = None
         self.overlap_hook = None
         self.lb_out = None
         self.h_status = self.h_nfev = self.h_nit = None
@@ -209,24 +210,34 @@ class BatchedBOEngine:
         self.phase_times[name] = self.phase_times.get(name, 0.0) + (t1 - t0)
         return t1
 
-    def _draw_noise(self, n):
-        """The 1e-8 PCA noise of the iteration that fits n points, drawn from each run's numpy stream (PCA_BO.py:376)."""
+    def _draw_noise(self, n, wait=True):
+        """The 1e-8 PCA noise of the iteration that fits n points, drawn from each run's numpy stream (PCA_BO.py:376) on
+        the thread pool (numpy fills the array without the GIL). wait=False returns with the draws in flight."""
         B, D = self.B, self.D
         hv_np = self.h_noise[:B * n * D].view(B, n, D).numpy()
 
         def _noise(b):
             hv_np[b] = self.np_rngs[b].normal(0, 1e-8, size=(n, D))
 
-        list(self.pool.map(_noise, range(B)))
+        self.noise_futs = [self.pool.submit(_noise, b) for b in range(B)]
         self.noise_ready_n = n
+        if wait:
+            self._wait_noise()
+
+    def _wait_noise(self):
+        if self.noise_futs:
+            for fu in self.noise_futs:
+                fu.result()
+            self.noise_futs = None
 
     def _prefetch_noise(self):
-        """Draw the NEXT iteration's noise while the optimiser kernel runs. The pinned buffer of this iteration has
-        been consumed (its H2D copy precedes the kernel on the stream) and the numpy streams are used for nothing else
-        between two iterations, so the draw order of every run is unchanged."""
+        """Start drawing the NEXT iteration's noise while the optimiser kernel runs; the host thread does not wait
+        for it (it is collected at the next model fit). The pinned buffer of this iteration has been consumed (its H2D
+        copy precedes the kernel on the stream) and the numpy streams are used for nothing else between two iterations,
+        so the draw order of every run is unchanged."""
         if self.owns_rngs and self.algorithm == "pca" and self.n + 1 < self.budget:
             self.noise_copied.synchronize()
-            self._draw_noise(self.n + 1)
+            self._draw_noise(self.n + 1, wait=False)
 
     def _fit_models(self):
         B, D, n = self.B, self.D, self.n
@@ -234,7 +245,9 @@ class BatchedBOEngine:
             tp = perf_counter()
             hv = self.h_noise[:B * n * D].view(B, n, D)
             if self.noise_ready_n != n:
+                self._wait_noise()
                 self._draw_noise(n)
+            self._wait_noise()
             self.noise_ready_n = -1
             tp = self._phase("host_noise_rng", tp)
             dv = self.d_noise[:B * n * D].view(B, n, D)
