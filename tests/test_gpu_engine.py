@@ -398,3 +398,37 @@ def test_engine_device_and_host_initial_conditions_agree():
     a._gens_to_host()
     for r in range(len(fids)):
         assert torch.equal(a.torch_gens[r].get_state(), b.torch_gens[r].get_state()), r
+
+
+def test_device_initial_conditions_fall_back_for_flagged_runs():
+    """A run the device pick flags as degenerate goes through the host path (generators synchronised from the device
+    states first): its initial conditions are the host pick's rows, the other runs keep the device pick."""
+    from pcabo_b200 import ops
+    from pcabo_b200.engine import BatchedBOEngine
+    from pcabo_b200.bbob import BatchedBBOB
+    D, budget, ndoe = 10, 150, 30
+    fids, insts = [15, 16, 17], [0, 1, 2]
+    prob = BatchedBBOB(fids, insts, D, device="cuda")
+    e = BatchedBOEngine(prob, D, prob.bounds, budget, ndoe, [1000 * f + 10 * D + i for f, i in zip(fids, insts)],
+                        optimizer="device")
+    e.initial_design()
+    e.step()
+    e._fit_models()
+    h = e._ic_launch(list(range(3)), None, 1)
+    assert h.get("fast")
+    h["done"].synchronize()
+    dev_pick = e.ic_out["ics"].clone()
+    e.h_flag[1] = 1                                   # pretend run 1 had degenerate raw values
+    d_ics = torch.zeros(3, e.num_restarts, D, dtype=torch.float64, device="cuda")
+    still = e._ic_finish(h, d_ics)
+    torch.cuda.synchronize()
+    assert still == [] and e.gens_on_host
+    assert torch.equal(d_ics[0], dev_pick[0]) and torch.equal(d_ics[2], dev_pick[2])
+    # run 1: rows of its raw samples chosen by the host path (a valid pick containing the arg-max)
+    vals = h["vals_dev"][1].cpu()
+    rows = h["x_raw"][1].cpu()
+    amax_row = rows[int(torch.argmax(vals))]
+    assert any(torch.equal(d_ics[1, r].cpu(), amax_row) for r in range(e.num_restarts))
+    # the engine keeps going from the synchronised generators
+    e.step()
+    assert e.n == ndoe + 2
