@@ -84,8 +84,10 @@ def main():
         match = [0] * len(insts)
         alive = [True] * len(insts)
         first_dev = [None] * len(insts)
+        k_hist = []
         for it in range(args.iters):
             eng.step()
+            k_hist.append(np.asarray(eng.last["k"], dtype=np.float64).copy())
             for b, o in enumerate(ora):
                 if not alive[b]:
                     continue
@@ -108,7 +110,12 @@ def main():
                     "median_best_oracle": float(np.median([o["best"] for o in ora])),
                     "oob_fraction_engine": float(np.mean([np.mean(np.array(eng.f_evals[b][3 * D:]) == 1000.0) for b in range(len(insts))])),
                     "oob_fraction_oracle": float(np.mean([np.mean(o["oob"]) for o in ora])),
-                    "retries": eng.stats["retries"]}
+                    "retries": eng.stats["retries"],
+                    # distribution-level agreement once the trajectories have decorrelated: number of components k
+                    "k_mean_engine_by_quarter": [float(np.mean(k_hist[q * args.iters // 4:(q + 1) * args.iters // 4]))
+                                                 for q in range(4)],
+                    "k_mean_oracle_by_quarter": [float(np.mean([o["k"][q * args.iters // 4:(q + 1) * args.iters // 4]
+                                                                for o in ora])) for q in range(4)]}
     print(json.dumps(out))
 
 
