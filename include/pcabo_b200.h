@@ -108,6 +108,13 @@ int pcabo_gp_fit(int B, int n, int kmax, int ld_n, int mode,
 int pcabo_gp_mll(int B, int n, int ld_n, const double *f, const double *ymean, const double *ystd,
                  const double *L, const double *alpha, double *mll, void *stream);
 
+/* Gradient of that marginal log-likelihood w.r.t. the Matern lengthscale and the noise variance, from the caches of
+ * pcabo_gp_fit: grad [B][2] = (dMLL/dl, dMLL/dsigma^2) = 1/2 alpha^T dK alpha - 1/2 tr(K^-1 dK), K^-1 = W^T W built tile
+ * by tile on the fly. The reference never fits its GP, so nothing on the BO path calls this; it is the
+ * building block of an opt-in hyper-parameter fit (north_star).                                                   */
+int pcabo_gp_mll_grad(int B, int n, int kmax, int ld_n, const int *k, const double *Zn, const double *W,
+                      const double *alpha, double lengthscale, double *grad, void *stream);
+
 /* log-EI (and optionally its gradient, posterior mean and sigma) at npts raw-space points per run.
  *   X [B][npts][kmax]; val [B][npts]; grad [B][npts][kmax] or NULL; mu, sigma [B][npts] or NULL.               */
 int pcabo_logei(const pcabo_gp_model *m, int npts, const double *X, double *val, double *grad,

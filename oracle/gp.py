@@ -144,6 +144,22 @@ class GPModel:
                      - 0.5 * self.n * _LOG_2PI)
 
 
+def mll_and_grad(model: "GPModel"):
+    """Exact marginal log-likelihood and its gradient w.r.t. (lengthscale, noise) by autograd (north_star item, no
+    reference call site: the reference never fits its GP). Direct-difference distances, as the kernels use."""
+    ls = torch.tensor(model.lengthscale, dtype=torch.float64, requires_grad=True)
+    nz = torch.tensor(model.noise, dtype=torch.float64, requires_grad=True)
+    X = model.train_xn
+    sq = (X.unsqueeze(0) - X.unsqueeze(1)).pow(2).sum(-1) / ls ** 2
+    d = sq.clamp_min(1e-30).sqrt()
+    K = torch.exp(-SQRT5 * d) * ((SQRT5 * d).add(1).add(5.0 / 3.0 * d ** 2)) + nz * torch.eye(model.n, dtype=torch.float64)
+    L = torch.linalg.cholesky(K)
+    alpha = torch.cholesky_solve(model.y_s.unsqueeze(-1), L).squeeze(-1)
+    mll = -0.5 * (model.y_s @ alpha) - torch.log(torch.diagonal(L)).sum() - 0.5 * model.n * _LOG_2PI
+    g_ls, g_nz = torch.autograd.grad(mll, (ls, nz))
+    return float(mll.detach()), float(g_ls), float(g_nz)
+
+
 # ----------------------------------------------------------------------------- acquisition
 def _phi(x):
     return _INV_SQRT_2PI * (-0.5 * x.square()).exp()

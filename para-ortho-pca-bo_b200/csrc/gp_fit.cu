@@ -458,7 +458,99 @@ __global__ void gp_mll_kernel(int n, int ld_n, const double *f, const double *ym
   if (threadIdx.x == 0) mll[b] = -0.5 * quad - logdet - 0.5 * (double)n * 1.8378770664093453;  // log(2 pi)
 }
 
+// --------------------------------------------------------------------------------------------- MLL gradient
+// d MLL / d theta = 1/2 alpha^T (dK/dtheta) alpha - 1/2 tr(K^-1 dK/dtheta) for theta = lengthscale and noise, with
+// K^-1 = W^T W never formed in memory: one block per 32 x 32 tile (ti >= tj) of the lower triangle builds its tile of
+// K^-1 as the product of two column panels of W (rows k >= ti * 32, where W is non-zero) staged through shared memory,
+// multiplies it by the tile of dK/dl computed on the fly from the normalised inputs, and adds its share of both traces
+// to the per-run outputs. Matern-5/2: k(a) = (1 + a + a^2/3) e^-a, a = sqrt5 r / l  =>  dk/dl = a^2 (1 + a) e^-a / (3 l).
+constexpr int GT = 32;   // tile
+constexpr int GK = 32;   // rows of W per staging step
+
+__global__ void __launch_bounds__(256) gp_mll_grad_kernel(int n, int kmax, int ld_n, const int *k, const double *Zn,
+                                                         const double *W, const double *alpha, double lengthscale,
+                                                         double *grad /* [B][2]: d/dl, d/dnoise */) {
+  __shared__ double wi[GK][GT + 1], wj[GK][GT + 1];
+  __shared__ double red[34];
+  const int b = blockIdx.y;
+  int t = blockIdx.x, ti = 0;
+  while (t >= ti + 1) { t -= ti + 1; ++ti; }
+  const int tj = t;
+  const int kk = k ? k[b] : kmax;
+  const double *Wb = W + (size_t)b * ld_n * ld_n;
+  const double *Zb = Zn + (size_t)b * ld_n * kmax;
+  const double *al = alpha + (size_t)b * ld_n;
+  const int tid = threadIdx.x;
+  // thread owns the 2 x 2 block (r0, r0 + 1) x (c0, c0 + 1) of the tile
+  const int r0 = (tid / 16) * 2, c0 = (tid % 16) * 2;
+  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  const int i0 = ti * GT, j0 = tj * GT;
+  for (int k0 = i0; k0 < n; k0 += GK) {     // W[k][i] = 0 for k < i: start at the tile's first row index
+    for (int idx = tid; idx < GK * GT; idx += 256) {
+      const int kr = idx / GT, c = idx % GT;
+      const int kg = k0 + kr;
+      double a = 0.0, bb = 0.0;
+      if (kg < n) {
+        const int gi = i0 + c, gj = j0 + c;
+        if (gi < n && gi <= kg) a = Wb[(size_t)kg * ld_n + gi];
+        if (gj < n && gj <= kg) bb = Wb[(size_t)kg * ld_n + gj];
+      }
+      wi[kr][c] = a;
+      wj[kr][c] = bb;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kr = 0; kr < GK; ++kr) {
+      const double a0 = wi[kr][r0], a1 = wi[kr][r0 + 1], b0 = wj[kr][c0], b1 = wj[kr][c0 + 1];
+      acc[0][0] = fma(a0, b0, acc[0][0]);
+      acc[0][1] = fma(a0, b1, acc[0][1]);
+      acc[1][0] = fma(a1, b0, acc[1][0]);
+      acc[1][1] = fma(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+  // contributions of this tile: off-diagonal tiles stand for both (i, j) and (j, i)
+  const double mult = (ti == tj) ? 1.0 : 2.0;
+  const double inv_l = 1.0 / lengthscale;
+  double g_l = 0.0, g_n = 0.0;
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const int gi = i0 + r0 + u, gj = j0 + c0 + v;
+      if (gi < n && gj < n) {
+        double sq = 0.0;
+        for (int d = 0; d < kk; ++d) {
+          const double df = Zb[(size_t)gi * kmax + d] - Zb[(size_t)gj * kmax + d];
+          sq = fma(df, df, sq);
+        }
+        const double a = SQRT5 * sqrt(fmax(sq * inv_l * inv_l, 1e-30));
+        const double dk = (gi == gj) ? 0.0 : a * a * (1.0 + a) * exp(-a) * inv_l / 3.0;
+        g_l += mult * 0.5 * (al[gi] * al[gj] - acc[u][v]) * dk;
+        if (gi == gj) g_n += 0.5 * (al[gi] * al[gi] - acc[u][v]);     // dK/dnoise = I
+      }
+    }
+  g_l = block_sum(g_l, red);
+  g_n = block_sum(g_n, red);
+  if (tid == 0) {
+    atomicAdd(&grad[2 * b + 0], g_l);
+    atomicAdd(&grad[2 * b + 1], g_n);
+  }
+}
+
 }  // namespace
+
+extern "C" int pcabo_gp_mll_grad(int B, int n, int kmax, int ld_n, const int *k, const double *Zn, const double *W,
+                                 const double *alpha, double lengthscale, double *grad, void *stream) {
+  if (B <= 0 || n < 1 || kmax < 1 || ld_n < n || !Zn || !W || !alpha || !grad || !(lengthscale > 0.0)) return PCABO_E_INVALID;
+  cudaStream_t st = as_stream(stream);
+  PCABO_CUDA_CHECK(cudaMemsetAsync(grad, 0, sizeof(double) * 2 * B, st));
+  const int nt = (n + GT - 1) / GT;
+  dim3 grid(nt * (nt + 1) / 2, B);
+  gp_mll_grad_kernel<<<grid, 256, 0, st>>>(n, kmax, ld_n, k, Zn, W, alpha, lengthscale, grad);
+  PCABO_LAUNCH_CHECK();
+  return PCABO_OK;
+}
 
 extern "C" int pcabo_gp_fit(int B, int n, int kmax, int ld_n, int mode, const double *Z, const int *k, const double *f,
                             const double *fix_lo, const double *fix_hi, double lengthscale, double noise,

@@ -133,6 +133,16 @@ def gp_mll(buf: GPBuffers, f):
     return out
 
 
+def gp_mll_grad(buf: GPBuffers):
+    """(dMLL/dlengthscale, dMLL/dnoise) of the standardised targets from the caches: [B, 2] (device)."""
+    lib = load_library()
+    out = torch.empty(buf.B, 2, dtype=torch.float64, device=buf.W.device)
+    check(lib.pcabo_gp_mll_grad(buf.B, buf.n, buf.kmax, buf.ld_n, _i(buf.k, "k") if buf.k is not None else None,
+                                _d(buf.Zn, "Zn"), _d(buf.W, "W"), _d(buf.alpha, "alpha"), float(buf.lengthscale),
+                                _d(out, "grad"), _stream()), "pcabo_gp_mll_grad")
+    return out
+
+
 def model_struct(buf: GPBuffers) -> GpModelStruct:
     m = GpModelStruct()
     m.B, m.n, m.kmax, m.ld_n = buf.B, buf.n, buf.kmax, buf.ld_n

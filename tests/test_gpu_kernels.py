@@ -377,3 +377,20 @@ def test_bbob_kernel_matches_oracle(D):
         ref = np.array([p(X[b, j]) for j in range(m)])
         assert np.max(np.abs(got_many[b] - ref) / np.maximum(1.0, np.abs(ref))) < 1e-11, (fid, inst)
         assert abs(got_one[b] - ref[2]) <= 1e-11 * max(1.0, abs(ref[2]))
+
+
+@pytest.mark.parametrize("D,n", [(5, 10), (10, 77), (20, 250), (40, 330), (40, 450)])
+def test_gp_mll_gradient(D, n):
+    """pcabo_gp_mll_grad (d MLL / d lengthscale, d MLL / d noise from the caches, K^-1 = W^T W built tile by tile)
+    against autograd through the oracle's marginal log-likelihood."""
+    B = 2
+    ops, hist, X, f, pca, buf = _fit_gp_batch(D, n, B, seed0=5)
+    from oracle import gp, acqf
+    g = ops.gp_mll_grad(buf).cpu().numpy()
+    for b in range(B):
+        k = int(pca["k"][b])
+        Z = pca["Z"][b, :n, :k].cpu().numpy()
+        model = gp.GPModel(Z, hist[b][1], norm_bounds=acqf.normalize_box_pca(Z))
+        mll, g_ls, g_nz = gp.mll_and_grad(model)
+        assert abs(g[b, 0] - g_ls) <= 1e-8 * max(1.0, abs(g_ls)), ("d/dl", g[b, 0], g_ls)
+        assert abs(g[b, 1] - g_nz) <= 1e-8 * max(1.0, abs(g_nz)), ("d/dnoise", g[b, 1], g_nz)
