@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--dims", dest="r", type=int, nargs="+", default=[8, 16, 32, 40])
     ap.add_argument("--n", type=int, default=450)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--cpu-baseline", action="store_true",
+                    help="also time the CPU oracle (torch FP64, all host cores) on 2^14 of the same candidates")
     args = ap.parse_args()
     from pcabo_b200 import ops
     from pcabo_b200.parallel import candidate_range, global_argmax
@@ -63,6 +65,25 @@ def main():
         sst[:r] = eng.sobolstate.to(torch.int32)
         shift, sst = shift.to(dev), sst.to(dev)
         ws = ops.SweepWorkspace(dev)
+        if args.cpu_baseline and rank == 0:
+            # reference-style evaluation (botorch LogExpectedImprovement on the gpytorch caches, restated in oracle/):
+            # dense k* R products in torch FP64 on all host cores, chunks of 4096 candidates
+            import time
+            from oracle import gp as ogp
+            ncpu = os.cpu_count() or 1
+            torch.set_num_threads(ncpu)
+            model = ogp.GPModel(Z, y, norm_bounds=None)
+            acq = ogp.LogExpectedImprovement(model, float(y.min()), maximize=False)
+            pts = -1 / 3 + (5 / 3) * torch.quasirandom.SobolEngine(r, scramble=True, seed=1234).draw(1 << 14, dtype=torch.float64)
+            with torch.no_grad():
+                acq(pts[:4096])
+                t0 = time.perf_counter()
+                vals = torch.cat([acq(c) for c in pts.split(4096)])
+                dt = time.perf_counter() - t0
+            print(json.dumps({"impl": "reference", "metric": "EI candidates/sec", "n": n, "r": r, "candidates": 1 << 14,
+                              "candidates_per_s": (1 << 14) / dt, "cores": ncpu, "kind": "port",
+                              "argmax": [float(vals.max()), int(vals.argmax())]}), flush=True)
+            torch.set_num_threads(1)
         for l2 in args.log2n:
             N = 1 << l2
             a, b = candidate_range(N, rank, world)
