@@ -547,7 +547,11 @@ class BatchedBOEngine:
         self.stats["d2h_bytes"] += B * 4
         ics = self._initial_conditions(st["runs"], k_host, first=st["ic"])
         st.update(k_host=k_host, ics=ics)
-        if self.optimizer == "device":
+        # the device-resident optimiser keeps the whole L-BFGS-B state of a chunk in shared memory; past that size
+        # (config C5 beyond n ~ 920 with k ~ 90) the iteration is driven by scipy's L-BFGS-B on the same kernels
+        st["use_device"] = self.optimizer == "device" and ops.lbfgsb_fits(self.n, self.D, int(k_host.max()),
+                                                                           self.batch_limit)
+        if st["use_device"]:
             st["t_launch"] = perf_counter()
             self.overlap_hook = self._prefetch_noise
             st["handle"] = self._launch_device(ics, k_host, out=self.lb_out)
@@ -557,7 +561,7 @@ class BatchedBOEngine:
         """The rest of optimize_acqf: returns device tensor z_new [B, D] and its log-EI values [B]."""
         B, D, R = self.B, self.D, self.num_restarts
         k_host, runs, ics = st["k_host"], st["runs"], st["ics"]
-        if self.optimizer == "scipy":
+        if not st["use_device"]:
             # the host optimiser needs the search box; the device one reads it in HBM
             box_lo, box_hi = self.gp.box_lo.cpu(), self.gp.box_hi.cpu()
             self.stats["d2h_bytes"] += 2 * B * D * 8

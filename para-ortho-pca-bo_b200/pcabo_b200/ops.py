@@ -191,6 +191,18 @@ LBFGSB_STATUS = {0: "CONVERGENCE: NORM OF PROJECTED GRADIENT <= PGTOL", 1: "CONV
                  2: "STOP: TOTAL NO. OF ITERATIONS REACHED LIMIT", 3: "ABNORMAL"}
 
 
+def lbfgsb_fits(n, kmax, k_bound, batch_limit=5):
+    """Whether pcabo_lbfgsb_logei_runs fits the 227 KB of shared memory of a block for n training points, column
+    capacity kmax and at most k_bound active dimensions (mirrors the sizing in csrc/lbfgsb.cu / logei_core.cuh /
+    lbfgsb_core.cuh; the library itself answers PCABO_E_UNSUPPORTED when it does not)."""
+    P = 5 if batch_limit <= 5 else 8
+    np_ = (n + 1) & ~1
+    scratch = P * kmax + 2 * P * np_ + max(P * np_, 256 * P) + 8 * 2 * P + 4 * P + 8
+    nv = batch_limit * min(max(int(k_bound), 1), kmax)
+    work = 9 * nv + 2 * 10 * nv + 4 * 100 + 400 + 5 * 20 + nv + (nv + 1) // 2 + 4
+    return (scratch + work + 2 + 8 + 2 + 8) * 8 <= 227 * 1024 and kmax <= 104 and batch_limit <= 8
+
+
 def lbfgsb_logei(buf: GPBuffers, ics, box_lo, box_hi, batch_limit=5, maxiter=200, factr=1e7, pgtol=1e-5, out=None,
                  prof=None, run_idx=None, k_bound=0):
     """ics [B, num_restarts, kmax] -> dict(cand [B, R, kmax], fval/status/nit/nfev [B, nchunks]); one kernel launch.
