@@ -432,3 +432,31 @@ def test_device_initial_conditions_fall_back_for_flagged_runs():
     # the engine keeps going from the synchronised generators
     e.step()
     assert e.n == ndoe + 2
+
+
+def test_device_optimizer_falls_back_when_shared_memory_does_not_fit(monkeypatch):
+    """Past the size the device-resident L-BFGS-B fits in shared memory (config C5 beyond n ~ 915) the engine drives
+    the iteration with scipy's L-BFGS-B on the same value+gradient kernel; the sizing rule mirrors the library's."""
+    from pcabo_b200 import ops
+    from pcabo_b200.engine import BatchedBOEngine
+    from pcabo_b200.bbob import BatchedBBOB
+    assert ops.lbfgsb_fits(450, 40, 40) and ops.lbfgsb_fits(303, 100, 90)
+    assert not ops.lbfgsb_fits(1050, 100, 90) and ops.lbfgsb_fits(1050, 100, 20)
+    prob = BatchedBBOB([15, 16], [0, 1], 10, device="cuda")
+    e = BatchedBOEngine(prob, 10, prob.bounds, 150, 30, [15100, 16101], optimizer="device")
+    e.initial_design()
+    e.step()
+    r0 = e.stats["lbfgsb_rounds"]
+    monkeypatch.setattr(ops, "lbfgsb_fits", lambda *a, **k: False)
+    e.step()                                        # scipy-driven: many value+gradient rounds, one launch each
+    assert e.n == 32 and e.stats["lbfgsb_rounds"] - r0 > 5
+    monkeypatch.undo()
+    e.step()
+    assert e.n == 33
+    # the library refuses the same size itself
+    buf = e.gp
+    big = ops.GPBuffers(1, 1050, 100, torch.device("cuda"))
+    big.n, big.k = 1050, torch.tensor([90], dtype=torch.int32, device="cuda")
+    ics = torch.zeros(1, 10, 100, dtype=torch.float64, device="cuda")
+    with pytest.raises(Exception):
+        ops.lbfgsb_logei(big, ics, big.box_lo, big.box_hi, k_bound=90)
