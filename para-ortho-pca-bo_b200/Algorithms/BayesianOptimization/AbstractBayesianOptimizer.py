@@ -73,75 +73,84 @@ def lhs(n: int, samples: Optional[int] = None, criterion: Optional[str] = None, 
     raise ValueError(f'Invalid value for "criterion": {criterion}')
 
 
+def _slot(name: str, convert=None, doc: str = ""):
+    """A read/write attribute kept in `name` whose setter runs `convert` (validation + normalisation) first: the
+    reference spells every one of these out as a property/setter pair; the behaviour (values accepted, exceptions raised)
+    is the same."""
+    def fget(self):
+        return getattr(self, name)
+
+    def fset(self, value):
+        setattr(self, name, value if convert is None else convert(value))
+
+    return property(fget, fset, doc=doc)
+
+
+_LHS_CRITERIA = ("center", "maximin", "centermaximin", "correlation")
+_LHS_SHORTHANDS = {"c": "center", "m": "maximin", "cm": "centermaximin", "corr": "correlation"}
+
+
+def _as_criterion(value) -> str:
+    if not isinstance(value, str):
+        raise ValueError("The new criterion is not a string!")
+    key = value.lower().strip()
+    if key in _LHS_CRITERIA:
+        return key
+    if key in _LHS_SHORTHANDS:
+        return _LHS_SHORTHANDS[key]
+    raise ValueError("The criterion is not matching the set ones!")
+
+
+def _as_iterations(value) -> int:
+    if not value > 0:
+        raise ValueError("Negative iterations not allowed")
+    return int(value)
+
+
 class LHS_sampler:
     """Latin Hypercube Sampling wrapper (reference :8-103): same criteria names, shorthands and errors."""
 
-    __default_criteria = ("center", "maximin", "centermaximin", "correlation")
-    __reduced_criteria = {"c": "center", "m": "maximin", "cm": "centermaximin", "corr": "correlation"}
+    criterion = _slot("_lhs_criterion", _as_criterion, "pyDOE criterion (full name)")
+    iterations = _slot("_lhs_iterations", _as_iterations, "iterations of the maximin / correlation searches")
+    sample_zero = _slot("_lhs_sample_zero", None, "replace the first design point by the origin")
 
     def __init__(self, criterion: str = "correlation", iterations: int = 1000, sample_zero: bool = False):
-        self.criterion = criterion
-        self.iterations = iterations
-        self.sample_zero = sample_zero
+        self.criterion, self.iterations, self.sample_zero = criterion, iterations, sample_zero
 
     def __call__(self, dim: int, n_samples: int) -> np.ndarray:
-        points = lhs(n=dim, samples=n_samples, criterion=self.criterion, iterations=self.iterations)
+        design = lhs(n=dim, samples=n_samples, criterion=self.criterion, iterations=self.iterations)
         if self.sample_zero:
-            points[0, :] = np.zeros_like(points[0, :])
-        return points.reshape((n_samples, dim))
+            design[0, :] = 0.0
+        return design.reshape((n_samples, dim))
 
-    @property
-    def criterion(self) -> str:
-        return self.__criterion
 
-    @criterion.setter
-    def criterion(self, new_criterion: str) -> None:
-        if not isinstance(new_criterion, str):
-            raise ValueError("The new criterion is not a string!")
-        new_criterion = new_criterion.lower().strip()
-        if new_criterion in self.__default_criteria:
-            self.__criterion = new_criterion
-        elif new_criterion in self.__reduced_criteria:
-            self.__criterion = self.__reduced_criteria[new_criterion]
-        else:
-            raise ValueError("The criterion is not matching the set ones!")
+def _as_budget(value) -> int:
+    assert value > 0
+    return int(value)
 
-    @property
-    def iterations(self) -> int:
-        return self.__iterations
 
-    @iterations.setter
-    def iterations(self, new_n_iter: int) -> None:
-        if new_n_iter > 0:
-            self.__iterations = int(new_n_iter)
-        else:
-            raise ValueError("Negative iterations not allowed")
-
-    @property
-    def sample_zero(self) -> bool:
-        return self.__sample_zero
-
-    @sample_zero.setter
-    def sample_zero(self, new_change: bool) -> None:
-        self.__sample_zero = new_change
+def _as_n_doe(value):
+    return int(value) if value >= 0 else None
 
 
 class AbstractBayesianOptimizer(AbstractAlgorithm):
     """Shared BO state: budget, DoE, evaluated points, best tracking (reference :106-270)."""
 
+    budget = _slot("_bo_budget", _as_budget, "total number of objective evaluations")
+    n_DoE = _slot("_bo_n_doe", _as_n_doe, "size of the initial design (0: the dimension)")
+    lhs_sampler = property(lambda self: self._bo_sampler)
+    f_evals = property(lambda self: self._bo_f)
+    x_evals = property(lambda self: self._bo_x)
+
     def __init__(self, budget: int, n_DoE: Optional[int] = 0, **kwargs):
         super().__init__(**kwargs)
-        self.budget = budget
-        self.n_DoE = n_DoE
-        doe_parameters = None
+        self.budget, self.n_DoE = budget, n_DoE
+        settings = {"criterion": "center", "iterations": 1000, "sample_zero": False}      # reference :121-133
         for key, item in kwargs.items():
-            if key.lower().strip() == "doe_parameters":
-                doe_parameters = item
-        full = self.__build_LHS_parameters(doe_parameters)
-        self.__lhs_sampler = LHS_sampler(criterion=full["criterion"], iterations=full["iterations"],
-                                         sample_zero=full["sample_zero"])
-        self.__x_evals = []
-        self.__f_evals = []
+            if key.lower().strip() == "doe_parameters" and isinstance(item, dict):
+                settings.update(item)
+        self._bo_sampler = LHS_sampler(**{k: settings[k] for k in ("criterion", "iterations", "sample_zero")})
+        self._bo_x, self._bo_f = [], []
 
     def __str__(self):
         pass
@@ -151,66 +160,28 @@ class AbstractBayesianOptimizer(AbstractAlgorithm):
         super().__call__(problem, dim, bounds, **kwargs)
         if not isinstance(self.n_DoE, int) or self.n_DoE == 0:
             self.n_DoE = self.dimension
-        init_points = self._rescale_lhs_points(self.lhs_sampler(self.dimension, self.n_DoE))
-        for point in init_points:
-            self.__x_evals.append(point)
-            self.__f_evals.append(problem(point))
+        for point in self._rescale_lhs_points(self.lhs_sampler(self.dimension, self.n_DoE)):
+            self._bo_x.append(point)
+            self._bo_f.append(problem(point))
         self.assign_new_best()
         self.number_of_function_evaluations = self.n_DoE
         if self.verbose:
             print("After Initial sampling...",
-                  f"Current Best: x:{self.__x_evals[self.current_best_index]} y:{self.current_best}", flush=True)
+                  f"Current Best: x:{self._bo_x[self.current_best_index]} y:{self.current_best}", flush=True)
 
     def _rescale_lhs_points(self, raw_lhs_points: np.ndarray):
-        out = np.empty_like(raw_lhs_points)
-        for d in range(self.dimension):
-            out[:, d] = (self.bounds[d, 1] - self.bounds[d, 0]) * raw_lhs_points[:, d] + self.bounds[d, 0]
-        return out
+        lo, hi = self.bounds[:self.dimension, 0], self.bounds[:self.dimension, 1]
+        return (hi - lo)[None, :] * raw_lhs_points + lo[None, :]
 
     @abstractmethod
     def assign_new_best(self):
-        self.current_best = max(self.__f_evals) if self.maximization else min(self.__f_evals)
-        self.current_best_index = self.__f_evals.index(self.current_best, self.current_best_index)
+        pick = max if self.maximization else min
+        self.current_best = pick(self._bo_f)
+        self.current_best_index = self._bo_f.index(self.current_best, self.current_best_index)
 
     def __repr__(self):
         return super(AbstractAlgorithm, self).__repr__()
 
-    def __build_LHS_parameters(self, params_dict: Union[dict, None]) -> dict:
-        full = {"criterion": "center", "iterations": 1000, "sample_zero": False}
-        if isinstance(params_dict, dict):
-            full.update(params_dict)
-        return full
-
     def reset(self) -> None:
         super().reset()
-        self.__x_evals = []
-        self.__f_evals = []
-
-    @property
-    def budget(self) -> int:
-        return self.__budget
-
-    @budget.setter
-    def budget(self, new_budget: int) -> None:
-        assert new_budget > 0
-        self.__budget = int(new_budget)
-
-    @property
-    def n_DoE(self) -> int:
-        return self.__n_DoE
-
-    @n_DoE.setter
-    def n_DoE(self, new_n_DOE: int) -> None:
-        self.__n_DoE = int(new_n_DOE) if new_n_DOE >= 0 else None
-
-    @property
-    def lhs_sampler(self) -> LHS_sampler:
-        return self.__lhs_sampler
-
-    @property
-    def f_evals(self) -> List[float]:
-        return self.__f_evals
-
-    @property
-    def x_evals(self) -> List[np.ndarray]:
-        return self.__x_evals
+        self._bo_x, self._bo_f = [], []
