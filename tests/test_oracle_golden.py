@@ -167,3 +167,54 @@ def test_oracle_loop_runs_and_penalises_out_of_bounds():
         if outside:
             assert rec["new_f"] == 1000      # PCA_BO.py:260-261
     assert r.current_best == min(r.f_evals)
+
+
+def test_oracle_mll_gradient_matches_finite_differences():
+    """oracle.gp.mll_and_grad (the autograd reference the MLL-gradient kernel is tested against) against central
+    finite differences of the oracle's own marginal log-likelihood."""
+    import numpy as np
+    from oracle import gp
+    rng = np.random.RandomState(1)
+    Z, y = rng.rand(40, 3), rng.randn(40)
+    m = gp.GPModel(Z, y, norm_bounds=None)
+    mll, g_ls, g_nz = gp.mll_and_grad(m)
+    # gpytorch's GEMM-form distances and the direct differences used here agree to rounding
+    assert abs(mll - m.mll()) < 1e-9 * abs(mll)
+    h = 1e-6
+    f = lambda ls, nz: gp.GPModel(Z, y, norm_bounds=None, lengthscale=ls, noise=nz).mll()
+    fd_ls = (f(m.lengthscale + h, m.noise) - f(m.lengthscale - h, m.noise)) / (2 * h)
+    fd_nz = (f(m.lengthscale, m.noise + h * 1e-2) - f(m.lengthscale, m.noise - h * 1e-2)) / (2 * h * 1e-2)
+    assert abs(g_ls - fd_ls) < 1e-5 * max(1.0, abs(fd_ls))
+    assert abs(g_nz - fd_nz) < 1e-4 * max(1.0, abs(fd_nz))
+
+
+def test_oracle_probability_of_improvement():
+    """oracle.gp.ProbabilityOfImprovement = Phi(u) with botorch's sign convention, its autograd gradient against finite
+    differences, and exp(logEI) / sigma = phi(u) + u Phi(u) on the same points (ties the two acquisitions together)."""
+    import numpy as np
+    import torch
+    from oracle import gp
+    rng = np.random.RandomState(2)
+    Z, y = rng.rand(30, 4), rng.randn(30)
+    m = gp.GPModel(Z, y, norm_bounds=None)
+    best = float(y.min())
+    for maximize in (False, True):
+        b = float(y.max()) if maximize else best
+        pi = gp.ProbabilityOfImprovement(m, b, maximize=maximize)
+        ei = gp.LogExpectedImprovement(m, b, maximize=maximize)
+        X = torch.from_numpy(rng.rand(6, 4))
+        v, g = pi.value_and_grad(X)
+        mean, sigma = pi.mean_sigma(X)
+        u = (mean - pi.best_f) / sigma
+        u = u if maximize else -u
+        Phi = 0.5 * torch.erfc(-u / np.sqrt(2.0))
+        assert torch.allclose(v, Phi, rtol=1e-12, atol=0)
+        phi = torch.exp(-0.5 * u * u) / np.sqrt(2 * np.pi)
+        assert torch.allclose(torch.exp(ei(X)) / sigma, phi + u * Phi, rtol=1e-9)
+        h = 1e-6
+        for j in range(4):
+            Xp, Xm = X.clone(), X.clone()
+            Xp[:, j] += h
+            Xm[:, j] -= h
+            fd = (pi(Xp) - pi(Xm)) / (2 * h)
+            assert torch.allclose(g[:, j], fd, rtol=1e-5, atol=1e-8)
