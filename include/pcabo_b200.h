@@ -104,6 +104,16 @@ int pcabo_gp_fit(int B, int n, int kmax, int ld_n, int mode,
                  double *ymean, double *ystd, double *ZnT, double *Zn, double *L, double *W, double *WT,
                  double *alpha, int *info, void *stream);
 
+/* pcabo_gp_fit with a per-run diagonal jitter [B] (NULL: none) added to K + noise I before the factorisation: the retry
+ * ladder of gpytorch's psd_safe_cholesky (1e-8, 1e-7, 1e-6; linear_operator, reached from the first posterior call of
+ * the model built at PCA_BO.py:535-544) for the runs whose info came back non-zero.                                */
+int pcabo_gp_fit_jitter(int B, int n, int kmax, int ld_n, int mode,
+                        const double *Z, const int *k, const double *f, const double *fix_lo, const double *fix_hi,
+                        double lengthscale, double noise, const double *jitter,
+                        double *norm_off, double *norm_coef, double *box_lo, double *box_hi,
+                        double *ymean, double *ystd, double *ZnT, double *Zn, double *L, double *W, double *WT,
+                        double *alpha, int *info, void *stream);
+
 /* Exact marginal log-likelihood of the standardised targets from the caches: mll [B]. ys = (f-ymean)/ystd. */
 int pcabo_gp_mll(int B, int n, int ld_n, const double *f, const double *ymean, const double *ystd,
                  const double *L, const double *alpha, double *mll, void *stream);

@@ -128,19 +128,22 @@ class PCA_BO(AbstractBayesianOptimizer):
 
     def _pull_iteration_state(self, eng) -> None:
         """Mirror the reference's per-iteration attributes (PCA_BO.py:364,386-399,408) on the host."""
+        self._pull_pca_state(eng, int(eng.k_host[0]), len(self.f_evals) - 1)
+        k = self.reduced_space_dim_num
+        self.__z_evals = self.__z_evals + [eng.last["z_new"][0, :k].copy()]
+        self.acquisition_function = self.acquisition_function_class(model=eng, best_f=self.current_best,
+                                                                    maximize=self.maximization)
+
+    def _pull_pca_state(self, eng, k: int, n_points: int) -> None:
         p = eng.pca
-        k = int(eng.k_host[0])
         comps = p["V"][0].cpu().numpy()
         self.data_mean = p["xbar"][0].cpu().numpy()
         self.component_matrix = np.copy(comps)
         self.explained_variance_ratio = p["evr"][0].cpu().numpy()
         self.reduced_space_dim_num = k
         self.pca = FittedPCA(comps, p["m2"][0].cpu().numpy(), p["lam"][0].cpu().numpy(), self.explained_variance_ratio, k)
-        n_prev = len(self.f_evals) - 1
-        Z = p["Z"][0, :n_prev, :k].cpu().numpy()
-        self.__z_evals = [Z[i, :] for i in range(Z.shape[0])] + [eng.last["z_new"][0, :k].copy()]
-        self.acquisition_function = self.acquisition_function_class(model=eng, best_f=self.current_best,
-                                                                    maximize=self.maximization)
+        Z = p["Z"][0, :n_points, :k].cpu().numpy()
+        self.__z_evals = [Z[i, :] for i in range(Z.shape[0])]
         if self.verbose:
             print(f"Using {k} principal components with "
                   f"{np.sum(self.explained_variance_ratio[:k]) * 100:.2f}% explained variance")
@@ -163,6 +166,66 @@ class PCA_BO(AbstractBayesianOptimizer):
         noise = torch.zeros(1, n, D, dtype=torch.float64, device=dev)
         logtab = torch.from_numpy(np.log(np.maximum(np.arange(n + 2), 1).astype(np.float64))).to(dev)
         return ops.weights_pca_fit(X, f, noise, logtab, n, self.var_threshold, self.n_components, self.maximization)
+
+    def _seam_engine(self):
+        """A one-run engine holding the CURRENT x_evals / f_evals, for callers that drive the reference's operator seams
+        one by one (PCA_BO.py:183, :186, :205) instead of through __call__. Draws from the process-global numpy / torch
+        generators like the reference does."""
+        from pcabo_b200.engine import BatchedBOEngine
+        n = len(self.f_evals)
+        if n < 2:
+            raise ValueError("the accelerated operator seams need at least two evaluated points")
+        eng = self._engine
+        if eng is None or eng.x_evals[0] is not self.x_evals or eng.n != n or eng.budget < n + 1:
+            eng = BatchedBOEngine([None], self.dimension, self.bounds, max(self.budget, n + 1), self.n_DoE,
+                                  [self.random_seed], algorithm="pca", var_threshold=self.var_threshold,
+                                  n_components=self.n_components, maximization=self.maximization,
+                                  optimizer=self.optimizer_backend,
+                                  num_restarts=self.torch_config["NUM_RESTARTS"],
+                                  raw_samples=self.torch_config["RAW_SAMPLES"],
+                                  np_rngs=[np.random.mtrand._rand], torch_gens=[torch.default_generator],
+                                  profile_timing=True, acquisition=self.acquisition_function_name)
+            eng.attach_history([self.x_evals], [self.f_evals])
+            self._engine = eng
+        return eng
+
+    def _transform_points_to_reduced_space(self) -> None:
+        """PCA_BO.py:343-408: rank weights, weighted PCA fit and projection of all evaluated points (one kernel);
+        fills pca, data_mean, component_matrix, explained_variance_ratio, reduced_space_dim_num and z_evals."""
+        eng = self._seam_engine()
+        eng._fit_pca()
+        k = int(eng.pca["k"][0].item())
+        eng.k_host[:] = k
+        self.timing_logs["pca"].append(eng.timing_logs["pca"][-1])
+        self._pull_pca_state(eng, k, len(self.f_evals))
+
+    def _initialize_model(self, **kwargs) -> None:
+        """PCA_BO.py:502-545: SingleTaskGP(train_z, train_obj, Matern-5/2, Standardize, Normalize) and, eagerly, the
+        prediction caches gpytorch would build on the first posterior call. Needs _transform_points_to_reduced_space()."""
+        eng = self._seam_engine()
+        if eng.pca is None:
+            raise AttributeError("call _transform_points_to_reduced_space() before _initialize_model()")
+        t0 = eng._sync_time()
+        eng._fit_gp()
+        self.timing_logs["SingleTaskGP"].append(eng._sync_time() - t0)
+        self.assign_new_best()
+        eng.current_best = [self.current_best]
+        eng._set_best_f()
+        self.acquisition_function = self.acquisition_function_class(model=eng, best_f=self.current_best,
+                                                                    maximize=self.maximization)
+
+    def optimize_acqf_and_get_observation(self) -> torch.Tensor:
+        """PCA_BO.py:547-621: optimize_acqf(q=1, num_restarts, raw_samples, batch_limit 5, maxiter 200) over the padded
+        box of the reduced space. Returns the new point as a CPU tensor of shape (1, k) like the reference."""
+        eng = self._seam_engine()
+        if eng.gp.n != len(self.f_evals):
+            raise AttributeError("call _initialize_model() before optimize_acqf_and_get_observation()")
+        t0 = eng._sync_time()
+        st = eng._propose_begin(eng._propose_launch())
+        z_new, _ = eng._propose_end(st)
+        self.timing_logs["optimize_acqf"].append(eng._sync_time() - t0)
+        k = int(eng.k_host[0])
+        return z_new[:, :k].detach().cpu().reshape(1, k)
 
     def _transform_point_to_original_space(self, z: np.ndarray) -> np.ndarray:
         """PCA_BO.py:410-434."""

@@ -37,6 +37,11 @@ class ExperimentRunner:
         self.device, self.optimizer_backend = device, optimizer_backend
         self.rank, self.world_size = rank, world_size
         self.results = []
+        # ioh keeps ONE problem object per (function, dimension, instance) for the whole suite and the reference attaches
+        # every algorithm's logger to that same suite (ExperimentRunner.py:90,135): the evaluation counter and the
+        # best-so-far of a problem carry over from one algorithm to the next (the shipped vanilla .dat files start at
+        # evaluation 76 with the PCA run's raw_y_best). Same state here, keyed by (fid, dim, instance).
+        self._problem_state = {}
 
     def _acquisition_long_name(self):
         """The runner hands `acquisition_function` to the optimiser classes (reference ExperimentRunner.py:154-170), whose
@@ -73,7 +78,9 @@ class ExperimentRunner:
                     seeds = [1000 * fid + 10 * dim + i for i in insts]           # :146
                     prob = BatchedBBOB([fid] * len(insts), insts, dim, device=self.device)
                     eng = BatchedBOEngine(prob, dim, prob.bounds, budget, n_doe, seeds, algorithm=algorithm,
-                                          var_threshold=self.var_threshold, n_components=self.pca_components or 0,
+                                          # like the reference, `pca_components` is only logged as an experiment
+                                          # attribute: PCA_BO is built without n_components (ExperimentRunner.py:167-177)
+                                          var_threshold=self.var_threshold, n_components=0,
                                           maximization=False, device=self.device, optimizer=self.optimizer_backend,
                                           profile_timing=True, acquisition=self._acquisition_long_name())
                     t0 = time()
@@ -96,22 +103,28 @@ class ExperimentRunner:
         with open(os.path.join(folder, dat_rel), "w") as fh:
             for b, inst in enumerate(insts):
                 fopt = float(prob.fopt[b])
+                st = self._problem_state.setdefault((fid, dim, inst), {"evals": 0, "best": np.inf, "best_eval": 0,
+                                                                         "best_x": None})
                 fh.write("evaluations raw_y raw_y_best " + " ".join(f"x{j}" for j in range(dim)) + "\n")
-                best = np.inf
-                best_eval, best_x = 0, None
-                for e, (x, y) in enumerate(zip(eng.x_evals[b], eng.f_evals[b]), start=1):
+                for x, y, oob in zip(eng.x_evals[b], eng.f_evals[b], eng.oob_evals[b]):
+                    if oob:
+                        # PCA_BO.py:259-263: an out-of-bounds proposal gets f = +-1000 WITHOUT calling problem(x), so
+                        # ioh's logger never sees it: no row, no evaluation counted
+                        continue
+                    st["evals"] += 1
                     raw = y - fopt                       # ioh's raw_y is the untransformed objective
-                    if raw < best:
-                        best, best_eval, best_x = raw, e, x
-                    fh.write(f"{e} {raw:.10f} {best:.10f} " + " ".join(f"{v:.6f}" for v in x) + "\n")
-                run = {"instance": inst, "evals": len(eng.f_evals[b]),
-                       "best": {"evals": best_eval, "y": best, "x": [float(v) for v in best_x]}}
+                    if raw < st["best"]:
+                        st["best"], st["best_eval"], st["best_x"] = raw, st["evals"], x
+                    fh.write(f"{st['evals']} {raw:.10f} {st['best']:.10f} " + " ".join(f"{v:.6f}" for v in x) + "\n")
+                run = {"instance": inst, "evals": st["evals"],
+                       "best": {"evals": st["best_eval"], "y": st["best"], "x": [float(v) for v in st["best_x"]]}}
                 for p in profiles:   # per-batch kernel time attributed evenly to the runs of the batch
                     run[f"{p}_time"] = float(sum(eng.timing_logs[p])) / len(insts)
                 run["time"] = wall / len(insts)
                 runs.append(run)
-        exp_attrs = [{"budget_factor": f"{self.budget_factor}"}, {"doe_factor": f"{self.doe_factor}"},
-                     {"acquisition_function": f"{self.acquisition_function}"}]
+        # ioh keeps the attributes in a sorted map (shipped JSON: alphabetical order)
+        exp_attrs = [{"acquisition_function": f"{self.acquisition_function}"}, {"budget_factor": f"{self.budget_factor}"},
+                     {"doe_factor": f"{self.doe_factor}"}]
         if algorithm == "pca":
             exp_attrs += [{"pca_components": f"{self.pca_components}"}, {"var_threshold": f"{self.var_threshold}"}]
         meta = {"version": "0.3.18", "suite": "BBOB", "function_id": fid, "function_name": name, "maximization": False,

@@ -131,7 +131,8 @@ __device__ __forceinline__ double matern52_from_sq(double sq, double inv_ell2) {
 constexpr int KT = 64;  // kernel-matrix tile
 
 __global__ void __launch_bounds__(256) gp_kmat_kernel(int n, int kmax, int ld_n, const int *k, const double *ZnT,
-                                                     double inv_ell2, double noise, double *Kout) {
+                                                     double inv_ell2, double noise, const double *jitter,
+                                                     double *Kout) {
   // grid: (tiles_lower, B); tile (ti >= tj)
   __shared__ double zi[8][KT];
   __shared__ double zj[8][KT];
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(256) gp_kmat_kernel(int n, int kmax, int ld_n,
   const int kk = k ? k[b] : kmax;
   const double *Zb = ZnT + (size_t)b * kmax * ld_n;
   double *Kb = Kout + (size_t)b * ld_n * ld_n;
+  const double diag_add = noise + (jitter ? jitter[b] : 0.0);   // psd_safe_cholesky adds its jitter to the diagonal
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;  // thread computes rows ty*4.., cols tx*4..
   double acc[4][4];
 #pragma unroll
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(256) gp_kmat_kernel(int n, int kmax, int ld_n,
       const int gi = ti * KT + ty * 4 + i, gj = tj * KT + tx * 4 + j;
       if (gi < n && gj <= gi) {
         double v = matern52_from_sq(acc[i][j], inv_ell2);
-        if (gi == gj) v += noise;
+        if (gi == gj) v += diag_add;
         Kb[(size_t)gi * ld_n + gj] = v;
       }
     }
@@ -571,11 +573,11 @@ extern "C" int pcabo_gp_mll_grad(int B, int n, int kmax, int ld_n, const int *k,
   return PCABO_OK;
 }
 
-extern "C" int pcabo_gp_fit(int B, int n, int kmax, int ld_n, int mode, const double *Z, const int *k, const double *f,
-                            const double *fix_lo, const double *fix_hi, double lengthscale, double noise,
-                            double *norm_off, double *norm_coef, double *box_lo, double *box_hi, double *ymean,
-                            double *ystd, double *ZnT, double *Zn, double *L, double *W, double *WT, double *alpha,
-                            int *info, void *stream) {
+extern "C" int pcabo_gp_fit_jitter(int B, int n, int kmax, int ld_n, int mode, const double *Z, const int *k,
+                                   const double *f, const double *fix_lo, const double *fix_hi, double lengthscale,
+                                   double noise, const double *jitter, double *norm_off, double *norm_coef,
+                                   double *box_lo, double *box_hi, double *ymean, double *ystd, double *ZnT, double *Zn,
+                                   double *L, double *W, double *WT, double *alpha, int *info, void *stream) {
   if (B <= 0 || n < 1 || kmax < 1 || ld_n < n || !Z || !f || !norm_off || !norm_coef || !box_lo || !box_hi || !ymean ||
       !ystd || !ZnT || !Zn || !L || !W || !WT || !alpha || !info || !(lengthscale > 0.0))
     return PCABO_E_INVALID;
@@ -596,7 +598,7 @@ extern "C" int pcabo_gp_fit(int B, int n, int kmax, int ld_n, int mode, const do
   {
     const int nt = (n + KT - 1) / KT;
     dim3 grid(nt * (nt + 1) / 2, B);
-    gp_kmat_kernel<<<grid, 256, 0, st>>>(n, kmax, ld_n, k, ZnT, 1.0 / (lengthscale * lengthscale), noise, L);
+    gp_kmat_kernel<<<grid, 256, 0, st>>>(n, kmax, ld_n, k, ZnT, 1.0 / (lengthscale * lengthscale), noise, jitter, L);
     PCABO_LAUNCH_CHECK();
   }
   {
@@ -608,6 +610,15 @@ extern "C" int pcabo_gp_fit(int B, int n, int kmax, int ld_n, int mode, const do
     PCABO_LAUNCH_CHECK();
   }
   return PCABO_OK;
+}
+
+extern "C" int pcabo_gp_fit(int B, int n, int kmax, int ld_n, int mode, const double *Z, const int *k, const double *f,
+                            const double *fix_lo, const double *fix_hi, double lengthscale, double noise,
+                            double *norm_off, double *norm_coef, double *box_lo, double *box_hi, double *ymean,
+                            double *ystd, double *ZnT, double *Zn, double *L, double *W, double *WT, double *alpha,
+                            int *info, void *stream) {
+  return pcabo_gp_fit_jitter(B, n, kmax, ld_n, mode, Z, k, f, fix_lo, fix_hi, lengthscale, noise, nullptr, norm_off,
+                             norm_coef, box_lo, box_hi, ymean, ystd, ZnT, Zn, L, W, WT, alpha, info, stream);
 }
 
 extern "C" int pcabo_gp_mll(int B, int n, int ld_n, const double *f, const double *ymean, const double *ystd,

@@ -244,7 +244,7 @@ extern "C" int pcabo_lbfgsb_logei_runs(const pcabo_gp_model *m, int nsel, const 
                                        double *fval, int *status, int *nit, int *nfev, long long *prof, void *stream) {
   if (!m || num_restarts <= 0 || batch_limit <= 0 || maxiter <= 0 || !ics || !box_lo || !box_hi || !cand || !fval ||
       !status || !nit || !nfev || m->B <= 0 || m->n < 1 || m->ld_n < m->n || !m->norm_off || !m->norm_coef || !m->ZnT ||
-      !m->alpha || !m->W || !m->ymean || !m->ystd || !m->best_f || !(m->lengthscale > 0.0))
+      !m->alpha || !m->W || !m->WT || !m->Zn || !m->ymean || !m->ystd || !m->best_f || !(m->lengthscale > 0.0))
     return PCABO_E_INVALID;
   if (run_idx ? (nsel <= 0 || nsel > m->B) : (nsel != m->B)) return PCABO_E_INVALID;
   if (k_bound <= 0 || k_bound > m->kmax) k_bound = m->kmax;

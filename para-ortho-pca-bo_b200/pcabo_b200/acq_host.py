@@ -11,6 +11,25 @@ import numpy as np
 import torch
 from scipy.optimize import _lbfgsb
 
+# `setulb` is a private scipy entry point: the Fortran wrapper of scipy <= 1.14 took (..., task, iprint, csave, lsave,
+# isave, dsave, maxls) with a byte-string `task`, the C translation of scipy >= 1.15 takes integer task words and an
+# `ln_task` array. LbfgsbProblem is written against the latter; any other signature must fail at import, not corrupt
+# memory in the middle of a run.
+_SETULB_SIGNATURE = "setulb(m, x, l, u, nbd, f, g, factr, pgtol, wa, iwa, task, lsave, isave, dsave, maxls, ln_task)"
+
+
+def _check_setulb_signature():
+    doc = (getattr(_lbfgsb.setulb, "__doc__", None) or "").strip().splitlines()
+    got = doc[0].strip() if doc else ""
+    if got != _SETULB_SIGNATURE:
+        import scipy
+        raise ImportError(f"pcabo_b200.acq_host drives scipy's L-BFGS-B through scipy.optimize._lbfgsb.setulb with the "
+                          f"signature of scipy >= 1.15 ({_SETULB_SIGNATURE}); scipy {scipy.__version__} exposes "
+                          f"'{got or 'no signature'}'. Use optimizer='device' or a matching scipy.")
+
+
+_check_setulb_signature()
+
 MAXCOR = 10
 FTOL = 2.2204460492503131e-09
 GTOL = 1e-5

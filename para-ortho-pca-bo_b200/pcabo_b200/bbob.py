@@ -4,7 +4,8 @@ The reference evaluates `problem(x)` through ioh's C++ BBOB suite (PCA_BO.py:263
 ioh is not installable here, so the COCO/ioh definitions are restated: instance data from the
 legacy COCO generator with `rseed = fid + 10000 * instance`, evaluation as one batched torch expression over B
 runs that works on CPU or CUDA tensors (one point per run per BO iteration). f15 and f20 are pinned against the
-reference's shipped IOHprofiler data (tests/test_bbob_doe.py); f16 / f17 are unpinned.
+reference's shipped IOHprofiler data (tests/test_host_logic.py::test_host_doe_and_bbob_match_reference_goldens,
+tests/test_oracle_golden.py); f16 / f17 are unpinned.
 This is the objective, not the hot path: plain torch ops are deliberate here.
 """
 import math

@@ -50,7 +50,7 @@ class BatchedBOEngine:
                  n_components=0, maximization=False, device="cuda:0", optimizer="scipy",
                  num_restarts=NUM_RESTARTS, raw_samples=RAW_SAMPLES, batch_limit=BATCH_LIMIT, maxiter=MAXITER,
                  np_rngs=None, torch_gens=None, profile_timing=False, batch_objective=None, host_threads=None,
-                 acquisition="expected_improvement"):
+                 acquisition="expected_improvement", lengthscale=ops.LENGTHSCALE, noise=ops.NOISE):
         if not torch.cuda.is_available():
             raise PcaboError("BatchedBOEngine needs a CUDA device: the PCA-BO hot path has no CPU fallback")
         if algorithm not in ("pca", "vanilla"):
@@ -63,6 +63,8 @@ class BatchedBOEngine:
             raise ValueError(f"acquisition '{acquisition}' is not available on the accelerated path "
                              f"(one of {sorted(ops.ACQ_KINDS)})")
         self.acquisition = acquisition
+        # GP hyper-parameters: the reference never fits its GP, these are gpytorch's / botorch's initial values
+        self.lengthscale, self.noise = float(lengthscale), float(noise)
         # `problems`: a list of B callables p(x) -> float, or one batched objective (e.g. pcabo_b200.bbob.BatchedBBOB)
         # exposing B, eval_many(b, X[m, D]) -> ndarray and __call__(X[B, D] device tensor) -> [B] device tensor
         self.batched_problem = problems if hasattr(problems, "eval_many") else None
@@ -109,20 +111,27 @@ class BatchedBOEngine:
         self.h_noise = torch.zeros(B * cap * D, dtype=torch.float64).pin_memory()
         self.gen_io = GeneratorStateIO(B)
         self.h_q = torch.zeros(B, self.raw_samples, dtype=torch.float64)
+        self.h_info = torch.zeros(B, dtype=torch.int32).pin_memory()   # Cholesky status of the last GP fit
+        self.d_mt_state_prev = self.d_mt_pos_prev = None
         self.state0 = sobol_state0(D).to(self.device)
         self.k_full = torch.full((B,), D, dtype=torch.int32, device=self.device)
-        torch.set_num_threads(1)   # host-side torch is RNG plumbing on tiny tensors: intra-op threads only add contention
+        if self.owns_rngs:
+            # host-side torch is RNG plumbing on tiny tensors: intra-op threads only add contention. Process-global, so
+            # only when the engine is the application (bench, ExperimentRunner); the drop-in classes, which share the
+            # process and its generators with user code, leave the setting alone
+            torch.set_num_threads(1)
         # per-run host RNG work (numpy normal, torch randint / multinomial) releases the GIL: spread it over the cores
         self.pool = ThreadPoolExecutor(max_workers=max(1, min(B, host_threads or (os.cpu_count() or 1))))
         self.n = 0
         self.x_evals = [[] for _ in range(B)]
         self.f_evals = [[] for _ in range(B)]
         self.z_evals = [None] * B
+        self.oob_evals = [[] for _ in range(B)]   # per point: True = out-of-bounds proposal, penalised, objective NOT called
         self.current_best = [(-math.inf if self.maximization else math.inf)] * B
         self.current_best_index = [0] * B
         self.k_host = np.full(B, D, dtype=np.int64)
         self.timing_logs = {"pca": [], "SingleTaskGP": [], "optimize_acqf": []}
-        self.stats = dict(kernel_launches=0, lbfgsb_rounds=0, h2d_bytes=0, d2h_bytes=0, retries=0,
+        self.stats = dict(kernel_launches=0, lbfgsb_rounds=0, h2d_bytes=0, d2h_bytes=0, retries=0, jitter_refits=0,
                           wait_opt_s=0.0, wait_ic_s=0.0)   # host time blocked on the optimiser / raw-sample events
         self.last = {}
         self.noise_ready_n = -1     # the pinned noise buffer holds the draw for the iteration with this many points
@@ -168,6 +177,7 @@ class BatchedBOEngine:
             for j, p in enumerate(designs[b]):
                 self.x_evals[b].append(p)
                 self.f_evals[b].append(float(vals[b, j]) if self.batched_problem is not None else self._evaluate(b, p))
+                self.oob_evals[b].append(False)
             self._assign_new_best(b)
         n0 = self.n_doe
         hx = torch.from_numpy(np.stack([np.stack(self.x_evals[b]) for b in range(B)]))
@@ -184,6 +194,7 @@ class BatchedBOEngine:
         if any(len(f) != n0 for f in f_lists) or n0 > self.cap:
             raise PcaboError("attach_history: all runs of a batch must hold the same number of points (<= budget)")
         self.x_evals, self.f_evals = list(x_lists), list(f_lists)
+        self.oob_evals = [[False] * n0 for _ in range(B)]
         hx = torch.from_numpy(np.stack([np.stack([np.asarray(x, dtype=np.float64) for x in x_lists[b]])
                                         for b in range(B)]))
         hf = torch.from_numpy(np.array([[float(v) for v in f_lists[b]] for b in range(B)], dtype=np.float64))
@@ -239,41 +250,84 @@ class BatchedBOEngine:
             self.noise_copied.synchronize()
             self._draw_noise(self.n + 1, wait=False)
 
-    def _fit_models(self):
+    def _fit_pca(self):
+        """_transform_points_to_reduced_space (PCA_BO.py:343-408): the 1e-8 noise from each run's numpy stream, then rank
+        weights + weighted PCA + projection in one kernel."""
         B, D, n = self.B, self.D, self.n
-        if self.algorithm == "pca":
-            tp = perf_counter()
-            hv = self.h_noise[:B * n * D].view(B, n, D)
-            if self.noise_ready_n != n:
-                self._wait_noise()
-                self._draw_noise(n)
+        tp = perf_counter()
+        hv = self.h_noise[:B * n * D].view(B, n, D)
+        if self.noise_ready_n != n:
             self._wait_noise()
-            self.noise_ready_n = -1
-            tp = self._phase("host_noise_rng", tp)
-            dv = self.d_noise[:B * n * D].view(B, n, D)
-            dv.copy_(hv, non_blocking=True)
-            self.noise_copied.record()
-            self.stats["h2d_bytes"] += hv.numel() * 8
-            t0 = self._sync_time()
-            self.pca = ops.weights_pca_fit(self.X, self.f, dv, self.logtab, n, self.var_threshold,
-                                           self.n_components, self.maximization, out=self.pca)
-            t1 = self._sync_time()
-            ops.gp_fit(self.gp, self.pca["Z"], self.pca["k"], self.f, n, mode=0)
-            t2 = self._sync_time()
-            self.stats["kernel_launches"] += 4
-            self.timing_logs["pca"].append(t1 - t0)
-            self.timing_logs["SingleTaskGP"].append(t2 - t1)
-        else:
-            t1 = self._sync_time()
-            ops.gp_fit(self.gp, self.X, None, self.f, n, mode=1, fix_lo=self.lo, fix_hi=self.hi)
-            t2 = self._sync_time()
-            self.stats["kernel_launches"] += 3
-            self.timing_logs["SingleTaskGP"].append(t2 - t1)
-        self._phase("pca_gp_kernels", tp if self.algorithm == "pca" else perf_counter())
-        # best_f as botorch stores it: torch.as_tensor(python float) -> float32
+            self._draw_noise(n)
+        self._wait_noise()
+        self.noise_ready_n = -1
+        self._phase("host_noise_rng", tp)
+        dv = self.d_noise[:B * n * D].view(B, n, D)
+        dv.copy_(hv, non_blocking=True)
+        self.noise_copied.record()
+        self.stats["h2d_bytes"] += hv.numel() * 8
+        t0 = self._sync_time()
+        self.pca = ops.weights_pca_fit(self.X, self.f, dv, self.logtab, n, self.var_threshold,
+                                       self.n_components, self.maximization, out=self.pca)
+        t1 = self._sync_time()
+        self.stats["kernel_launches"] += 1
+        self.timing_logs["pca"].append(t1 - t0)
+
+    def _set_best_f(self):
+        """best_f as botorch stores it: torch.as_tensor(python float) -> float32 (PCA_BO.py:199-203)."""
         bf = torch.tensor([float(torch.as_tensor(float(v))) for v in self.current_best], dtype=torch.float64)
         self.gp.best_f.copy_(bf)
-        self.stats["h2d_bytes"] += B * 8
+        self.stats["h2d_bytes"] += self.B * 8
+
+    def _fit_models(self):
+        tp = perf_counter()
+        if self.algorithm == "pca":
+            self._fit_pca()
+        t1 = self._sync_time()
+        self._fit_gp()
+        t2 = self._sync_time()
+        self.stats["kernel_launches"] += 3
+        self.timing_logs["SingleTaskGP"].append(t2 - t1)
+        self._phase("pca_gp_kernels", tp)
+        self._set_best_f()
+
+    def _fit_gp(self, jitter=None):
+        """_initialize_model (PCA_BO.py:502-545 / Vanilla_BO.py:166-195) + gpytorch's prediction caches; the Cholesky
+        status of every run is read back asynchronously and examined in _propose_begin."""
+        if self.algorithm == "pca":
+            ops.gp_fit(self.gp, self.pca["Z"], self.pca["k"], self.f, self.n, mode=0, lengthscale=self.lengthscale,
+                       noise=self.noise, jitter=jitter)
+        else:
+            ops.gp_fit(self.gp, self.X, None, self.f, self.n, mode=1, fix_lo=self.lo, fix_hi=self.hi,
+                       lengthscale=self.lengthscale, noise=self.noise, jitter=jitter)
+        self.h_info.copy_(self.gp.info, non_blocking=True)
+        self.stats["d2h_bytes"] += self.B * 4
+
+    def _refit_failed_cholesky(self, st):
+        """A non-positive pivot in some run's Cholesky: gpytorch's psd_safe_cholesky (linear_operator, reached from the
+        first posterior call on the model of PCA_BO.py:535-544) retries with 1e-8, 1e-7, 1e-6 added to the diagonal and
+        raises NotPSDError after that. The raw samples of this iteration were scored with the failed factor: the
+        generators are put back to where they were and the initial conditions are drawn again from the refitted model,
+        so the RNG streams advance exactly as in the reference (where the retry happens inside the factorisation)."""
+        B = self.B
+        bad = np.nonzero(self.h_info.numpy())[0]
+        jitter = torch.zeros(B, dtype=torch.float64)
+        for jit in (1e-8, 1e-7, 1e-6):
+            jitter[torch.from_numpy(bad)] = jit
+            self._fit_gp(jitter=jitter.to(self.device))
+            torch.cuda.current_stream().synchronize()
+            self.stats["jitter_refits"] += len(bad)
+            self.stats["kernel_launches"] += 3
+            bad = np.nonzero(self.h_info.numpy())[0]
+            if len(bad) == 0:
+                break
+        else:
+            raise PcaboError(f"Matrix not positive definite after repeatedly adding jitter up to 1.0e-06 (runs {bad.tolist()})")
+        if st["ic"].get("fast"):
+            self.d_mt_state.copy_(self.d_mt_state_prev)
+            self.d_mt_pos.copy_(self.d_mt_pos_prev)
+        st["ic"] = self._ic_launch(st["runs"], None, 1)
+        st["ic"]["done"].synchronize()
 
     def _gens_to_host(self):
         """Bring the torch CPU generators up to date with the device-resident MT19937 states (fast path)."""
@@ -293,6 +347,10 @@ class BatchedBOEngine:
             self.gens_on_host = False
             self.stats["h2d_bytes"] += st.numel() * 4 + pos.numel() * 4
         k_dev = self.pca["k"] if self.algorithm == "pca" else self.k_full
+        if self.d_mt_state_prev is None or self.d_mt_state_prev.shape != self.d_mt_state.shape:
+            self.d_mt_state_prev, self.d_mt_pos_prev = torch.empty_like(self.d_mt_state), torch.empty_like(self.d_mt_pos)
+        self.d_mt_state_prev.copy_(self.d_mt_state)      # kept for the (rare) jitter refit of a failed Cholesky
+        self.d_mt_pos_prev.copy_(self.d_mt_pos)
         d_shift, d_dots = ops.sobol_scramble_bits(k_dev, self.d_mt_state, self.d_mt_pos, D)
         x_raw = ops.sobol_points(self.raw_samples, k_dev, d_shift, d_dots, self.state0, self.gp.box_lo, self.gp.box_hi)
         vals_dev = ops.logei(self.gp, x_raw)["val"]
@@ -542,6 +600,8 @@ class BatchedBOEngine:
         tw = perf_counter()
         st["ic"]["done"].synchronize()
         self.stats["wait_ic_s"] += perf_counter() - tw
+        if self.h_info.numpy().any():
+            self._refit_failed_cholesky(st)
         k_host = self.h_k.numpy().astype(np.int64) if self.algorithm == "pca" else np.full(B, D, np.int64)
         self.k_host = k_host
         self.stats["d2h_bytes"] += B * 4
@@ -656,6 +716,7 @@ class BatchedBOEngine:
                 new_f[b] = f_dev[b] if f_dev is not None else self._evaluate(b, x_new[b])
             self.x_evals[b].append(x_new[b].copy())
             self.f_evals[b].append(float(new_f[b]))
+            self.oob_evals[b].append(bool(oob[b]))
             self._update_best_with_last(b)
         self.X[:, n].copy_(torch.from_numpy(x_new))
         self.f[:, n].copy_(torch.from_numpy(new_f))
@@ -694,6 +755,10 @@ class PipelinedEngines:
     def __init__(self, engines):
         self.engines = list(engines)
         self.streams = [torch.cuda.Stream(device=e.device) for e in self.engines]
+        # the engines' buffers were allocated and zero-filled on the stream that was current at construction: order the
+        # side streams after that work before their first use
+        for e, st in zip(self.engines, self.streams):
+            st.wait_stream(torch.cuda.current_stream(e.device))
         self.B = sum(e.B for e in self.engines)
 
     def initial_design(self):

@@ -7,7 +7,7 @@ _LIB = None
 
 EXPORTED_SYMBOLS = [
     "pcabo_abi_version", "pcabo_error_string", "pcabo_last_cuda_error",
-    "pcabo_weights_pca_fit", "pcabo_inverse_map", "pcabo_gp_fit", "pcabo_gp_mll", "pcabo_gp_mll_grad",
+    "pcabo_weights_pca_fit", "pcabo_inverse_map", "pcabo_gp_fit", "pcabo_gp_fit_jitter", "pcabo_gp_mll", "pcabo_gp_mll_grad",
     "pcabo_logei", "pcabo_argmax", "pcabo_lbfgsb_logei", "pcabo_lbfgsb_logei_prof", "pcabo_lbfgsb_logei_runs", "pcabo_ei_sweep",
     "pcabo_sobol_points", "pcabo_sobol_scramble_bits", "pcabo_gather_rows", "pcabo_bbob_eval", "pcabo_select_initial_conditions",
 ]
@@ -59,6 +59,8 @@ def load_library(build_if_missing: bool = False):
     lib.pcabo_inverse_map.argtypes = [ci, ci] + [vp] * 9 + [vp]
     lib.pcabo_gp_fit.restype = ci
     lib.pcabo_gp_fit.argtypes = [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, cd, cd] + [vp] * 13 + [vp]
+    lib.pcabo_gp_fit_jitter.restype = ci
+    lib.pcabo_gp_fit_jitter.argtypes = [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, cd, cd, vp] + [vp] * 13 + [vp]
     lib.pcabo_gp_mll.restype = ci
     lib.pcabo_gp_mll.argtypes = [ci, ci, ci] + [vp] * 6 + [vp]
     lib.pcabo_gp_mll_grad.restype = ci

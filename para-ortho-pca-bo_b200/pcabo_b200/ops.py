@@ -108,14 +108,16 @@ class GPBuffers:
         self.lengthscale = LENGTHSCALE
 
 
-def gp_fit(buf: GPBuffers, Z, k, f, n, mode=0, fix_lo=None, fix_hi=None, lengthscale=LENGTHSCALE, noise=NOISE):
-    """Z [B, ld_n, kmax], k [B] int32 or None, f [B, ld_n]. Fills `buf`."""
+def gp_fit(buf: GPBuffers, Z, k, f, n, mode=0, fix_lo=None, fix_hi=None, lengthscale=LENGTHSCALE, noise=NOISE,
+           jitter=None):
+    """Z [B, ld_n, kmax], k [B] int32 or None, f [B, ld_n]. Fills `buf`. jitter: optional [B] device tensor added to the
+    diagonal of K + noise I (psd_safe_cholesky's retry ladder for runs whose buf.info came back non-zero)."""
     lib = load_library()
     B, ld_n, kmax = Z.shape
     if (B, ld_n, kmax) != (buf.B, buf.ld_n, buf.kmax):
         raise PcaboError("gp_fit: buffer shape mismatch")
-    check(lib.pcabo_gp_fit(B, n, kmax, ld_n, int(mode), _d(Z, "Z"), _i(k, "k"), _d(f, "f"), _d(fix_lo, "fix_lo"),
-                           _d(fix_hi, "fix_hi"), float(lengthscale), float(noise),
+    check(lib.pcabo_gp_fit_jitter(B, n, kmax, ld_n, int(mode), _d(Z, "Z"), _i(k, "k"), _d(f, "f"), _d(fix_lo, "fix_lo"),
+                           _d(fix_hi, "fix_hi"), float(lengthscale), float(noise), _d(jitter, "jitter"),
                            _d(buf.norm_off, "norm_off"), _d(buf.norm_coef, "norm_coef"), _d(buf.box_lo, "box_lo"),
                            _d(buf.box_hi, "box_hi"), _d(buf.ymean, "ymean"), _d(buf.ystd, "ystd"), _d(buf.ZnT, "ZnT"),
                            _d(buf.Zn, "Zn"), _d(buf.L, "L"), _d(buf.W, "W"), _d(buf.WT, "WT"), _d(buf.alpha, "alpha"),

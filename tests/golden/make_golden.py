@@ -9,6 +9,9 @@ Writes tests/golden/reference_kats.json:
                             usable as (x, f(x)) known answers at 1e-6 input precision only
   * best[fid]             : full-precision (x, y) of the `best` entry of each run in
                             pca-experiment/IOHprofiler_f*.json
+  * ioh_format            : the layout of the shipped IOHprofiler_f15_RastriginRotated.json / ..._DIM5.dat of both
+                            experiments (key order, attribute names, header line, the first rows of the first run
+                            block verbatim) -- the known answer for the repo's IOHprofiler writer
 `raw_y` is ioh's untransformed objective, i.e. f(x) - f_opt.
 """
 import json
@@ -46,6 +49,21 @@ def main():
         kat["best"][str(fid)] = [{"instance": r["instance"], "x": r["best"]["x"], "y": r["best"]["y"],
                                   "evals": r["best"]["evals"]}
                                  for r in js["scenarios"][0]["runs"]]
+    fmt = {}
+    for alg in ("pca", "vanilla"):
+        js = json.load(open(f"{REF}/{alg}-experiment/IOHprofiler_f15_RastriginRotated.json"))
+        lines = open(f"{REF}/{alg}-experiment/data_f15_RastriginRotated/IOHprofiler_f15_DIM5.dat").read().splitlines()
+        run0 = js["scenarios"][0]["runs"][0]
+        fmt[alg] = {
+            "top_keys": list(js.keys()), "algorithm": js["algorithm"], "version": js["version"], "suite": js["suite"],
+            "experiment_attribute_names": [list(a.keys())[0] for a in js["experiment_attributes"]],
+            "run_attributes": js["run_attributes"], "attributes": js["attributes"],
+            "scenario_keys": list(js["scenarios"][0].keys()), "path": js["scenarios"][0]["path"],
+            "run_keys": list(run0.keys()), "best_keys": list(run0["best"].keys()),
+            "run0_evals": run0["evals"], "dat_first_lines": lines[:4], "dat_block_lines": 76,
+            "dat_blocks": sum(1 for l in lines if l.startswith("evaluations")),
+        }
+    kat["ioh_format"] = fmt
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_kats.json")
     with open(out, "w") as fh:
         json.dump(kat, fh)

@@ -218,3 +218,62 @@ def test_dropin_acquisition_choices():
         ExperimentRunner(["pca"], [5], [15], num_runs=1, acquisition_function="UCB")._acquisition_long_name()
     assert ExperimentRunner(["pca"], [5], [15], num_runs=1, acquisition_function="PI")._acquisition_long_name() == \
         "probability_of_improvement"
+
+
+def test_iohprofiler_writer_matches_reference_layout(tmp_path):
+    """The IOHprofiler writer against the layout of the reference's shipped pca-/vanilla-experiment files (fixture
+    `ioh_format`, extracted by tests/golden/make_golden.py): key order, attribute names, header, and -- because the
+    DoE, BBOB f15 and the run's best point are pinned -- the first data rows VERBATIM, including ioh's carry-over of the
+    evaluation counter and best-so-far into the second algorithm's file (ExperimentRunner.py:90-135). Out-of-bounds
+    proposals are penalised without calling problem(x) (PCA_BO.py:259-263), so they must not appear as rows."""
+    import json as _json
+    from types import SimpleNamespace
+    from Algorithms.Experiment.ExperimentRunner import ExperimentRunner
+    from pcabo_b200.bbob import BatchedBBOB, NAMES
+    from pcabo_b200.engine import lhs_center, rescale_lhs
+    kat = _json.load(open(os.path.join(ROOT, "tests", "golden", "reference_kats.json")))
+    fmt = kat["ioh_format"]
+    fid, D, inst = 15, 5, 0
+    prob = BatchedBBOB([fid], [inst], D)
+    doe_x = rescale_lhs(lhs_center(np.random.RandomState(1000 * fid + 10 * D + inst), D, 10), prob.bounds)
+    best_x = np.array(kat["best"][str(fid)][inst]["x"])
+    rng = np.random.RandomState(0)
+    runner = ExperimentRunner(["pca", "vanilla"], [D], [fid], num_runs=1, budget_factor=5, doe_factor=2.0,
+                              root_dir=str(tmp_path), experiment_name="experiment", pca_components=0)
+
+    def fake_engine(n_logged, with_oob):
+        xs, oob = [x for x in doe_x], [False] * 10
+        while len(xs) - sum(oob) < n_logged:
+            logged = len(xs) - sum(oob)
+            if with_oob and logged in (20, 21, 60) and not oob[-1]:
+                xs.append(np.full(D, 7.0)); oob.append(True)              # penalised, never evaluated
+            elif with_oob and logged == 47:
+                xs.append(best_x); oob.append(False)                      # the reference run's best point, evaluation 48
+            else:
+                xs.append(rng.uniform(-5, 5, D) * 0 + np.array([5.0, -5.0, 5.0, -5.0, 5.0])); oob.append(False)
+        fs = [1000.0 if o else float(prob.eval_many(0, x)[0]) for x, o in zip(xs, oob)]
+        return SimpleNamespace(x_evals=[xs], f_evals=[fs], oob_evals=[oob],
+                               timing_logs={"pca": [0.1], "SingleTaskGP": [0.2], "optimize_acqf": [0.3]})
+
+    for alg in ("pca", "vanilla"):
+        eng = fake_engine(75, with_oob=(alg == "pca"))
+        runner._write_iohprofiler(alg, fid, NAMES[fid], D, [inst], eng, prob, 1.5)
+        js = _json.load(open(tmp_path / f"{alg}-experiment" / f"IOHprofiler_f{fid}_{NAMES[fid]}.json"))
+        ref = fmt[alg]
+        assert list(js.keys()) == ref["top_keys"]
+        assert js["algorithm"] == ref["algorithm"] and js["version"] == ref["version"] and js["suite"] == ref["suite"]
+        assert js["run_attributes"] == ref["run_attributes"] and js["attributes"] == ref["attributes"]
+        names = [list(a.keys())[0] for a in js["experiment_attributes"]]
+        assert names == sorted(names) and set(ref["experiment_attribute_names"]) <= set(names)
+        sc = js["scenarios"][0]
+        assert list(sc.keys()) == ref["scenario_keys"] and sc["path"] == ref["path"] and sc["dimension"] == D
+        run0 = sc["runs"][0]
+        assert list(run0.keys()) == ref["run_keys"] and list(run0["best"].keys()) == ref["best_keys"]
+        assert run0["evals"] == ref["run0_evals"]                          # 75, then 150 (ioh's counter carries over)
+        lines = open(tmp_path / f"{alg}-experiment" / sc["path"]).read().splitlines()
+        assert lines[:4] == ref["dat_first_lines"]                         # verbatim, incl. 76 ... 73.0856639101
+        assert len(lines) == ref["dat_block_lines"]                        # header + 75 rows: OOB proposals not logged
+        assert [int(l.split()[0]) for l in lines[1:]] == list(range(run0["evals"] - 74, run0["evals"] + 1))
+        if alg == "pca":
+            assert run0["best"]["evals"] == kat["best"][str(fid)][inst]["evals"]
+            assert abs(run0["best"]["y"] - kat["best"][str(fid)][inst]["y"]) < 1e-9
