@@ -211,6 +211,14 @@ int pcabo_bbob_eval(int B, int m, int D, const int *fid, const double *xopt, con
                     const double *sign, const double *fopt, const double *lam, double f0, const double *X,
                     double *out, void *stream);
 
+/* pcabo_bbob_eval plus the functions that need per-peak instance data: f21 / f22 (Gallagher's 101 / 21 Gaussian peaks),
+ * and f23 Katsuura / f24 Lunacek bi-Rastrigin (which only need xopt, M and, for f24, sign = sign of xopt) -- the set
+ * BASELINE config C5 runs (f20-f24). aux [B][aux_stride] per problem: P, heights [P], rotated peak centres [P][D], axis
+ * scales [P][D] (zeros for non-Gallagher problems); R = the global rotation of f21 / f22.                          */
+int pcabo_bbob_eval_aux(int B, int m, int D, const int *fid, const double *xopt, const double *R, const double *M,
+                        const double *sign, const double *fopt, const double *lam, double f0, const double *aux,
+                        int aux_stride, const double *X, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,10 +123,11 @@ class BBOBProblem:
     (Algorithms/AbstractAlgorithm.py:73-83): `.dim`, `.bounds` ([-5, 5]^D), minimisation.
     """
 
-    NAMES = {15: "RastriginRotated", 16: "Weierstrass", 17: "Schaffers10", 20: "Schwefel"}
+    NAMES = {15: "RastriginRotated", 16: "Weierstrass", 17: "Schaffers10", 20: "Schwefel", 21: "Gallagher101",
+             22: "Gallagher21", 23: "Katsuura", 24: "LunacekBiRastrigin"}
 
     def __init__(self, fid: int, dim: int, instance: int):
-        if fid not in (15, 16, 17, 20):
+        if fid not in self.NAMES:
             raise ValueError(f"BBOB f{fid} is not restated in the oracle")
         self.fid, self.dim, self.instance = fid, dim, instance
         self.rseed = fid + 10000 * instance
@@ -158,6 +159,41 @@ class BBOBProblem:
             self.sign = np.where(u - 0.5 < 0, -1.0, 1.0)
             self.xopt = self.sign * 0.5 * 4.2096874637
             self.lam = np.power(math.sqrt(10.0), idx)
+        elif fid in (21, 22):
+            # COCO legacy f21 / f22 (Gallagher's Gaussian peaks): 101 peaks, first condition sqrt(1000), optimum
+            # in 0.8 [-5, 5]; 21 peaks, first condition 1000, optimum in 0.8 [-4.9, 4.9]. One global rotation.
+            npk = 101 if fid == 21 else 21
+            bb, cc = (10.0, 5.0) if fid == 21 else (9.8, 4.9)
+            maxcond = 1000.0
+            self.rot = compute_rotation(self.rseed, D)
+            rperm = np.argsort(unif(npk - 1, self.rseed), kind="stable")
+            cond = np.empty(npk)
+            cond[0] = math.sqrt(maxcond) if fid == 21 else maxcond
+            self.peakvalues = np.empty(npk)
+            self.peakvalues[0] = 10.0
+            for i in range(1, npk):
+                cond[i] = math.pow(maxcond, rperm[i - 1] / (npk - 2.0))
+                self.peakvalues[i] = (i - 1) / (npk - 2.0) * (9.1 - 1.1) + 1.1
+            self.scales = np.empty((npk, D))
+            for i in range(npk):
+                rp = np.argsort(unif(D, self.rseed + 1000 * i), kind="stable")
+                self.scales[i] = np.power(cond[i], rp / (D - 1.0) - 0.5) if D > 1 else 1.0
+            pk = unif(D * npk, self.rseed)
+            self.xopt = 0.8 * (bb * pk[:D] - cc)
+            self.xlocal = (bb * pk.reshape(npk, D) - cc) @ self.rot.T       # [peak][coordinate], rotated
+            self.xlocal[0] *= 0.8
+        elif fid == 23:
+            # Katsuura: z = R1 diag(sqrt(100)^(i/(D-1))) R2 (x - xopt)
+            self.xopt = compute_xopt(self.rseed, D)
+            rot1, rot2 = compute_rotation(self.rseed + 1000000, D), compute_rotation(self.rseed, D)
+            self.M = (rot1 * np.power(math.sqrt(100.0), idx)[None, :]) @ rot2
+        elif fid == 24:
+            # Lunacek bi-Rastrigin: xopt = +-mu1/2 by the sign of a Gaussian draw, same conditioning map as f23
+            g = gauss(D, self.rseed)
+            self.sign = np.where(g < 0, -1.0, 1.0)
+            self.xopt = 0.5 * 2.5 * self.sign
+            rot1, rot2 = compute_rotation(self.rseed + 1000000, D), compute_rotation(self.rseed, D)
+            self.M = (rot1 * np.power(math.sqrt(100.0), idx)[None, :]) @ rot2
 
     # ------------------------------------------------------------------ evaluation
     def batch(self, X: np.ndarray) -> np.ndarray:
@@ -181,6 +217,30 @@ class BBOBProblem:
             s = z[:, :-1] ** 2 + z[:, 1:] ** 2
             r = np.sum(np.power(s, 0.25) * (1.0 + np.sin(50.0 * np.power(s, 0.1)) ** 2), axis=-1)
             y = np.power(r / (D - 1.0), 2) + 10.0 * f_pen(X)
+        elif self.fid in (21, 22):
+            tmx = X @ self.rot.T
+            d = tmx[:, None, :] - self.xlocal[None, :, :]
+            q = np.sum(self.scales[None] * d * d, axis=-1)                    # [points, peaks]
+            f = 10.0 - np.max(self.peakvalues[None] * np.exp((-0.5 / D) * q), axis=-1)
+            y = t_osz(f) ** 2 + f_pen(X)
+        elif self.fid == 23:
+            z = (X - self.xopt) @ self.M.T
+            p2 = np.power(2.0, np.arange(1, 33))
+            arr = z[..., None] * p2
+            rnd = np.sign(arr) * np.floor(np.abs(arr) + 0.5)                  # C round(): halves away from zero
+            t = np.sum(np.abs(arr - rnd) / p2, axis=-1)
+            prod = np.prod(1.0 + t * np.arange(1, D + 1), axis=-1)
+            y = 10.0 / D / D * (-1.0 + np.power(prod, 10.0 / math.pow(D, 1.2))) + f_pen(X)
+        elif self.fid == 24:
+            mu1, dd = 2.5, 1.0
+            sfac = 1.0 - 0.5 / (math.sqrt(D + 20.0) - 4.1)
+            mu2 = -math.sqrt((mu1 * mu1 - dd) / sfac)
+            tmx = 2.0 * X * self.sign
+            s1 = np.sum((tmx - mu1) ** 2, axis=-1)
+            s2 = np.sum((tmx - mu2) ** 2, axis=-1)
+            z = (tmx - mu1) @ self.M.T
+            y = np.minimum(s1, dd * D + sfac * s2) + 10.0 * (D - np.sum(np.cos(2.0 * math.pi * z), axis=-1)) \
+                + 1e4 * f_pen(X)
         else:  # 20
             xh = 2.0 * self.sign * X
             zh = xh.copy()

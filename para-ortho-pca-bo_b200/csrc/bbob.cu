@@ -1,5 +1,6 @@
-// Batched BBOB objectives on the device: f15 Rastrigin (rotated), f16 Weierstrass, f17 Schaffers F7 and
-// f20 Schwefel, one thread block per (problem, point). Replaces the per-iteration host call `problem(x)` of the
+// Batched BBOB objectives on the device: f15 Rastrigin (rotated), f16 Weierstrass, f17 Schaffers F7,
+// f20 Schwefel, f21 / f22 Gallagher's Gaussian peaks, f23 Katsuura and f24 Lunacek bi-Rastrigin (config C5 runs f20-f24),
+// one thread block per (problem, point). Replaces the per-iteration host call `problem(x)` of the
 // reference (ioh's C++ objective, PCA_BO.py:263 / AbstractBayesianOptimizer.py:163) for the synthetic BBOB workloads of
 // BASELINE configs C1-C3; the instance data (x_opt, rotations, f_opt) are built on the host exactly like ioh / COCO
 // build them (pcabo_b200/bbob.py) and passed in. One launch instead of ~100 small tensor operations per lock-step
@@ -20,6 +21,8 @@ struct BbobArgs {
   const double *fopt;      // [B]
   const double *lam;       // [D] sqrt(10)^(i / (D - 1)) (f20)
   double f0;               // Weierstrass constant
+  const double *aux;       // [B][aux_stride] Gallagher: P, heights [P], rotated centres [P][D], axis scales [P][D]
+  int aux_stride;
   const double *X;         // [B][m][D]
   double *out;             // [B][m]
 };
@@ -48,7 +51,84 @@ __global__ void __launch_bounds__(128) bbob_eval_kernel(BbobArgs a) {
   const bool on = i < D;
   const double xi = on ? x[i] : 0.0;
   double f;
-  if (fid == 20) {
+  if ((fid == 21 || fid == 22) && a.aux == nullptr) {
+    // no per-peak instance data was passed (pcabo_bbob_eval): refuse loudly instead of reading out of bounds
+    if (i == 0) a.out[(size_t)b * a.m + p] = nan("");
+    return;
+  }
+  if (fid == 21 || fid == 22) {
+    // Gallagher: y = R x; f = T_osz(10 - max_p h_p exp(-(1/2D) sum_j s_pj (y_j - c_pj)^2))^2 + penalty
+    const double *Rb = a.R + (size_t)b * D * D;
+    const double *ax = a.aux + (size_t)b * a.aux_stride;
+    const int P = (int)ax[0];
+    const double *height = ax + 1, *centres = ax + 1 + P, *scales = centres + (size_t)P * D;
+    ys[i] = xi;
+    const double pe = on ? fmax(fabs(xi) - 5.0, 0.0) : 0.0;
+    const double pen = block_sum(pe * pe, red);      // (contains the barrier that publishes ys)
+    double y = 0.0;
+    if (on)
+      for (int j = 0; j < D; ++j) y = fma(Rb[(size_t)i * D + j], ys[j], y);
+    zs[i] = y;
+    __syncthreads();
+    const int warp = i >> 5, lane = i & 31;
+    double best = 0.0;                               // every term is positive
+    for (int p2 = warp; p2 < P; p2 += 4) {
+      double q = 0.0;
+      for (int j = lane; j < D; j += 32) {
+        const double d = zs[j] - centres[(size_t)p2 * D + j];
+        q = fma(scales[(size_t)p2 * D + j] * d, d, q);
+      }
+      q = warp_sum(q);
+      best = fmax(best, height[p2] * exp(q * (-0.5 / D)));
+    }
+    __syncthreads();
+    if (lane == 0) ys[warp] = best;
+    __syncthreads();
+    const double g = 10.0 - fmax(fmax(ys[0], ys[1]), fmax(ys[2], ys[3]));
+    const double tg = t_osz(g);
+    f = tg * tg + pen;
+  } else if (fid == 23) {
+    // Katsuura: z = M (x - xopt); prod_i (1 + (i+1) sum_{j=1..32} |2^j z_i - round(2^j z_i)| / 2^j)
+    const double *Mb = a.M + (size_t)b * D * D;
+    ys[i] = on ? xi - xo[i] : 0.0;
+    const double pe = on ? fmax(fabs(xi) - 5.0, 0.0) : 0.0;
+    const double pen = block_sum(pe * pe, red);
+    double term = 1.0;
+    if (on) {
+      double z = 0.0;
+      for (int j = 0; j < D; ++j) z = fma(Mb[(size_t)i * D + j], ys[j], z);
+      double t = 0.0, p2 = 1.0;
+      for (int j = 1; j < 33; ++j) {
+        p2 *= 2.0;
+        const double arr = z * p2;
+        t += fabs(arr - round(arr)) / p2;
+      }
+      term = 1.0 + t * (double)(i + 1);
+    }
+    // block product (fixed tree): warp shuffles, then the four warp products
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) term *= __shfl_xor_sync(0xffffffffu, term, o);
+    __syncthreads();
+    if ((i & 31) == 0) zs[i >> 5] = term;
+    __syncthreads();
+    const double prod = (zs[0] * zs[1]) * (zs[2] * zs[3]);
+    f = 10.0 / D / D * (pow(prod, 10.0 / pow((double)D, 1.2)) - 1.0) + pen;
+  } else if (fid == 24) {
+    // Lunacek bi-Rastrigin: y = 2 sign(xopt) x; min(sum (y - mu1)^2, D + s sum (y - mu2)^2) + 10 (D - sum cos(2 pi M (y - mu1)))
+    const double *Mb = a.M + (size_t)b * D * D;
+    const double mu1 = 2.5, sfac = 1.0 - 0.5 / (sqrt((double)D + 20.0) - 4.1), mu2 = -sqrt((mu1 * mu1 - 1.0) / sfac);
+    const double y = on ? 2.0 * a.sign[(size_t)b * D + i] * xi : 0.0;
+    ys[i] = on ? y - mu1 : 0.0;
+    const double pe = on ? fmax(fabs(xi) - 5.0, 0.0) : 0.0;
+    const double pen = block_sum(pe * pe, red);
+    const double s1 = block_sum(on ? (y - mu1) * (y - mu1) : 0.0, red);
+    const double s2 = block_sum(on ? (y - mu2) * (y - mu2) : 0.0, red);
+    double z = 0.0;
+    if (on)
+      for (int j = 0; j < D; ++j) z = fma(Mb[(size_t)i * D + j], ys[j], z);
+    const double c = block_sum(on ? cos(TWO_PI * z) : 0.0, red);
+    f = fmin(s1, (double)D + sfac * s2) + 10.0 * ((double)D - c) + 1e4 * pen;
+  } else if (fid == 20) {
     // Schwefel: x_hat = 2 sign x; z_hat_i = x_hat_i + 0.25 (x_hat_{i-1} - 2 |xopt_{i-1}|); z = 100 (Lambda (z_hat - 2|xopt|) + 2|xopt|)
     const double sg = on ? a.sign[(size_t)b * D + i] : 0.0;
     ys[i] = 2.0 * sg * xi;
@@ -120,16 +200,24 @@ __global__ void __launch_bounds__(128) bbob_eval_kernel(BbobArgs a) {
 
 }  // namespace
 
-extern "C" int pcabo_bbob_eval(int B, int m, int D, const int *fid, const double *xopt, const double *R, const double *M,
-                               const double *sign, const double *fopt, const double *lam, double f0, const double *X,
-                               double *out, void *stream) {
+extern "C" int pcabo_bbob_eval_aux(int B, int m, int D, const int *fid, const double *xopt, const double *R,
+                                   const double *M, const double *sign, const double *fopt, const double *lam, double f0,
+                                   const double *aux, int aux_stride, const double *X, double *out, void *stream) {
   if (B <= 0 || m <= 0 || D <= 0 || !fid || !xopt || !R || !M || !sign || !fopt || !lam || !X || !out) return PCABO_E_INVALID;
+  if (aux && aux_stride < 1) return PCABO_E_INVALID;
   if (D > 128 || m > 65535 * 32) return PCABO_E_UNSUPPORTED;
   BbobArgs a;
   a.B = B; a.m = m; a.D = D; a.fid = fid; a.xopt = xopt; a.R = R; a.M = M; a.sign = sign; a.fopt = fopt; a.lam = lam;
-  a.f0 = f0; a.X = X; a.out = out;
+  a.f0 = f0; a.X = X; a.out = out; a.aux = aux; a.aux_stride = aux_stride;
   dim3 grid(m, B);
   bbob_eval_kernel<<<grid, 128, 0, as_stream(stream)>>>(a);
   PCABO_LAUNCH_CHECK();
   return PCABO_OK;
+}
+
+// f15 / f16 / f17 / f20 / f23 / f24 only (no per-peak instance data): Gallagher problems evaluate to NaN
+extern "C" int pcabo_bbob_eval(int B, int m, int D, const int *fid, const double *xopt, const double *R, const double *M,
+                               const double *sign, const double *fopt, const double *lam, double f0, const double *X,
+                               double *out, void *stream) {
+  return pcabo_bbob_eval_aux(B, m, D, fid, xopt, R, M, sign, fopt, lam, f0, nullptr, 0, X, out, stream);
 }

@@ -1,11 +1,12 @@
-"""Batched BBOB objectives (f15 RastriginRotated, f16 Weierstrass, f17 Schaffers F7, f20 Schwefel) in torch.
+"""Batched BBOB objectives (f15 RastriginRotated, f16 Weierstrass, f17 Schaffers F7, f20 Schwefel, f21 / f22 Gallagher
+101 / 21 peaks, f23 Katsuura, f24 Lunacek bi-Rastrigin: the multi-modal group the BASELINE configs draw from) in torch.
 
 The reference evaluates `problem(x)` through ioh's C++ BBOB suite (PCA_BO.py:263, AbstractBayesianOptimizer.py:163);
 ioh is not installable here, so the COCO/ioh definitions are restated: instance data from the
 legacy COCO generator with `rseed = fid + 10000 * instance`, evaluation as one batched torch expression over B
 runs that works on CPU or CUDA tensors (one point per run per BO iteration). f15 and f20 are pinned against the
 reference's shipped IOHprofiler data (tests/test_host_logic.py::test_host_doe_and_bbob_match_reference_goldens,
-tests/test_oracle_golden.py); f16 / f17 are unpinned.
+tests/test_oracle_golden.py); f16 / f17 / f21-f24 are unpinned (the reference ships no vectors for them).
 This is the objective, not the hot path: plain torch ops are deliberate here.
 """
 import math
@@ -13,7 +14,27 @@ import math
 import numpy as np
 import torch
 
-NAMES = {15: "RastriginRotated", 16: "Weierstrass", 17: "Schaffers10", 20: "Schwefel"}
+NAMES = {15: "RastriginRotated", 16: "Weierstrass", 17: "Schaffers10", 20: "Schwefel", 21: "Gallagher101",
+         22: "Gallagher21", 23: "Katsuura", 24: "LunacekBiRastrigin"}
+GALLAGHER = {21: (101, 10.0, 5.0, math.sqrt(1000.0)), 22: (21, 9.8, 4.9, 1000.0)}   # peaks, b, c, condition of peak 0
+
+
+def _order(u: np.ndarray) -> np.ndarray:
+    """The permutation COCO obtains by qsort-ing indices on the uniform draws."""
+    return np.argsort(u, kind="stable")
+
+
+def _gallagher_instance(fid: int, rseed: int, D: int):
+    """Peak heights [P], rotated peak centres [P, D] and per-peak axis scales [P, D] of COCO's f21 / f22."""
+    P, b, c, cond0 = GALLAGHER[fid]
+    rot = _rotation(rseed, D)
+    rank = _order(_unif(P - 1, rseed))
+    cond = np.concatenate([[cond0], np.power(1000.0, rank / (P - 2.0))])
+    height = np.concatenate([[10.0], 1.1 + 8.0 * np.arange(P - 1) / (P - 2.0)])
+    scales = np.stack([np.power(cond[i], _order(_unif(D, rseed + 1000 * i)) / max(D - 1.0, 1.0) - 0.5) for i in range(P)])
+    centres = b * _unif(D * P, rseed).reshape(P, D) - c
+    centres[0] *= 0.8
+    return rot, height, centres @ rot.T, scales, centres[0].copy()
 
 
 def _unif(n: int, inseed: int) -> np.ndarray:
@@ -103,11 +124,32 @@ class BatchedBBOB:
         M = np.zeros((self.B, D, D))
         sign = np.ones((self.B, D))
         fopt = np.zeros(self.B)
+        # Gallagher instance data, one row per problem: [P, heights (P), rotated centres (P x D), axis scales (P x D)]
+        pmax = max([GALLAGHER[f][0] for f in fids if f in GALLAGHER], default=0)
+        self.aux_stride = 1 + pmax * (1 + 2 * D) if pmax else 1
+        aux = np.zeros((self.B, self.aux_stride))
         for b, (fid, inst) in enumerate(zip(fids, instances)):
             if fid not in NAMES:
                 raise ValueError(f"BBOB f{fid} is not available")
             rseed = fid + 10000 * inst
             fopt[b] = _fopt(fid, inst)
+            if fid in GALLAGHER:
+                rot, height, centres, scales, xo = _gallagher_instance(fid, rseed, D)
+                P = len(height)
+                R[b], xopt[b] = rot, xo
+                aux[b, 0] = P
+                aux[b, 1:1 + P] = height
+                aux[b, 1 + P:1 + P + P * D] = centres.reshape(-1)
+                aux[b, 1 + P + P * D:1 + P + 2 * P * D] = scales.reshape(-1)
+                continue
+            if fid in (23, 24):
+                if fid == 23:
+                    xopt[b] = _xopt(rseed, D)
+                else:
+                    sign[b] = np.where(_gauss(D, rseed) < 0, -1.0, 1.0)
+                    xopt[b] = 1.25 * sign[b]
+                M[b] = (_rotation(rseed + 1000000, D) * np.power(10.0, idx)[None, :]) @ _rotation(rseed, D)
+                continue
             if fid == 20:
                 u = _unif(D, rseed)
                 sign[b] = np.where(u - 0.5 < 0, -1.0, 1.0)
@@ -124,6 +166,7 @@ class BatchedBBOB:
                 M[b] = np.power(math.sqrt(10.0), idx)[:, None] * rot2
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
         self.xopt, self.R, self.M, self.sign, self.fopt = t(xopt), t(R), t(M), t(sign), t(fopt)
+        self.aux = t(aux)
         self.fid_t = torch.tensor(fids, device=device)
         self.lam = t(np.power(math.sqrt(10.0), idx))
         k = np.arange(12)
@@ -147,8 +190,34 @@ class BatchedBBOB:
             pen = (z.abs() - 500.0).clamp_min(0.0).pow(2).sum(-1)
             s = (z * torch.sin(z.abs().sqrt())).sum(-1)
             return 0.01 * (pen + 418.9828872724339 - s / D)
-        z = torch.einsum("bij,bj->bi", self.R[sel], x - self.xopt[sel])
         pen = (x.abs() - 5.0).clamp_min(0.0).pow(2).sum(-1)
+        if fid in GALLAGHER:
+            P = GALLAGHER[fid][0]
+            a = self.aux[sel]
+            height = a[:, 1:1 + P]
+            centres = a[:, 1 + P:1 + P + P * D].reshape(-1, P, D)
+            scales = a[:, 1 + P + P * D:1 + P + 2 * P * D].reshape(-1, P, D)
+            y = torch.einsum("bij,bj->bi", self.R[sel], x)
+            q = (scales * (y[:, None, :] - centres) ** 2).sum(-1)
+            f = 10.0 - (height * torch.exp(q * (-0.5 / D))).max(-1).values
+            return _t_osz(f) ** 2 + pen
+        if fid == 23:
+            z = torch.einsum("bij,bj->bi", self.M[sel], x - self.xopt[sel])
+            p2 = torch.pow(2.0, torch.arange(1, 33, dtype=x.dtype, device=x.device))
+            arr = z.unsqueeze(-1) * p2
+            nearest = torch.sign(arr) * torch.floor(arr.abs() + 0.5)        # C round()
+            t = ((arr - nearest).abs() / p2).sum(-1)
+            prod = (1.0 + t * torch.arange(1, D + 1, dtype=x.dtype, device=x.device)).prod(-1)
+            return (10.0 / (D * D)) * (prod.pow(10.0 / D ** 1.2) - 1.0) + pen
+        if fid == 24:
+            mu1 = 2.5
+            sfac = 1.0 - 0.5 / (math.sqrt(D + 20.0) - 4.1)
+            mu2 = -math.sqrt((mu1 * mu1 - 1.0) / sfac)
+            y = 2.0 * self.sign[sel] * x
+            z = torch.einsum("bij,bj->bi", self.M[sel], y - mu1)
+            sphere = torch.minimum(((y - mu1) ** 2).sum(-1), D + sfac * ((y - mu2) ** 2).sum(-1))
+            return sphere + 10.0 * (D - torch.cos(2.0 * math.pi * z).sum(-1)) + 1e4 * pen
+        z = torch.einsum("bij,bj->bi", self.R[sel], x - self.xopt[sel])
         if fid == 15:
             z = torch.einsum("bij,bj->bi", self.M[sel], _t_asy(_t_osz(z), 0.2))
             return 10.0 * (D - torch.cos(2.0 * math.pi * z).sum(-1)) + (z * z).sum(-1)
@@ -167,7 +236,7 @@ class BatchedBBOB:
         if self._fid32 is None:
             self._fid32 = self.fid_t.to(torch.int32)
         return ops.bbob_eval(self._fid32, self.xopt, self.R, self.M, self.sign, self.fopt, self.lam, self.f0,
-                             X3.contiguous())
+                             X3.contiguous(), aux=self.aux)
 
     def __call__(self, X: torch.Tensor) -> torch.Tensor:
         """X [B, D] (one point per problem) -> objective values [B] (with f_opt added, like ioh's `problem(x)`)."""

@@ -9,7 +9,7 @@ EXPORTED_SYMBOLS = [
     "pcabo_abi_version", "pcabo_error_string", "pcabo_last_cuda_error",
     "pcabo_weights_pca_fit", "pcabo_inverse_map", "pcabo_gp_fit", "pcabo_gp_fit_jitter", "pcabo_gp_mll", "pcabo_gp_mll_grad",
     "pcabo_logei", "pcabo_argmax", "pcabo_lbfgsb_logei", "pcabo_lbfgsb_logei_prof", "pcabo_lbfgsb_logei_runs", "pcabo_ei_sweep",
-    "pcabo_sobol_points", "pcabo_sobol_scramble_bits", "pcabo_gather_rows", "pcabo_bbob_eval", "pcabo_select_initial_conditions",
+    "pcabo_sobol_points", "pcabo_sobol_scramble_bits", "pcabo_gather_rows", "pcabo_bbob_eval", "pcabo_bbob_eval_aux", "pcabo_select_initial_conditions",
 ]
 
 
@@ -86,6 +86,8 @@ def load_library(build_if_missing: bool = False):
     lib.pcabo_select_initial_conditions.argtypes = [ci, ci, ci, ci, cd] + [vp] * 7 + [vp]
     lib.pcabo_bbob_eval.restype = ci
     lib.pcabo_bbob_eval.argtypes = [ci, ci, ci] + [vp] * 7 + [cd, vp, vp, vp]
+    lib.pcabo_bbob_eval_aux.restype = ci
+    lib.pcabo_bbob_eval_aux.argtypes = [ci, ci, ci] + [vp] * 7 + [cd, vp, ci, vp, vp, vp]
     lib.pcabo_argmax.restype = ci
     lib.pcabo_argmax.argtypes = [ci, ci, vp, vp, vp, vp]
     _LIB = lib

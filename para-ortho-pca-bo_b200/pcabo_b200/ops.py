@@ -302,15 +302,17 @@ def ei_sweep(buf: GPBuffers, ws: SweepWorkspace, ncand, idx0=0, run=0, X=None, s
     return ws.best_val, ws.best_idx
 
 
-def bbob_eval(fid, xopt, R, M, sign, fopt, lam, f0, X, out=None):
-    """Batched BBOB f15 / f16 / f17 / f20: X [B, m, D] (device) -> out [B, m] (f_opt included)."""
+def bbob_eval(fid, xopt, R, M, sign, fopt, lam, f0, X, out=None, aux=None):
+    """Batched BBOB f15-f17 / f20-f24: X [B, m, D] (device) -> out [B, m] (f_opt included). aux [B, stride]: the
+    Gallagher peak data of f21 / f22 (include/pcabo_b200.h)."""
     lib = load_library()
     B, m, D = X.shape
     if out is None:
         out = torch.empty(B, m, dtype=torch.float64, device=X.device)
-    check(lib.pcabo_bbob_eval(B, m, D, _i(fid, "fid"), _d(xopt, "xopt"), _d(R, "R"), _d(M, "M"), _d(sign, "sign"),
-                              _d(fopt, "fopt"), _d(lam, "lam"), float(f0), _d(X, "X"), _d(out, "out"), _stream()),
-          "pcabo_bbob_eval")
+    check(lib.pcabo_bbob_eval_aux(B, m, D, _i(fid, "fid"), _d(xopt, "xopt"), _d(R, "R"), _d(M, "M"), _d(sign, "sign"),
+                                  _d(fopt, "fopt"), _d(lam, "lam"), float(f0), _d(aux, "aux"),
+                                  int(aux.shape[1]) if aux is not None else 0, _d(X, "X"), _d(out, "out"), _stream()),
+          "pcabo_bbob_eval_aux")
     return out
 
 

@@ -356,14 +356,14 @@ def test_probability_of_improvement_value_grad(D, n, npts, maximization):
         assert np.max(np.abs(g - gr) / scale) < 1e-7, "PI gradient (per-point max-norm relative)"
 
 
-@pytest.mark.parametrize("D", [2, 5, 10, 40])
+@pytest.mark.parametrize("D", [2, 5, 10, 40, 100])
 def test_bbob_kernel_matches_oracle(D):
-    """pcabo_bbob_eval (f15, f16, f17, f20; several instances) against the CPU oracle's BBOB restatement, on points
+    """pcabo_bbob_eval_aux (f15-f17, f20-f24; several instances) against the CPU oracle's BBOB restatement, on points
     inside and outside the box (boundary penalty), one point per problem and many points per problem."""
     from pcabo_b200.bbob import BatchedBBOB
     from oracle import bbob
-    fids = [15, 16, 17, 20, 15, 16, 17, 20]
-    insts = [0, 0, 0, 0, 3, 7, 11, 29]
+    fids = [15, 16, 17, 20, 15, 16, 17, 20, 21, 22, 23, 24, 21, 22, 23, 24]
+    insts = [0, 0, 0, 0, 3, 7, 11, 29, 0, 0, 0, 0, 5, 13, 21, 29]
     prob = BatchedBBOB(fids, insts, D, device="cuda")
     rng = np.random.RandomState(D)
     m = 9

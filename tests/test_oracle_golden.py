@@ -218,3 +218,26 @@ def test_oracle_probability_of_improvement():
             Xm[:, j] -= h
             fd = (pi(Xp) - pi(Xm)) / (2 * h)
             assert torch.allclose(g[:, j], fd, rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("fid", [21, 22, 23, 24])
+def test_bbob_f21_f24_definitions(fid):
+    """f21-f24 (config C5) are restated from the COCO definitions and UNPINNED (the reference ships no vectors for them).
+    What can be checked without ioh: the optimum value is attained at x_opt exactly, nothing in the box is below it,
+    the boundary penalty is active outside, and the product's independent torch restatement agrees to 1e-11."""
+    from oracle import bbob
+    from pcabo_b200.bbob import BatchedBBOB
+    for D in (2, 5, 20):
+        for inst in (0, 7):
+            p = bbob.BBOBProblem(fid, D, inst)
+            assert p(p.xopt) == p.fopt
+            assert np.all(np.abs(p.xopt) <= 5.0)
+            rng = np.random.RandomState(fid * 100 + D + inst)
+            X = rng.uniform(-5, 5, size=(300, D))
+            y = p.batch(X)
+            assert np.all(y >= p.fopt)
+            Xo = X.copy()
+            Xo[:, 0] = 6.5
+            assert np.all(p.batch(Xo) >= p.fopt + (1e4 if fid == 24 else 1.0) * 1.5 ** 2 - 1e-9)   # boundary penalty
+            got = BatchedBBOB([fid], [inst], D).eval_all(X[None])[0]
+            assert np.max(np.abs(got - y) / np.maximum(1.0, np.abs(y))) < 1e-11

@@ -2,7 +2,7 @@
 
 C1: PCA-BO f15 D=10, 1 run (budget 150, n_doe 30)                       -- the reference's own CPU-runnable case
 C2: vanilla BO and PCA-BO on f15/f20 D=20, 30 runs each (budget 250, n_doe 60)
-C5: PCA-BO D=100, budget 1050, n_doe 300, 30 runs x 4 functions (f15-f17, f20: f21-f24 are not restated yet);
+C5: PCA-BO D=100, budget 1050, n_doe 300, 30 runs x 5 functions (f20-f24);
     the device optimiser fits shared memory (sized by the batch's largest k) up to n ~ 920 of the 1050 points, one
     block per SM; both optimisers are reported at the start of the run
 Run on the GPU box: python tools/bench_configs.py [--steps 5]
@@ -57,8 +57,8 @@ def main():
         for alg in ("vanilla", "pca"):
             measure("C2", fids, insts, 20, alg, "device", a.steps)
     if not want or "C5" in want:
-        fids = [f for f in (15, 16, 17, 20) for _ in range(30)]
-        insts = [i for _ in range(4) for i in range(30)]
+        fids = [f for f in (20, 21, 22, 23, 24) for _ in range(30)]
+        insts = [i for _ in range(5) for i in range(30)]
         measure("C5", fids, insts, 100, "pca", "scipy", max(2, a.steps // 2), warmup=1)
         try:
             measure("C5", fids, insts, 100, "pca", "device", max(2, a.steps // 2), warmup=1)
