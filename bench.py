@@ -1,17 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- PCA-BO iterations/sec on BASELINE config C3 (D=40, f15-f17 x 30 instances, budget 450, n_doe 120).
+"""bench.py -- PCA-BO iterations/sec on BASELINE config C3 (D=40, f15-f17 x 30 instances = 90 runs, budget 450,
+n_doe 120), plus the EI-candidates/sec half of the metric (config C4) as a sub-record of the same JSON line.
 
-A "step" is ONE lock-step BO iteration of the whole per-GPU batch (90 runs: rank weights + weighted PCA fit, GP
-caches, 512 raw log-EI samples, 10 restarts of L-BFGS-B on log-EI, inverse map, objective, bookkeeping), i.e. 90 BO
-iterations. Runs are independent, so at N GPUs every rank owns its own 90 runs (instances 30*rank .. 30*rank+29 of
-f15, f16, f17) and there is no data-path collective: scaling is "weak" and `value` is the whole-job
-iterations/sec = N * 90 * K / (max over ranks of the device-synchronised time of K steps).
+A "step" is ONE lock-step BO iteration of every run a GPU owns (rank weights + weighted PCA fit, GP caches, 512 raw
+log-EI samples, 10 restarts of L-BFGS-B on log-EI, inverse map, objective, bookkeeping).
+
+Scaling. BASELINE states the config as "the 90 runs sharded over 1/2/4/8 B200": that is STRONG scaling and it is the
+default for --gpus > 1 (round-robin `shard_runs`, no data-path collective; value = 90 K / max-over-ranks time).
+`--scaling weak` gives every rank its own 90 runs (instances 30 rank .. 30 rank + 29); with --gpus > 1 a short weak
+measurement is added under `weak_scaling` unless --no-weak.
+
+Window. Without --steps the timed region is the WHOLE run (327 steps after 3 warm-ups, n = 123 .. 450). A short
+--steps K (K <= 60) is STRATIFIED over the n range of a run: three windows of K/3 steps at n = 120 + W, 285 and 430
+(the engine is fast-forwarded, untimed, between them), because a step at n = 445 costs twice a step at n = 125. The
+reference arm times the same windows, its workers continuing oracle-generated histories committed under
+tests/golden/bench_histories_c3.npz (tests/golden/make_bench_histories.py); it never loads the CUDA library.
 
     python bench.py --gpus N --steps K --warmup W            # ours (torchrun launches it for N > 1)
     python bench.py --impl reference --steps K --warmup W    # the CPU oracle on the host cores (reference arm)
-
-The JSON line also carries `roofline` (dominant kernel, CUDA-event timed inside the timed region), `cpu_baseline`
-(the CPU oracle on a bounded sample of the same workload, rank 0 at N=1), `e2e`, `clocks` and `gpu_launches`.
 """
 import argparse
 import json
@@ -28,28 +34,38 @@ sys.path.insert(0, os.path.join(ROOT, "para-ortho-pca-bo_b200"))
 DIM = 40
 FIDS = (15, 16, 17)
 RUNS_PER_FID = 30
+N_RUNS = len(FIDS) * RUNS_PER_FID
 BUDGET, N_DOE = 10 * DIM + 50, 3 * DIM
 METRIC = "PCA-BO iterations/sec (30 runs x f15-f17, D=40)"
 UNIT = "BO iterations/s"
+STRATA = (285, 430)          # later windows of a stratified run start at these n
+HISTORIES = os.path.join(ROOT, "tests", "golden", "bench_histories_c3.npz")
 
 
-def workload_config(n_start, steps, warmup, optimizer, extra=None):
-    cfg = {"workload": "C3: PCA-BO D=40, f15-f17 x 30 instances (90 runs per GPU), budget 450, n_doe 120, log-EI, "
-                       "num_restarts 10, raw_samples 512, batch_limit 5, maxiter 200, var_threshold 0.95",
-           "runs_per_gpu": len(FIDS) * RUNS_PER_FID, "dim": DIM, "budget": BUDGET, "n_doe": N_DOE,
-           "n_points_range": [n_start + warmup, n_start + warmup + steps],
-           "optimizer": optimizer,
-           "sub_batches": "the 90 runs of a GPU advance as S lock-step sub-batches on S CUDA streams, software-pipelined by "
-                          "one host thread (S in the `sub_batches` key; results do not depend on S)",
-           "l2_policy": "per-step inputs exceed L2: every step refits PCA/GP from new data and streams "
-                        "90 x n^2/2 FP64 cache matrices; no result is reused between steps"}
-    if extra:
-        cfg.update(extra)
-    return cfg
+def plan_windows(steps, warmup):
+    """[(n_start, timed steps)]: one contiguous window, or three strata for a short run."""
+    whole = BUDGET - N_DOE - warmup
+    steps = max(1, min(steps, whole))
+    if steps > 60 or steps < 3:
+        return [(N_DOE + warmup, steps)]
+    a = (steps + 2) // 3
+    b = (steps - a + 1) // 2
+    return [(N_DOE + warmup, a), (max(STRATA[0], N_DOE + warmup + a), b), (STRATA[1], steps - a - b)]
+
+
+def workload_config(windows, warmup, scaling, world):
+    """Identical in both arms (the driver compares it): workload, sizes, windows. Arm-specific facts go in `run_info`."""
+    return {"workload": "C3: PCA-BO D=40, f15-f17 x 30 instances (90 runs), budget 450, n_doe 120, log-EI, "
+                        "num_restarts 10, raw_samples 512, batch_limit 5, maxiter 200, var_threshold 0.95",
+            "runs": N_RUNS if scaling == "strong" else N_RUNS * world, "dim": DIM, "budget": BUDGET, "n_doe": N_DOE,
+            "n_points_windows": [[n0, n0 + k] for n0, k in windows], "warmup_steps": warmup,
+            "l2_policy": "per-step inputs exceed L2: every step refits PCA/GP from new data and streams "
+                         "runs x n^2/2 FP64 cache matrices; no result is reused between steps"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU oracle arm
 def _oracle_worker(args):
+    """One oracle run from its DoE for n_iter BO iterations (whole-run reference arm)."""
     fid, inst, n_iter, budget_s = args
     import torch
     torch.set_num_threads(1)
@@ -69,7 +85,7 @@ def _oracle_worker(args):
 
 
 def _oracle_worker_primed(args):
-    """cpu_baseline sample: the oracle continues a run from a given history (x, f prefix) for n_iter BO iterations."""
+    """The oracle continues a run from a given history (x, f prefix) for n_iter BO iterations."""
     fid, inst, X, f, n_iter = args
     import numpy as np
     import torch
@@ -109,53 +125,74 @@ def _pool_map(fn, jobs, cores):
                 os.environ[k] = v
 
 
-def oracle_sampled_throughput(histories, n_points, iters_per_point, cores=None):
-    """cpu_baseline of the GPU arm: `cores` oracle runs (one per host core, 1 thread each) continue the histories the
-    engine produced (histories[j] = (fid, inst, x_evals, f_evals)) from each n in n_points for iters_per_point BO
-    iterations (the first one of each segment is warm-up). Returns (iterations/s, cores, seconds, description)."""
-    cores = min(cores or os.cpu_count() or 1, len(histories))
+def oracle_windows_throughput(histories, windows, cores=None, warm=1):
+    """`cores` oracle runs (one per host core, 1 thread each; histories reused cyclically when there are more cores than
+    histories) continue histories[j] = (fid, inst, X, f) from the start of every window for its number of steps (+ `warm`
+    untimed iterations). The workers are independent, so a window costs its slowest worker. Returns
+    (iterations/s, cores, seconds, timed iterations per worker)."""
+    cores = cores or os.cpu_count() or 1
     total_it, total_s = 0, 0.0
-    for n0 in n_points:
-        jobs = [(fid, inst, X[:n0], f[:n0], iters_per_point) for fid, inst, X, f in histories[:cores]]
+    for n0, k in windows:
+        jobs = []
+        for j in range(cores):
+            fid, inst, X, f = histories[j % len(histories)]
+            jobs.append((fid, inst, X[:n0], f[:n0], k + warm))
         res = _pool_map(_oracle_worker_primed, jobs, cores)
-        total_s += max(sum(t[1:]) for t in res)          # workers run concurrently: the slowest one bounds the segment
-        total_it += cores * (iters_per_point - 1)
+        total_s += max(sum(t[warm:]) for t in res)
+        total_it += cores * k
     return total_it / total_s, cores, total_s
 
 
 def oracle_throughput(steps, warmup, cores=None, budget_s=None):
-    """Reference CPU path: one oracle run per core (1 intra-op thread each), `cores` runs in parallel,
-    each doing warmup+steps BO iterations from its DoE (cut short after `budget_s` seconds of wall time).
-    Returns (iterations/s over the timed steps, cores, seconds, steps actually timed, per-step seconds)."""
+    """Whole-run reference arm: one oracle run per core from its DoE, warmup + steps BO iterations (cut short after
+    `budget_s` seconds). Returns (iterations/s over the timed steps, cores, seconds, steps timed, per-step seconds)."""
     cores = cores or os.cpu_count() or 1
     steps = min(steps, BUDGET - N_DOE - warmup)
     jobs = [(FIDS[j % len(FIDS)], j // len(FIDS), warmup + steps, budget_s) for j in range(cores)]
     res = _pool_map(_oracle_worker, jobs, cores)
     done = min(len(r[1]) for r in res)          # iterations every worker finished inside the budget
     steps = max(1, done - warmup)
-    # the workers run concurrently and independently (no lock-step on the CPU): the job's wall time for the timed
-    # iterations is the slowest worker's total
     timed = max(sum(r[1][warmup:warmup + steps]) for r in res)
     per_step = [max(r[1][i] for r in res) for i in range(warmup + steps)]
     return cores * steps / timed, cores, timed, steps, per_step
+
+
+def load_histories():
+    import numpy as np
+    d = np.load(HISTORIES)
+    return [(int(d["fid"][j]), int(d["inst"][j]), d["X"][j], d["f"][j]) for j in range(d["X"].shape[0])]
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    its, cores, secs, steps, per_step = oracle_throughput(args.steps, args.warmup, budget_s=args.ref_budget_s)
-    sample = (f"{cores} of the 90 runs (one per host core, 1 torch thread each), BO iterations "
-              f"{args.warmup}..{args.warmup + steps} from the DoE (n = {N_DOE + args.warmup}..{N_DOE + args.warmup + steps})"
-              + ("" if steps == args.steps else f"; cut at the {args.ref_budget_s:.0f} s wall-time budget after {steps} of {args.steps} steps"))
-    line = {"impl": "reference", "metric": METRIC, "value": its, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (BBOB f15-f17 restated)",
-            "config": workload_config(N_DOE, steps, args.warmup, "scipy L-BFGS-B (CPU oracle)"),
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    scaling = args.scaling or ("strong" if max(world, args.gpus) > 1 else "weak")
+    windows = plan_windows(args.steps, args.warmup)
+    if len(windows) > 1:
+        hist = load_histories()
+        its, cores, secs = oracle_windows_throughput(hist, windows)
+        steps = sum(k for _, k in windows)
+        sample = (f"{cores} oracle workers (one per host core, 1 torch thread each) continuing {len(hist)} committed "
+                  f"oracle histories of C3 runs from n = {[n0 for n0, _ in windows]} for {[k for _, k in windows]} timed BO "
+                  f"iterations (+1 warm-up each); {secs:.1f} s")
+        per_step = None
+    else:
+        its, cores, secs, steps, per_step = oracle_throughput(windows[0][1], args.warmup, budget_s=args.ref_budget_s)
+        windows = [(windows[0][0], steps)]
+        sample = (f"{cores} of the 90 runs (one per host core, 1 torch thread each) from their DoE, BO iterations "
+                  f"{args.warmup}..{args.warmup + steps}"
+                  + ("" if steps == args.steps else f"; cut at the {args.ref_budget_s:.0f} s wall-time budget"))
+    line = {"impl": "reference", "metric": METRIC, "value": its, "unit": UNIT, "n_gpus": max(world, args.gpus),
+            "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic (BBOB f15-f17 restated)",
+            "config": workload_config(windows, args.warmup, scaling, max(world, args.gpus)),
+            "run_info": {"optimizer": "scipy L-BFGS-B (CPU oracle)"},
             "cpu_baseline": {"value": its, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
-    if args.trace:
+    if args.trace and per_step:
         json.dump({"n_first": N_DOE, "step_ms_max_over_workers": [1e3 * t for t in per_step]}, open(args.trace, "w"))
 
 
@@ -201,11 +238,140 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def measure_dgemm_tflops(dev, n=4096, reps=6):
+    """FP64 yardstick measured in this run: cuBLAS DGEMM n^3 (FP64 tensor pipe, DMMA), best of `reps` (CUDA events)."""
+    import torch
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    c = torch.empty_like(a)
+    torch.matmul(a, b, out=c)
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e-3)
+    return 2.0 * n ** 3 / best / 1e12
+
+
+def measure_ei_sweep(dev, rank, world, dgemm_tflops, log2n=24, n=450, r=40, reps=2):
+    """EI candidates/sec (BASELINE config C4): 2^log2n scrambled-Sobol candidates in the reduced space (r = 40) against a
+    fitted GP with n = 450 (Z ~ U[1/12, 11/12]^r, y ~ N(0,1), candidates in [-1/3, 4/3]^r), candidate-sharded
+    over the ranks, fused arg-max in the kernel and ONE all_gather of (value, global index) over NCCL."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pcabo_b200 import ops
+    from pcabo_b200.parallel import candidate_range, global_argmax
+    kmax = r + (r & 1)
+    rng = np.random.RandomState(0)
+    Z = rng.uniform(1 / 12, 11 / 12, size=(n, r))
+    y = rng.randn(n)
+    buf = ops.GPBuffers(1, n + (n & 1), kmax, dev)
+    Zd = torch.zeros(1, buf.ld_n, kmax, dtype=torch.float64)
+    Zd[0, :n, :r] = torch.from_numpy(Z)
+    fd = torch.zeros(1, buf.ld_n, dtype=torch.float64)
+    fd[0, :n] = torch.from_numpy(y)
+    lo = torch.full((kmax,), -1 / 3, dtype=torch.float64, device=dev)
+    hi = torch.full((kmax,), 4 / 3, dtype=torch.float64, device=dev)
+    ops.gp_fit(buf, Zd.to(dev), torch.tensor([r], dtype=torch.int32, device=dev), fd.to(dev), n, mode=1,
+               fix_lo=lo, fix_hi=hi)
+    buf.best_f[0] = float(torch.as_tensor(float(y.min())))
+    eng = torch.quasirandom.SobolEngine(r, scramble=True, seed=1234)
+    shift = torch.zeros(kmax, dtype=torch.int32)
+    sst = torch.zeros(kmax, 30, dtype=torch.int32)
+    shift[:r] = eng.shift.to(torch.int32)
+    sst[:r] = eng.sobolstate.to(torch.int32)
+    shift, sst = shift.to(dev), sst.to(dev)
+    ws = ops.SweepWorkspace(dev)
+    N = 1 << log2n
+    a, b = candidate_range(N, rank, world)
+    times, best = [], None
+    for rep in range(reps + 1):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        bv, bi = ops.ei_sweep(buf, ws, b - a, a, sobol=(shift, sst, lo, hi))
+        gv, gi = global_argmax(bv, bi)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) * 1e-3
+        if world > 1:
+            tt = torch.tensor([t], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt)
+        if rep > 0:
+            times.append(t)
+        best = (float(gv), int(gi))
+    t = min(times)
+    flops = N * (n * n + 3 * n * r + 16 * n)
+    tf = flops / t / 1e12 / world
+    return {"metric": "EI candidates/sec/GPU", "value": N / t / world, "unit": "candidates/s/GPU",
+            "whole_job_candidates_per_s": N / t, "n_gpus": world, "n_train": n, "r": r, "log2_candidates": log2n,
+            "ms": 1e3 * t, "kernel": "ei_sweep_kernel (DMMA m8n8k4.f64, fused arg-max) + NCCL all_gather of (value, index)",
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": dgemm_tflops, "unit": "TFLOP/s",
+                         "frac": tf / dgemm_tflops, "flops_per_candidate": n * n + 3 * n * r + 16 * n,
+                         "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (FP64 tensor pipe)"},
+            "argmax": {"value": best[0], "index": best[1]}}
+
+
+def build_engines(fids, insts, dev, args, world):
+    from pcabo_b200.bbob import BatchedBBOB
+    from pcabo_b200.engine import BatchedBOEngine, PipelinedEngines
+    seeds = [1000 * f + 10 * DIM + i for f, i in zip(fids, insts)]
+    S = max(1, min(args.sub_batches, len(fids)))
+    subs = []
+    for s_ in range(S):
+        sel = list(range(s_, len(fids), S))
+        prob = BatchedBBOB([fids[i] for i in sel], [insts[i] for i in sel], DIM, device=dev)
+        subs.append(BatchedBOEngine(prob, DIM, prob.bounds, BUDGET, N_DOE, [seeds[i] for i in sel], algorithm="pca",
+                                    device=dev, optimizer=args.optimizer,
+                                    host_threads=max(1, (os.cpu_count() or 1) // max(1, world))))
+    eng = subs[0] if S == 1 else PipelinedEngines(subs)
+    return eng, subs, S
+
+
+def timed_windows(eng, subs, S, windows, warmup, barrier, record_events):
+    """Runs the engine through the windows; returns (seconds over the timed steps [max(wall, device) per window, summed],
+    per-window seconds)."""
+    import torch
+
+    def advance(k):
+        if k <= 0:
+            return
+        if S == 1:
+            for _ in range(k):
+                eng.step()
+        else:
+            eng.run_steps(k)
+
+    secs = []
+    for n0, k in windows:
+        advance(n0 - eng.n)                      # untimed: warm-up steps / fast-forward to the window
+        barrier()
+        for e_ in subs:
+            e_.kernel_events = record_events.setdefault(id(e_), []) if record_events is not None else None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        advance(k)
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        for e_ in subs:
+            e_.kernel_events = None
+        secs.append(max(wall, ev0.elapsed_time(ev1) * 1e-3))
+    return sum(secs), secs
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from pcabo_b200.bbob import BatchedBBOB
-    from pcabo_b200.engine import BatchedBOEngine, PipelinedEngines
+    from pcabo_b200.parallel import shard_runs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -215,160 +381,153 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
-
-    fids = [f for f in FIDS for _ in range(RUNS_PER_FID)]
-    insts = [RUNS_PER_FID * rank + i for _ in FIDS for i in range(RUNS_PER_FID)]
-    seeds = [1000 * f + 10 * DIM + i for f, i in zip(fids, insts)]
-    S = max(1, args.sub_batches)
-    subs = []
-    for s_ in range(S):
-        sel = list(range(s_, len(fids), S))
-        prob = BatchedBBOB([fids[i] for i in sel], [insts[i] for i in sel], DIM, device=dev)
-        subs.append(BatchedBOEngine(prob, DIM, prob.bounds, BUDGET, N_DOE, [seeds[i] for i in sel], algorithm="pca",
-                                    device=dev, optimizer=args.optimizer,
-                                    host_threads=max(1, (os.cpu_count() or 1) // max(1, world))))
-    eng = subs[0] if S == 1 else PipelinedEngines(subs)
-    eng.initial_design()
-    if args.n_start > N_DOE:                       # optional fast-forward (untimed) to a later point of the runs
-        if S == 1:
-            for _ in range(args.n_start - N_DOE):
-                eng.step()
-        else:
-            eng.run_steps(args.n_start - N_DOE)
+    scaling = args.scaling or ("strong" if world > 1 else "weak")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def advance(k):
-        if S == 1:
-            for _ in range(k):
-                eng.step()
-        else:
-            eng.run_steps(k)
+    def max_over_ranks(v):
+        if world > 1:
+            t = torch.tensor([v], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t)
+        return v
 
-    args.steps = max(1, min(args.steps, BUDGET - eng.n - args.warmup))
-    advance(args.warmup)
-    barrier()
-    stats0 = dict(eng.stats)
-    for e_ in subs:
-        e_.kernel_events = []                       # CUDA-event pairs around every optimiser-kernel launch
-        if args.phases:
+    def runs_of(mode):
+        if mode == "strong":     # the SAME 90 runs, dealt round-robin to the ranks (ExperimentRunner.py:93,137 loops them)
+            allr = [(f, i) for f in FIDS for i in range(RUNS_PER_FID)]
+            mine = shard_runs(allr, rank, world)
+        else:                    # every rank its own 90 runs
+            mine = [(f, RUNS_PER_FID * rank + i) for f in FIDS for i in range(RUNS_PER_FID)]
+        return [f for f, _ in mine], [i for _, i in mine]
+
+    windows = plan_windows(args.steps, args.warmup)
+    steps = sum(k for _, k in windows)
+    fids, insts = runs_of(scaling)
+    eng, subs, S = build_engines(fids, insts, dev, args, world)
+    eng.initial_design()
+    if args.phases:
+        for e_ in subs:
             e_.phase_times = {}
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_first = eng.n
-    t0 = time.perf_counter()
-    ev0.record()
-    step_ms, step_phases = [], []
-    if args.trace and S == 1:
-        for _ in range(args.steps):
-            ts = time.perf_counter()
-            p0 = dict(eng.phase_times) if args.phases else None
-            eng.step()
-            torch.cuda.synchronize()
-            step_ms.append(1e3 * (time.perf_counter() - ts))
-            if args.phases:
-                step_phases.append({k_: round(1e3 * (v_ - p0.get(k_, 0.0)), 3) for k_, v_ in eng.phase_times.items()})
-    else:
-        advance(args.steps)
-    ev1.record()
-    barrier()
-    wall = time.perf_counter() - t0
-    dev_s = ev0.elapsed_time(ev1) * 1e-3
+    stats0 = dict(eng.stats)
+    events = {}
+    secs, win_secs = timed_windows(eng, subs, S, windows, args.warmup, barrier, events)
     clocks = sampler.stop() if rank == 0 else None
-    secs = max(wall, dev_s)
-    if world > 1:
-        t = torch.tensor([secs], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        secs = float(t)
-    B = sum(e_.B for e_ in subs)
-    its = world * B * args.steps / secs
+    secs = max_over_ranks(secs)
     stats1 = eng.stats
-    launches = stats1["kernel_launches"] - stats0["kernel_launches"]
-    h2d = (stats1["h2d_bytes"] - stats0["h2d_bytes"]) / args.steps
-    d2h = (stats1["d2h_bytes"] - stats0["d2h_bytes"]) / args.steps
+    total_runs = N_RUNS if scaling == "strong" else N_RUNS * world
+    its = total_runs * steps / secs
+    # counters cover the timed windows AND the untimed fast-forward between them: scale to the timed share
+    all_steps = eng.n - N_DOE
+    share = steps / max(1, all_steps)
+    launches = (stats1["kernel_launches"] - stats0["kernel_launches"]) * share
+    h2d = (stats1["h2d_bytes"] - stats0["h2d_bytes"]) / max(1, all_steps)
+    d2h = (stats1["d2h_bytes"] - stats0["d2h_bytes"]) / max(1, all_steps)
 
-    # roofline of the dominant kernel: the value+gradient log-EI launch of the L-BFGS-B rounds (HBM/L2 bound:
-    # per run it streams the n x n lower-triangular FP64 cache L^-1 for 10 points, 2.5 flop/byte)
+    dgemm = measure_dgemm_tflops(dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
     roof = None
-    evs = [ev for e_ in subs for ev in (e_.kernel_events or [])]
+    evs = [ev for lst in events.values() for ev in lst]
     if evs:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        tot_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
-        tot_bytes = sum(nb for _, _, nb in evs)
-        achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
-        roof = {"kernel": ("lbfgsb_logei_kernel<5> (device L-BFGS-B incl. log-EI value+grad)" if args.optimizer == "device" else "logei_kernel<16,true> (value+grad, L-BFGS-B rounds)"), "bound": "hbm",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at n = 122 from the ncu --set full capture
-                # (profiles/r01_lbfgsb_ncu_raw_summary.csv): the n^2 caches are served from L2, DRAM sees ~2 % of
-                # the algorithmic bytes of that launch (1.2 GB)
-                "traffic": (26.124032e6 + 9.216e3) if args.optimizer == "device" else None,
-                "traffic_note": "ncu capture of the launch at n = 122; algorithmic bytes of that launch 1.2e9 (L2-resident caches)",
-                "launches": len(evs),
-                # the S sub-batches' launches overlap on the GPU: `achieved` is per launch (one sub-batch) as defined;
-                # the GPU-wide rate while they overlap is S times that
-                "concurrent_launches": S,
-                # what actually feeds the kernel is L2 (DRAM sees ~2 % of these bytes): both triangles (L^-1 and its
-                # transpose) are streamed per evaluation, summed over the S overlapping launches, against the ~12.4 TB/s
-                # (6300 B/clk) the L2 slices deliver chip-wide (B300_MICROARCH.md); run average -- during the triangular
-                # passes at n = 400 the rate is 4.8 TB/s
-                "l2": {"achieved_gbs": 2.0 * tot_bytes / secs / 1e9, "peak_gbs": 12400.0,
-                       "frac": 2.0 * tot_bytes / secs / 1e9 / 12400.0}, "avg_launch_us": 1e3 * tot_ms / len(evs),
+        tot_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
+        tot_bytes = sum(e[2] for e in evs)
+        tot_flops = sum(e[3] for e in evs)
+        tf = tot_flops / (tot_ms * 1e-3) / 1e12
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        gbs = tot_bytes / (tot_ms * 1e-3) / 1e9
+        device_opt = args.optimizer == "device"
+        roof = {"kernel": ("lbfgsb_logei_kernel (device L-BFGS-B incl. log-EI value+gradient)" if device_opt
+                           else "logei_kernel<16,true> (value+gradient, scipy-driven L-BFGS-B rounds)"),
+                # the nearest roof of this kernel is the FP64 pipe (DRAM carries ~2 % of its bytes, L2 hit
+                # rate 99 %), but what bounds it is the LATENCY of up to 200 dependent L-BFGS-B iterations per launch
+                "bound": "tensor", "achieved": tf, "peak": dgemm, "unit": "TFLOP/s", "frac": tf / dgemm,
+                "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (FP64 tensor pipe; MEASURED_PEAKS.json has no FP64 entry)",
+                "flops_note": "algorithmic: sum over chunks of nfev x points x (2 n^2 + 11 n k + 16 n), per launch",
+                "traffic": None,
+                "traffic_note": "not re-measured in this run; ncu --set full captures are under profiles/ (r02_*_ncu_raw_summary.csv)",
+                "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
+                        "bytes_note": "algorithmic: nfev x (4 n^2 + 8 n k + 8 n) per chunk (served from L2)"},
+                "launches": len(evs), "concurrent_launches": S, "avg_launch_us": 1e3 * tot_ms / len(evs),
                 "share_of_step": tot_ms * 1e-3 / secs / S}
+
     cpu_base = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
-        # the CPU oracle continues the first `cores` runs from histories this run produced, at points spread over the
-        # n range that was timed (a bounded sample: ~10-30 s of host work)
-        n_lo, n_hi = n_first, eng.n
-        npts = [n_lo] if n_hi - n_lo < 30 else [n_lo, (n_lo + n_hi) // 2, max(n_lo, n_hi - args.cpu_steps)]
+        # the CPU oracle continues `cores` of THIS run's histories at the start of every window (stratified run) or at
+        # three points of a contiguous window: a bounded sample, ~10-30 s of host work
+        if len(windows) > 1:
+            cwin = [(n0, min(k, args.cpu_steps)) for n0, k in windows]
+        else:
+            n_lo, n_hi = windows[0][0], windows[0][0] + windows[0][1]
+            pts = [n_lo] if n_hi - n_lo < 30 else [n_lo, (n_lo + n_hi) // 2, max(n_lo, n_hi - args.cpu_steps - 1)]
+            cwin = [(p_, args.cpu_steps) for p_ in pts]
         allh = []
         for s_, e_ in enumerate(subs):            # sub-batch s_ holds runs s_, s_ + S, ... of the rank's list
             allh += [(fids[s_ + S * j], insts[s_ + S * j], e_.x_evals[j], e_.f_evals[j]) for j in range(e_.B)]
-        hist = allh[::max(1, B // (os.cpu_count() or 1))]
-        cits, cores, csecs = oracle_sampled_throughput(hist, npts, args.cpu_steps)
+        ncores = os.cpu_count() or 1
+        hist = allh[::max(1, len(allh) // ncores)][:ncores]
+        cits, cores, csecs = oracle_windows_throughput(hist, cwin, cores=min(ncores, len(hist)))
         cpu_base = {"value": cits, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"{cores} of the 90 runs, one per host core (1 torch thread each), continuing this run's "
-                              f"histories at n = {npts} for {args.cpu_steps - 1} timed BO iterations each (+1 warm-up), "
-                              f"{csecs:.1f} s of wall time"}
-    if rank == 0:
-        line = {"metric": METRIC, "value": its, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (BBOB f15-f17 restated)",
-                "config": workload_config(n_first - args.warmup, args.steps, args.warmup, args.optimizer,
-                                          {"lbfgsb_rounds_per_step": (stats1["lbfgsb_rounds"] - stats0["lbfgsb_rounds"]) / args.steps,
-                                           "retries": stats1["retries"] - stats0["retries"],
-                                           "host_blocked_ms_per_step": {
-                                               "optimiser_kernel": 1e3 * (stats1["wait_opt_s"] - stats0["wait_opt_s"]) / args.steps,
-                                               "fit_and_raw_samples": 1e3 * (stats1["wait_ic_s"] - stats0["wait_ic_s"]) / args.steps}}),
-                "roofline": roof, "cpu_baseline": cpu_base, "sub_batches": S,
-                "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "note": "every step is driven through the public engine API with host-generated RNG inputs "
-                                "(PCA noise, Sobol samples) copied in and proposals/objective values read back inside "
-                                "the timed region"},
-                "gpu_launches": launches, "clocks": clocks}
-        print(json.dumps(line), flush=True)
-    if args.trace and rank == 0 and step_ms:
-        json.dump({"n_first": n_first, "step_ms": step_ms, "k_mean_last": float(subs[0].k_host.mean()),
-                   "step_phases_ms": step_phases},
-                  open(args.trace, "w"))
+                              f"histories at n = {[n0 for n0, _ in cwin]} for {[k for _, k in cwin]} timed BO iterations "
+                              f"each (+1 warm-up), {csecs:.1f} s of wall time"}
+
+    sweep = None
+    if not args.no_sweep:
+        sweep = measure_ei_sweep(torch.device(dev), rank, world, dgemm, log2n=args.sweep_log2n)
+
     if args.phases and rank == 0:
         pt = {}
         for e_ in subs:
-            for k_, v_ in e_.phase_times.items():
+            for k_, v_ in (e_.phase_times or {}).items():
                 pt[k_] = pt.get(k_, 0.0) + v_
-        tot = sum(pt.values())
-        print(json.dumps({"phase_ms_per_step": {k: 1e3 * v / args.steps for k, v in pt.items()},
-                          "sum_ms_per_step": 1e3 * tot / args.steps}), file=sys.stderr, flush=True)
+        print(json.dumps({"phase_ms_per_step": {k: 1e3 * v / max(1, all_steps) for k, v in pt.items()}}),
+              file=sys.stderr, flush=True)
+
+    weak = None
+    if world > 1 and scaling == "strong" and not args.no_weak:
+        del eng, subs
+        torch.cuda.empty_cache()
+        wf, wi = runs_of("weak")
+        weng, wsubs, wS = build_engines(wf, wi, dev, args, world)
+        weng.initial_design()
+        wwin = [(N_DOE + args.warmup, min(12, steps))]
+        wsecs, _ = timed_windows(weng, wsubs, wS, wwin, args.warmup, barrier, None)
+        wsecs = max_over_ranks(wsecs)
+        weak = {"scaling": "weak", "runs": N_RUNS * world, "value": N_RUNS * world * wwin[0][1] / wsecs, "unit": UNIT,
+                "steps": wwin[0][1], "n_points_windows": [[wwin[0][0], wwin[0][0] + wwin[0][1]]],
+                "note": "every rank its own 90 runs (instances 30 rank .. 30 rank + 29): what round 1 reported"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": its, "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True,
+                "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic (BBOB f15-f17 restated)",
+                "config": workload_config(windows, args.warmup, scaling, world),
+                "run_info": {"optimizer": args.optimizer, "sub_batches": S, "runs_per_gpu": len(fids),
+                             "window_seconds": win_secs, "dgemm_fp64_tflops": dgemm,
+                             "lbfgsb_rounds_per_step": (stats1["lbfgsb_rounds"] - stats0["lbfgsb_rounds"]) / max(1, all_steps),
+                             "retries": stats1["retries"] - stats0["retries"],
+                             "jitter_refits": stats1.get("jitter_refits", 0),
+                             "host_blocked_ms_per_step": {
+                                 "optimiser_kernel": 1e3 * (stats1["wait_opt_s"] - stats0["wait_opt_s"]) / max(1, all_steps),
+                                 "fit_and_raw_samples": 1e3 * (stats1["wait_ic_s"] - stats0["wait_ic_s"]) / max(1, all_steps)},
+                             "sub_batches_note": "the runs of a GPU advance as S lock-step sub-batches on S CUDA streams, "
+                                                 "software-pipelined by one host thread; results do not depend on S"},
+                "roofline": roof, "cpu_baseline": cpu_base, "ei_sweep": sweep, "weak_scaling": weak,
+                "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "note": "every step is driven through the public engine API with host-generated RNG inputs "
+                                "(PCA noise) copied in and proposals/objective values read back inside the timed region"},
+                "gpu_launches": int(round(launches)), "clocks": clocks}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -377,19 +536,24 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=BUDGET - N_DOE - 3,
-                    help="timed BO iterations per run (default: the whole C3 run after the warm-up steps)")
+                    help="timed BO iterations per run (default: the whole C3 run after the warm-up steps; <= 60: "
+                         "stratified over n = 120 + W, 285, 430)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--optimizer", default="device", choices=["scipy", "device"])
-    ap.add_argument("--n-start", type=int, default=N_DOE, help="fast-forward (untimed) until n points before warm-up")
-    ap.add_argument("--cpu-steps", type=int, default=6,
-                    help="BO iterations per core and sample point of the cpu_baseline leg (the first is warm-up)")
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
+                    help="default: strong (the same 90 runs sharded over the GPUs) when --gpus > 1")
+    ap.add_argument("--cpu-steps", type=int, default=5,
+                    help="timed BO iterations per core and sample point of the cpu_baseline leg (+1 warm-up)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the EI-candidates/sec sub-record")
+    ap.add_argument("--no-weak", action="store_true", help="skip the extra weak-scaling measurement (N > 1)")
+    ap.add_argument("--sweep-log2n", type=int, default=24)
     ap.add_argument("--sub-batches", type=int, default=3,
                     help="split the per-GPU batch into S sub-batches on S CUDA streams, software-pipelined by one host "
                          "thread (the optimiser kernel of one overlaps the host work of the next)")
-    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="wall-time budget of the reference arm")
-    ap.add_argument("--trace", default=None, help="write per-step wall times (ms) to this JSON file (adds a sync per step)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="wall-time budget of the whole-run reference arm")
+    ap.add_argument("--trace", default=None, help="reference arm, whole run: per-step wall times (ms) to this JSON file")
     ap.add_argument("--phases", action="store_true", help="print a host wall-time breakdown per phase (adds syncs)")
     args = ap.parse_args()
     if args.impl == "reference":

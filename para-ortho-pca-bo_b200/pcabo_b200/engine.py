@@ -501,7 +501,8 @@ class BatchedBOEngine:
                 e1.record()
                 n = self.n
                 nbytes = sum(4 * n * n + 8 * n * int(kb) + 8 * n + R * (16 * int(kb) + 8) for kb in k_host)
-                self.kernel_events.append((e0, e1, nbytes))
+                nflops = sum(R * (2 * n * n + 11 * n * int(kb) + 16 * n) for kb in k_host)
+                self.kernel_events.append((e0, e1, nbytes, nflops))
             else:
                 out = ops.logei(self.gp, d_x, want_grad=True, out=out)
             val = out["val"].cpu().numpy()
@@ -575,7 +576,11 @@ class BatchedBOEngine:
             # L^-1 once (4 n^2), the training set and alpha (8 n k + 8 n); times the evaluations actually done
             nbytes = sum(int(nfev[b, c]) * (4 * n * n + 8 * n * int(k_host[b]) + 8 * n)
                          for b in sel for c in range(nfev.shape[1]))
-            self.kernel_events.append((ev[0], ev[1], nbytes))
+            # algorithmic flops: F_vg = 2 n^2 + 11 n k + 16 n per point and value+gradient evaluation
+            nflops = sum(int(nfev[b, c]) * min(self.batch_limit, self.num_restarts - c * self.batch_limit)
+                         * (2 * n * n + 11 * n * int(k_host[b]) + 16 * n)
+                         for b in sel for c in range(nfev.shape[1]))
+            self.kernel_events.append((ev[0], ev[1], nbytes, nflops))
         self.stats["kernel_launches"] += 1
         self.stats["lbfgsb_rounds"] += int(nfev[sel].max())
         self.stats["d2h_bytes"] += status.size * 12
