@@ -146,8 +146,9 @@ int pcabo_lbfgsb_logei(const pcabo_gp_model *m, int num_restarts, int batch_limi
 
 /* Same as pcabo_lbfgsb_logei with optional per-chunk cycle counters prof [B][nchunks][32] (clock64 ticks of the
  * optimiser warp per phase: 1 cauchy, 2 formk, 3 cmprlb, 4 subsm, 5 line-search setup, 6 step to next point,
- * 7 log-EI evaluation, 8 dcsrch, 9 update, 0 convergence tests, 10-14 sub-phases; 16-20 phases inside the log-EI
- * evaluation: k vector, t = W k, posterior head, s = W^T t, gradient; 31 scratch); prof may be NULL. Tuning aid.                     */
+ * 7 log-EI evaluation, 8 dcsrch, 9 update, 0 convergence tests, 10-14 sub-phases; phases inside the log-EI
+ * evaluation: 16 k vector, 17 sweep over the panels of W (t = W k and s = W^T t), 22 posterior head, 19 gradient
+ * coefficients, 20 gradient; 31 scratch); prof may be NULL. Tuning aid.                                              */
 int pcabo_lbfgsb_logei_prof(const pcabo_gp_model *m, int num_restarts, int batch_limit, int maxiter, double factr,
                             double pgtol, const double *ics, const double *box_lo, const double *box_hi,
                             double *cand, double *fval, int *status, int *nit, int *nfev, long long *prof,
@@ -156,11 +157,28 @@ int pcabo_lbfgsb_logei_prof(const pcabo_gp_model *m, int num_restarts, int batch
 /* General form: optimise only the runs listed in run_idx [nsel] (device ints; NULL = all runs, nsel = B) and size the
  * per-block shared memory for k <= k_bound (0 = kmax; a run with k > k_bound gets status -1 and is left untouched).
  * Outputs are indexed by RUN (not by position in run_idx), so a retry of a subset updates the same arrays in place:
- * this is botorch's retry_on_optimization_warning (optimize_acqf re-optimises only the problem that warned).         */
+ * this is botorch's retry_on_optimization_warning (optimize_acqf re-optimises only the problem that warned).
+ * The rows of W are staged by 16-byte bulk copies: m->ld_n must be even (PCABO_E_INVALID otherwise).                  */
 int pcabo_lbfgsb_logei_runs(const pcabo_gp_model *m, int nsel, const int *run_idx, int k_bound, int num_restarts,
                             int batch_limit, int maxiter, double factr, double pgtol, const double *ics,
                             const double *box_lo, const double *box_hi, double *cand, double *fval, int *status,
                             int *nit, int *nfev, long long *prof, void *stream);
+
+/* Same as pcabo_lbfgsb_logei_runs for problems whose L-BFGS-B state does not fit the 227 KB of shared memory of a
+ * block next to the evaluation scratch (config C5: n up to 1050, k ~ 90): the BFGS pairs (2 x 10 x batch_limit x
+ * k_bound doubles per chunk) then live in `workspace` (device, caller-owned, L2-resident; nothing is allocated by the
+ * callee). pcabo_lbfgsb_workspace_doubles returns the number of doubles needed for `nsel` runs (0: shared memory
+ * suffices and workspace may be NULL; -1: the problem does not fit either way -> PCABO_E_UNSUPPORTED).              */
+long long pcabo_lbfgsb_workspace_doubles(int n, int kmax, int k_bound, int num_restarts, int batch_limit, int nsel);
+/* The shared-memory plan the launcher would choose (host only, no device work): plan6 = {panel rows (8 / 16), ring
+ * capacity in doubles, 1 if every panel of W stays resident in the ring, 1 if panels are released behind a barrier of
+ * their own (small ring), 1 if the BFGS pairs live in the workspace, dynamic shared memory in bytes}.                */
+int pcabo_lbfgsb_plan(int n, int kmax, int k_bound, int batch_limit, int have_workspace, int *plan6);
+int pcabo_lbfgsb_logei_runs_ws(const pcabo_gp_model *m, int nsel, const int *run_idx, int k_bound, int num_restarts,
+                               int batch_limit, int maxiter, double factr, double pgtol, const double *ics,
+                               const double *box_lo, const double *box_hi, double *cand, double *fval, int *status,
+                               int *nit, int *nfev, long long *prof, double *workspace, long long workspace_doubles,
+                               void *stream);
 
 /* log-EI sweep with fused arg-max over `ncand` candidates against run `run` of the model (BASELINE config C4).
  * Candidates: explicit X [ncand][kmax] (raw space), or X = NULL and generated in-kernel as scrambled Sobol points

@@ -7,11 +7,11 @@
 // lbfgsb_core.cuh (validated on the host against scipy, tests/test_lbfgsb_core.py); tolerances are scipy's defaults
 // (factr = 2.22e-9 / eps = 1e7, pgtol = 1e-5, m = 10, maxls = 20).
 #include "lbfgsb_core.cuh"
-#include "logei_core.cuh"
+#include "lbfgsb_eval.cuh"
 
 namespace {
 
-constexpr int LB_THREADS = logei::LE_THREADS;
+constexpr int LB_THREADS = lbeval::NT;
 
 enum Cmd { CMD_EVAL = 1, CMD_FORMK = 2, CMD_EXIT = 3 };
 
@@ -116,11 +116,11 @@ struct CudaWarpTeam {
   }
 };
 
-template <int PT>
+template <int PT, int R, int TI>
 struct LogEiObjective {
-  logei::Ctx ctx;
+  lbeval::Ctx ctx;
   int pcount, kk;
-  double *vals;  // smem [PT]
+  double *vals;  // smem [8]
   // called by warp 0 (the team); posts the evaluation to the whole block
   __device__ double operator()(CudaWarpTeam &tm, const double *x, double *g) {
     if (tm.lane == 0) tm.mb->cmd = CMD_EVAL;
@@ -129,7 +129,7 @@ struct LogEiObjective {
   }
   // executed by all LB_THREADS threads
   __device__ double run(const double *x, double *g) {
-    logei::eval_points<PT, true>(ctx, pcount, x, kk, vals, g, kk, kk, -1.0, nullptr, nullptr);
+    lbeval::eval<PT, R, TI>(ctx, pcount, x, vals, g, -1.0);
     double f = 0.0;
     for (int p = 0; p < pcount; ++p) f -= vals[p];
     return f;
@@ -146,17 +146,22 @@ struct LbArgs {
   long long *prof;   // optional [B][nchunks][32] cycle counters
   const int *run_idx;  // optional [gridDim.y] runs to optimise (nullptr: all runs, blockIdx.y)
   int k_bound;         // shared memory was sized for k <= k_bound
+  int ring_cap;        // doubles of the W panel ring
+  int resident;        // every panel fits the ring
+  int tight;           // small ring: panels are released behind a barrier of their own
+  double *wsy;         // optional global home of the BFGS pairs [gridDim.y][gridDim.x][2 M nvar_max] (nullptr: shared memory)
+  int nvar_max;
 };
 
-template <int PT>
-__global__ void __launch_bounds__(LB_THREADS, 2) lbfgsb_logei_kernel(LbArgs a) {
+template <int PT, int R, int TI>
+__global__ void __launch_bounds__(LB_THREADS, 1) lbfgsb_logei_kernel(LbArgs a) {
   extern __shared__ __align__(16) double sm[];
   const int b = a.run_idx ? a.run_idx[blockIdx.y] : blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int nchunks = gridDim.x;
   const int p0 = chunk * a.batch_limit;
   const int pcount = min(a.batch_limit, a.num_restarts - p0);
-  LogEiObjective<PT> obj;
-  load_ctx(obj.ctx, a.m, b);
+  LogEiObjective<PT, R, TI> obj;
+  lbeval::load_ctx(obj.ctx, a.m, b);
   const int kk = obj.ctx.kk, kmax = a.m.kmax;
   const int nvar = pcount * kk;
   if (kk > a.k_bound) {   // the caller's bound on k was wrong: refuse (status -1) instead of overrunning shared memory
@@ -167,16 +172,22 @@ __global__ void __launch_bounds__(LB_THREADS, 2) lbfgsb_logei_kernel(LbArgs a) {
     return;
   }
   double *q = sm;
-  carve_ctx(obj.ctx, PT, true, q);
-  q += logei::scratch_doubles(PT, kmax, a.m.n, true);
+  obj.ctx.L = lbeval::make_layout(PT, kmax, a.m.n, R);
+  obj.ctx.base = q;
+  obj.ctx.ring_cap = a.ring_cap;
+  obj.ctx.resident = a.resident != 0;
+  obj.ctx.tight = a.tight != 0;
+  q += obj.ctx.L.o_ring + a.ring_cap;
   lbfgsb::Work w;
-  lbfgsb::carve(w, nvar, q);
-  q += lbfgsb::work_doubles(nvar);
+  double *wsy = a.wsy ? a.wsy + ((size_t)blockIdx.y * nchunks + chunk) * (size_t)(2 * lbfgsb::M) * a.nvar_max : nullptr;
+  lbfgsb::carve(w, nvar, q, wsy);
+  q += lbfgsb::work_doubles(nvar, wsy != nullptr);
   Mailbox *mb = reinterpret_cast<Mailbox *>(q); q += 2;
   obj.vals = q; q += 8;
   int *flag = reinterpret_cast<int *>(q); q += 2;
   obj.pcount = pcount; obj.kk = kk;
   if (a.prof) obj.ctx.prof = a.prof + ((size_t)b * nchunks + chunk) * 32;
+  lbeval::init(obj.ctx, PT);   // barriers, zero padding, first panel requests (ends with a block barrier)
 
   const double *ic = a.ics + ((size_t)b * a.num_restarts + p0) * kmax;
   const double *blo = a.box_lo + (size_t)b * kmax, *bhi = a.box_hi + (size_t)b * kmax;
@@ -210,7 +221,7 @@ __global__ void __launch_bounds__(LB_THREADS, 2) lbfgsb_logei_kernel(LbArgs a) {
       }
     }
   }
-  __syncthreads();
+  lbeval::drain(obj.ctx);   // no bulk copy may outlive the block (ends with a block barrier)
   double *out = a.cand + ((size_t)b * a.num_restarts + p0) * kmax;
   for (int i = tid; i < pcount * kmax; i += LB_THREADS) {
     const int p = i / kmax, j = i % kmax;
@@ -222,41 +233,125 @@ __global__ void __launch_bounds__(LB_THREADS, 2) lbfgsb_logei_kernel(LbArgs a) {
   }
 }
 
-template <int PT>
-int launch(const LbArgs &a, int nsel, cudaStream_t st) {
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+constexpr int TAIL_DOUBLES = 2 + 8 + 2 + 8;
+
+// Shared-memory plan of one launch: panel height, ring capacity, where the BFGS pairs live.
+struct Plan {
+  int R, TI, ring_cap, resident, tight, pairs_global;
+  size_t smem;
+};
+
+inline bool make_plan(int PT, int n, int kmax, int nvar_max, bool have_ws, Plan &pl) {
+  const int tiles = (n + 7) / 8;
+  pl.TI = (tiles + lbeval::NW - 1) / lbeval::NW;
+  // preference: pairs in shared memory before pairs in the workspace; 16-row panels before 8-row panels; the ring takes
+  // all the shared memory that is left (at most all panels). A ring too small for the two-barrier schedule (checked by
+  // replaying it on the host) releases every panel behind a barrier of its own ("tight"); it must hold the largest panel.
+  for (int pairs_global = 0; pairs_global <= (have_ws ? 1 : 0); ++pairs_global) {
+    const size_t work = lbfgsb::work_doubles(nvar_max, pairs_global != 0) + TAIL_DOUBLES;
+    for (int pass = 0; pass < 3; ++pass) {   // 0: everything resident, 32-row panels; 1: two-barrier streaming; 2: "tight"
+      for (int R = (pass == 0 ? 32 : 16); R >= (pass == 0 ? 32 : 8); R -= 8) {
+        const lbeval::Layout L = lbeval::make_layout(PT, kmax, n, R);
+        const size_t fixed = ((size_t)L.o_ring + work) * sizeof(double);
+        if (fixed >= SMEM_LIMIT) continue;
+        const long long avail = (long long)((SMEM_LIMIT - fixed) / sizeof(double)) & ~1LL;
+        if (avail < L.max_panel) continue;
+        const bool resident = L.all_panels <= avail && L.npanels <= lbeval::NBAR;
+        if (pass == 0 && !resident) continue;
+        const int cap = (int)(avail < L.all_panels ? avail : L.all_panels);
+        const bool loose_ok = resident || lbeval::ring_schedule_ok(n, R, cap, false, false);
+        if (!loose_ok && (pass < 2 || !lbeval::ring_schedule_ok(n, R, cap, false, true))) continue;
+        pl.R = R;
+        pl.resident = resident ? 1 : 0;
+        pl.tight = loose_ok ? 0 : 1;
+        pl.ring_cap = cap;
+        pl.pairs_global = pairs_global;
+        pl.smem = ((size_t)L.o_ring + cap + work) * sizeof(double);
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+template <int PT, int R, int TI>
+int launch_one(const LbArgs &a, int nsel, size_t smem, cudaStream_t st) {
   const int nchunks = (a.num_restarts + a.batch_limit - 1) / a.batch_limit;
-  const int nvar_max = a.batch_limit * a.k_bound;
-  const size_t smem = (logei::scratch_doubles(PT, a.m.kmax, a.m.n, true) + lbfgsb::work_doubles(nvar_max) +
-                       2 + 8 + 2 + 8) * sizeof(double);
-  if (smem > 227 * 1024) return PCABO_E_UNSUPPORTED;
-  PCABO_CUDA_CHECK(cudaFuncSetAttribute(lbfgsb_logei_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PCABO_CUDA_CHECK(cudaFuncSetAttribute(lbfgsb_logei_kernel<PT, R, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(nchunks, nsel);
-  lbfgsb_logei_kernel<PT><<<grid, LB_THREADS, smem, st>>>(a);
+  lbfgsb_logei_kernel<PT, R, TI><<<grid, LB_THREADS, smem, st>>>(a);
   PCABO_LAUNCH_CHECK();
   return PCABO_OK;
 }
 
+int launch(LbArgs &a, int nsel, double *workspace, long long workspace_doubles, cudaStream_t st) {
+  constexpr int PT = 5;
+  const int nchunks = (a.num_restarts + a.batch_limit - 1) / a.batch_limit;
+  a.nvar_max = a.batch_limit * a.k_bound;
+  const long long ws_need = (long long)nsel * nchunks * 2 * lbfgsb::M * a.nvar_max;
+  Plan pl;
+  if (!make_plan(PT, a.m.n, a.m.kmax, a.nvar_max, workspace != nullptr && workspace_doubles >= ws_need, pl))
+    return PCABO_E_UNSUPPORTED;
+  a.ring_cap = pl.ring_cap; a.resident = pl.resident; a.tight = pl.tight; a.wsy = pl.pairs_global ? workspace : nullptr;
+  if (pl.R == 32 && pl.TI <= 8) return launch_one<PT, 32, 8>(a, nsel, pl.smem, st);
+  if (pl.R == 32) return PCABO_E_UNSUPPORTED;
+  if (pl.TI <= 8) return pl.R == 16 ? launch_one<PT, 16, 8>(a, nsel, pl.smem, st) : launch_one<PT, 8, 8>(a, nsel, pl.smem, st);
+  if (pl.TI <= 17) return pl.R == 16 ? launch_one<PT, 16, 17>(a, nsel, pl.smem, st) : launch_one<PT, 8, 17>(a, nsel, pl.smem, st);
+  return PCABO_E_UNSUPPORTED;
+}
+
 }  // namespace
 
-extern "C" int pcabo_lbfgsb_logei_runs(const pcabo_gp_model *m, int nsel, const int *run_idx, int k_bound,
-                                       int num_restarts, int batch_limit, int maxiter, double factr, double pgtol,
-                                       const double *ics, const double *box_lo, const double *box_hi, double *cand,
-                                       double *fval, int *status, int *nit, int *nfev, long long *prof, void *stream) {
+extern "C" long long pcabo_lbfgsb_workspace_doubles(int n, int kmax, int k_bound, int num_restarts, int batch_limit,
+                                                    int nsel) {
+  if (n < 1 || kmax < 1 || num_restarts < 1 || batch_limit < 1 || batch_limit > 5 || nsel < 1) return -1;
+  if (k_bound <= 0 || k_bound > kmax) k_bound = kmax;
+  Plan pl;
+  const int nvar_max = batch_limit * k_bound;
+  if (make_plan(5, n, kmax, nvar_max, false, pl)) return 0;          // everything fits shared memory
+  if (!make_plan(5, n, kmax, nvar_max, true, pl)) return -1;         // does not fit either way
+  const int nchunks = (num_restarts + batch_limit - 1) / batch_limit;
+  return (long long)nsel * nchunks * 2 * lbfgsb::M * nvar_max;
+}
+
+extern "C" int pcabo_lbfgsb_plan(int n, int kmax, int k_bound, int batch_limit, int have_workspace, int *plan6) {
+  if (n < 1 || kmax < 1 || batch_limit < 1 || batch_limit > 5 || !plan6) return PCABO_E_INVALID;
+  if (k_bound <= 0 || k_bound > kmax) k_bound = kmax;
+  Plan pl;
+  if (!make_plan(5, n, kmax, batch_limit * k_bound, have_workspace != 0, pl)) return PCABO_E_UNSUPPORTED;
+  plan6[0] = pl.R; plan6[1] = pl.ring_cap; plan6[2] = pl.resident; plan6[3] = pl.tight; plan6[4] = pl.pairs_global;
+  plan6[5] = (int)pl.smem;
+  return PCABO_OK;
+}
+
+extern "C" int pcabo_lbfgsb_logei_runs_ws(const pcabo_gp_model *m, int nsel, const int *run_idx, int k_bound,
+                                          int num_restarts, int batch_limit, int maxiter, double factr, double pgtol,
+                                          const double *ics, const double *box_lo, const double *box_hi, double *cand,
+                                          double *fval, int *status, int *nit, int *nfev, long long *prof,
+                                          double *workspace, long long workspace_doubles, void *stream) {
   if (!m || num_restarts <= 0 || batch_limit <= 0 || maxiter <= 0 || !ics || !box_lo || !box_hi || !cand || !fval ||
-      !status || !nit || !nfev || m->B <= 0 || m->n < 1 || m->ld_n < m->n || !m->norm_off || !m->norm_coef || !m->ZnT ||
-      !m->alpha || !m->W || !m->WT || !m->Zn || !m->ymean || !m->ystd || !m->best_f || !(m->lengthscale > 0.0))
+      !status || !nit || !nfev || m->B <= 0 || m->n < 1 || m->ld_n < m->n || (m->ld_n & 1) || !m->norm_off ||
+      !m->norm_coef || !m->ZnT || !m->alpha || !m->W || !m->Zn || !m->ymean || !m->ystd || !m->best_f ||
+      !(m->lengthscale > 0.0))
     return PCABO_E_INVALID;
   if (run_idx ? (nsel <= 0 || nsel > m->B) : (nsel != m->B)) return PCABO_E_INVALID;
   if (k_bound <= 0 || k_bound > m->kmax) k_bound = m->kmax;
-  if (m->kmax > 104 || m->n > 4096 || batch_limit > 8) return PCABO_E_UNSUPPORTED;
+  if (m->kmax > 104 || m->n > 1088 || batch_limit > 5) return PCABO_E_UNSUPPORTED;
   LbArgs a;
   a.m = *m; a.num_restarts = num_restarts; a.batch_limit = batch_limit; a.maxiter = maxiter;
   a.factr = factr; a.pgtol = pgtol; a.ics = ics; a.box_lo = box_lo; a.box_hi = box_hi;
   a.cand = cand; a.fval = fval; a.status = status; a.nit = nit; a.nfev = nfev; a.prof = prof;
   a.run_idx = run_idx; a.k_bound = k_bound;
-  cudaStream_t st = as_stream(stream);
-  if (batch_limit <= 5) return launch<5>(a, nsel, st);
-  return launch<8>(a, nsel, st);
+  return launch(a, nsel, workspace, workspace_doubles, as_stream(stream));
+}
+
+extern "C" int pcabo_lbfgsb_logei_runs(const pcabo_gp_model *m, int nsel, const int *run_idx, int k_bound,
+                                       int num_restarts, int batch_limit, int maxiter, double factr, double pgtol,
+                                       const double *ics, const double *box_lo, const double *box_hi, double *cand,
+                                       double *fval, int *status, int *nit, int *nfev, long long *prof, void *stream) {
+  return pcabo_lbfgsb_logei_runs_ws(m, nsel, run_idx, k_bound, num_restarts, batch_limit, maxiter, factr, pgtol, ics,
+                                    box_lo, box_hi, cand, fval, status, nit, nfev, prof, nullptr, 0, stream);
 }
 
 extern "C" int pcabo_lbfgsb_logei_prof(const pcabo_gp_model *m, int num_restarts, int batch_limit, int maxiter,

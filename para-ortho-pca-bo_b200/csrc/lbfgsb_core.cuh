@@ -67,16 +67,18 @@ struct Work {
   double *rsy, *rsq, *wt_rd, *wn_rd;
 };
 
-LB_HD inline size_t work_doubles(int n) {
-  return (size_t)9 * n + (size_t)2 * M * n + 4 * M * M + M2 * M2 + 5 * M2 + n + (n + 1) / 2 + 4;
+// pairs_external: the BFGS pairs ws / wy (2 M n doubles) live in a buffer of the caller's instead of the work area
+LB_HD inline size_t work_doubles(int n, bool pairs_external = false) {
+  return (size_t)9 * n + (pairs_external ? 0 : (size_t)2 * M * n) + 4 * M * M + M2 * M2 + 5 * M2 + n + (n + 1) / 2 + 4;
 }
 
-LB_HD inline void carve(Work &w, int n, double *base) {
+LB_HD inline void carve(Work &w, int n, double *base, double *pairs = nullptr) {
   w.n = n;
   double *q = base;
   w.x = q; q += n; w.l = q; q += n; w.u = q; q += n; w.g = q; q += n; w.z = q; q += n;
   w.d = q; q += n; w.t = q; q += n; w.r = q; q += n; w.xp = q; q += n;
-  w.ws = q; q += M * n; w.wy = q; q += M * n;
+  if (pairs) { w.ws = pairs; w.wy = pairs + M * n; }
+  else { w.ws = q; q += M * n; w.wy = q; q += M * n; }
   w.sy = q; q += M * M; w.ss = q; q += M * M; w.wt = q; q += M * M; w.jinv = q; q += M * M;
   w.rsy = w.jinv; w.rsq = w.jinv + M; w.wt_rd = w.jinv + 2 * M; w.wn_rd = w.jinv + 3 * M;
   w.wn = q; q += M2 * M2;
@@ -94,49 +96,75 @@ namespace dev {
 constexpr unsigned FULL = 0xffffffffu;
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
 
-// Right-looking Cholesky R^T R = A of the leading n x n block (n <= 32) of the upper-stored A (ld = lda) in shared
-// memory; R overwrites A, rdiag[j] = 1 / R[j][j]. Lane j owns column j. For pivots k < nsplit the rows/columns >= nsplit
-// receive +r_ki r_kj instead of -r_ki r_kj: with nsplit = col on the 2 col x 2 col matrix of formk this is the LEL^T
-// factorisation (Cholesky of the (1,1) block, R12 = R11^-T A12, Cholesky of A22 + R12^T R12) in one sweep.
-// Compact loops on purpose: the optimiser warp runs alone on its scheduler, so straight-line unrolled code only
-// thrashes the instruction cache. Returns 0 or 1 + index of the first non-positive pivot.
-// Row k is published through shared memory (three warp barriers per pivot) and every lane only loops over the rows of
-// its own column; a variant that broadcasts row k by shuffles instead was slower for the 2m x 2m matrix (n - k - 1
-// broadcasts per pivot on every lane: 18.8 k -> 29 k cycles on B200).
+// Upper triangle of a 20 x 20 matrix enumerated column by column: entry e -> i | (j << 8), i <= j (0xffff: padding).
+__device__ const unsigned short kTri20[224] = {
+    0, 256, 257, 512, 513, 514, 768, 769, 770, 771, 1024, 1025, 1026, 1027, 1028, 1280,
+    1281, 1282, 1283, 1284, 1285, 1536, 1537, 1538, 1539, 1540, 1541, 1542, 1792, 1793, 1794, 1795,
+    1796, 1797, 1798, 1799, 2048, 2049, 2050, 2051, 2052, 2053, 2054, 2055, 2056, 2304, 2305, 2306,
+    2307, 2308, 2309, 2310, 2311, 2312, 2313, 2560, 2561, 2562, 2563, 2564, 2565, 2566, 2567, 2568,
+    2569, 2570, 2816, 2817, 2818, 2819, 2820, 2821, 2822, 2823, 2824, 2825, 2826, 2827, 3072, 3073,
+    3074, 3075, 3076, 3077, 3078, 3079, 3080, 3081, 3082, 3083, 3084, 3328, 3329, 3330, 3331, 3332,
+    3333, 3334, 3335, 3336, 3337, 3338, 3339, 3340, 3341, 3584, 3585, 3586, 3587, 3588, 3589, 3590,
+    3591, 3592, 3593, 3594, 3595, 3596, 3597, 3598, 3840, 3841, 3842, 3843, 3844, 3845, 3846, 3847,
+    3848, 3849, 3850, 3851, 3852, 3853, 3854, 3855, 4096, 4097, 4098, 4099, 4100, 4101, 4102, 4103,
+    4104, 4105, 4106, 4107, 4108, 4109, 4110, 4111, 4112, 4352, 4353, 4354, 4355, 4356, 4357, 4358,
+    4359, 4360, 4361, 4362, 4363, 4364, 4365, 4366, 4367, 4368, 4369, 4608, 4609, 4610, 4611, 4612,
+    4613, 4614, 4615, 4616, 4617, 4618, 4619, 4620, 4621, 4622, 4623, 4624, 4625, 4626, 4864, 4865,
+    4866, 4867, 4868, 4869, 4870, 4871, 4872, 4873, 4874, 4875, 4876, 4877, 4878, 4879, 4880, 4881,
+    4882, 4883, 65535, 65535, 65535, 65535, 65535, 65535, 65535, 65535, 65535, 65535, 65535, 65535, 65535, 65535,
+};
+
+// Right-looking Cholesky R^T R = A of the leading n x n block (n <= 20 = 2 m) of the upper-stored A (ld = lda) in shared
+// memory; R overwrites A, rdiag[j] = 1 / R[j][j]. For pivots k < nsplit the rows/columns >= nsplit receive
+// +a_ki a_kj / a_kk instead of -a_ki a_kj / a_kk: with nsplit = col on the 2 col x 2 col matrix of formk this is the
+// LEL^T factorisation (Cholesky of the (1,1) block, R12 = R11^-T A12, Cholesky of A22 + R12^T R12) in one sweep.
+// The 210 entries of the triangle are dealt flat to the 32 lanes (seven each, fixed for the whole factorisation), so a
+// pivot costs every lane at most seven updates a_ij -= a_ki a_kj / a_kk read from the UNSCALED pivot row and one warp
+// barrier; the rows are scaled by 1 / sqrt(a_kk) in one pass at the end. (Round 1 gave lane j the whole column j and
+// published the scaled pivot row through three warp barriers per pivot: 18.8 k cycles for 20 x 20 against ~5 k.)
+// Returns 0 or 1 + index of the first non-positive pivot.
 __device__ inline int chol_upper_warp(double *A, int lda, int n, int nsplit, double *rdiag) {
   const int lane = threadIdx.x & 31;
+  constexpr int EPL = 7;
+  int ei[EPL], ej[EPL];
+#pragma unroll
+  for (int q = 0; q < EPL; ++q) {
+    const unsigned v = kTri20[lane + 32 * q];
+    const int i = v & 0xff, j = v >> 8;
+    ei[q] = (j < n) ? i : 0x7fff;   // 0x7fff / padding: never updated (no pivot k with k < i < ... reaches it)
+    ej[q] = j;
+  }
   int bad = 0;
   for (int k = 0; k < n; ++k) {
     double piv = A[k * lda + k];
     if (!(piv > 0.0)) { if (bad == 0) bad = k + 1; piv = 1.0; }
-    const double rinv = rsqrt(piv);
-    const double rkj = (lane > k && lane < n) ? A[k * lda + lane] * rinv : 0.0;
-    __syncwarp();
-    if (lane == k) { A[k * lda + k] = piv * rinv; rdiag[k] = rinv; }
-    else if (lane > k && lane < n) A[k * lda + lane] = rkj;
-    __syncwarp();
-    if (lane > k && lane < n) {
-      const bool plus_k = k < nsplit;
-      const double *__restrict__ rk = A + k * lda;   // row k (final), read only below
-      int i = k + 1;
-      for (; i + 3 <= lane; i += 4) {                // own column, four rows at a time: loads, then stores
-        double r4[4], a4[4];
+    const double pinv = 1.0 / piv;
+    const double *__restrict__ rk = A + k * lda;
+    const bool plus_k = k < nsplit;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { r4[u] = rk[i + u]; a4[u] = A[(i + u) * lda + lane]; }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const double prod = r4[u] * rkj;
-          A[(i + u) * lda + lane] = (plus_k && i + u >= nsplit) ? a4[u] + prod : a4[u] - prod;
-        }
-      }
-      for (; i <= lane; ++i) {
-        const double prod = rk[i] * rkj;
-        double *aij = A + i * lda + lane;
+    for (int q = 0; q < EPL; ++q) {
+      const int i = ei[q], j = ej[q];
+      if (i > k && i != 0x7fff) {
+        const double prod = rk[i] * rk[j] * pinv;
+        double *aij = A + i * lda + j;
         *aij = (plus_k && i >= nsplit) ? *aij + prod : *aij - prod;
       }
     }
+    if (lane == 0) rdiag[k] = rsqrt(piv);
     __syncwarp();
   }
+  // scale: R[i][j] = a_ij / sqrt(a_ii) (the diagonal: sqrt(a_ii), 1 for a substituted pivot)
+#pragma unroll
+  for (int q = 0; q < EPL; ++q) {
+    const int i = ei[q], j = ej[q];
+    if (i != 0x7fff) {
+      const double rinv = rdiag[i];
+      double *aij = A + i * lda + j;
+      const double a = *aij;
+      *aij = (i == j) ? ((a > 0.0) ? a * rinv : 1.0) : a * rinv;
+    }
+  }
+  __syncwarp();
   return bad;
 }
 

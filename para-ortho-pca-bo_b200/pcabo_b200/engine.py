@@ -139,6 +139,7 @@ class BatchedBOEngine:
         self.noise_futs = None
         self.overlap_hook = None
         self.lb_out = None
+        self.lb_ws = None         # device workspace of the L-BFGS-B pairs when they do not fit shared memory (C5)
         self.h_status = self.h_nfev = self.h_nit = None
         self.h_vals = self.h_state_back = self.h_pos_back = self.h_k = self.h_flag = None
         self.d_mt_state = self.d_mt_pos = self.ic_out = None
@@ -543,8 +544,14 @@ class BatchedBOEngine:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
         run_idx = None if runs is None else torch.tensor(sel, dtype=torch.int32).to(self.device, non_blocking=True)
+        k_bound = int(max(k_host[b] for b in sel))
+        need = ops.lbfgsb_workspace_doubles(self.n, self.D, k_bound, self.num_restarts, self.batch_limit, len(sel))
+        if need > 0 and (self.lb_ws is None or self.lb_ws.numel() < need):
+            # sized once for the whole batch at the largest k (never reallocated inside the loop after that)
+            full = ops.lbfgsb_workspace_doubles(self.n, self.D, self.D, self.num_restarts, self.batch_limit, B)
+            self.lb_ws = torch.empty(max(need, full), dtype=torch.float64, device=self.device)
         out = ops.lbfgsb_logei(self.gp, d_x, self.gp.box_lo, self.gp.box_hi, self.batch_limit, self.maxiter, out=out,
-                               run_idx=run_idx, k_bound=int(max(k_host[b] for b in sel)))
+                               run_idx=run_idx, k_bound=k_bound, workspace=self.lb_ws)
         if ev is not None:
             ev[1].record()
         if self.h_status is None or self.h_status.shape != out["status"].shape:
@@ -612,10 +619,12 @@ class BatchedBOEngine:
         self.stats["d2h_bytes"] += B * 4
         ics = self._initial_conditions(st["runs"], k_host, first=st["ic"])
         st.update(k_host=k_host, ics=ics)
-        # the device-resident optimiser keeps the whole L-BFGS-B state of a chunk in shared memory; past that size
-        # (config C5 beyond n ~ 920 with k ~ 90) the iteration is driven by scipy's L-BFGS-B on the same kernels
-        st["use_device"] = self.optimizer == "device" and ops.lbfgsb_fits(self.n, self.D, int(k_host.max()),
-                                                                           self.batch_limit)
+        # the device-resident optimiser keeps the L-BFGS-B state of a chunk in shared memory and, past that size (config
+        # C5: n up to 1050 with k ~ 90), the BFGS pairs in an L2-resident workspace; there is no host fallback
+        st["use_device"] = self.optimizer == "device"
+        if st["use_device"] and not ops.lbfgsb_fits(self.n, self.D, int(k_host.max()), self.batch_limit):
+            raise PcaboError(f"device optimiser: n = {self.n}, k = {int(k_host.max())} is beyond what pcabo_lbfgsb_logei_runs_ws "
+                             "supports; use optimizer='scipy'")
         if st["use_device"]:
             st["t_launch"] = perf_counter()
             self.overlap_hook = self._prefetch_noise

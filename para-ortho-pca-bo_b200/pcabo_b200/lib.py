@@ -8,7 +8,8 @@ _LIB = None
 EXPORTED_SYMBOLS = [
     "pcabo_abi_version", "pcabo_error_string", "pcabo_last_cuda_error",
     "pcabo_weights_pca_fit", "pcabo_inverse_map", "pcabo_gp_fit", "pcabo_gp_fit_jitter", "pcabo_gp_mll", "pcabo_gp_mll_grad",
-    "pcabo_logei", "pcabo_argmax", "pcabo_lbfgsb_logei", "pcabo_lbfgsb_logei_prof", "pcabo_lbfgsb_logei_runs", "pcabo_ei_sweep",
+    "pcabo_logei", "pcabo_argmax", "pcabo_lbfgsb_logei", "pcabo_lbfgsb_logei_prof", "pcabo_lbfgsb_logei_runs", "pcabo_lbfgsb_logei_runs_ws",
+    "pcabo_lbfgsb_workspace_doubles", "pcabo_lbfgsb_plan", "pcabo_ei_sweep",
     "pcabo_sobol_points", "pcabo_sobol_scramble_bits", "pcabo_gather_rows", "pcabo_bbob_eval", "pcabo_bbob_eval_aux", "pcabo_select_initial_conditions",
 ]
 
@@ -73,6 +74,13 @@ def load_library(build_if_missing: bool = False):
     lib.pcabo_lbfgsb_logei_prof.argtypes = [ctypes.POINTER(GpModelStruct), ci, ci, ci, cd, cd] + [vp] * 9 + [vp]
     lib.pcabo_lbfgsb_logei_runs.restype = ci
     lib.pcabo_lbfgsb_logei_runs.argtypes = [ctypes.POINTER(GpModelStruct), ci, vp, ci, ci, ci, ci, cd, cd] + [vp] * 9 + [vp]
+    lib.pcabo_lbfgsb_logei_runs_ws.restype = ci
+    lib.pcabo_lbfgsb_logei_runs_ws.argtypes = [ctypes.POINTER(GpModelStruct), ci, vp, ci, ci, ci, ci, cd, cd] + [vp] * 9 + \
+                                              [vp, ctypes.c_longlong, vp]
+    lib.pcabo_lbfgsb_workspace_doubles.restype = ctypes.c_longlong
+    lib.pcabo_lbfgsb_workspace_doubles.argtypes = [ci] * 6
+    lib.pcabo_lbfgsb_plan.restype = ci
+    lib.pcabo_lbfgsb_plan.argtypes = [ci] * 5 + [ctypes.POINTER(ci)]
     lib.pcabo_ei_sweep.restype = ci
     lib.pcabo_ei_sweep.argtypes = [ctypes.POINTER(GpModelStruct), ci, ctypes.c_longlong, ctypes.c_longlong] + [vp] * 8 + \
                                   [ci, vp, vp, vp]

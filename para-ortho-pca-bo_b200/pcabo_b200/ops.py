@@ -193,24 +193,36 @@ LBFGSB_STATUS = {0: "CONVERGENCE: NORM OF PROJECTED GRADIENT <= PGTOL", 1: "CONV
                  2: "STOP: TOTAL NO. OF ITERATIONS REACHED LIMIT", 3: "ABNORMAL"}
 
 
+def lbfgsb_workspace_doubles(n, kmax, k_bound, num_restarts=10, batch_limit=5, nsel=1):
+    """Doubles of caller-owned device workspace pcabo_lbfgsb_logei_runs_ws needs for `nsel` runs: 0 when the whole
+    L-BFGS-B state fits shared memory, -1 when the problem is not supported at all (the library answers
+    PCABO_E_UNSUPPORTED)."""
+    return int(load_library().pcabo_lbfgsb_workspace_doubles(int(n), int(kmax), int(k_bound), int(num_restarts),
+                                                             int(batch_limit), int(nsel)))
+
+
+def lbfgsb_plan(n, kmax, k_bound, batch_limit=5, have_workspace=True):
+    """The launcher's shared-memory plan as a dict (panel_rows, ring_doubles, resident, tight, pairs_in_workspace,
+    smem_bytes)."""
+    out = (ctypes.c_int * 6)()
+    check(load_library().pcabo_lbfgsb_plan(int(n), int(kmax), int(k_bound), int(batch_limit), int(bool(have_workspace)), out),
+          "pcabo_lbfgsb_plan")
+    return dict(zip(("panel_rows", "ring_doubles", "resident", "tight", "pairs_in_workspace", "smem_bytes"), list(out)))
+
+
 def lbfgsb_fits(n, kmax, k_bound, batch_limit=5):
-    """Whether pcabo_lbfgsb_logei_runs fits the 227 KB of shared memory of a block for n training points, column
-    capacity kmax and at most k_bound active dimensions (mirrors the sizing in csrc/lbfgsb.cu / logei_core.cuh /
-    lbfgsb_core.cuh; the library itself answers PCABO_E_UNSUPPORTED when it does not)."""
-    P = 5 if batch_limit <= 5 else 8
-    np_ = (n + 1) & ~1
-    scratch = P * kmax + 2 * P * np_ + max(P * np_, 256 * P) + 8 * 2 * P + 4 * P + 8
-    nv = batch_limit * min(max(int(k_bound), 1), kmax)
-    work = 9 * nv + 2 * 10 * nv + 4 * 100 + 400 + 5 * 20 + nv + (nv + 1) // 2 + 4
-    return (scratch + work + 2 + 8 + 2 + 8) * 8 <= 227 * 1024 and kmax <= 104 and batch_limit <= 8
+    """Whether the device optimiser accepts this size (with a workspace if it needs one)."""
+    return kmax <= 104 and batch_limit <= 5 and lbfgsb_workspace_doubles(n, kmax, k_bound, 10, batch_limit) >= 0
 
 
 def lbfgsb_logei(buf: GPBuffers, ics, box_lo, box_hi, batch_limit=5, maxiter=200, factr=1e7, pgtol=1e-5, out=None,
-                 prof=None, run_idx=None, k_bound=0):
+                 prof=None, run_idx=None, k_bound=0, workspace=None):
     """ics [B, num_restarts, kmax] -> dict(cand [B, R, kmax], fval/status/nit/nfev [B, nchunks]); one kernel launch.
 
     run_idx (device int32 [nsel]): optimise only these runs, the rows of the other runs in `out` stay as they are.
-    k_bound: an upper bound of k over the runs optimised (sizes the shared memory; 0 = kmax)."""
+    k_bound: an upper bound of k over the runs optimised (sizes the shared memory; 0 = kmax).
+    workspace: device float64 tensor for the BFGS pairs of problems that do not fit shared memory (config C5); allocated
+    here when it is needed and not given (pass one to keep the hot loop allocation-free)."""
     lib = load_library()
     B, R, kmax = ics.shape
     if B != buf.B or kmax != buf.kmax:
@@ -225,12 +237,18 @@ def lbfgsb_logei(buf: GPBuffers, ics, box_lo, box_hi, batch_limit=5, maxiter=200
                    nfev=torch.empty(B, nch, dtype=torch.int32, device=dev))
     m = model_struct(buf)
     nsel = B if run_idx is None else int(run_idx.numel())
-    check(lib.pcabo_lbfgsb_logei_runs(ctypes.byref(m), nsel, _i(run_idx, "run_idx"), int(k_bound), R, int(batch_limit),
-                                      int(maxiter), float(factr), float(pgtol),
-                                      _d(ics, "ics"), _d(box_lo, "box_lo"), _d(box_hi, "box_hi"),
-                                      _d(out["cand"], "cand"), _d(out["fval"], "fval"), _i(out["status"], "status"),
-                                      _i(out["nit"], "nit"), _i(out["nfev"], "nfev"),
-                                      _dev_ptr(prof, torch.int64, "prof"), _stream()), "pcabo_lbfgsb_logei_runs")
+    need = lbfgsb_workspace_doubles(buf.n, kmax, k_bound, R, batch_limit, nsel)
+    if need > 0 and (workspace is None or workspace.numel() < need):
+        workspace = torch.empty(need, dtype=torch.float64, device=dev)
+    check(lib.pcabo_lbfgsb_logei_runs_ws(ctypes.byref(m), nsel, _i(run_idx, "run_idx"), int(k_bound), R, int(batch_limit),
+                                         int(maxiter), float(factr), float(pgtol),
+                                         _d(ics, "ics"), _d(box_lo, "box_lo"), _d(box_hi, "box_hi"),
+                                         _d(out["cand"], "cand"), _d(out["fval"], "fval"), _i(out["status"], "status"),
+                                         _i(out["nit"], "nit"), _i(out["nfev"], "nfev"),
+                                         _dev_ptr(prof, torch.int64, "prof"),
+                                         _d(workspace, "workspace") if need > 0 else None,
+                                         int(workspace.numel()) if need > 0 else 0, _stream()),
+          "pcabo_lbfgsb_logei_runs_ws")
     return out
 
 

@@ -434,29 +434,22 @@ def test_device_initial_conditions_fall_back_for_flagged_runs():
     assert e.n == ndoe + 2
 
 
-def test_device_optimizer_falls_back_when_shared_memory_does_not_fit(monkeypatch):
-    """Past the size the device-resident L-BFGS-B fits in shared memory (config C5 beyond n ~ 915) the engine drives
-    the iteration with scipy's L-BFGS-B on the same value+gradient kernel; the sizing rule mirrors the library's."""
+def test_device_optimizer_workspace_and_no_host_fallback(monkeypatch):
+    """The device-resident L-BFGS-B keeps its state in shared memory; where that does not fit (config C5: n up to 1050,
+    k ~ 90) the BFGS pairs move to a caller-owned L2-resident workspace (pcabo_lbfgsb_logei_runs_ws). There is no host
+    fallback: a size the library cannot take raises."""
     from pcabo_b200 import ops
     from pcabo_b200.engine import BatchedBOEngine
     from pcabo_b200.bbob import BatchedBBOB
-    assert ops.lbfgsb_fits(450, 40, 40) and ops.lbfgsb_fits(303, 100, 90)
-    assert not ops.lbfgsb_fits(1050, 100, 90) and ops.lbfgsb_fits(1050, 100, 20)
+    from pcabo_b200.lib import PcaboError
+    assert ops.lbfgsb_workspace_doubles(450, 40, 40) == 0 and ops.lbfgsb_workspace_doubles(150, 10, 10) == 0
+    need = ops.lbfgsb_workspace_doubles(1050, 100, 90, 10, 5, 3)
+    assert need == 3 * 2 * 2 * 10 * 5 * 90                      # runs x chunks x (S, Y) x m x nvar
+    assert ops.lbfgsb_fits(1050, 100, 90) and ops.lbfgsb_fits(1050, 100, 100)
     prob = BatchedBBOB([15, 16], [0, 1], 10, device="cuda")
     e = BatchedBOEngine(prob, 10, prob.bounds, 150, 30, [15100, 16101], optimizer="device")
     e.initial_design()
     e.step()
-    r0 = e.stats["lbfgsb_rounds"]
     monkeypatch.setattr(ops, "lbfgsb_fits", lambda *a, **k: False)
-    e.step()                                        # scipy-driven: many value+gradient rounds, one launch each
-    assert e.n == 32 and e.stats["lbfgsb_rounds"] - r0 > 5
-    monkeypatch.undo()
-    e.step()
-    assert e.n == 33
-    # the library refuses the same size itself
-    buf = e.gp
-    big = ops.GPBuffers(1, 1050, 100, torch.device("cuda"))
-    big.n, big.k = 1050, torch.tensor([90], dtype=torch.int32, device="cuda")
-    ics = torch.zeros(1, 10, 100, dtype=torch.float64, device="cuda")
-    with pytest.raises(Exception):
-        ops.lbfgsb_logei(big, ics, big.box_lo, big.box_hi, k_bound=90)
+    with pytest.raises(PcaboError, match="beyond"):
+        e.step()

@@ -92,12 +92,13 @@ def test_weights_pca_fit_ncomponents_and_ties():
     assert (fb == 1000.0).sum() > 5
 
 
-def _fit_gp_batch(D, n, B, maximization=False, seed0=0):
+def _fit_gp_batch(D, n, B, maximization=False, seed0=0, ld_n=None):
     ops = _ops()
+    ld_n = n if ld_n is None else ld_n
     hist = [synthetic_history(D, n, seed0 + 31 * D + n + b, maximization=maximization) for b in range(B)]
-    X, f, nz, logtab = batch_to_device([h[0] for h in hist], [h[1] for h in hist], [h[2] for h in hist], n)
+    X, f, nz, logtab = batch_to_device([h[0] for h in hist], [h[1] for h in hist], [h[2] for h in hist], ld_n)
     pca = ops.weights_pca_fit(X, f, nz, logtab, n, 0.95, 0, maximization)
-    buf = ops.GPBuffers(B, n, D, X.device)
+    buf = ops.GPBuffers(B, ld_n, D, X.device)
     ops.gp_fit(buf, pca["Z"], pca["k"], f, n, mode=0)
     torch.cuda.synchronize()
     return ops, hist, X, f, pca, buf
@@ -331,7 +332,8 @@ def test_device_lbfgsb_large_configs(D, n):
     the oracle (the reference's gen_candidates_scipy) from the same initial conditions."""
     from oracle import gp, acqf
     B = 2
-    ops, hist, X, f, pca, buf = _fit_gp_batch(D, n, B)
+    # the optimiser kernel stages rows of W with 16-byte bulk copies: the leading dimension must be even
+    ops, hist, X, f, pca, buf = _fit_gp_batch(D, n, B, ld_n=n + (n & 1))
     rng = np.random.RandomState(11)
     ics = torch.zeros(B, 10, D, dtype=torch.float64)
     accs, boxes = [], []
