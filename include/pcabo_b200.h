@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PCABO_ABI_VERSION 1
+#define PCABO_ABI_VERSION 2   /* 2: pcabo_gp_model gained Wp / wp_stride (packed W for the bulk-copy engine) */
 
 #define PCABO_OK 0
 #define PCABO_E_INVALID (-1)      /* bad argument (null pointer, n < 2, ...) */
@@ -66,6 +66,8 @@ typedef struct pcabo_gp_model {
   const double *best_f;     /* [B] incumbent, already rounded to float32 as botorch stores it */
   const double *WT;         /* [B][ld_n][ld_n] (L^-1)^T, upper triangular, row-major (column j of W contiguous) */
   const double *Zn;         /* [B][ld_n][kmax] normalised training inputs, row-major */
+  const double *Wp;         /* [B][wp_stride] W packed in 8-row groups by pcabo_gp_pack_w (pcabo_lbfgsb_logei* only) */
+  long long wp_stride;      /* doubles between the packed W of consecutive runs (even, >= pcabo_gp_packed_doubles(n)) */
 } pcabo_gp_model;
 
 /* Rank weights + weighted PCA + projection, one CTA per run.
@@ -114,6 +116,14 @@ int pcabo_gp_fit_jitter(int B, int n, int kmax, int ld_n, int mode,
                         double *ymean, double *ystd, double *ZnT, double *Zn, double *L, double *W, double *WT,
                         double *alpha, int *info, void *stream);
 
+/* W (from pcabo_gp_fit) repacked for the bulk-copy (TMA) engine: the lower triangle in groups of 8 rows, group g =
+ * rows 8g..8g+7 x columns 0..8g+7 (zero right of the diagonal and below row n), row stride 8g + (g odd ? 12 : 20)
+ * doubles (a multiple of 4 congruent 4 mod 16: bank-conflict free for both FP64 MMA operand patterns), groups back to
+ * back, so that any run of consecutive groups is ONE contiguous cp.async.bulk. pcabo_gp_packed_doubles(n) doubles per
+ * run; Wp [B][wp_stride]. Part of _initialize_model's cache construction (PCA_BO.py:502-545) for the device optimiser. */
+long long pcabo_gp_packed_doubles(int n);
+int pcabo_gp_pack_w(int B, int n, int ld_n, const double *W, double *Wp, long long wp_stride, void *stream);
+
 /* Exact marginal log-likelihood of the standardised targets from the caches: mll [B]. ys = (f-ymean)/ystd. */
 int pcabo_gp_mll(int B, int n, int ld_n, const double *f, const double *ymean, const double *ystd,
                  const double *L, const double *alpha, double *mll, void *stream);
@@ -158,7 +168,7 @@ int pcabo_lbfgsb_logei_prof(const pcabo_gp_model *m, int num_restarts, int batch
  * per-block shared memory for k <= k_bound (0 = kmax; a run with k > k_bound gets status -1 and is left untouched).
  * Outputs are indexed by RUN (not by position in run_idx), so a retry of a subset updates the same arrays in place:
  * this is botorch's retry_on_optimization_warning (optimize_acqf re-optimises only the problem that warned).
- * The rows of W are staged by 16-byte bulk copies: m->ld_n must be even (PCABO_E_INVALID otherwise).                  */
+ * W is read in its packed form m->Wp (pcabo_gp_pack_w), one bulk copy per panel; m->W / m->WT are not used here.     */
 int pcabo_lbfgsb_logei_runs(const pcabo_gp_model *m, int nsel, const int *run_idx, int k_bound, int num_restarts,
                             int batch_limit, int maxiter, double factr, double pgtol, const double *ics,
                             const double *box_lo, const double *box_hi, double *cand, double *fval, int *status,

@@ -19,6 +19,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, u
   asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_addr(bar)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
   unsigned ok;
   asm volatile(

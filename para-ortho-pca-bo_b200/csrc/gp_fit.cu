@@ -13,6 +13,7 @@
 //                      diagonal blocks factored + inverted in shared memory, TRSM by forward substitution),
 //                      blocked triangular inverse W = L^-1, alpha = W^T (W y_s).
 #include "common.cuh"
+#include "w_packed.cuh"
 
 namespace {
 
@@ -463,6 +464,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) gp_chol_kernel(CholArgs a) {
   if (tid == 0) a.info[b] = s.info;
 }
 
+// W (row-major lower triangle) -> the packed 8-row groups the optimiser kernel streams (w_packed.cuh). grid (groups, B).
+__global__ void __launch_bounds__(256) gp_pack_w_kernel(int n, int ld_n, const double *W, double *Wp, long long wp_stride) {
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int RS = lbeval::grp_rs(g);
+  const double *Wb = W + (size_t)b * ld_n * ld_n;
+  double *out = Wp + (size_t)b * (size_t)wp_stride + lbeval::grp_off(g);
+  for (int idx = threadIdx.x; idx < 8 * RS; idx += blockDim.x) {
+    const int r = idx / RS, c = idx % RS, i = 8 * g + r;
+    out[idx] = (i < n && c <= i) ? Wb[(size_t)i * ld_n + c] : 0.0;
+  }
+}
+
 __global__ void gp_mll_kernel(int n, int ld_n, const double *f, const double *ymean, const double *ystd,
                               const double *L, const double *alpha, double *mll) {
   __shared__ double red[34];
@@ -625,6 +638,16 @@ extern "C" int pcabo_gp_mll(int B, int n, int ld_n, const double *f, const doubl
                             const double *L, const double *alpha, double *mll, void *stream) {
   if (B <= 0 || n < 1 || ld_n < n || !f || !ymean || !ystd || !L || !alpha || !mll) return PCABO_E_INVALID;
   gp_mll_kernel<<<B, 256, 0, as_stream(stream)>>>(n, ld_n, f, ymean, ystd, L, alpha, mll);
+  PCABO_LAUNCH_CHECK();
+  return PCABO_OK;
+}
+
+extern "C" long long pcabo_gp_packed_doubles(int n) { return n < 1 ? -1 : lbeval::packed_doubles(n); }
+
+extern "C" int pcabo_gp_pack_w(int B, int n, int ld_n, const double *W, double *Wp, long long wp_stride, void *stream) {
+  if (B <= 0 || n < 1 || ld_n < n || !W || !Wp || wp_stride < lbeval::packed_doubles(n) || (wp_stride & 1)) return PCABO_E_INVALID;
+  dim3 grid(lbeval::ngroups(n), B);
+  gp_pack_w_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, ld_n, W, Wp, wp_stride);
   PCABO_LAUNCH_CHECK();
   return PCABO_OK;
 }

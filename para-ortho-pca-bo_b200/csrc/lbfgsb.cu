@@ -110,9 +110,9 @@ struct CudaWarpTeam {
   }
   __device__ void formk_products(const lbfgsb::Work &w, int col, double theta) {
     if (lane == 0) { mb->cmd = CMD_FORMK; mb->col = col; mb->theta = theta; }
-    __syncthreads();
+    lbeval::cta_sync();
     formk_products_block(w, col, theta);
-    __syncthreads();
+    lbeval::cta_sync();
   }
 };
 
@@ -124,7 +124,7 @@ struct LogEiObjective {
   // called by warp 0 (the team); posts the evaluation to the whole block
   __device__ double operator()(CudaWarpTeam &tm, const double *x, double *g) {
     if (tm.lane == 0) tm.mb->cmd = CMD_EVAL;
-    __syncthreads();
+    lbeval::cta_sync();
     return run(x, g);
   }
   // executed by all LB_THREADS threads
@@ -148,13 +148,12 @@ struct LbArgs {
   int k_bound;         // shared memory was sized for k <= k_bound
   int ring_cap;        // doubles of the W panel ring
   int resident;        // every panel fits the ring
-  int tight;           // small ring: panels are released behind a barrier of their own
   double *wsy;         // optional global home of the BFGS pairs [gridDim.y][gridDim.x][2 M nvar_max] (nullptr: shared memory)
   int nvar_max;
 };
 
 template <int PT, int R, int TI>
-__global__ void __launch_bounds__(LB_THREADS, 1) lbfgsb_logei_kernel(LbArgs a) {
+__global__ void __launch_bounds__(lbeval::NT_ALL, 1) lbfgsb_logei_kernel(LbArgs a) {   // 9 warps: one scheduler hosts 3 -> 168 registers
   extern __shared__ __align__(16) double sm[];
   const int b = a.run_idx ? a.run_idx[blockIdx.y] : blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int nchunks = gridDim.x;
@@ -176,7 +175,6 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgsb_logei_kernel(LbArgs a) {
   obj.ctx.base = q;
   obj.ctx.ring_cap = a.ring_cap;
   obj.ctx.resident = a.resident != 0;
-  obj.ctx.tight = a.tight != 0;
   q += obj.ctx.L.o_ring + a.ring_cap;
   lbfgsb::Work w;
   double *wsy = a.wsy ? a.wsy + ((size_t)blockIdx.y * nchunks + chunk) * (size_t)(2 * lbfgsb::M) * a.nvar_max : nullptr;
@@ -185,45 +183,54 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgsb_logei_kernel(LbArgs a) {
   Mailbox *mb = reinterpret_cast<Mailbox *>(q); q += 2;
   obj.vals = q; q += 8;
   int *flag = reinterpret_cast<int *>(q); q += 2;
+  long long *sprof = reinterpret_cast<long long *>(q); q += 32;   // cycle counters live in shared memory, flushed at the end
   obj.pcount = pcount; obj.kk = kk;
-  if (a.prof) obj.ctx.prof = a.prof + ((size_t)b * nchunks + chunk) * 32;
-  lbeval::init(obj.ctx, PT);   // barriers, zero padding, first panel requests (ends with a block barrier)
-
-  const double *ic = a.ics + ((size_t)b * a.num_restarts + p0) * kmax;
-  const double *blo = a.box_lo + (size_t)b * kmax, *bhi = a.box_hi + (size_t)b * kmax;
-  for (int i = tid; i < nvar; i += LB_THREADS) {
-    const int p = i / kk, j = i % kk;
-    const double lo = blo[j], hi = bhi[j];
-    w.l[i] = lo; w.u[i] = hi;
-    w.x[i] = fmax(fmin(ic[(size_t)p * kmax + j], hi), lo);   // columnwise_clamp of the initial conditions
+  if (a.prof) {
+    if (tid < 32) sprof[tid] = 0;
+    obj.ctx.prof = sprof;
   }
-  __syncthreads();
+  lbeval::init(obj.ctx, PT);   // mbarriers, zero padding (all threads; ends with a block barrier)
+  const double *blo = a.box_lo + (size_t)b * kmax, *bhi = a.box_hi + (size_t)b * kmax;
   lbfgsb::Result r;
-  if (tid < 32) {
-    CudaWarpTeam tm;
-    tm.tid = tid; tm.nt = 32; tm.lane = tid; tm.nl = 32; tm.w0 = true; tm.mb = mb; tm.wk = &w;
-    tm.prof = a.prof ? a.prof + ((size_t)b * nchunks + chunk) * 32 : nullptr;
-    tm.last = clock64();
-    r = lbfgsb::minimize(tm, w, obj, a.maxiter, a.factr, a.pgtol, flag);
-    if (tid == 0) mb->cmd = CMD_EXIT;
-    __syncthreads();
+  if (tid >= LB_THREADS) {
+    // ---- producer warp: keeps the panel ring of W full for the whole launch (lane 0), then waits at the final barrier
+    if (tid == LB_THREADS) lbeval::producer_loop(obj.ctx);
+    __syncwarp();
   } else {
-    for (;;) {
-      __syncthreads();
-      const int c = mb->cmd;
-      if (c == CMD_EVAL) {
-        obj.run(w.x, w.g);
-      } else if (c == CMD_FORMK) {
-        formk_products_block(w, mb->col, mb->theta);
-        __syncthreads();
-      } else {
-        break;
+    const double *ic = a.ics + ((size_t)b * a.num_restarts + p0) * kmax;
+    for (int i = tid; i < nvar; i += LB_THREADS) {
+      const int p = i / kk, j = i % kk;
+      const double lo = blo[j], hi = bhi[j];
+      w.l[i] = lo; w.u[i] = hi;
+      w.x[i] = fmax(fmin(ic[(size_t)p * kmax + j], hi), lo);   // columnwise_clamp of the initial conditions
+    }
+    lbeval::cta_sync();
+    if (tid < 32) {
+      CudaWarpTeam tm;
+      tm.tid = tid; tm.nt = 32; tm.lane = tid; tm.nl = 32; tm.w0 = true; tm.mb = mb; tm.wk = &w;
+      tm.prof = a.prof ? sprof : nullptr;
+      tm.last = clock64();
+      r = lbfgsb::minimize(tm, w, obj, a.maxiter, a.factr, a.pgtol, flag);
+      if (tid == 0) { mb->cmd = CMD_EXIT; lbeval::signal_exit(obj.ctx); }
+      lbeval::cta_sync();
+    } else {
+      for (;;) {
+        lbeval::cta_sync();
+        const int c = mb->cmd;
+        if (c == CMD_EVAL) {
+          obj.run(w.x, w.g);
+        } else if (c == CMD_FORMK) {
+          formk_products_block(w, mb->col, mb->theta);
+          lbeval::cta_sync();
+        } else {
+          break;
+        }
       }
     }
   }
-  lbeval::drain(obj.ctx);   // no bulk copy may outlive the block (ends with a block barrier)
+  __syncthreads();   // every bulk copy has landed (the producer drained the ring before it got here)
   double *out = a.cand + ((size_t)b * a.num_restarts + p0) * kmax;
-  for (int i = tid; i < pcount * kmax; i += LB_THREADS) {
+  for (int i = tid; i < pcount * kmax; i += lbeval::NT_ALL) {
     const int p = i / kmax, j = i % kmax;
     out[i] = (j < kk) ? fmax(fmin(w.x[p * kk + j], bhi[j]), blo[j]) : 0.0;
   }
@@ -231,45 +238,42 @@ __global__ void __launch_bounds__(LB_THREADS, 1) lbfgsb_logei_kernel(LbArgs a) {
     const size_t o = (size_t)b * nchunks + chunk;
     a.status[o] = r.status; a.nit[o] = r.nit; a.nfev[o] = r.nfev; a.fval[o] = r.f;
   }
+  if (a.prof && tid < 32) a.prof[((size_t)b * nchunks + chunk) * 32 + tid] += sprof[tid];
 }
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
-constexpr int TAIL_DOUBLES = 2 + 8 + 2 + 8;
+constexpr int TAIL_DOUBLES = 2 + 8 + 2 + 32 + 8;
 
 // Shared-memory plan of one launch: panel height, ring capacity, where the BFGS pairs live.
 struct Plan {
-  int R, TI, ring_cap, resident, tight, pairs_global;
+  int R, TI, ring_cap, resident, pairs_global;
   size_t smem;
 };
 
 inline bool make_plan(int PT, int n, int kmax, int nvar_max, bool have_ws, Plan &pl) {
   const int tiles = (n + 7) / 8;
   pl.TI = (tiles + lbeval::NW - 1) / lbeval::NW;
-  // preference: pairs in shared memory before pairs in the workspace; 16-row panels before 8-row panels; the ring takes
-  // all the shared memory that is left (at most all panels). A ring too small for the two-barrier schedule (checked by
-  // replaying it on the host) releases every panel behind a barrier of its own ("tight"); it must hold the largest panel.
+  // preference: pairs in shared memory before pairs in the workspace; everything resident (32-row panels) before
+  // streaming; 16-row panels when two of the largest fit the ring, else 8-row panels (the ring must hold the largest).
+  // The ring takes all the shared memory that is left (at most all panels).
   for (int pairs_global = 0; pairs_global <= (have_ws ? 1 : 0); ++pairs_global) {
     const size_t work = lbfgsb::work_doubles(nvar_max, pairs_global != 0) + TAIL_DOUBLES;
-    for (int pass = 0; pass < 3; ++pass) {   // 0: everything resident, 32-row panels; 1: two-barrier streaming; 2: "tight"
-      for (int R = (pass == 0 ? 32 : 16); R >= (pass == 0 ? 32 : 8); R -= 8) {
-        const lbeval::Layout L = lbeval::make_layout(PT, kmax, n, R);
-        const size_t fixed = ((size_t)L.o_ring + work) * sizeof(double);
-        if (fixed >= SMEM_LIMIT) continue;
-        const long long avail = (long long)((SMEM_LIMIT - fixed) / sizeof(double)) & ~1LL;
-        if (avail < L.max_panel) continue;
-        const bool resident = L.all_panels <= avail && L.npanels <= lbeval::NBAR;
-        if (pass == 0 && !resident) continue;
-        const int cap = (int)(avail < L.all_panels ? avail : L.all_panels);
-        const bool loose_ok = resident || lbeval::ring_schedule_ok(n, R, cap, false, false);
-        if (!loose_ok && (pass < 2 || !lbeval::ring_schedule_ok(n, R, cap, false, true))) continue;
-        pl.R = R;
-        pl.resident = resident ? 1 : 0;
-        pl.tight = loose_ok ? 0 : 1;
-        pl.ring_cap = cap;
-        pl.pairs_global = pairs_global;
-        pl.smem = ((size_t)L.o_ring + cap + work) * sizeof(double);
-        return true;
-      }
+    for (int pass = 0; pass < 3; ++pass) {
+      const int R = pass == 0 ? 32 : pass == 1 ? 16 : 8;
+      const lbeval::Layout L = lbeval::make_layout(PT, kmax, n, R);
+      const size_t fixed = ((size_t)L.o_ring + work) * sizeof(double);
+      if (fixed >= SMEM_LIMIT) continue;
+      const long long avail = (long long)((SMEM_LIMIT - fixed) / sizeof(double)) & ~1LL;
+      const bool resident = L.all_panels <= avail && L.npanels <= lbeval::NBAR;
+      if (pass == 0 && !resident) continue;
+      if (pass == 1 && !resident && avail < 2LL * L.max_panel) continue;
+      if (avail < L.max_panel) continue;
+      pl.R = R;
+      pl.resident = resident ? 1 : 0;
+      pl.ring_cap = (int)(avail < L.all_panels ? avail : L.all_panels);
+      pl.pairs_global = pairs_global;
+      pl.smem = ((size_t)L.o_ring + pl.ring_cap + work) * sizeof(double);
+      return true;
     }
   }
   return false;
@@ -280,7 +284,7 @@ int launch_one(const LbArgs &a, int nsel, size_t smem, cudaStream_t st) {
   const int nchunks = (a.num_restarts + a.batch_limit - 1) / a.batch_limit;
   PCABO_CUDA_CHECK(cudaFuncSetAttribute(lbfgsb_logei_kernel<PT, R, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(nchunks, nsel);
-  lbfgsb_logei_kernel<PT, R, TI><<<grid, LB_THREADS, smem, st>>>(a);
+  lbfgsb_logei_kernel<PT, R, TI><<<grid, lbeval::NT_ALL, smem, st>>>(a);
   PCABO_LAUNCH_CHECK();
   return PCABO_OK;
 }
@@ -293,7 +297,7 @@ int launch(LbArgs &a, int nsel, double *workspace, long long workspace_doubles, 
   Plan pl;
   if (!make_plan(PT, a.m.n, a.m.kmax, a.nvar_max, workspace != nullptr && workspace_doubles >= ws_need, pl))
     return PCABO_E_UNSUPPORTED;
-  a.ring_cap = pl.ring_cap; a.resident = pl.resident; a.tight = pl.tight; a.wsy = pl.pairs_global ? workspace : nullptr;
+  a.ring_cap = pl.ring_cap; a.resident = pl.resident; a.wsy = pl.pairs_global ? workspace : nullptr;
   if (pl.R == 32 && pl.TI <= 8) return launch_one<PT, 32, 8>(a, nsel, pl.smem, st);
   if (pl.R == 32) return PCABO_E_UNSUPPORTED;
   if (pl.TI <= 8) return pl.R == 16 ? launch_one<PT, 16, 8>(a, nsel, pl.smem, st) : launch_one<PT, 8, 8>(a, nsel, pl.smem, st);
@@ -320,7 +324,7 @@ extern "C" int pcabo_lbfgsb_plan(int n, int kmax, int k_bound, int batch_limit, 
   if (k_bound <= 0 || k_bound > kmax) k_bound = kmax;
   Plan pl;
   if (!make_plan(5, n, kmax, batch_limit * k_bound, have_workspace != 0, pl)) return PCABO_E_UNSUPPORTED;
-  plan6[0] = pl.R; plan6[1] = pl.ring_cap; plan6[2] = pl.resident; plan6[3] = pl.tight; plan6[4] = pl.pairs_global;
+  plan6[0] = pl.R; plan6[1] = pl.ring_cap; plan6[2] = pl.resident; plan6[3] = 0; plan6[4] = pl.pairs_global;
   plan6[5] = (int)pl.smem;
   return PCABO_OK;
 }
@@ -331,8 +335,9 @@ extern "C" int pcabo_lbfgsb_logei_runs_ws(const pcabo_gp_model *m, int nsel, con
                                           double *fval, int *status, int *nit, int *nfev, long long *prof,
                                           double *workspace, long long workspace_doubles, void *stream) {
   if (!m || num_restarts <= 0 || batch_limit <= 0 || maxiter <= 0 || !ics || !box_lo || !box_hi || !cand || !fval ||
-      !status || !nit || !nfev || m->B <= 0 || m->n < 1 || m->ld_n < m->n || (m->ld_n & 1) || !m->norm_off ||
-      !m->norm_coef || !m->ZnT || !m->alpha || !m->W || !m->Zn || !m->ymean || !m->ystd || !m->best_f ||
+      !status || !nit || !nfev || m->B <= 0 || m->n < 1 || m->ld_n < m->n || !m->norm_off ||
+      !m->norm_coef || !m->ZnT || !m->alpha || !m->Wp || (m->wp_stride & 1) ||
+      m->wp_stride < lbeval::packed_doubles(m->n) || !m->Zn || !m->ymean || !m->ystd || !m->best_f ||
       !(m->lengthscale > 0.0))
     return PCABO_E_INVALID;
   if (run_idx ? (nsel <= 0 || nsel > m->B) : (nsel != m->B)) return PCABO_E_INVALID;

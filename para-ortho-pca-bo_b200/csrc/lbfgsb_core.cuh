@@ -115,78 +115,94 @@ __device__ const unsigned short kTri20[224] = {
 };
 
 // Right-looking Cholesky R^T R = A of the leading n x n block (n <= 20 = 2 m) of the upper-stored A (ld = lda) in shared
-// memory; R overwrites A, rdiag[j] = 1 / R[j][j]. For pivots k < nsplit the rows/columns >= nsplit receive
-// +a_ki a_kj / a_kk instead of -a_ki a_kj / a_kk: with nsplit = col on the 2 col x 2 col matrix of formk this is the
-// LEL^T factorisation (Cholesky of the (1,1) block, R12 = R11^-T A12, Cholesky of A22 + R12^T R12) in one sweep.
-// The 210 entries of the triangle are dealt flat to the 32 lanes (seven each, fixed for the whole factorisation), so a
-// pivot costs every lane at most seven updates a_ij -= a_ki a_kj / a_kk read from the UNSCALED pivot row and one warp
-// barrier; the rows are scaled by 1 / sqrt(a_kk) in one pass at the end. (Round 1 gave lane j the whole column j and
-// published the scaled pivot row through three warp barriers per pivot: 18.8 k cycles for 20 x 20 against ~5 k.)
+// memory. What is left in A is the UNIT triangular factor U = D^-1 R (U_ij = R_ij / R_ii for j > i; the diagonal is not
+// used) together with rdiag[i] = 1 / R_ii, so that the triangular solves below have no multiplication on their serial
+// chain. For pivots k < nsplit the rows/columns >= nsplit receive +a_ki a_kj / a_kk instead of -a_ki a_kj / a_kk: with
+// nsplit = col on the 2 col x 2 col matrix of formk this is the LEL^T factorisation (Cholesky of the (1,1) block,
+// R12 = R11^-T A12, Cholesky of A22 + R12^T R12) in one sweep.
+// The 210 entries of the triangle are dealt flat to the 32 lanes (seven each, fixed for the whole factorisation). A
+// pivot costs: one reciprocal, then for all seven entries at once (branch free, so their FP64 latencies of 23 cycles
+// overlap) a_ij -= a_ki a_kj / a_kk from the UNSCALED pivot row, and one warp barrier. (Round 1 gave lane j the whole
+// column j and published the scaled pivot row through three warp barriers per pivot: 18.8 k cycles for 20 x 20.)
 // Returns 0 or 1 + index of the first non-positive pivot.
 __device__ inline int chol_upper_warp(double *A, int lda, int n, int nsplit, double *rdiag) {
   const int lane = threadIdx.x & 31;
   constexpr int EPL = 7;
-  int ei[EPL], ej[EPL];
+  int off[EPL], oi[EPL], oj[EPL], row[EPL];
+  bool sgn[EPL];
 #pragma unroll
   for (int q = 0; q < EPL; ++q) {
     const unsigned v = kTri20[lane + 32 * q];
     const int i = v & 0xff, j = v >> 8;
-    ei[q] = (j < n) ? i : 0x7fff;   // 0x7fff / padding: never updated (no pivot k with k < i < ... reaches it)
-    ej[q] = j;
+    const bool on = j < n;              // (padding has j = 255)
+    row[q] = on ? i : -1;               // -1: never updated
+    off[q] = on ? i * lda + j : 0;      // a valid address either way: loads are unconditional
+    oi[q] = on ? i : 0;
+    oj[q] = on ? j : 0;
+    sgn[q] = on && i >= nsplit;
   }
   int bad = 0;
   for (int k = 0; k < n; ++k) {
-    double piv = A[k * lda + k];
+    const double *__restrict__ rk = A + k * lda;
+    double piv = rk[k];
+    double a[EPL], ri[EPL], rj[EPL];
+#pragma unroll
+    for (int q = 0; q < EPL; ++q) { a[q] = A[off[q]]; ri[q] = rk[oi[q]]; rj[q] = rk[oj[q]]; }
     if (!(piv > 0.0)) { if (bad == 0) bad = k + 1; piv = 1.0; }
     const double pinv = 1.0 / piv;
-    const double *__restrict__ rk = A + k * lda;
+    if (lane == 0) rdiag[k] = piv;      // turned into 1 / sqrt(piv) after the sweep
     const bool plus_k = k < nsplit;
 #pragma unroll
     for (int q = 0; q < EPL; ++q) {
-      const int i = ei[q], j = ej[q];
-      if (i > k && i != 0x7fff) {
-        const double prod = rk[i] * rk[j] * pinv;
-        double *aij = A + i * lda + j;
-        *aij = (plus_k && i >= nsplit) ? *aij + prod : *aij - prod;
-      }
+      const double prod = (ri[q] * pinv) * rj[q];
+      const double v = (plus_k && sgn[q]) ? a[q] + prod : a[q] - prod;
+      if (row[q] > k) A[off[q]] = v;
     }
-    if (lane == 0) rdiag[k] = rsqrt(piv);
     __syncwarp();
   }
-  // scale: R[i][j] = a_ij / sqrt(a_ii) (the diagonal: sqrt(a_ii), 1 for a substituted pivot)
+  // unit factor: U_ij = a_ij / a_ii (j > i)
+  const double pv = (lane < n) ? rdiag[lane] : 1.0;
+  __syncwarp();
 #pragma unroll
   for (int q = 0; q < EPL; ++q) {
-    const int i = ei[q], j = ej[q];
-    if (i != 0x7fff) {
-      const double rinv = rdiag[i];
-      double *aij = A + i * lda + j;
-      const double a = *aij;
-      *aij = (i == j) ? ((a > 0.0) ? a * rinv : 1.0) : a * rinv;
-    }
+    if (row[q] >= 0 && oj[q] > oi[q]) A[off[q]] = A[off[q]] / rdiag[oi[q]];
   }
+  __syncwarp();
+  if (lane < n) rdiag[lane] = rsqrt(pv);
   __syncwarp();
   return bad;
 }
 
-// In place on b (shared memory, length n <= 32): trans ? R^T x = b : R x = b, R upper triangular (shared memory) with
-// reciprocal diagonal; the right-hand side lives in one register per lane and travels by shuffles.
+// In place on b (shared memory, length n <= 32): trans ? R^T x = b : R x = b with R = D U from chol_upper_warp (U unit
+// upper triangular in shared memory, rdiag = 1 / diag(R)). The right-hand side lives in one register per lane and
+// travels by shuffles; the serial chain per step is one shuffle and one FMA (the diagonal scaling is done for all lanes
+// at once, before or after).
 __device__ inline void tri_solve_warp(const double *R, int ldr, int n, double *b, const double *rdiag, bool trans) {
   const int lane = threadIdx.x & 31;
-  double bi = (lane < n) ? b[lane] : 0.0;
-  if (trans) {
+  const bool on = lane < n;
+  double bi = on ? b[lane] : 0.0;
+  const double rd = on ? rdiag[lane] : 0.0;
+  // (the factor entry of step j + 1 is loaded before the shuffle of step j: its latency stays off the serial chain)
+  if (trans) {   // U^T y = b, x = D^-1 y
+    double u = (lane > 0 && on) ? R[lane] : 0.0;
     for (int j = 0; j < n; ++j) {
-      const double rji = (lane > j && lane < n) ? R[j * ldr + lane] : 0.0;
-      const double xj = shfl(bi, j) * rdiag[j];
-      bi = (lane == j) ? xj : fma(-rji, xj, bi);
+      const double un = (lane > j + 1 && on && j + 1 < n) ? R[(j + 1) * ldr + lane] : 0.0;
+      const double yj = shfl(bi, j);
+      bi = fma(-u, yj, bi);
+      u = un;
     }
-  } else {
+    bi *= rd;
+  } else {       // U x = D^-1 b
+    bi *= rd;
+    double u = (lane < n - 1) ? R[lane * ldr + n - 1] : 0.0;
     for (int j = n - 1; j >= 0; --j) {
-      const double rij = (lane < j) ? R[lane * ldr + j] : 0.0;
-      const double xj = shfl(bi, j) * rdiag[j];
-      bi = (lane == j) ? xj : fma(-rij, xj, bi);
+      const double un = (j >= 1 && lane < j - 1) ? R[lane * ldr + j - 1] : 0.0;
+      const double xj = shfl(bi, j);
+      bi = fma(-u, xj, bi);
+      u = un;
     }
   }
-  if (lane < n) b[lane] = bi;
+  if (on) b[lane] = bi;
   __syncwarp();
 }
 }  // namespace dev

@@ -8,17 +8,20 @@
 //     (a row of t only needs the columns left of the diagonal) and is used at once for s += W_I^T t_I. Both products
 //     run on the FP64 tensor cores (mma.sync m8n8k4, SASS DMMA.8x8x4; the 5 points of a chunk are padded to the 8
 //     columns of the B operand), which also does the cross-lane reductions of the dot products.
-//   * The panels are staged by the bulk-copy (TMA) engine: one elected thread issues cp.async.bulk row copies that
-//     signal an mbarrier per panel with their byte count. The ring is a byte FIFO of variable-size panels; while a
-//     panel is consumed the next ones are in flight, and after the last panel of an evaluation the first panels of the
-//     NEXT evaluation are requested, so they land while the optimiser warp does its L-BFGS-B bookkeeping. If all
-//     panels fit the ring (n up to ~200) they are loaded once per launch and every later evaluation runs from shared
-//     memory only.
+//   * The panels are staged by the bulk-copy (TMA) engine: a dedicated producer warp (the ninth warp of the block; it
+//     takes no part in the block barriers of the eight compute warps, which use a named barrier) issues cp.async.bulk
+//     row copies that signal a "full" mbarrier per panel with their byte count; the compute warps hand a panel back
+//     through an "empty" mbarrier (one arrival per warp) after its transposed product. The ring is a byte FIFO of
+//     variable-size panels and the panel sequence is cyclic: after the last panel of an evaluation the first panels of
+//     the NEXT evaluation are already requested and land while the optimiser warp does its L-BFGS-B bookkeeping. If
+//     all panels fit the ring (n up to ~200) they are loaded once per launch and every later evaluation runs from
+//     shared memory only.
 //   * s stays in the accumulator registers of the warps that own the column tiles and is turned into the gradient
 //     coefficients c_j = dk_j/d(dist^2) (dlogEI/dmu alpha_j - 2 dlogEI/dvar s_j) straight from there.
 #pragma once
 #include "async_copy.cuh"
 #include "logei_core.cuh"
+#include "w_packed.cuh"
 
 namespace lbeval {
 
@@ -26,7 +29,10 @@ constexpr int NT = 256;         // threads per block
 constexpr int NW = NT / 32;
 constexpr int NBAR = 16;        // panels in flight (one mbarrier each)
 constexpr int NPOFF = 32;       // ring offsets of the last NPOFF issued panels
-constexpr int PRODUCER = NT - 1;
+constexpr int NT_ALL = NT + 32;  // + the producer warp
+
+// block barrier of the NT compute threads (the producer warp never joins it)
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
 // smallest y >= x with y % 16 == 4: a row stride (in doubles) that makes both DMMA operand access patterns of the
 // sweep (8 rows x 4 columns and 4 rows x 8 columns per warp) bank-conflict free, and keeps rows 16-byte aligned
@@ -34,13 +40,9 @@ __host__ __device__ inline int pad4mod16(int x) { return ((x + 11) / 16) * 16 + 
 
 __host__ __device__ inline int imin(int a, int b) { return a < b ? a : b; }
 
-// row stride of panel I (rows I R .. I R + R - 1, columns 0 .. min((I + 1) R, n) - 1)
-// (the column count is rounded up to a whole 8-column tile: the transposed product reads whole tiles)
-__host__ __device__ inline int panel_rs(int I, int R, int n) { return pad4mod16((imin((I + 1) * R, n) + 7) & ~7); }
-
 struct Layout {   // offsets in doubles from the start of the evaluation scratch (all even: 16-byte aligned)
   int S, R, npanels;
-  int o_xn, o_kst, o_gf, o_alpha, o_part, o_red, o_bar, o_poff, o_ring;
+  int o_xn, o_kst, o_gf, o_alpha, o_zero, o_part, o_red, o_bar, o_poff, o_ring;
   int max_panel;          // doubles of the largest panel
   long long all_panels;   // doubles of all panels together
 };
@@ -48,35 +50,32 @@ struct Layout {   // offsets in doubles from the start of the evaluation scratch
 __host__ __device__ inline Layout make_layout(int PT, int kmax, int n, int R) {
   Layout L;
   L.R = R;
-  L.S = pad4mod16((n + 3) & ~3);
+  L.S = pad4mod16((n + 7) & ~7);   // whole 8-column tiles of the last group
   L.npanels = (n + R - 1) / R;
   int o = 0;
   L.o_xn = o; o += (PT * kmax + 1) & ~1;
   L.o_kst = o; o += PT * L.S;
   L.o_gf = o; o += PT * L.S;
   L.o_alpha = o; o += L.S;
+  L.o_zero = o; o += L.S;          // zeros: the B operand of the MMA lanes that hold none of the PT points
   const int part_a = 2 * NW * 8 * 12, part_g = NT * PT;   // double-buffered split-K partials of t (NSPLIT R = 8 NW rows of
   L.o_part = o; o += (part_a > part_g ? part_a : part_g);  // 12) / partials of the gradient (never live together)
   L.o_red = o; o += NW * PT + NW * 8 + 2 * PT + 2 + ((NW * PT + 2 * PT) & 1);
-  L.o_bar = o; o += NBAR;
+  L.o_bar = o; o += 2 * NBAR + 2;   // full[NBAR], empty[NBAR], exit flag
   L.o_poff = o; o += NPOFF / 2;
   L.o_ring = o;
-  long long all = 0;
-  int mx = 0;
-  for (int I = 0; I < L.npanels; ++I) {
-    const int sz = R * panel_rs(I, R, n);
-    all += sz;
-    if (sz > mx) mx = sz;
-  }
-  L.all_panels = all;
-  L.max_panel = mx;
+  const int G = R / 8, ng = ngroups(n);
+  L.all_panels = packed_doubles(n);
+  const int last_full = ((ng - 1) / G) * G;   // first group of the last panel
+  long long mx = grp_off(ng) - grp_off(last_full);
+  if (last_full >= G && grp_off(last_full) - grp_off(last_full - G) > mx) mx = grp_off(last_full) - grp_off(last_full - G);
+  L.max_panel = (int)mx;
   return L;
 }
 
 // Producer-side state of the panel ring: a byte FIFO of variable-size panels (all offsets in doubles).
 struct RingState {
   unsigned next, oldest;   // sequence numbers: next panel to request, oldest panel not yet released
-  unsigned cons;           // next panel to consume
   int lo, hi;              // live region: [lo, hi), or [lo, end) + [0, hi) when wrapped
   bool wrapped;
 };
@@ -103,54 +102,16 @@ __host__ __device__ inline void ring_pop(RingState &r, int new_lo) {
   }
 }
 
-__host__ __device__ inline bool ring_may_request(const RingState &r, int npanels, bool resident) {
-  if (resident ? (r.next >= (unsigned)npanels) : (r.next >= r.cons + (unsigned)npanels)) return false;   // one evaluation ahead
-  return r.next - r.oldest < (unsigned)NBAR;
-}
-
-// Host replay of the request / release schedule of eval() for `evals` evaluations: true when a consumer never meets a
-// panel that cannot have been requested (which would dead-lock the block). tight: the panel is released behind an
-// extra block barrier right after its transposed product instead of at the first barrier of the next panel.
-inline bool ring_schedule_ok(int n, int R, int cap, bool resident, bool tight, int evals = 3) {
-  const int np = (n + R - 1) / R;
-  RingState r{0, 0, 0, 0, 0, false};
-  int poff[NPOFF];
-  auto pump = [&]() {
-    while (ring_may_request(r, np, resident)) {
-      int off;
-      if (!ring_place(r, R * panel_rs((int)(r.next % (unsigned)np), R, n), cap, off)) break;
-      poff[r.next & (NPOFF - 1)] = off;
-      ++r.next;
-    }
-  };
-  auto pop = [&]() { ring_pop(r, poff[(r.oldest + 1) & (NPOFF - 1)]); };
-  pump();
-  for (int e = 0; e < evals; ++e) {
-    for (int I = 0; I < np; ++I) {
-      const unsigned seq = resident ? (unsigned)I : r.cons;
-      if (seq >= r.next) return false;
-      if (!resident && !tight && I > 0) pop();
-      pump();
-      ++r.cons;
-      if (!resident && tight) { pop(); pump(); }
-    }
-    if (!resident && !tight) pop();
-    pump();
-  }
-  return true;
-}
-
 struct Ctx {
   int n, kmax, kk, ld, acq;
-  const double *ZnT, *Zn, *W, *alpha_g, *off, *coef;
+  const double *ZnT, *Zn, *Wp, *alpha_g, *off, *coef;   // Wp: packed W of this run
   double inv_ell2, ymean, ystd, best_f, sgn;
   Layout L;
   double *base;        // shared-memory scratch
   int ring_cap;        // doubles
   bool resident;       // every panel stays in the ring for the whole launch
-  bool tight;          // ring smaller than three of the largest panels: release each panel behind its own barrier
   bool loaded;         // resident panels have been waited for once
-  RingState rs;        // cons is kept by every thread, the rest by the PRODUCER thread only
+  unsigned cons;       // sequence number of the next panel to consume (all compute threads agree)
   long long *prof;     // optional cycle counters (slots 16..22, stamp in 31)
 };
 
@@ -167,7 +128,7 @@ __device__ inline void load_ctx(Ctx &c, const pcabo_gp_model &m, int b) {
   c.kk = m.k ? m.k[b] : m.kmax;
   c.ZnT = m.ZnT + (size_t)b * m.kmax * m.ld_n;
   c.Zn = m.Zn + (size_t)b * m.ld_n * m.kmax;
-  c.W = m.W + (size_t)b * m.ld_n * m.ld_n;
+  c.Wp = m.Wp + (size_t)b * (size_t)m.wp_stride;
   c.alpha_g = m.alpha + (size_t)b * m.ld_n;
   c.off = m.norm_off + (size_t)b * m.kmax;
   c.coef = m.norm_coef + (size_t)b * m.kmax;
@@ -177,70 +138,76 @@ __device__ inline void load_ctx(Ctx &c, const pcabo_gp_model &m, int b) {
   c.prof = nullptr;
 }
 
-// ---- producer side of the panel ring (thread PRODUCER only)
-__device__ inline void ring_pump(Ctx &c) {
+// ---- producer side of the panel ring: lane 0 of the producer warp runs this for the whole launch
+__device__ inline void producer_loop(const Ctx &c) {
   const Layout &L = c.L;
-  unsigned long long *bars = reinterpret_cast<unsigned long long *>(c.base + L.o_bar);
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(c.base + L.o_bar);
+  unsigned long long *empty = full + NBAR;
+  volatile int *exit_flag = reinterpret_cast<volatile int *>(c.base + L.o_bar + 2 * NBAR);
   int *poff = reinterpret_cast<int *>(c.base + L.o_poff);
   double *ring = c.base + L.o_ring;
   const int R = L.R, n = c.n, np = L.npanels;
-  RingState &r = c.rs;
-  while (ring_may_request(r, np, c.resident)) {
-    const int I = (int)(r.next % (unsigned)np);
-    const int RS = panel_rs(I, R, n);
-    int off;
-    if (!ring_place(r, R * RS, c.ring_cap, off)) break;
+  RingState r{0u, 0u, 0, 0, false};
+  int I = 0;   // panel index of sequence number r.next (the sequence is cyclic over the panels)
+  bool stop = false;
+  while (!stop) {
+    if (c.resident && r.next >= (unsigned)np) break;   // everything requested once: done
+    const int g0 = I * (R / 8), g1 = imin(g0 + R / 8, ngroups(n));
+    const long long src_off = grp_off(g0);
+    const int sz = (int)(grp_off(g1) - src_off);
+    int off = 0;
+    // make room: hand-backs arrive in order, so the oldest live panel is the one to wait for
+    while (r.next - r.oldest >= (unsigned)NBAR || !ring_place(r, sz, c.ring_cap, off)) {
+      unsigned long long *eb = &empty[r.oldest & (NBAR - 1)];
+      const unsigned par = (r.oldest >> 4) & 1u;
+      while (!acp::mbar_try_wait(eb, par)) {
+        if (*exit_flag) { stop = true; break; }
+        __nanosleep(200);   // the optimiser warp shares this scheduler: do not spin on its issue slots
+      }
+      if (stop) break;
+      ring_pop(r, poff[(r.oldest + 1) & (NPOFF - 1)]);
+    }
+    if (stop) break;
     poff[r.next & (NPOFF - 1)] = off;
-    const int r0 = I * R, nrows = imin(R, n - r0);
-    const unsigned bytes = (unsigned)(((imin(r0 + R, n) + 1) & ~1) * 8);
-    unsigned long long *bar = &bars[r.next & (NBAR - 1)];
+    unsigned long long *bar = &full[r.next & (NBAR - 1)];
     acp::fence_proxy_async();
-    acp::mbar_arrive_expect_tx(bar, (unsigned)nrows * bytes);
-    const double *src = c.W + (size_t)r0 * c.ld;
-    double *dst = ring + off;
-    for (int q = 0; q < nrows; ++q) acp::bulk_g2s(dst + q * RS, src + (size_t)q * c.ld, bytes, bar);
+    acp::mbar_arrive_expect_tx(bar, (unsigned)sz * 8u);
+    acp::bulk_g2s(ring + off, c.Wp + src_off, (unsigned)sz * 8u, bar);   // the whole panel: one contiguous copy
     ++r.next;
+    if (++I == np) I = 0;
   }
+  // no bulk copy may outlive the block: wait for everything that was requested and not handed back yet (resident
+  // panels were all waited for by the first evaluation)
+  if (!c.resident)
+    for (unsigned s = r.oldest; s != r.next; ++s) acp::mbar_wait(&full[s & (NBAR - 1)], (s >> 4) & 1u);
 }
 
-// the oldest panel has been consumed by every warp
-__device__ inline void ring_release(Ctx &c) {
-  const int *poff = reinterpret_cast<const int *>(c.base + c.L.o_poff);
-  ring_pop(c.rs, poff[(c.rs.oldest + 1) & (NPOFF - 1)]);
-}
-
-// Called once per launch by all threads (ends with __syncthreads): barriers, zero padding, alpha, first requests.
+// Called once per launch by ALL threads of the block (ends with __syncthreads): barriers, zero padding, alpha.
 __device__ inline void init(Ctx &c, int PT) {
   const Layout &L = c.L;
   const int tid = threadIdx.x;
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(c.base + L.o_bar);
   if (tid == 0) {
-    for (int i = 0; i < NBAR; ++i) acp::mbar_init(&bars[i], 1);
+    for (int i = 0; i < NBAR; ++i) { acp::mbar_init(&bars[i], 1); acp::mbar_init(&bars[NBAR + i], NW); }
+    *reinterpret_cast<int *>(c.base + L.o_bar + 2 * NBAR) = 0;
     acp::fence_barrier_init();
   }
   // kst / gf / alpha: entries >= n must be (and stay) zero: they meet the zero padding of the panels in the MMAs
-  for (int i = tid; i < 2 * PT * L.S + L.S; i += NT) c.base[L.o_kst + i] = 0.0;
-  for (int i = tid; i < c.ring_cap; i += NT) c.base[L.o_ring + i] = 0.0;   // never multiply uninitialised bits by zero
+  for (int i = tid; i < 2 * PT * L.S + 2 * L.S; i += NT_ALL) c.base[L.o_kst + i] = 0.0;
   __syncthreads();
-  for (int i = tid; i < c.n; i += NT) c.base[L.o_alpha + i] = c.alpha_g[i];
+  for (int i = tid; i < c.n; i += NT_ALL) c.base[L.o_alpha + i] = c.alpha_g[i];
   c.loaded = false;
-  c.rs.next = 0; c.rs.oldest = 0; c.rs.cons = 0; c.rs.lo = 0; c.rs.hi = 0; c.rs.wrapped = false;
-  if (tid == PRODUCER) ring_pump(c);
+  c.cons = 0;
   __syncthreads();
 }
 
-// Called by all threads before the block exits (ends with __syncthreads): no bulk copy may still be in flight.
-__device__ inline void drain(Ctx &c) {
-  if (threadIdx.x == PRODUCER) {
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(c.base + c.L.o_bar);
-    const unsigned first = c.resident ? (c.loaded ? c.rs.next : 0u) : c.rs.cons;
-    for (unsigned s = first; s != c.rs.next; ++s) acp::mbar_wait(&bars[s & (NBAR - 1)], (s >> 4) & 1u);
-  }
-  __syncthreads();
+// The optimiser is done: tell the producer (thread 0 of the compute warps).
+__device__ inline void signal_exit(const Ctx &c) {
+  *reinterpret_cast<volatile int *>(c.base + c.L.o_bar + 2 * NBAR) = 1;
 }
 
 // Value and gradient at pcount <= PT points. X: raw coordinates, point p at X + p * kk. val[p] <- acquisition value,
-// grad[p * kk + j] <- gscale * d value / d x_j. All NT threads must call; ends with __syncthreads().
+// grad[p * kk + j] <- gscale * d value / d x_j. All NT compute threads must call; ends with their block barrier.
 template <int PT, int R, int TI>
 __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *grad, double gscale) {
   using logei::SQRT5;
@@ -251,6 +218,7 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
   double *xn = c.base + L.o_xn, *kst = c.base + L.o_kst, *gf = c.base + L.o_gf, *alpha = c.base + L.o_alpha;
   double *part = c.base + L.o_part, *red = c.base + L.o_red, *ring = c.base + L.o_ring;
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(c.base + L.o_bar);
+  unsigned long long *empty = bars + NBAR;
   const int *poff = reinterpret_cast<const int *>(c.base + L.o_poff);
   const double inv_ell2 = c.inv_ell2;
 
@@ -259,7 +227,7 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
     const int p = idx / kmax, j = idx % kmax;
     xn[idx] = (p < pcount && j < kk) ? (X[p * kk + j] - c.off[j]) / c.coef[j] : 0.0;
   }
-  __syncthreads();
+  cta_sync();
   // ---- k vector and dk/d(dist^2) factor: thread per training point, coalesced ZnT, eight loads in flight
   double mpart[PT];
 #pragma unroll
@@ -295,7 +263,7 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
       gf[p * S + i] = (s2 > 1e-30) ? -(5.0 / 3.0) * (1.0 + SQRT5 * d) * e * inv_ell2 : 0.0;
     }
   }
-  __syncthreads();
+  cta_sync();
   ev_tick(c, 16);
 
   // ---- the sweep over the row panels of W. Per panel: phase A (t_I = W_I k: warp -> row tile warp % RT and every
@@ -311,66 +279,89 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
   const int lr = lane >> 2, lc = lane & 3;
   const int wrt = warp % RT, wsp = warp / RT;
   for (int I = 0; I < L.npanels; ++I) {
-    const unsigned seq = c.resident ? (unsigned)I : c.rs.cons;
+    const unsigned seq = c.resident ? (unsigned)I : c.cons;
     if (!c.resident || !c.loaded) acp::mbar_wait(&bars[seq & (NBAR - 1)], (seq >> 4) & 1u);
     const double *pan = ring + poff[seq & (NPOFF - 1)];
-    const int r0 = I * R, c1 = imin(r0 + R, n), RS = panel_rs(I, R, n);
+    const int g0 = I * RT, ng = imin(RT, ngroups(n) - g0);    // groups of this panel (RT except at the end)
+    const int r0 = I * R, c1 = imin(r0 + 8 * ng, n);
+    const long long pbase = grp_off(g0);
     double *pbuf = part + (I & 1) * (NSPLIT * R * PLD);
     {
       double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, c0 = 0.0, c1v = 0.0, d0 = 0.0, d1 = 0.0;
-      const int ksteps = (c1 + 3) >> 2;
-      const double *arow = pan + (wrt * 8 + lr) * RS + lc;
-      const double *brow = kst + lr * S + lc;
-      const bool bon = lr < PT;
-      int ks = wsp;
-      for (; ks + 3 * NSPLIT < ksteps; ks += 4 * NSPLIT) {
-        const double w0 = arow[4 * ks], w1 = arow[4 * (ks + NSPLIT)], w2 = arow[4 * (ks + 2 * NSPLIT)],
-                     w3 = arow[4 * (ks + 3 * NSPLIT)];
-        const double k0 = bon ? brow[4 * ks] : 0.0, k1 = bon ? brow[4 * (ks + NSPLIT)] : 0.0,
-                     k2 = bon ? brow[4 * (ks + 2 * NSPLIT)] : 0.0, k3 = bon ? brow[4 * (ks + 3 * NSPLIT)] : 0.0;
-        acp::dmma_8x8x4(a0, a1, w0, k0);
-        acp::dmma_8x8x4(b0, b1, w1, k1);
-        acp::dmma_8x8x4(c0, c1v, w2, k2);
-        acp::dmma_8x8x4(d0, d1, w3, k3);
+      if (wrt < ng) {   // this warp's row tile (= group g0 + wrt) exists
+        const int ksteps = 2 * (g0 + wrt) + 2;                 // its columns: 0 .. 8 (g0 + wrt) + 7
+        const double *pa = pan + (int)(grp_off(g0 + wrt) - pbase) + lr * grp_rs(g0 + wrt) + lc + 4 * wsp;
+        const double *pb = ((lr < PT) ? kst + lr * S : c.base + L.o_zero) + lc + 4 * wsp;
+        int left = (ksteps - wsp + NSPLIT - 1) / NSPLIT;       // k steps wsp, wsp + NSPLIT, ... of this warp
+        constexpr int ST = 4 * NSPLIT;                         // doubles between them
+        for (; left >= 4; left -= 4, pa += 4 * ST, pb += 4 * ST) {
+          const double w0 = pa[0], w1 = pa[ST], w2 = pa[2 * ST], w3 = pa[3 * ST];
+          const double k0 = pb[0], k1 = pb[ST], k2 = pb[2 * ST], k3 = pb[3 * ST];
+          acp::dmma_8x8x4(a0, a1, w0, k0);
+          acp::dmma_8x8x4(b0, b1, w1, k1);
+          acp::dmma_8x8x4(c0, c1v, w2, k2);
+          acp::dmma_8x8x4(d0, d1, w3, k3);
+        }
+        if (left >= 2) {
+          const double w0 = pa[0], w1 = pa[ST], k0 = pb[0], k1 = pb[ST];
+          acp::dmma_8x8x4(a0, a1, w0, k0);
+          acp::dmma_8x8x4(b0, b1, w1, k1);
+          pa += 2 * ST; pb += 2 * ST; left -= 2;
+        }
+        if (left >= 1) acp::dmma_8x8x4(c0, c1v, pa[0], pb[0]);
       }
-      for (; ks < ksteps; ks += NSPLIT) acp::dmma_8x8x4(a0, a1, arow[4 * ks], bon ? brow[4 * ks] : 0.0);
       *reinterpret_cast<double2 *>(pbuf + (wsp * R + wrt * 8 + lr) * PLD + 2 * lc) =
           make_double2((a0 + b0) + (c0 + d0), (a1 + b1) + (c1v + d1));
     }
-    __syncthreads();
-    if (tid == PRODUCER) {   // every warp is past phase B of the previous panel
-      if (!c.resident && !c.tight && I > 0) ring_release(c);
-      ring_pump(c);
-    }
+    cta_sync();
     {
       double bf[KQ];
 #pragma unroll
       for (int kq = 0; kq < KQ; ++kq) {
         const int r = 4 * kq + lc;
-        double t = 0.0;
+        double tp[NSPLIT];
 #pragma unroll
-        for (int sp = 0; sp < NSPLIT; ++sp) t += pbuf[(sp * R + r) * PLD + lr];
-        bf[kq] = (r0 + r < n) ? t : 0.0;
+        for (int sp = 0; sp < NSPLIT; ++sp) tp[sp] = pbuf[(sp * R + r) * PLD + lr];
+#pragma unroll
+        for (int st = 1; st < NSPLIT; st *= 2)      // pairwise tree: log2(NSPLIT) dependent additions
+#pragma unroll
+          for (int sp = 0; sp + st < NSPLIT; sp += 2 * st) tp[sp] += tp[sp + st];
+        bf[kq] = tp[0];   // (rows >= n are zero in the packed panel: t is exactly 0 there)
       }
       if (warp == (I & (NW - 1))) {
 #pragma unroll
         for (int kq = 0; kq < KQ; ++kq) vacc = fma(bf[kq], bf[kq], vacc);
       }
-      const double *acol = pan + lc * RS + lr;
-      const int ntile = (c1 + 7) >> 3;
+      // A fragments of the transposed product: rows 4 kq + (lane & 3) of the panel live in group kq / 2
+      const double *acol[KQ];
 #pragma unroll
       for (int kq = 0; kq < KQ; ++kq) {
+        const int gj = imin(kq >> 1, ng - 1);   // (a missing group has t = 0: any valid address will do)
+        acol[kq] = pan + (int)(grp_off(g0 + gj) - pbase) + ((4 * kq & 7) + lc) * grp_rs(g0 + gj) + lr;
+      }
+      const int ntile = (c1 + 7) >> 3;
+      // tile outer, k step inner: the tiles are independent accumulator chains, and a tile right of the diagonal block
+      // is skipped by a uniform branch (predicated-off DMMAs measured slower than the chains they were meant to hide)
 #pragma unroll
-        for (int ti = 0; ti < TI; ++ti) {
-          const int ct = warp + NW * ti;
-          if (ct < ntile) acp::dmma_8x8x4(sf[ti][0], sf[ti][1], acol[4 * kq * RS + ct * 8], bf[kq]);
+      for (int ti = 0; ti < TI; ++ti) {
+        const int ct = warp + NW * ti;
+        if (ct <= g0) {          // left of every group's diagonal block: all k steps, operands loaded up front
+          double av[KQ];
+#pragma unroll
+          for (int kq = 0; kq < KQ; ++kq) av[kq] = acol[kq][ct * 8];
+#pragma unroll
+          for (int kq = 0; kq < KQ; ++kq) acp::dmma_8x8x4(sf[ti][0], sf[ti][1], av[kq], bf[kq]);
+        } else if (ct < ntile) {  // a diagonal tile of the panel: only the groups at or below it hold something there
+#pragma unroll
+          for (int kq = 0; kq < KQ; ++kq)
+            if (ct <= g0 + (kq >> 1)) acp::dmma_8x8x4(sf[ti][0], sf[ti][1], acol[kq][ct * 8], bf[kq]);
         }
       }
     }
-    ++c.rs.cons;
-    if (c.tight) {   // small ring: hand the panel back at once so that the next large one can be requested
-      __syncthreads();
-      if (tid == PRODUCER) { ring_release(c); ring_pump(c); }
+    ++c.cons;
+    if (!c.resident) {   // this warp is done with the panel
+      __syncwarp();
+      if (lane == 0) acp::mbar_arrive(&empty[seq & (NBAR - 1)]);
     }
   }
   c.loaded = true;
@@ -387,11 +378,7 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     if (lc == 0) red[NW * PT + warp * 8 + lr] = v;
   }
-  __syncthreads();
-  if (tid == PRODUCER) {
-    if (!c.resident && !c.tight) ring_release(c);
-    ring_pump(c);   // the first panels of the next evaluation travel while the optimiser warp works
-  }
+  cta_sync();
   ev_tick(c, 17);
   double *res = red + NW * PT + NW * 8;   // [2][PT]: d value / d mu_s, d value / d var_s
   if (tid < PT) {
@@ -426,7 +413,7 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
     res[p] = dmu;
     res[PT + p] = dvar;
   }
-  __syncthreads();
+  cta_sync();
   ev_tick(c, 22);
   // ---- gradient coefficients straight from the accumulators: c_j = gf_j (dmu alpha_j - 2 dvar s_j), over the k vector
 #pragma unroll
@@ -441,7 +428,7 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
       }
     }
   }
-  __syncthreads();
+  cta_sync();
   ev_tick(c, 19);
   // ---- grad[p][j] = gscale (1 / coef_j) sum_i c_i (xn_j - zn_ij): thread (ig, j), every IG-th training point
   {
@@ -472,7 +459,7 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
 #pragma unroll
       for (int p = 0; p < PT; ++p) part[(ig * PT + p) * kk + j] = acc[p];
     }
-    __syncthreads();
+    cta_sync();
     for (int idx = tid; idx < pcount * kk; idx += NT) {
       const int p = idx / kk, jj = idx % kk;
       double sv = 0.0;
@@ -480,7 +467,7 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
       grad[idx] = gscale * sv / c.coef[jj];
     }
   }
-  __syncthreads();
+  cta_sync();
   ev_tick(c, 20);
 }
 

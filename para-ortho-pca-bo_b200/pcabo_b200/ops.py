@@ -98,6 +98,9 @@ class GPBuffers:
         self.L = torch.zeros(B, ld_n, ld_n, **f64)
         self.W = torch.zeros(B, ld_n, ld_n, **f64)
         self.WT = torch.zeros(B, ld_n, ld_n, **f64)
+        # W packed in 8-row groups for the optimiser kernel's bulk copies (pcabo_gp_pack_w; ~ld_n^2 / 2 doubles per run)
+        self.wp_stride = int(load_library().pcabo_gp_packed_doubles(int(ld_n)))
+        self.Wp = torch.zeros(B, self.wp_stride, **f64)
         self.alpha = torch.zeros(B, ld_n, **f64)
         self.info = torch.zeros(B, dtype=torch.int32, device=device)
         self.best_f = torch.zeros(B, **f64)
@@ -123,6 +126,7 @@ def gp_fit(buf: GPBuffers, Z, k, f, n, mode=0, fix_lo=None, fix_hi=None, lengths
                            _d(buf.Zn, "Zn"), _d(buf.L, "L"), _d(buf.W, "W"), _d(buf.WT, "WT"), _d(buf.alpha, "alpha"),
                            _i(buf.info, "info"), _stream()),
           "pcabo_gp_fit")
+    check(lib.pcabo_gp_pack_w(B, n, ld_n, _d(buf.W, "W"), _d(buf.Wp, "Wp"), buf.wp_stride, _stream()), "pcabo_gp_pack_w")
     buf.n, buf.k, buf.lengthscale = n, k, lengthscale
     return buf
 
@@ -156,6 +160,7 @@ def model_struct(buf: GPBuffers) -> GpModelStruct:
     m.ZnT, m.alpha, m.W = _d(buf.ZnT, "ZnT"), _d(buf.alpha, "alpha"), _d(buf.W, "W")
     m.ymean, m.ystd, m.best_f = _d(buf.ymean, "ymean"), _d(buf.ystd, "ystd"), _d(buf.best_f, "best_f")
     m.WT, m.Zn = _d(buf.WT, "WT"), _d(buf.Zn, "Zn")
+    m.Wp, m.wp_stride = _d(buf.Wp, "Wp"), int(buf.wp_stride)
     return m
 
 

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(EXPORTED_SYMBOLS), declared ^ set(EXPORTED_SYMBOLS)
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.pcabo_abi_version() == 1
+    assert lib.pcabo_abi_version() == 2
     assert lib.pcabo_error_string(-2).decode().startswith("size not supported")
     # argument validation happens before any CUDA call
     assert lib.pcabo_argmax(0, 0, None, None, None, None) == -1

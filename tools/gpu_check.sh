@@ -9,3 +9,10 @@ import json
 d=json.load(open("gpurun_out/b_$tag.json")); print(d["value"], d["ms_per_step"], d["run_info"]["window_seconds"], d["roofline"]["avg_launch_us"])
 d=json.load(open("gpurun_out/p_${tag}_n123.json")); w=d["worst_chunk"]; print(d["kernel_ms"], w["nit"],w["nfev"],w["Mcycles"]); print({k:round(v) for k,v in w["cycles_per_iteration"].items() if v>0})
 EOF
+if [ -n "$2" ]; then
+timeout 200 python tools/profile_lbfgsb.py $2 > gpurun_out/p_${tag}_late.json 2>/dev/null
+python - <<EOF
+import json
+d=json.load(open("gpurun_out/p_${tag}_late.json")); w=d["worst_chunk"]; print(d["kernel_ms"], d["n"], w["nit"],w["nfev"],w["Mcycles"]); print({k:round(v) for k,v in w["cycles_per_iteration"].items() if v>0})
+EOF
+fi
