@@ -20,6 +20,9 @@ extern const char *pcabo_set_cuda_error(cudaError_t e);
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// gp_chol.cu: Cholesky / inverse / alpha / transpose pipeline on the kernel matrix stored in L (lower triangle)
+int pcabo_chol_pipeline(int B, int n, int ld_n, double *L, double *W, double *WT, double *alpha, int *info, cudaStream_t st);
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -614,6 +614,15 @@ extern "C" int pcabo_gp_fit_jitter(int B, int n, int kmax, int ld_n, int mode, c
     gp_kmat_kernel<<<grid, 256, 0, st>>>(n, kmax, ld_n, k, ZnT, 1.0 / (lengthscale * lengthscale), noise, jitter, L);
     PCABO_LAUNCH_CHECK();
   }
+  return pcabo_chol_pipeline(B, n, ld_n, L, W, WT, alpha, info, st);
+}
+
+extern "C" int pcabo_gp_fit_onecta(int B, int n, int kmax, int ld_n, double *L, double *W, double *WT, double *alpha,
+                                   int *info, void *stream) {
+  // round-1 factorisation (one thread block per run), kept as a yardstick for tools/measure_fp64.py: L holds K on entry
+  if (B <= 0 || n < 1 || ld_n < n || !L || !W || !WT || !alpha || !info) return PCABO_E_INVALID;
+  (void)kmax;
+  cudaStream_t st = as_stream(stream);
   {
     CholArgs a;
     a.B = B; a.n = n; a.ld_n = ld_n; a.L = L; a.W = W; a.WT = WT; a.alpha = alpha; a.info = info;

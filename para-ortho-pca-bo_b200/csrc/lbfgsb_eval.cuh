@@ -42,7 +42,7 @@ __host__ __device__ inline int imin(int a, int b) { return a < b ? a : b; }
 
 struct Layout {   // offsets in doubles from the start of the evaluation scratch (all even: 16-byte aligned)
   int S, R, npanels;
-  int o_xn, o_kst, o_gf, o_alpha, o_zero, o_part, o_red, o_bar, o_poff, o_ring;
+  int o_xn, o_kst, o_gf, o_alpha, o_part, o_red, o_bar, o_poff, o_ring;
   int max_panel;          // doubles of the largest panel
   long long all_panels;   // doubles of all panels together
 };
@@ -57,7 +57,6 @@ __host__ __device__ inline Layout make_layout(int PT, int kmax, int n, int R) {
   L.o_kst = o; o += PT * L.S;
   L.o_gf = o; o += PT * L.S;
   L.o_alpha = o; o += L.S;
-  L.o_zero = o; o += L.S;          // zeros: the B operand of the MMA lanes that hold none of the PT points
   const int part_a = 2 * NW * 8 * 12, part_g = NT * PT;   // double-buffered split-K partials of t (NSPLIT R = 8 NW rows of
   L.o_part = o; o += (part_a > part_g ? part_a : part_g);  // 12) / partials of the gradient (never live together)
   L.o_red = o; o += NW * PT + NW * 8 + 2 * PT + 2 + ((NW * PT + 2 * PT) & 1);
@@ -193,7 +192,7 @@ __device__ inline void init(Ctx &c, int PT) {
     acp::fence_barrier_init();
   }
   // kst / gf / alpha: entries >= n must be (and stay) zero: they meet the zero padding of the panels in the MMAs
-  for (int i = tid; i < 2 * PT * L.S + 2 * L.S; i += NT_ALL) c.base[L.o_kst + i] = 0.0;
+  for (int i = tid; i < 2 * PT * L.S + L.S; i += NT_ALL) c.base[L.o_kst + i] = 0.0;
   __syncthreads();
   for (int i = tid; i < c.n; i += NT_ALL) c.base[L.o_alpha + i] = c.alpha_g[i];
   c.loaded = false;
@@ -291,7 +290,8 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
       if (wrt < ng) {   // this warp's row tile (= group g0 + wrt) exists
         const int ksteps = 2 * (g0 + wrt) + 2;                 // its columns: 0 .. 8 (g0 + wrt) + 7
         const double *pa = pan + (int)(grp_off(g0 + wrt) - pbase) + lr * grp_rs(g0 + wrt) + lc + 4 * wsp;
-        const double *pb = ((lr < PT) ? kst + lr * S : c.base + L.o_zero) + lc + 4 * wsp;
+        // (the 8 - PT padding columns of the B operand repeat real points: whatever they produce is never read)
+        const double *pb = kst + (lr < PT ? lr : lr - PT) * S + lc + 4 * wsp;
         int left = (ksteps - wsp + NSPLIT - 1) / NSPLIT;       // k steps wsp, wsp + NSPLIT, ... of this warp
         constexpr int ST = 4 * NSPLIT;                         // doubles between them
         for (; left >= 4; left -= 4, pa += 4 * ST, pb += 4 * ST) {

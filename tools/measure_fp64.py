@@ -33,13 +33,14 @@ def main():
         t = timed(lambda: torch.linalg.cholesky(A))
         out[f"potrf_batched_B{B}_n{n}_ms"] = t * 1e3
         out[f"potrf_batched_B{B}_n{n}_gflops"] = B * n ** 3 / 3 / t / 1e9
-    # our batched GP fit (K build + Cholesky + L^-1 + alpha + transposition, one CTA per run) on the same shapes
+    # our batched GP fit (K build + Cholesky + L^-1 + alpha + transposition + packing: the tile pipeline of gp_chol.cu)
+    # on the same shapes
     try:
         import os
         ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         sys.path.insert(0, os.path.join(ROOT, "para-ortho-pca-bo_b200"))
         from pcabo_b200 import ops
-        for (B, n, k) in [(90, 450, 36), (90, 285, 36), (150, 1050, 90)]:
+        for (B, n, k) in [(90, 450, 36), (30, 450, 36), (90, 285, 36), (150, 1050, 90)]:
             kmax = 40 if k <= 40 else 100
             Z = torch.rand(B, n, kmax, dtype=torch.float64, device="cuda")
             f = torch.randn(B, n, dtype=torch.float64, device="cuda")
