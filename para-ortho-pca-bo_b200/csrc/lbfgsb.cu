@@ -13,54 +13,91 @@ namespace {
 
 constexpr int LB_THREADS = lbeval::NT;
 
-enum Cmd { CMD_EVAL = 1, CMD_FORMK = 2, CMD_EXIT = 3 };
+enum Cmd { CMD_EVAL = 1, CMD_FORMK = 2, CMD_EXIT = 3, CMD_SHIFT = 4 };
 
-// Raw inner products of formk (see lbfgsb::formk_products_range for the layout) by the whole block: 8 lanes share one
-// entry (k = seg, seg + 8, ...), 32 entries per pass, only the 2 col (col+1)/2 + col^2 entries that are used; the
-// free / active split is a 0/1 multiplier instead of a branch. Deterministic (fixed xor-shuffle tree).
-__device__ void formk_products_block(const lbfgsb::Work &w, int col, double theta) {
+// Raw inner products of formk (see lbfgsb::formk_products_range for the layout) by the whole block. 8 lanes share one
+// ROW of a block of the matrix (k = seg, seg + 8, ...): rows 0..col-1 of Y'ZZ'Y (entries j >= i), of S'AA'S (j >= i) and
+// of the mixed block (all jy for one iy), 3 col <= 30 row tasks = 240 threads, ONE pass. The row's own vector and the
+// free / active indicator are loaded once per k for up to 10 entries (round 1 dealt single entries to the lane groups:
+// three loads per FMA and seven passes, shared-memory bound at 14 k cycles). The free / active split is a 0/1 multiplier
+// instead of a branch; per entry the summation order is the same fixed xor-shuffle tree as before (bit-identical).
+// (force-inlined into the kernel so that the pointers of `w` keep their shared-memory provenance: as a separate function
+// it reads them from the struct and every access becomes a generic load)
+__device__ __forceinline__ void formk_products_block(const lbfgsb::Work &w, int col, double theta) {
   using lbfgsb::M;
   using lbfgsb::M2;
-  const int n = w.n, tid = threadIdx.x, seg = tid & 7, slot = tid >> 3;
-  const int T = col * (col + 1) / 2, nent = 2 * T + col * col;
+  const int n = w.n, ldp = w.ldp, tid = threadIdx.x, seg = tid & 7, task = tid >> 3;
   const double *__restrict__ wy = w.wy;
   const double *__restrict__ ws = w.ws;
   const int *__restrict__ iw = w.iwhere;
-  for (int e0 = 0; e0 < nent; e0 += LB_THREADS / 8) {
-    const int e = e0 + slot;
-    double s = 0.0;
-    int blk = 3, i = 0, j = 0;
-    if (e < nent) {
-      if (e < 2 * T) {
-        blk = e / T;
-        int t = e % T;
-        // upper-triangular index t -> (i, j), i <= j
-        j = 0;
-        while (t >= j + 1) { t -= j + 1; ++j; }
-        i = t;
-      } else {
-        blk = 2;
-        i = (e - 2 * T) / col;   // jy (Y index)
-        j = (e - 2 * T) % col;   // iy (S index)
-      }
-      const double *a, *b2;
-      bool want_free;
-      if (blk == 0) { a = wy + i * n; b2 = wy + j * n; want_free = true; }
-      else if (blk == 1) { a = ws + i * n; b2 = ws + j * n; want_free = false; }
-      else { a = ws + j * n; b2 = wy + i * n; want_free = !(i < j); }
+  const int blk = task / col, i = task % col;   // tasks >= 3 col: nothing to do (but they join the shuffles)
+  double s[M];
+#pragma unroll
+  for (int j = 0; j < M; ++j) s[j] = 0.0;
+  if (blk < 3) {
+    // row vector a (indexed by i) and the vectors b_j it meets; entry j is used for j >= j0 (triangular blocks)
+    const double *a = (blk == 0) ? wy + i * ldp : ws + i * ldp;
+    const double *bb = (blk == 1) ? ws : wy;
+    // Every entry j < M is accumulated, from a valid row, whether it is used or not (the unused ones are dropped when
+    // the results are stored): no branch and no select per entry. The 0/1 indicator of the free / active split is
+    // folded into the row's own value (a_k * m is exact), so an entry costs ONE FMA per k. The phase is bound by
+    // instruction issue (8 warps on 4 schedulers): with a select and a separate multiplication per entry it took
+    // 11.5 k cycles (ncu: 170 M instructions on that one source line).
+    int roff[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) roff[j] = (j < col ? j : col - 1) * ldp;
+    if (blk < 2) {   // Y'ZZ'Y (free variables) / S'AA'S (active variables): one indicator for the whole row
       for (int k = seg; k < n; k += 8) {
-        const double mk = ((iw[k] <= 0) == want_free) ? 1.0 : 0.0;
-        s = fma(a[k] * b2[k], mk, s);
+        const bool fr = iw[k] <= 0;
+        const double akm = (fr == (blk == 0)) ? a[k] : 0.0;
+        double bv[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) bv[j] = bb[roff[j] + k];
+#pragma unroll
+        for (int j = 0; j < M; ++j) s[j] = fma(akm, bv[j], s[j]);
+      }
+    } else {         // row iy = i of S against column jy = j of Y: free variables if jy >= iy, active ones otherwise
+      for (int k = seg; k < n; k += 8) {
+        const bool fr = iw[k] <= 0;
+        const double ak = a[k];
+        const double a_hi = fr ? ak : 0.0, a_lo = fr ? 0.0 : ak;
+        double bv[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) bv[j] = bb[roff[j] + k];
+#pragma unroll
+        for (int j = 0; j < M; ++j) s[j] = fma((j < i) ? a_lo : a_hi, bv[j], s[j]);
       }
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (e < nent && seg == 0) {
-      if (blk == 0) w.wn[i * M2 + j] = s / theta + ((i == j) ? w.sy[i * M + i] : 0.0);
-      else if (blk == 1) w.wn[(col + i) * M2 + col + j] = s * theta;
-      else w.wn[i * M2 + col + j] = (i < j) ? -s : s;
+  }
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 1);
+    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 2);
+    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 4);
+  }
+  if (blk < 3 && seg == 0) {
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      if (j < col) {
+        if (blk == 0) { if (j >= i) w.wn[i * M2 + j] = s[j] / theta + ((i == j) ? w.sy[i * M + i] : 0.0); }
+        else if (blk == 1) { if (j >= i) w.wn[(col + i) * M2 + col + j] = s[j] * theta; }
+        else w.wn[j * M2 + col + i] = (j < i) ? -s[j] : s[j];   // row jy = j, column col + iy
+      }
     }
+  }
+}
+
+// The oldest pair leaves the memory: rows 1..M-1 of S and Y move up by one, all threads of the block (a thread per
+// variable; loads first, then stores).
+__device__ __forceinline__ void shift_pairs_block(const lbfgsb::Work &w) {
+  using lbfgsb::M;
+  const int n = w.n, ldp = w.ldp;
+  for (int i = threadIdx.x; i < n; i += LB_THREADS) {
+    double a[M - 1], b[M - 1];
+#pragma unroll
+    for (int j = 0; j < M - 1; ++j) { a[j] = w.ws[(j + 1) * ldp + i]; b[j] = w.wy[(j + 1) * ldp + i]; }
+#pragma unroll
+    for (int j = 0; j < M - 1; ++j) { w.ws[j * ldp + i] = a[j]; w.wy[j * ldp + i] = b[j]; }
   }
 }
 
@@ -79,6 +116,7 @@ struct CudaWarpTeam {
   Mailbox *mb;
   const lbfgsb::Work *wk;
   long long *prof;      // optional [16] cycle counters of this block (lane 0), or nullptr
+  double *red;          // shared-memory scratch of sum_n: [20][33] + [20]
   long long last;
   // attribute the cycles since the previous tick to the phase that just ended (id = phase that STARTS now)
   __device__ void tick(int id) {
@@ -91,14 +129,23 @@ struct CudaWarpTeam {
   __device__ void wsync() { __syncwarp(); }
   __device__ double sum(double v) { return warp_sum(v); }
   __device__ double max(double v) { return warp_max(v); }
-  __device__ void sum_n(double *vals, int cnt) {
-    // butterfly level by level over all values: 20 independent shuffles per level instead of 20 dependent chains
+  // Sums over the warp of M2 = 20 values per lane, through shared memory: lane j adds column j of the 32 x 20 table
+  // (row stride 33: conflict free both ways) in four chains. A butterfly over all 20 values costs 200 shuffle
+  // instructions per call site, and the optimiser warp is bound by instruction fetch (the kernel is ~600 KB of code).
+  // Returns the 20 sums (shared memory).
+  __device__ const double *sum_n(const double *vals) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int j = 0; j < lbfgsb::M2; ++j) vals[j] += __shfl_xor_sync(0xffffffffu, vals[j], o);
+    for (int j = 0; j < lbfgsb::M2; ++j) red[j * 33 + lane] = vals[j];
+    __syncwarp();
+    if (lane < lbfgsb::M2) {
+      const double *r = red + lane * 33;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 2
+      for (int i = 0; i < 32; i += 4) { a0 += r[i]; a1 += r[i + 1]; a2 += r[i + 2]; a3 += r[i + 3]; }
+      red[lbfgsb::M2 * 33 + lane] = (a0 + a1) + (a2 + a3);
     }
-    (void)cnt;
+    __syncwarp();
+    return red + lbfgsb::M2 * 33;
   }
   __device__ void argmin(double &val, int &idx) {
 #pragma unroll
@@ -109,9 +156,19 @@ struct CudaWarpTeam {
     }
   }
   __device__ void formk_products(const lbfgsb::Work &w, int col, double theta) {
+    tick(23);
     if (lane == 0) { mb->cmd = CMD_FORMK; mb->col = col; mb->theta = theta; }
     lbeval::cta_sync();
+    tick(24);
     formk_products_block(w, col, theta);
+    tick(25);
+    lbeval::cta_sync();
+    tick(26);
+  }
+  __device__ void shift_pairs(const lbfgsb::Work &w) {
+    if (lane == 0) mb->cmd = CMD_SHIFT;
+    lbeval::cta_sync();
+    shift_pairs_block(w);
     lbeval::cta_sync();
   }
 };
@@ -152,7 +209,7 @@ struct LbArgs {
   int nvar_max;
 };
 
-template <int PT, int R, int TI>
+template <int PT, int R, int TI, bool PG>
 __global__ void __launch_bounds__(lbeval::NT_ALL, 1) lbfgsb_logei_kernel(LbArgs a) {   // 9 warps: one scheduler hosts 3 -> 168 registers
   extern __shared__ __align__(16) double sm[];
   const int b = a.run_idx ? a.run_idx[blockIdx.y] : blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
@@ -177,13 +234,14 @@ __global__ void __launch_bounds__(lbeval::NT_ALL, 1) lbfgsb_logei_kernel(LbArgs 
   obj.ctx.resident = a.resident != 0;
   q += obj.ctx.L.o_ring + a.ring_cap;
   lbfgsb::Work w;
-  double *wsy = a.wsy ? a.wsy + ((size_t)blockIdx.y * nchunks + chunk) * (size_t)(2 * lbfgsb::M) * a.nvar_max : nullptr;
-  lbfgsb::carve(w, nvar, q, wsy);
-  q += lbfgsb::work_doubles(nvar, wsy != nullptr);
+  double *wsy = PG ? a.wsy + ((size_t)blockIdx.y * nchunks + chunk) * (size_t)(2 * lbfgsb::M) * lbfgsb::pair_stride(a.nvar_max) : nullptr;
+  lbfgsb::carve<PG>(w, nvar, q, wsy);   // PG: the BFGS pairs live in the caller's workspace (global memory)
+  q += lbfgsb::work_doubles(nvar, PG);
   Mailbox *mb = reinterpret_cast<Mailbox *>(q); q += 2;
   obj.vals = q; q += 8;
   int *flag = reinterpret_cast<int *>(q); q += 2;
   long long *sprof = reinterpret_cast<long long *>(q); q += 32;   // cycle counters live in shared memory, flushed at the end
+  double *tred = q; q += 20 * 33 + 20;
   obj.pcount = pcount; obj.kk = kk;
   if (a.prof) {
     if (tid < 32) sprof[tid] = 0;
@@ -198,6 +256,9 @@ __global__ void __launch_bounds__(lbeval::NT_ALL, 1) lbfgsb_logei_kernel(LbArgs 
     __syncwarp();
   } else {
     const double *ic = a.ics + ((size_t)b * a.num_restarts + p0) * kmax;
+    // rows of S / Y beyond the pairs stored so far take part in the unguarded products (their sums are never read):
+    // start them from zero rather than from whatever the memory held
+    for (int i = tid; i < 2 * lbfgsb::M * w.ldp; i += LB_THREADS) w.ws[i] = 0.0;
     for (int i = tid; i < nvar; i += LB_THREADS) {
       const int p = i / kk, j = i % kk;
       const double lo = blo[j], hi = bhi[j];
@@ -209,6 +270,7 @@ __global__ void __launch_bounds__(lbeval::NT_ALL, 1) lbfgsb_logei_kernel(LbArgs 
       CudaWarpTeam tm;
       tm.tid = tid; tm.nt = 32; tm.lane = tid; tm.nl = 32; tm.w0 = true; tm.mb = mb; tm.wk = &w;
       tm.prof = a.prof ? sprof : nullptr;
+      tm.red = tred;
       tm.last = clock64();
       r = lbfgsb::minimize(tm, w, obj, a.maxiter, a.factr, a.pgtol, flag);
       if (tid == 0) { mb->cmd = CMD_EXIT; lbeval::signal_exit(obj.ctx); }
@@ -221,6 +283,9 @@ __global__ void __launch_bounds__(lbeval::NT_ALL, 1) lbfgsb_logei_kernel(LbArgs 
           obj.run(w.x, w.g);
         } else if (c == CMD_FORMK) {
           formk_products_block(w, mb->col, mb->theta);
+          lbeval::cta_sync();
+        } else if (c == CMD_SHIFT) {
+          shift_pairs_block(w);
           lbeval::cta_sync();
         } else {
           break;
@@ -242,7 +307,7 @@ __global__ void __launch_bounds__(lbeval::NT_ALL, 1) lbfgsb_logei_kernel(LbArgs 
 }
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
-constexpr int TAIL_DOUBLES = 2 + 8 + 2 + 32 + 8;
+constexpr int TAIL_DOUBLES = 2 + 8 + 2 + 32 + 20 * 33 + 20 + 8;
 
 // Shared-memory plan of one launch: panel height, ring capacity, where the BFGS pairs live.
 struct Plan {
@@ -260,6 +325,7 @@ inline bool make_plan(int PT, int n, int kmax, int nvar_max, bool have_ws, Plan 
     const size_t work = lbfgsb::work_doubles(nvar_max, pairs_global != 0) + TAIL_DOUBLES;
     for (int pass = 0; pass < 3; ++pass) {
       const int R = pass == 0 ? 32 : pass == 1 ? 16 : 8;
+      if (R != 8 && (pl.TI > 8 || (pairs_global && R == 32))) continue;   // kernel variants that are not instantiated
       const lbeval::Layout L = lbeval::make_layout(PT, kmax, n, R);
       const size_t fixed = ((size_t)L.o_ring + work) * sizeof(double);
       if (fixed >= SMEM_LIMIT) continue;
@@ -279,12 +345,12 @@ inline bool make_plan(int PT, int n, int kmax, int nvar_max, bool have_ws, Plan 
   return false;
 }
 
-template <int PT, int R, int TI>
+template <int PT, int R, int TI, bool PG>
 int launch_one(const LbArgs &a, int nsel, size_t smem, cudaStream_t st) {
   const int nchunks = (a.num_restarts + a.batch_limit - 1) / a.batch_limit;
-  PCABO_CUDA_CHECK(cudaFuncSetAttribute(lbfgsb_logei_kernel<PT, R, TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PCABO_CUDA_CHECK(cudaFuncSetAttribute(lbfgsb_logei_kernel<PT, R, TI, PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(nchunks, nsel);
-  lbfgsb_logei_kernel<PT, R, TI><<<grid, lbeval::NT_ALL, smem, st>>>(a);
+  lbfgsb_logei_kernel<PT, R, TI, PG><<<grid, lbeval::NT_ALL, smem, st>>>(a);
   PCABO_LAUNCH_CHECK();
   return PCABO_OK;
 }
@@ -293,15 +359,25 @@ int launch(LbArgs &a, int nsel, double *workspace, long long workspace_doubles, 
   constexpr int PT = 5;
   const int nchunks = (a.num_restarts + a.batch_limit - 1) / a.batch_limit;
   a.nvar_max = a.batch_limit * a.k_bound;
-  const long long ws_need = (long long)nsel * nchunks * 2 * lbfgsb::M * a.nvar_max;
+  const long long ws_need = (long long)nsel * nchunks * 2 * lbfgsb::M * lbfgsb::pair_stride(a.nvar_max);
   Plan pl;
   if (!make_plan(PT, a.m.n, a.m.kmax, a.nvar_max, workspace != nullptr && workspace_doubles >= ws_need, pl))
     return PCABO_E_UNSUPPORTED;
   a.ring_cap = pl.ring_cap; a.resident = pl.resident; a.wsy = pl.pairs_global ? workspace : nullptr;
-  if (pl.R == 32 && pl.TI <= 8) return launch_one<PT, 32, 8>(a, nsel, pl.smem, st);
-  if (pl.R == 32) return PCABO_E_UNSUPPORTED;
-  if (pl.TI <= 8) return pl.R == 16 ? launch_one<PT, 16, 8>(a, nsel, pl.smem, st) : launch_one<PT, 8, 8>(a, nsel, pl.smem, st);
-  if (pl.TI <= 17) return pl.R == 16 ? launch_one<PT, 16, 17>(a, nsel, pl.smem, st) : launch_one<PT, 8, 17>(a, nsel, pl.smem, st);
+  // instantiated: shared-memory pairs with (R, TI) = (32, 8), (16, 8), (8, 8), (8, 17); workspace pairs with (16, 8),
+  // (8, 8), (8, 17). make_plan only produces these (n > 512 always streams 8-row panels).
+  if (!pl.pairs_global) {
+    if (pl.TI <= 8) {
+      if (pl.R == 32) return launch_one<PT, 32, 8, false>(a, nsel, pl.smem, st);
+      if (pl.R == 16) return launch_one<PT, 16, 8, false>(a, nsel, pl.smem, st);
+      return launch_one<PT, 8, 8, false>(a, nsel, pl.smem, st);
+    }
+    if (pl.TI <= 17 && pl.R == 8) return launch_one<PT, 8, 17, false>(a, nsel, pl.smem, st);
+  } else {
+    if (pl.TI <= 8 && pl.R == 16) return launch_one<PT, 16, 8, true>(a, nsel, pl.smem, st);
+    if (pl.TI <= 8 && pl.R == 8) return launch_one<PT, 8, 8, true>(a, nsel, pl.smem, st);
+    if (pl.TI <= 17 && pl.R == 8) return launch_one<PT, 8, 17, true>(a, nsel, pl.smem, st);
+  }
   return PCABO_E_UNSUPPORTED;
 }
 
@@ -316,7 +392,7 @@ extern "C" long long pcabo_lbfgsb_workspace_doubles(int n, int kmax, int k_bound
   if (make_plan(5, n, kmax, nvar_max, false, pl)) return 0;          // everything fits shared memory
   if (!make_plan(5, n, kmax, nvar_max, true, pl)) return -1;         // does not fit either way
   const int nchunks = (num_restarts + batch_limit - 1) / batch_limit;
-  return (long long)nsel * nchunks * 2 * lbfgsb::M * nvar_max;
+  return (long long)nsel * nchunks * 2 * lbfgsb::M * lbfgsb::pair_stride(nvar_max);
 }
 
 extern "C" int pcabo_lbfgsb_plan(int n, int kmax, int k_bound, int batch_limit, int have_workspace, int *plan6) {

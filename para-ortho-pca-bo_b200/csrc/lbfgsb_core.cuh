@@ -48,14 +48,16 @@ struct HostTeam {
   void wsync() {}
   double sum(double v) { return v; }
   double max(double v) { return v; }
-  void sum_n(double *, int) {}
+  const double *sum_n(const double *v) { return v; }   // sums over the team of M2 values per thread
   void argmin(double &, int &) {}
   inline void formk_products(const struct Work &w, int col, double theta);
+  inline void shift_pairs(const struct Work &w);
   void tick(int) {}
 };
 
 struct Work {
   int n;
+  int ldp;                                       // row stride of ws / wy (pair_stride(n))
   double *x, *l, *u, *g, *z, *d, *t, *r, *xp;  // [n]
   double *ws, *wy;                               // [M][n]  stored pairs, oldest first
   double *sy, *ss, *wt, *jinv;                   // [M][M]
@@ -67,18 +69,28 @@ struct Work {
   double *rsy, *rsq, *wt_rd, *wn_rd;
 };
 
-// pairs_external: the BFGS pairs ws / wy (2 M n doubles) live in a buffer of the caller's instead of the work area
+// Row stride of the stored pairs: a multiple of 8 congruent 8 mod 16, so that consecutive rows start in opposite halves of
+// the shared-memory banks (the block-wide products of formk read 8 consecutive entries of 4 rows per warp; with the
+// stride n = 5 k a multiple of 16 that was a 4-way bank conflict: 12 k cycles per formk).
+LB_HD inline int pair_stride(int n) { return ((n + 15) & ~15) + 8; }
+
+// pairs_external: the BFGS pairs ws / wy (2 M pair_stride(n) doubles) live in a buffer of the caller's instead of the work area
 LB_HD inline size_t work_doubles(int n, bool pairs_external = false) {
-  return (size_t)9 * n + (pairs_external ? 0 : (size_t)2 * M * n) + 4 * M * M + M2 * M2 + 5 * M2 + n + (n + 1) / 2 + 4;
+  return (size_t)9 * n + (pairs_external ? 0 : (size_t)2 * M * pair_stride(n)) + 4 * M * M + M2 * M2 + 5 * M2 + n + (n + 1) / 2 + 4;
 }
 
+// EXT (compile time): the pairs live in `pairs` (global memory) instead of the work area. A run-time choice would hide
+// the address space of ws / wy from the compiler, which then issues generic loads (LD.E) for them everywhere instead of
+// shared-memory loads (LDS): measured 3-4x slower phases.
+template <bool EXT = false>
 LB_HD inline void carve(Work &w, int n, double *base, double *pairs = nullptr) {
   w.n = n;
   double *q = base;
   w.x = q; q += n; w.l = q; q += n; w.u = q; q += n; w.g = q; q += n; w.z = q; q += n;
   w.d = q; q += n; w.t = q; q += n; w.r = q; q += n; w.xp = q; q += n;
-  if (pairs) { w.ws = pairs; w.wy = pairs + M * n; }
-  else { w.ws = q; q += M * n; w.wy = q; q += M * n; }
+  w.ldp = pair_stride(n);
+  if (EXT) { w.ws = pairs; w.wy = pairs + M * w.ldp; }
+  else { w.ws = q; q += M * w.ldp; w.wy = q; q += M * w.ldp; }
   w.sy = q; q += M * M; w.ss = q; q += M * M; w.wt = q; q += M * M; w.jinv = q; q += M * M;
   w.rsy = w.jinv; w.rsq = w.jinv + M; w.wt_rd = w.jinv + 2 * M; w.wn_rd = w.jinv + 3 * M;
   w.wn = q; q += M2 * M2;
@@ -377,11 +389,9 @@ LB_PHASE void cauchy(T &tm, Work &w, int col, double theta, double sbgnrm, int &
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-        for (int j = 0; j < M; ++j) {
-          if (j < col) {
-            part[j] += wyx[j * n + i] * neggi;
-            part[M + j] += wsx[j * n + i] * neggi;
-          }
+        for (int j = 0; j < M; ++j) {   // (rows >= col hold stale but finite pairs: their sums are never read)
+          part[j] += wyx[j * w.ldp + i] * neggi;
+          part[M + j] += wsx[j * w.ldp + i] * neggi;
         }
         if (neggi < 0.0) tb = tl / (-neggi);
         else if (neggi > 0.0) tb = tu / neggi;
@@ -394,14 +404,12 @@ LB_PHASE void cauchy(T &tm, Work &w, int col, double theta, double sbgnrm, int &
   }
   f1 = tm.sum(f1);
   const int nbreak = (int)(tm.sum(nbrk_local) + 0.5);
-  tm.sum_n(part, M2);
-  if (tm.tid == 0) {
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-    for (int j = 0; j < M; ++j)
-      if (j < col) { w.p[j] = part[j]; w.p[col + j] = theta * part[M + j]; }
-    for (int j = 0; j < 2 * col; ++j) w.c[j] = 0.0;
+  {
+    const double *S = tm.sum_n(part);
+    if (tm.tid == 0) {
+      for (int j = 0; j < col; ++j) { w.p[j] = S[j]; w.p[col + j] = theta * S[M + j]; }
+      for (int j = 0; j < 2 * col; ++j) w.c[j] = 0.0;
+    }
   }
   tm.sync();
   tm.tick(11);
@@ -455,7 +463,7 @@ LB_PHASE void cauchy(T &tm, Work &w, int col, double theta, double sbgnrm, int &
     if (col > 0) {
       for (int j = tm.tid; j < 2 * col; j += tm.nt) {
         w.c[j] += dt * w.p[j];
-        w.wbp[j] = (j < col) ? w.wy[j * n + ibp] : theta * w.ws[(j - col) * n + ibp];
+        w.wbp[j] = (j < col) ? w.wy[j * w.ldp + ibp] : theta * w.ws[(j - col) * w.ldp + ibp];
       }
       tm.sync();
       bmv(tm, w, col, w.wbp, w.v);
@@ -494,21 +502,21 @@ LB_HD inline void formk_products_range(const Work &w, int col, double theta, int
     if (blk == 0) {          // (1,1), i <= j
       if (i > j) continue;
       double s = 0.0;
-      for (int k = 0; k < n; ++k) if (w.iwhere[k] <= 0) s += w.wy[i * n + k] * w.wy[j * n + k];
+      for (int k = 0; k < n; ++k) if (w.iwhere[k] <= 0) s += w.wy[i * w.ldp + k] * w.wy[j * w.ldp + k];
       w.wn[i * M2 + j] = s / theta + ((i == j) ? w.sy[i * M + i] : 0.0);
     } else if (blk == 1) {   // (2,2), i <= j
       if (i > j) continue;
       double s = 0.0;
-      for (int k = 0; k < n; ++k) if (w.iwhere[k] > 0) s += w.ws[i * n + k] * w.ws[j * n + k];
+      for (int k = 0; k < n; ++k) if (w.iwhere[k] > 0) s += w.ws[i * w.ldp + k] * w.ws[j * w.ldp + k];
       w.wn[(col + i) * M2 + col + j] = s * theta;
     } else {                 // (1,2): row jy = i (Y index), column col + iy, iy = j (S index)
       const int jy = i, iy = j;
       double s = 0.0;
       if (jy < iy) {         // -L_a(iy, jy): active variables
-        for (int k = 0; k < n; ++k) if (w.iwhere[k] > 0) s += w.ws[iy * n + k] * w.wy[jy * n + k];
+        for (int k = 0; k < n; ++k) if (w.iwhere[k] > 0) s += w.ws[iy * w.ldp + k] * w.wy[jy * w.ldp + k];
         s = -s;
       } else {               // R_z(iy, jy): free variables
-        for (int k = 0; k < n; ++k) if (w.iwhere[k] <= 0) s += w.ws[iy * n + k] * w.wy[jy * n + k];
+        for (int k = 0; k < n; ++k) if (w.iwhere[k] <= 0) s += w.ws[iy * w.ldp + k] * w.wy[jy * w.ldp + k];
       }
       w.wn[jy * M2 + col + iy] = s;
     }
@@ -516,6 +524,10 @@ LB_HD inline void formk_products_range(const Work &w, int col, double theta, int
 }
 
 inline void HostTeam::formk_products(const Work &w, int col, double theta) { formk_products_range(w, col, theta, 0, 1); }
+inline void HostTeam::shift_pairs(const Work &w) {
+  for (int i = 0; i < w.n; ++i)
+    for (int j = 0; j < M - 1; ++j) { w.ws[j * w.ldp + i] = w.ws[(j + 1) * w.ldp + i]; w.wy[j * w.ldp + i] = w.wy[(j + 1) * w.ldp + i]; }
+}
 
 // LEL^T factorisation of the indefinite K (formk). Free set: iwhere <= 0. Returns 0 or a failure code.
 template <class T>
@@ -570,7 +582,7 @@ LB_PHASE void cmprlb(T &tm, Work &w, int col, double theta) {
       double ri = 0.0;
       if (iwx[i] <= 0) {
         ri = -theta * (zx[i] - xx[i]) - gx[i];
-        for (int j = 0; j < col; ++j) ri += wyx[j * n + i] * px[j] + wsx[j * n + i] * (theta * px[col + j]);
+        for (int j = 0; j < col; ++j) ri += wyx[j * w.ldp + i] * px[j] + wsx[j * w.ldp + i] * (theta * px[col + j]);
       }
       rx[i] = ri;
     }
@@ -594,17 +606,13 @@ LB_PHASE void subsm(T &tm, Work &w, int col, double theta) {
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-      for (int j = 0; j < M; ++j)
-        if (j < col) { part[j] += w.wy[j * n + i] * di; part[M + j] += w.ws[j * n + i] * di; }
+      for (int j = 0; j < M; ++j) { part[j] += w.wy[j * w.ldp + i] * di; part[M + j] += w.ws[j * w.ldp + i] * di; }
     }
   }
-  tm.sum_n(part, M2);
-  if (tm.tid == 0) {
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-    for (int j = 0; j < M; ++j)
-      if (j < col) { w.wv[j] = part[j]; w.wv[col + j] = theta * part[M + j]; }
+  {
+    const double *S = tm.sum_n(part);
+    if (tm.tid == 0)
+      for (int j = 0; j < col; ++j) { w.wv[j] = S[j]; w.wv[col + j] = theta * S[M + j]; }
   }
   tm.sync();
   // wv <- K^-1 wv through the LEL^T factor
@@ -630,7 +638,7 @@ LB_PHASE void subsm(T &tm, Work &w, int col, double theta) {
     w.xp[i] = w.z[i];
     if (w.iwhere[i] <= 0) {
       double di = w.r[i];
-      for (int j = 0; j < col; ++j) di += w.wy[j * n + i] * w.wv[j] * rtheta + w.ws[j * n + i] * w.wv[col + j];
+      for (int j = 0; j < col; ++j) di += w.wy[j * w.ldp + i] * w.wv[j] * rtheta + w.ws[j * w.ldp + i] * w.wv[col + j];
       di *= rtheta;
       w.r[i] = di;  // r now holds the Newton direction on the free variables
       double xk = w.z[i] + di;
@@ -808,17 +816,7 @@ LB_PHASE int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, do
                        int *flag) {
   const int n = w.n;
   if (col == M) {  // drop the oldest pair
-    for (int i = tm.tid; i < n; i += tm.nt) {   // each thread shifts its own columns: loads first, then stores
-      double a[M - 1], b[M - 1];
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-      for (int j = 0; j < M - 1; ++j) { a[j] = w.ws[(j + 1) * n + i]; b[j] = w.wy[(j + 1) * n + i]; }
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-      for (int j = 0; j < M - 1; ++j) { w.ws[j * n + i] = a[j]; w.wy[j * n + i] = b[j]; }
-    }
+    tm.shift_pairs(w);   // rows 1..M-1 of S and Y move up by one (the team may hand this to more threads than itself)
     tm.sync();
 #ifdef __CUDA_ARCH__
     if constexpr (T::kWarpRegs) {
@@ -842,7 +840,7 @@ LB_PHASE int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, do
     col = M - 1;
   }
   const int c = col;
-  for (int i = tm.tid; i < n; i += tm.nt) { w.ws[c * n + i] = w.d[i]; w.wy[c * n + i] = w.r[i]; }
+  for (int i = tm.tid; i < n; i += tm.nt) { w.ws[c * w.ldp + i] = w.d[i]; w.wy[c * w.ldp + i] = w.r[i]; }
   tm.sync();
   tm.tick(13);
   theta = rr / dr;
@@ -857,18 +855,15 @@ LB_PHASE int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, do
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-    for (int j = 0; j < M; ++j)
-      if (j < c) { part[j] += di * w.wy[j * n + i]; part[M + j] += w.ws[j * n + i] * di; }
+    for (int j = 0; j < M; ++j) { part[j] += di * w.wy[j * w.ldp + i]; part[M + j] += w.ws[j * w.ldp + i] * di; }
   }
-  tm.sum_n(part, M2);
-  if (tm.tid == 0) {
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-    for (int j = 0; j < M; ++j)
-      if (j < c) { w.sy[c * M + j] = part[j]; w.ss[j * M + c] = part[M + j]; }
-    w.ss[c * M + c] = (stp == 1.0) ? dtd : stp * stp * dtd;
-    w.sy[c * M + c] = dr;
+  {
+    const double *S = tm.sum_n(part);
+    if (tm.tid == 0) {
+      for (int j = 0; j < c; ++j) { w.sy[c * M + j] = S[j]; w.ss[j * M + c] = S[M + j]; }
+      w.ss[c * M + c] = (stp == 1.0) ? dtd : stp * stp * dtd;
+      w.sy[c * M + c] = dr;
+    }
   }
   col = c + 1;
   tm.sync();
@@ -912,93 +907,104 @@ LB_HD Result minimize(T &tm, Work &w, Fn &fn, int maxiter, double factr, double 
     w.iwhere[i] = (w.u[i] - w.l[i] <= 0.0) ? 3 : 0;
   }
   tm.sync();
-  double f = fn(tm, w.x, w.g);
-  res.nfev = 1;
+  // The objective has ONE call site (inside the line-search loop): the first pass of the main loop only evaluates f, g at
+  // the start point. On the GPU the evaluation is inlined at its call site and the optimiser warp is bound by
+  // instruction fetch, so every further copy of it costs.
+  double f = 0.0;
   int col = 0;
   double theta = 1.0;
   bool updatd = false;
   (void)updatd;
-  double sbgnrm = projgr(tm, w);
-  if (sbgnrm <= pgtol) { res.status = CONV_PGTOL; res.f = f; return res; }
+  double sbgnrm = 0.0;
   int iter = 0;
   int passes = 0;
+  bool first = true;
   while (true) {
-    // every pass either completes an iteration or discards the BFGS memory once; the guard only fires on NaN storms
-    if (++passes > 3 * maxiter + 20) { res.status = ABNORMAL; break; }
-    int nseg;
-    tm.tick(0);
-    cauchy(tm, w, col, theta, sbgnrm, nseg);
-    tm.tick(1);
-    // free variables at the Cauchy point
-    double nfree_l = 0.0;
-    for (int i = tm.tid; i < n; i += tm.nt) nfree_l += (w.iwhere[i] <= 0) ? 1.0 : 0.0;
-    const int nfree = (int)(tm.sum(nfree_l) + 0.5);
-    if (nfree != 0 && col != 0) {
-      const int info = formk(tm, w, col, theta, flag);
-      if (info != 0) {  // refresh the memory and restart the iteration
-        col = 0; theta = 1.0; updatd = false;
-        continue;
-      }
-      tm.tick(2);
-      cmprlb(tm, w, col, theta);
-      tm.tick(3);
-      subsm(tm, w, col, theta);
-      tm.tick(4);
-    }
-    // search direction and line search
-    double dtd_l = 0.0;
-    for (int i = tm.tid; i < n; i += tm.nt) {
-      const double di = w.z[i] - w.x[i];
-      w.d[i] = di;
-      dtd_l += di * di;
-    }
-    const double dtd = tm.sum(dtd_l);
-    const double dnorm = sqrt(dtd);
-    (void)dnorm;
-    double stpmx = BIG;
-    if (iter == 0) stpmx = 1.0;
-    else {
-      double smx = BIG;
-      for (int i = tm.tid; i < n; i += tm.nt) {
-        const double a1 = w.d[i];
-        if (a1 < 0.0) {
-          const double a2 = w.l[i] - w.x[i];
-          if (a2 >= 0.0) smx = 0.0;
-          else if (a1 * smx < a2) smx = a2 / a1;
-        } else if (a1 > 0.0) {
-          const double a2 = w.u[i] - w.x[i];
-          if (a2 <= 0.0) smx = 0.0;
-          else if (a1 * smx > a2) smx = a2 / a1;
-        }
-      }
-      stpmx = -tm.max(-smx);
-    }
-    double stp = 1.0;  // boxed problem: the first step is 1 as well
-    for (int i = tm.tid; i < n; i += tm.nt) { w.t[i] = w.x[i]; w.r[i] = w.g[i]; }
-    tm.sync();
-    const double fold = f;
+    double dtd = 0.0, stpmx = BIG, stp = 1.0, fold = f, gd = 0.0, gdold = 0.0;
     int ifun = 0, iback = 0;
-    double gd = dot(tm, w.g, w.d, n);
-    const double gdold = gd;
     LineSearch ls;
     bool ls_failed = false;
-    if (gd >= 0.0) ls_failed = true;  // not a descent direction
-    else if (dcsrch_start(ls, f, gd, stp, stpmx) < 0) ls_failed = true;
-    tm.tick(5);
+    if (!first) {
+      // every pass either completes an iteration or discards the BFGS memory once; the guard only fires on NaN storms
+      if (++passes > 3 * maxiter + 20) { res.status = ABNORMAL; break; }
+      int nseg;
+      tm.tick(0);
+      cauchy(tm, w, col, theta, sbgnrm, nseg);
+      tm.tick(1);
+      // free variables at the Cauchy point
+      double nfree_l = 0.0;
+      for (int i = tm.tid; i < n; i += tm.nt) nfree_l += (w.iwhere[i] <= 0) ? 1.0 : 0.0;
+      const int nfree = (int)(tm.sum(nfree_l) + 0.5);
+      if (nfree != 0 && col != 0) {
+        const int info = formk(tm, w, col, theta, flag);
+        if (info != 0) {  // refresh the memory and restart the iteration
+          col = 0; theta = 1.0; updatd = false;
+          continue;
+        }
+        tm.tick(2);
+        cmprlb(tm, w, col, theta);
+        tm.tick(3);
+        subsm(tm, w, col, theta);
+        tm.tick(4);
+      }
+      // search direction and line search
+      double dtd_l = 0.0;
+      for (int i = tm.tid; i < n; i += tm.nt) {
+        const double di = w.z[i] - w.x[i];
+        w.d[i] = di;
+        dtd_l += di * di;
+      }
+      dtd = tm.sum(dtd_l);
+      if (iter == 0) stpmx = 1.0;
+      else {
+        double smx = BIG;
+        for (int i = tm.tid; i < n; i += tm.nt) {
+          const double a1 = w.d[i];
+          if (a1 < 0.0) {
+            const double a2 = w.l[i] - w.x[i];
+            if (a2 >= 0.0) smx = 0.0;
+            else if (a1 * smx < a2) smx = a2 / a1;
+          } else if (a1 > 0.0) {
+            const double a2 = w.u[i] - w.x[i];
+            if (a2 <= 0.0) smx = 0.0;
+            else if (a1 * smx > a2) smx = a2 / a1;
+          }
+        }
+        stpmx = -tm.max(-smx);
+      }
+      // (boxed problem: the first step is 1 as well)
+      for (int i = tm.tid; i < n; i += tm.nt) { w.t[i] = w.x[i]; w.r[i] = w.g[i]; }
+      tm.sync();
+      gd = dot(tm, w.g, w.d, n);
+      gdold = gd;
+      if (gd >= 0.0) ls_failed = true;  // not a descent direction
+      else if (dcsrch_start(ls, f, gd, stp, stpmx) < 0) ls_failed = true;
+      tm.tick(5);
+    }
     if (!ls_failed) {
       while (true) {
-        ++ifun; ++res.nfev; iback = ifun - 1;
-        if (stp == 1.0) { for (int i = tm.tid; i < n; i += tm.nt) w.x[i] = w.z[i]; }
-        else { for (int i = tm.tid; i < n; i += tm.nt) w.x[i] = stp * w.d[i] + w.t[i]; }
-        tm.sync();
+        if (!first) {
+          ++ifun; ++res.nfev; iback = ifun - 1;
+          if (stp == 1.0) { for (int i = tm.tid; i < n; i += tm.nt) w.x[i] = w.z[i]; }
+          else { for (int i = tm.tid; i < n; i += tm.nt) w.x[i] = stp * w.d[i] + w.t[i]; }
+          tm.sync();
+        }
         tm.tick(6);
         f = fn(tm, w.x, w.g);
         tm.tick(7);
+        if (first) break;
         gd = dot(tm, w.g, w.d, n);
         const int r = dcsrch_step(ls, f, gd, stp, stpmx);
         if (r != 0) break;
         if (iback + 1 >= MAXLS) { ls_failed = true; break; }
       }
+    }
+    if (first) {
+      first = false;
+      res.nfev = 1;
+      sbgnrm = projgr(tm, w);
+      if (sbgnrm <= pgtol) { res.status = CONV_PGTOL; break; }
+      continue;
     }
     if (ls_failed) {
       // restore the previous iterate

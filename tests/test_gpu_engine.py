@@ -444,7 +444,7 @@ def test_device_optimizer_workspace_and_no_host_fallback(monkeypatch):
     from pcabo_b200.lib import PcaboError
     assert ops.lbfgsb_workspace_doubles(450, 40, 40) == 0 and ops.lbfgsb_workspace_doubles(150, 10, 10) == 0
     need = ops.lbfgsb_workspace_doubles(1050, 100, 90, 10, 5, 3)
-    assert need == 3 * 2 * 2 * 10 * 5 * 90                      # runs x chunks x (S, Y) x m x nvar
+    assert need == 3 * 2 * 2 * 10 * (((5 * 90 + 15) & ~15) + 8)   # runs x chunks x (S, Y) x m x padded row of nvar
     assert ops.lbfgsb_fits(1050, 100, 90) and ops.lbfgsb_fits(1050, 100, 100)
     prob = BatchedBBOB([15, 16], [0, 1], 10, device="cuda")
     e = BatchedBOEngine(prob, 10, prob.bounds, 150, 30, [15100, 16101], optimizer="device")
