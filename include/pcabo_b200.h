@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PCABO_ABI_VERSION 2   /* 2: pcabo_gp_model gained Wp / wp_stride (packed W for the bulk-copy engine) */
+#define PCABO_ABI_VERSION 2   /* 2: pcabo_gp_model gained Wp / wp_stride (packed W for the bulk-copy engine) and lengthscales */
 
 #define PCABO_OK 0
 #define PCABO_E_INVALID (-1)      /* bad argument (null pointer, n < 2, ...) */
@@ -68,6 +68,7 @@ typedef struct pcabo_gp_model {
   const double *Zn;         /* [B][ld_n][kmax] normalised training inputs, row-major */
   const double *Wp;         /* [B][wp_stride] W packed in 8-row groups by pcabo_gp_pack_w (pcabo_lbfgsb_logei* only) */
   long long wp_stride;      /* doubles between the packed W of consecutive runs (even, >= pcabo_gp_packed_doubles(n)) */
+  const double *lengthscales; /* [B] per-run Matern lengthscale (opt-in hyper-parameter fit) or NULL: `lengthscale` for all */
 } pcabo_gp_model;
 
 /* Rank weights + weighted PCA + projection, one CTA per run.
@@ -116,6 +117,17 @@ int pcabo_gp_fit_jitter(int B, int n, int kmax, int ld_n, int mode,
                         double *ymean, double *ystd, double *ZnT, double *Zn, double *L, double *W, double *WT,
                         double *alpha, int *info, void *stream);
 
+/* pcabo_gp_fit_jitter with per-run hyper-parameters lengthscales [B] / noises [B] (either may be NULL: the scalar is
+ * used). The reference never fits its GP; this is the evaluation step of the opt-in hyper-parameter fit
+ * (pcabo_b200/hyperfit.py: maximise (MLL + log p_LogNormal(-4,1)(noise)) / n like botorch's fit_gpytorch_mll would). */
+int pcabo_gp_fit_hyper(int B, int n, int kmax, int ld_n, int mode,
+                       const double *Z, const int *k, const double *f, const double *fix_lo, const double *fix_hi,
+                       double lengthscale, double noise, const double *lengthscales, const double *noises,
+                       const double *jitter,
+                       double *norm_off, double *norm_coef, double *box_lo, double *box_hi,
+                       double *ymean, double *ystd, double *ZnT, double *Zn, double *L, double *W, double *WT,
+                       double *alpha, int *info, void *stream);
+
 /* W (from pcabo_gp_fit) repacked for the bulk-copy (TMA) engine: the lower triangle in groups of 8 rows, group g =
  * rows 8g..8g+7 x columns 0..8g+7 (zero right of the diagonal and below row n), row stride 8g + (g odd ? 12 : 20)
  * doubles (a multiple of 4 congruent 4 mod 16: bank-conflict free for both FP64 MMA operand patterns), groups back to
@@ -134,6 +146,11 @@ int pcabo_gp_mll(int B, int n, int ld_n, const double *f, const double *ymean, c
  * building block of an opt-in hyper-parameter fit (north_star).                                                   */
 int pcabo_gp_mll_grad(int B, int n, int kmax, int ld_n, const int *k, const double *Zn, const double *W,
                       const double *alpha, double lengthscale, double *grad, void *stream);
+
+/* pcabo_gp_mll_grad with per-run lengthscales [B] (NULL: the scalar). */
+int pcabo_gp_mll_grad_hyper(int B, int n, int kmax, int ld_n, const int *k, const double *Zn, const double *W,
+                            const double *alpha, double lengthscale, const double *lengthscales, double *grad,
+                            void *stream);
 
 /* log-EI (and optionally its gradient, posterior mean and sigma) at npts raw-space points per run.
  *   X [B][npts][kmax]; val [B][npts]; grad [B][npts][kmax] or NULL; mu, sigma [B][npts] or NULL.               */

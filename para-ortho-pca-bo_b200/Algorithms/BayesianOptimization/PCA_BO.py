@@ -70,6 +70,8 @@ class PCA_BO(AbstractBayesianOptimizer):
             raise NotImplementedError("visualize=True needs the reference's matplotlib Visualizer, which is outside "
                                       "the accelerated hot path")
         self.optimizer_backend = kwargs.get("optimizer_backend", "scipy")
+        # extension (not in the reference, which never fits its GP): per-iteration MAP fit of (lengthscale, noise)
+        self.fit_hyperparameters = bool(kwargs.get("fit_hyperparameters", False))
         self.__z_evals = []
         self._engine = None
 
@@ -96,7 +98,8 @@ class PCA_BO(AbstractBayesianOptimizer):
                               num_restarts=self.__torch_config["NUM_RESTARTS"],
                               raw_samples=self.__torch_config["RAW_SAMPLES"],
                               np_rngs=[np.random.mtrand._rand], torch_gens=[torch.default_generator],
-                              profile_timing=True, acquisition=self.acquisition_function_name)
+                              profile_timing=True, acquisition=self.acquisition_function_name,
+                              fit_hyperparameters=self.fit_hyperparameters)
         eng.attach_history([self.x_evals], [self.f_evals])
         self._engine = eng
         for _ in range(self.budget - self.n_DoE):

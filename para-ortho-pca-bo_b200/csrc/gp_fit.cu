@@ -133,7 +133,7 @@ constexpr int KT = 64;  // kernel-matrix tile
 
 __global__ void __launch_bounds__(256) gp_kmat_kernel(int n, int kmax, int ld_n, const int *k, const double *ZnT,
                                                      double inv_ell2, double noise, const double *jitter,
-                                                     double *Kout) {
+                                                     const double *ls_run, const double *nz_run, double *Kout) {
   // grid: (tiles_lower, B); tile (ti >= tj)
   __shared__ double zi[8][KT];
   __shared__ double zj[8][KT];
@@ -144,7 +144,9 @@ __global__ void __launch_bounds__(256) gp_kmat_kernel(int n, int kmax, int ld_n,
   const int kk = k ? k[b] : kmax;
   const double *Zb = ZnT + (size_t)b * kmax * ld_n;
   double *Kb = Kout + (size_t)b * ld_n * ld_n;
-  const double diag_add = noise + (jitter ? jitter[b] : 0.0);   // psd_safe_cholesky adds its jitter to the diagonal
+  // per-run hyper-parameters (opt-in fit) override the reference's fixed prior values
+  if (ls_run) inv_ell2 = 1.0 / (ls_run[b] * ls_run[b]);
+  const double diag_add = (nz_run ? nz_run[b] : noise) + (jitter ? jitter[b] : 0.0);   // psd_safe_cholesky adds its jitter to the diagonal
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;  // thread computes rows ty*4.., cols tx*4..
   double acc[4][4];
 #pragma unroll
@@ -503,6 +505,7 @@ constexpr int GK = 32;   // rows of W per staging step
 
 __global__ void __launch_bounds__(256) gp_mll_grad_kernel(int n, int kmax, int ld_n, const int *k, const double *Zn,
                                                          const double *W, const double *alpha, double lengthscale,
+                                                         const double *ls_run,
                                                          double *grad /* [B][2]: d/dl, d/dnoise */) {
   __shared__ double wi[GK][GT + 1], wj[GK][GT + 1];
   __shared__ double red[34];
@@ -545,7 +548,7 @@ __global__ void __launch_bounds__(256) gp_mll_grad_kernel(int n, int kmax, int l
   }
   // contributions of this tile: off-diagonal tiles stand for both (i, j) and (j, i)
   const double mult = (ti == tj) ? 1.0 : 2.0;
-  const double inv_l = 1.0 / lengthscale;
+  const double inv_l = 1.0 / (ls_run ? ls_run[b] : lengthscale);
   double g_l = 0.0, g_n = 0.0;
 #pragma unroll
   for (int u = 0; u < 2; ++u)
@@ -574,25 +577,33 @@ __global__ void __launch_bounds__(256) gp_mll_grad_kernel(int n, int kmax, int l
 
 }  // namespace
 
-extern "C" int pcabo_gp_mll_grad(int B, int n, int kmax, int ld_n, const int *k, const double *Zn, const double *W,
-                                 const double *alpha, double lengthscale, double *grad, void *stream) {
-  if (B <= 0 || n < 1 || kmax < 1 || ld_n < n || !Zn || !W || !alpha || !grad || !(lengthscale > 0.0)) return PCABO_E_INVALID;
+extern "C" int pcabo_gp_mll_grad_hyper(int B, int n, int kmax, int ld_n, const int *k, const double *Zn, const double *W,
+                                       const double *alpha, double lengthscale, const double *lengthscales, double *grad,
+                                       void *stream) {
+  if (B <= 0 || n < 1 || kmax < 1 || ld_n < n || !Zn || !W || !alpha || !grad || (!lengthscales && !(lengthscale > 0.0)))
+    return PCABO_E_INVALID;
   cudaStream_t st = as_stream(stream);
   PCABO_CUDA_CHECK(cudaMemsetAsync(grad, 0, sizeof(double) * 2 * B, st));
   const int nt = (n + GT - 1) / GT;
   dim3 grid(nt * (nt + 1) / 2, B);
-  gp_mll_grad_kernel<<<grid, 256, 0, st>>>(n, kmax, ld_n, k, Zn, W, alpha, lengthscale, grad);
+  gp_mll_grad_kernel<<<grid, 256, 0, st>>>(n, kmax, ld_n, k, Zn, W, alpha, lengthscale, lengthscales, grad);
   PCABO_LAUNCH_CHECK();
   return PCABO_OK;
 }
 
-extern "C" int pcabo_gp_fit_jitter(int B, int n, int kmax, int ld_n, int mode, const double *Z, const int *k,
-                                   const double *f, const double *fix_lo, const double *fix_hi, double lengthscale,
-                                   double noise, const double *jitter, double *norm_off, double *norm_coef,
-                                   double *box_lo, double *box_hi, double *ymean, double *ystd, double *ZnT, double *Zn,
-                                   double *L, double *W, double *WT, double *alpha, int *info, void *stream) {
+extern "C" int pcabo_gp_mll_grad(int B, int n, int kmax, int ld_n, const int *k, const double *Zn, const double *W,
+                                 const double *alpha, double lengthscale, double *grad, void *stream) {
+  return pcabo_gp_mll_grad_hyper(B, n, kmax, ld_n, k, Zn, W, alpha, lengthscale, nullptr, grad, stream);
+}
+
+extern "C" int pcabo_gp_fit_hyper(int B, int n, int kmax, int ld_n, int mode, const double *Z, const int *k,
+                                  const double *f, const double *fix_lo, const double *fix_hi, double lengthscale,
+                                  double noise, const double *lengthscales, const double *noises, const double *jitter,
+                                  double *norm_off, double *norm_coef, double *box_lo, double *box_hi, double *ymean,
+                                  double *ystd, double *ZnT, double *Zn, double *L, double *W, double *WT, double *alpha,
+                                  int *info, void *stream) {
   if (B <= 0 || n < 1 || kmax < 1 || ld_n < n || !Z || !f || !norm_off || !norm_coef || !box_lo || !box_hi || !ymean ||
-      !ystd || !ZnT || !Zn || !L || !W || !WT || !alpha || !info || !(lengthscale > 0.0))
+      !ystd || !ZnT || !Zn || !L || !W || !WT || !alpha || !info || (!lengthscales && !(lengthscale > 0.0)))
     return PCABO_E_INVALID;
   if (mode != 0 && (!fix_lo || !fix_hi)) return PCABO_E_INVALID;
   if (kmax > 104 || n > 4096) return PCABO_E_UNSUPPORTED;
@@ -611,10 +622,20 @@ extern "C" int pcabo_gp_fit_jitter(int B, int n, int kmax, int ld_n, int mode, c
   {
     const int nt = (n + KT - 1) / KT;
     dim3 grid(nt * (nt + 1) / 2, B);
-    gp_kmat_kernel<<<grid, 256, 0, st>>>(n, kmax, ld_n, k, ZnT, 1.0 / (lengthscale * lengthscale), noise, jitter, L);
+    gp_kmat_kernel<<<grid, 256, 0, st>>>(n, kmax, ld_n, k, ZnT, lengthscales ? 1.0 : 1.0 / (lengthscale * lengthscale), noise,
+                                         jitter, lengthscales, noises, L);
     PCABO_LAUNCH_CHECK();
   }
   return pcabo_chol_pipeline(B, n, ld_n, L, W, WT, alpha, info, st);
+}
+
+extern "C" int pcabo_gp_fit_jitter(int B, int n, int kmax, int ld_n, int mode, const double *Z, const int *k,
+                                   const double *f, const double *fix_lo, const double *fix_hi, double lengthscale,
+                                   double noise, const double *jitter, double *norm_off, double *norm_coef,
+                                   double *box_lo, double *box_hi, double *ymean, double *ystd, double *ZnT, double *Zn,
+                                   double *L, double *W, double *WT, double *alpha, int *info, void *stream) {
+  return pcabo_gp_fit_hyper(B, n, kmax, ld_n, mode, Z, k, f, fix_lo, fix_hi, lengthscale, noise, nullptr, nullptr, jitter,
+                            norm_off, norm_coef, box_lo, box_hi, ymean, ystd, ZnT, Zn, L, W, WT, alpha, info, stream);
 }
 
 extern "C" int pcabo_gp_fit_onecta(int B, int n, int kmax, int ld_n, double *L, double *W, double *WT, double *alpha,

@@ -241,7 +241,9 @@ __global__ void __launch_bounds__(lbeval::NT_ALL, 1) lbfgsb_logei_kernel(LbArgs 
   obj.vals = q; q += 8;
   int *flag = reinterpret_cast<int *>(q); q += 2;
   long long *sprof = reinterpret_cast<long long *>(q); q += 32;   // cycle counters live in shared memory, flushed at the end
-  double *tred = q; q += 20 * 33 + 20;
+  // scratch of the optimiser warp's 20-value reductions: the partial-sum area of the evaluation (2 x 8 x 8 x 12 doubles),
+  // which is only live inside an evaluation
+  double *tred = obj.ctx.base + obj.ctx.L.o_part;
   obj.pcount = pcount; obj.kk = kk;
   if (a.prof) {
     if (tid < 32) sprof[tid] = 0;
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(lbeval::NT_ALL, 1) lbfgsb_logei_kernel(LbArgs 
 }
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
-constexpr int TAIL_DOUBLES = 2 + 8 + 2 + 32 + 20 * 33 + 20 + 8;
+constexpr int TAIL_DOUBLES = 2 + 8 + 2 + 32 + 8;
 
 // Shared-memory plan of one launch: panel height, ring capacity, where the BFGS pairs live.
 struct Plan {
@@ -414,7 +416,7 @@ extern "C" int pcabo_lbfgsb_logei_runs_ws(const pcabo_gp_model *m, int nsel, con
       !status || !nit || !nfev || m->B <= 0 || m->n < 1 || m->ld_n < m->n || !m->norm_off ||
       !m->norm_coef || !m->ZnT || !m->alpha || !m->Wp || (m->wp_stride & 1) ||
       m->wp_stride < lbeval::packed_doubles(m->n) || !m->Zn || !m->ymean || !m->ystd || !m->best_f ||
-      !(m->lengthscale > 0.0))
+      (!m->lengthscales && !(m->lengthscale > 0.0)))
     return PCABO_E_INVALID;
   if (run_idx ? (nsel <= 0 || nsel > m->B) : (nsel != m->B)) return PCABO_E_INVALID;
   if (k_bound <= 0 || k_bound > m->kmax) k_bound = m->kmax;

@@ -131,7 +131,7 @@ __device__ inline void load_ctx(Ctx &c, const pcabo_gp_model &m, int b) {
   c.alpha_g = m.alpha + (size_t)b * m.ld_n;
   c.off = m.norm_off + (size_t)b * m.kmax;
   c.coef = m.norm_coef + (size_t)b * m.kmax;
-  c.inv_ell2 = 1.0 / (m.lengthscale * m.lengthscale);
+  { const double ell = m.lengthscales ? m.lengthscales[b] : m.lengthscale; c.inv_ell2 = 1.0 / (ell * ell); }
   c.ymean = m.ymean[b]; c.ystd = m.ystd[b]; c.best_f = m.best_f[b];
   c.sgn = m.maximize ? 1.0 : -1.0;
   c.prof = nullptr;

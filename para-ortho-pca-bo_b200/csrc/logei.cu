@@ -76,7 +76,7 @@ __global__ void argmax_kernel(int mcols, const double *v, double *best_val, int 
 extern "C" int pcabo_logei(const pcabo_gp_model *m, int npts, const double *X, double *val, double *grad, double *mu,
                            double *sigma, void *stream) {
   if (!m || npts <= 0 || !X || !val || m->B <= 0 || m->n < 1 || m->ld_n < m->n || !m->norm_off || !m->norm_coef ||
-      !m->ZnT || !m->alpha || !m->W || !m->WT || !m->ymean || !m->ystd || !m->best_f || !(m->lengthscale > 0.0))
+      !m->ZnT || !m->alpha || !m->W || !m->WT || !m->ymean || !m->ystd || !m->best_f || (!m->lengthscales && !(m->lengthscale > 0.0)))
     return PCABO_E_INVALID;
   if (grad && !m->Zn) return PCABO_E_INVALID;   // the gradient pass reads the row-major training inputs
   if (m->kmax > 104 || m->n > 4096) return PCABO_E_UNSUPPORTED;

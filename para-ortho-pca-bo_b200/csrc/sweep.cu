@@ -214,7 +214,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
   const double *Zn = m.Zn + (size_t)b * ld * kmax;
   const double *alpha = m.alpha + (size_t)b * ld;
   const double *off = m.norm_off + (size_t)b * kmax, *coef = m.norm_coef + (size_t)b * kmax;
-  const double inv_ell2 = 1.0 / (m.lengthscale * m.lengthscale);
+  const double ell = m.lengthscales ? m.lengthscales[b] : m.lengthscale;
+  const double inv_ell2 = 1.0 / (ell * ell);
   const double ystd = m.ystd[b], ymean = m.ymean[b], best_f = m.best_f[b], sgn = m.maximize ? 1.0 : -1.0;
   const double d0 = 1e-15;
   const double kss = (SQRT5 * d0 + 1.0 + (5.0 / 3.0) * (d0 * d0)) * exp(-SQRT5 * d0);

@@ -236,7 +236,9 @@ class LbfgsbProblem:
     __slots__ = ("n", "x", "f", "g", "lo", "hi", "nbd", "wa", "iwa", "task", "ln_task", "lsave", "isave", "dsave",
                  "nit", "nfev", "maxiter", "done", "warnflag")
 
-    def __init__(self, x0, lo, hi, maxiter=200):
+    def __init__(self, x0, lo, hi, maxiter=200, nbd=None):
+        """nbd: scipy's bound codes per variable (0 none, 1 lower, 2 both, 3 upper); default: all boxed."""
+        x0 = np.asarray(x0, dtype=np.float64)
         n = x0.size
         m = MAXCOR
         self.n = n
@@ -245,7 +247,7 @@ class LbfgsbProblem:
         self.g = np.zeros(n, dtype=np.float64)
         self.lo = np.array(lo, dtype=np.float64)
         self.hi = np.array(hi, dtype=np.float64)
-        self.nbd = np.full(n, 2, dtype=np.int32)
+        self.nbd = np.full(n, 2, dtype=np.int32) if nbd is None else np.asarray(nbd, dtype=np.int32).copy()
         self.wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m, np.float64)
         self.iwa = np.zeros(3 * n, dtype=np.int32)
         self.task = np.zeros(2, dtype=np.int32)

@@ -50,7 +50,8 @@ class BatchedBOEngine:
                  n_components=0, maximization=False, device="cuda:0", optimizer="scipy",
                  num_restarts=NUM_RESTARTS, raw_samples=RAW_SAMPLES, batch_limit=BATCH_LIMIT, maxiter=MAXITER,
                  np_rngs=None, torch_gens=None, profile_timing=False, batch_objective=None, host_threads=None,
-                 acquisition="expected_improvement", lengthscale=ops.LENGTHSCALE, noise=ops.NOISE):
+                 acquisition="expected_improvement", lengthscale=ops.LENGTHSCALE, noise=ops.NOISE,
+                 fit_hyperparameters=False):
         if not torch.cuda.is_available():
             raise PcaboError("BatchedBOEngine needs a CUDA device: the PCA-BO hot path has no CPU fallback")
         if algorithm not in ("pca", "vanilla"):
@@ -65,6 +66,8 @@ class BatchedBOEngine:
         self.acquisition = acquisition
         # GP hyper-parameters: the reference never fits its GP, these are gpytorch's / botorch's initial values
         self.lengthscale, self.noise = float(lengthscale), float(noise)
+        self.fit_hyperparameters = bool(fit_hyperparameters)
+        self.last_hyper = None
         # `problems`: a list of B callables p(x) -> float, or one batched objective (e.g. pcabo_b200.bbob.BatchedBBOB)
         # exposing B, eval_many(b, X[m, D]) -> ndarray and __call__(X[B, D] device tensor) -> [B] device tensor
         self.batched_problem = problems if hasattr(problems, "eval_many") else None
@@ -295,12 +298,24 @@ class BatchedBOEngine:
     def _fit_gp(self, jitter=None):
         """_initialize_model (PCA_BO.py:502-545 / Vanilla_BO.py:166-195) + gpytorch's prediction caches; the Cholesky
         status of every run is read back asynchronously and examined in _propose_begin."""
+        if self.fit_hyperparameters and jitter is None:
+            # opt-in (the reference never fits its GP, SURVEY F2): per-run (lengthscale, noise) by maximum a posteriori
+            # marginal likelihood, as botorch's fit_gpytorch_mll would do for this model; the caches are left at the fit
+            from .hyperfit import fit_hyperparameters
+            pca = self.algorithm == "pca"
+            self.last_hyper = fit_hyperparameters(
+                self.gp, self.pca["Z"] if pca else self.X, self.pca["k"] if pca else None, self.f, self.n,
+                mode=0 if pca else 1, fix_lo=None if pca else self.lo, fix_hi=None if pca else self.hi)
+            self.h_info.copy_(self.gp.info, non_blocking=True)
+            self.stats["d2h_bytes"] += self.B * 4
+            return
+        hyper = dict(lengthscales=self.gp.lengthscales, noises=self.gp.noises) if self.fit_hyperparameters else {}
         if self.algorithm == "pca":
             ops.gp_fit(self.gp, self.pca["Z"], self.pca["k"], self.f, self.n, mode=0, lengthscale=self.lengthscale,
-                       noise=self.noise, jitter=jitter)
+                       noise=self.noise, jitter=jitter, **hyper)
         else:
             ops.gp_fit(self.gp, self.X, None, self.f, self.n, mode=1, fix_lo=self.lo, fix_hi=self.hi,
-                       lengthscale=self.lengthscale, noise=self.noise, jitter=jitter)
+                       lengthscale=self.lengthscale, noise=self.noise, jitter=jitter, **hyper)
         self.h_info.copy_(self.gp.info, non_blocking=True)
         self.stats["d2h_bytes"] += self.B * 4
 

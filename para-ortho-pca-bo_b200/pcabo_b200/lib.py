@@ -7,7 +7,7 @@ _LIB = None
 
 EXPORTED_SYMBOLS = [
     "pcabo_abi_version", "pcabo_error_string", "pcabo_last_cuda_error",
-    "pcabo_weights_pca_fit", "pcabo_inverse_map", "pcabo_gp_fit", "pcabo_gp_fit_jitter", "pcabo_gp_pack_w",
+    "pcabo_weights_pca_fit", "pcabo_inverse_map", "pcabo_gp_fit", "pcabo_gp_fit_jitter", "pcabo_gp_fit_hyper", "pcabo_gp_mll_grad_hyper", "pcabo_gp_pack_w",
     "pcabo_gp_packed_doubles", "pcabo_gp_mll", "pcabo_gp_mll_grad",
     "pcabo_logei", "pcabo_argmax", "pcabo_lbfgsb_logei", "pcabo_lbfgsb_logei_prof", "pcabo_lbfgsb_logei_runs", "pcabo_lbfgsb_logei_runs_ws",
     "pcabo_lbfgsb_workspace_doubles", "pcabo_lbfgsb_plan", "pcabo_ei_sweep",
@@ -30,6 +30,7 @@ class GpModelStruct(ctypes.Structure):
         ("ymean", ctypes.c_void_p), ("ystd", ctypes.c_void_p), ("best_f", ctypes.c_void_p),
         ("WT", ctypes.c_void_p), ("Zn", ctypes.c_void_p),
         ("Wp", ctypes.c_void_p), ("wp_stride", ctypes.c_longlong),
+        ("lengthscales", ctypes.c_void_p),
     ]
 
 
@@ -64,6 +65,10 @@ def load_library(build_if_missing: bool = False):
     lib.pcabo_gp_fit.argtypes = [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, cd, cd] + [vp] * 13 + [vp]
     lib.pcabo_gp_fit_jitter.restype = ci
     lib.pcabo_gp_fit_jitter.argtypes = [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, cd, cd, vp] + [vp] * 13 + [vp]
+    lib.pcabo_gp_fit_hyper.restype = ci
+    lib.pcabo_gp_fit_hyper.argtypes = [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, cd, cd, vp, vp, vp] + [vp] * 13 + [vp]
+    lib.pcabo_gp_mll_grad_hyper.restype = ci
+    lib.pcabo_gp_mll_grad_hyper.argtypes = [ci, ci, ci, ci, vp, vp, vp, vp, cd, vp, vp, vp]
     lib.pcabo_gp_pack_w.restype = ci
     lib.pcabo_gp_pack_w.argtypes = [ci, ci, ci, vp, vp, ctypes.c_longlong, vp]
     lib.pcabo_gp_packed_doubles.restype = ctypes.c_longlong

@@ -109,25 +109,31 @@ class GPBuffers:
         self.maximize = False
         self.acq = ACQ_LOG_EI       # PCABO_ACQ_LOG_EI / PCABO_ACQ_PI (include/pcabo_b200.h)
         self.lengthscale = LENGTHSCALE
+        self.lengthscales = None    # [B] per-run lengthscales after an opt-in hyper-parameter fit (hyperfit.py)
+        self.noises = None          # [B] per-run noise variances, ditto
 
 
 def gp_fit(buf: GPBuffers, Z, k, f, n, mode=0, fix_lo=None, fix_hi=None, lengthscale=LENGTHSCALE, noise=NOISE,
-           jitter=None):
+           jitter=None, lengthscales=None, noises=None):
     """Z [B, ld_n, kmax], k [B] int32 or None, f [B, ld_n]. Fills `buf`. jitter: optional [B] device tensor added to the
-    diagonal of K + noise I (psd_safe_cholesky's retry ladder for runs whose buf.info came back non-zero)."""
+    diagonal of K + noise I (psd_safe_cholesky's retry ladder for runs whose buf.info came back non-zero).
+    lengthscales / noises: optional [B] device tensors of per-run hyper-parameters (opt-in fit; the reference uses the
+    fixed prior values for every run)."""
     lib = load_library()
     B, ld_n, kmax = Z.shape
     if (B, ld_n, kmax) != (buf.B, buf.ld_n, buf.kmax):
         raise PcaboError("gp_fit: buffer shape mismatch")
-    check(lib.pcabo_gp_fit_jitter(B, n, kmax, ld_n, int(mode), _d(Z, "Z"), _i(k, "k"), _d(f, "f"), _d(fix_lo, "fix_lo"),
-                           _d(fix_hi, "fix_hi"), float(lengthscale), float(noise), _d(jitter, "jitter"),
-                           _d(buf.norm_off, "norm_off"), _d(buf.norm_coef, "norm_coef"), _d(buf.box_lo, "box_lo"),
-                           _d(buf.box_hi, "box_hi"), _d(buf.ymean, "ymean"), _d(buf.ystd, "ystd"), _d(buf.ZnT, "ZnT"),
-                           _d(buf.Zn, "Zn"), _d(buf.L, "L"), _d(buf.W, "W"), _d(buf.WT, "WT"), _d(buf.alpha, "alpha"),
-                           _i(buf.info, "info"), _stream()),
+    check(lib.pcabo_gp_fit_hyper(B, n, kmax, ld_n, int(mode), _d(Z, "Z"), _i(k, "k"), _d(f, "f"), _d(fix_lo, "fix_lo"),
+                                 _d(fix_hi, "fix_hi"), float(lengthscale), float(noise), _d(lengthscales, "lengthscales"),
+                                 _d(noises, "noises"), _d(jitter, "jitter"),
+                                 _d(buf.norm_off, "norm_off"), _d(buf.norm_coef, "norm_coef"), _d(buf.box_lo, "box_lo"),
+                                 _d(buf.box_hi, "box_hi"), _d(buf.ymean, "ymean"), _d(buf.ystd, "ystd"), _d(buf.ZnT, "ZnT"),
+                                 _d(buf.Zn, "Zn"), _d(buf.L, "L"), _d(buf.W, "W"), _d(buf.WT, "WT"), _d(buf.alpha, "alpha"),
+                                 _i(buf.info, "info"), _stream()),
           "pcabo_gp_fit")
     check(lib.pcabo_gp_pack_w(B, n, ld_n, _d(buf.W, "W"), _d(buf.Wp, "Wp"), buf.wp_stride, _stream()), "pcabo_gp_pack_w")
     buf.n, buf.k, buf.lengthscale = n, k, lengthscale
+    buf.lengthscales, buf.noises = lengthscales, noises
     return buf
 
 
@@ -143,9 +149,10 @@ def gp_mll_grad(buf: GPBuffers):
     """(dMLL/dlengthscale, dMLL/dnoise) of the standardised targets from the caches: [B, 2] (device)."""
     lib = load_library()
     out = torch.empty(buf.B, 2, dtype=torch.float64, device=buf.W.device)
-    check(lib.pcabo_gp_mll_grad(buf.B, buf.n, buf.kmax, buf.ld_n, _i(buf.k, "k") if buf.k is not None else None,
-                                _d(buf.Zn, "Zn"), _d(buf.W, "W"), _d(buf.alpha, "alpha"), float(buf.lengthscale),
-                                _d(out, "grad"), _stream()), "pcabo_gp_mll_grad")
+    check(lib.pcabo_gp_mll_grad_hyper(buf.B, buf.n, buf.kmax, buf.ld_n, _i(buf.k, "k") if buf.k is not None else None,
+                                      _d(buf.Zn, "Zn"), _d(buf.W, "W"), _d(buf.alpha, "alpha"), float(buf.lengthscale),
+                                      _d(buf.lengthscales, "lengthscales"), _d(out, "grad"), _stream()),
+          "pcabo_gp_mll_grad")
     return out
 
 
@@ -161,6 +168,7 @@ def model_struct(buf: GPBuffers) -> GpModelStruct:
     m.ymean, m.ystd, m.best_f = _d(buf.ymean, "ymean"), _d(buf.ystd, "ystd"), _d(buf.best_f, "best_f")
     m.WT, m.Zn = _d(buf.WT, "WT"), _d(buf.Zn, "Zn")
     m.Wp, m.wp_stride = _d(buf.Wp, "Wp"), int(buf.wp_stride)
+    m.lengthscales = _d(buf.lengthscales, "lengthscales") if buf.lengthscales is not None else None
     return m
 
 

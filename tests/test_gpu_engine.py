@@ -453,3 +453,23 @@ def test_device_optimizer_workspace_and_no_host_fallback(monkeypatch):
     monkeypatch.setattr(ops, "lbfgsb_fits", lambda *a, **k: False)
     with pytest.raises(PcaboError, match="beyond"):
         e.step()
+
+
+def test_engine_with_hyperparameter_fit_opt_in():
+    """fit_hyperparameters=True (extension; the reference never fits): the engine fits per-run (lengthscale, noise) every
+    iteration and proposes from the fitted model; default stays the reference's fixed prior values."""
+    from pcabo_b200.engine import BatchedBOEngine
+    from pcabo_b200.bbob import BatchedBBOB
+    prob = BatchedBBOB([15, 20], [0, 1], 10, device="cuda")
+    e = BatchedBOEngine(prob, 10, prob.bounds, 150, 30, [15100, 20101], optimizer="device", fit_hyperparameters=True)
+    e.initial_design()
+    e.step()
+    e.step()
+    assert e.n == 32 and e.last_hyper is not None
+    ls, nz = e.last_hyper["lengthscale"], e.last_hyper["noise"]
+    assert (ls > 0).all() and (nz >= 1e-4).all() and (e.last_hyper["nfev"] >= 1).all()
+    assert e.gp.lengthscales is not None and abs(float(e.gp.lengthscales[0]) - ls[0]) < 1e-12
+    d = BatchedBOEngine(prob, 10, prob.bounds, 150, 30, [15100, 20101], optimizer="device")
+    d.initial_design()
+    d.step()
+    assert d.last_hyper is None and d.gp.lengthscales is None

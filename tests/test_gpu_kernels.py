@@ -449,3 +449,51 @@ def test_gp_mll_gradient(D, n):
         mll, g_ls, g_nz = gp.mll_and_grad(model)
         assert abs(g[b, 0] - g_ls) <= 1e-8 * max(1.0, abs(g_ls)), ("d/dl", g[b, 0], g_ls)
         assert abs(g[b, 1] - g_nz) <= 1e-8 * max(1.0, abs(g_nz)), ("d/dnoise", g[b, 1], g_nz)
+
+
+@pytest.mark.parametrize("D,n", [(10, 60), (20, 150)])
+def test_hyperparameter_fit_matches_oracle(D, n):
+    """Opt-in MAP fit of (lengthscale, noise) per run (pcabo_b200/hyperfit.py: lock-step L-BFGS-B driving
+    pcabo_gp_fit_hyper + pcabo_gp_mll + pcabo_gp_mll_grad_hyper) against its CPU twin (oracle/hyperfit.py: scipy on the
+    oracle's autograd MLL): fitted values to 1e-6, and the caches / log-EI at the fitted values to 1e-8. The reference
+    never fits: parity here is against the restated botorch fit_gpytorch_mll objective (unpinned)."""
+    from oracle import gp, acqf, hyperfit as ohf
+    from pcabo_b200.hyperfit import fit_hyperparameters
+    B = 3
+    ops, hist, X, f, pca, buf = _fit_gp_batch(D, n, B)
+    res = fit_hyperparameters(buf, pca["Z"], pca["k"], f, n, mode=0)
+    torch.cuda.synchronize()
+    for b in range(B):
+        k = int(pca["k"][b])
+        Z = pca["Z"][b, :n, :k].cpu().numpy()
+        ls, nz, obj, r = ohf.fit(Z, hist[b][1], norm_bounds=acqf.normalize_box_pca(Z))
+        assert abs(res["lengthscale"][b] - ls) <= 1e-6 * ls, (b, res["lengthscale"][b], ls)
+        assert abs(res["noise"][b] - nz) <= 1e-6 * max(nz, 1e-4), (b, res["noise"][b], nz)
+        assert abs(res["objective"][b] - obj) <= 1e-9 * max(1.0, abs(obj))
+        assert res["objective"][b] <= -(gp.GPModel(Z, hist[b][1], norm_bounds=acqf.normalize_box_pca(Z)).mll()) / n + 1.0
+        # caches and log-EI at the fitted hyper-parameters
+        model = gp.GPModel(Z, hist[b][1], norm_bounds=acqf.normalize_box_pca(Z), lengthscale=float(res["lengthscale"][b]),
+                           noise=float(res["noise"][b]))
+        _, L, alpha, _ = model.caches()
+        assert rel_err(buf.alpha[b, :n].cpu().numpy(), alpha.numpy(), 1e-300) < 1e-7
+    # log-EI through the per-run lengthscales
+    rng = np.random.RandomState(3)
+    kmax = D
+    Xq = torch.zeros(B, 4, kmax, dtype=torch.float64)
+    refs = []
+    for b in range(B):
+        k = int(pca["k"][b])
+        Z = pca["Z"][b, :n, :k].cpu().numpy()
+        box = acqf.search_box_pca(Z)
+        P = np.asarray(box[0]) + (np.asarray(box[1]) - np.asarray(box[0])) * rng.rand(4, k)
+        Xq[b, :, :k] = torch.from_numpy(P)
+        model = gp.GPModel(Z, hist[b][1], norm_bounds=acqf.normalize_box_pca(Z), lengthscale=float(res["lengthscale"][b]),
+                           noise=float(res["noise"][b]))
+        best = float(np.min(hist[b][1]))
+        buf.best_f[b] = gp.best_f_as_botorch(best)
+        acq = gp.LogExpectedImprovement(model, best, maximize=False)
+        with torch.no_grad():
+            refs.append(acq(torch.from_numpy(P)).numpy())
+    out = ops.logei(buf, Xq.cuda())
+    for b in range(B):
+        assert rel_err(out["val"][b].cpu().numpy(), refs[b], 1e-300) < 1e-7

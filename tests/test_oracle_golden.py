@@ -241,3 +241,29 @@ def test_bbob_f21_f24_definitions(fid):
             assert np.all(p.batch(Xo) >= p.fopt + (1e4 if fid == 24 else 1.0) * 1.5 ** 2 - 1e-9)   # boundary penalty
             got = BatchedBBOB([fid], [inst], D).eval_all(X[None])[0]
             assert np.max(np.abs(got - y) / np.maximum(1.0, np.abs(y))) < 1e-11
+
+
+def test_oracle_hyperparameter_fit_is_a_stationary_point():
+    """oracle/hyperfit.py (the CPU twin of the opt-in fit): the fitted (lengthscale, noise) improve the MAP objective of
+    the prior values, respect the noise bound, and the objective's gradient vanishes there (finite differences)."""
+    import math
+    from helpers import synthetic_history, oracle_state
+    from oracle import hyperfit, acqf, gp
+    X, f, nz = synthetic_history(8, 40, 5)
+    st, model, box, acq = oracle_state(X, f, nz)
+    Z = st["Z"]
+    nb = acqf.normalize_box_pca(Z)
+    ls, noise, obj, res = hyperfit.fit(Z, f, norm_bounds=nb, maxiter=100)
+    assert noise >= hyperfit.NOISE_LOWER and ls > 0
+
+    def objective(l_, s_):
+        m = gp.GPModel(Z, f, norm_bounds=nb, lengthscale=l_, noise=s_)
+        lx = math.log(s_)
+        return -(m.mll() - lx - 0.5 * math.log(2 * math.pi) - 0.5 * (lx + 4.0) ** 2) / len(f)
+
+    assert abs(objective(ls, noise) - obj) < 1e-12
+    assert obj <= objective(gp.LENGTHSCALE, gp.NOISE) + 1e-12
+    h = 1e-5
+    assert abs(objective(ls + h, noise) - objective(ls - h, noise)) / (2 * h) < 1e-3
+    if noise > hyperfit.NOISE_LOWER * 1.01:
+        assert abs(objective(ls, noise * (1 + h)) - objective(ls, noise * (1 - h))) / (2 * h * noise) < 1e-2

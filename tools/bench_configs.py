@@ -2,10 +2,10 @@
 
 C1: PCA-BO f15 D=10, 1 run (budget 150, n_doe 30)                       -- the reference's own CPU-runnable case
 C2: vanilla BO and PCA-BO on f15/f20 D=20, 30 runs each (budget 250, n_doe 60)
-C5: PCA-BO D=100, budget 1050, n_doe 300, 30 runs x 5 functions (f20-f24);
-    the device optimiser fits shared memory (sized by the batch's largest k) up to n ~ 920 of the 1050 points, one
-    block per SM; both optimisers are reported at the start of the run
-Run on the GPU box: python tools/bench_configs.py [--steps 5]
+C5: PCA-BO D=100, budget 1050, n_doe 300, 30 runs x 5 functions (f20-f24); the device optimiser covers the whole run
+    (past n ~ 500 its BFGS pairs live in an L2-resident workspace); both optimisers are reported at the start of the
+    run, and --whole-c5 runs all 750 BO iterations of the 150 runs with the device optimiser (iterations/s per quarter)
+Run on the GPU box: python tools/bench_configs.py [--steps 5] [--only C5] [--whole-c5]
 """
 import argparse
 import json
@@ -42,10 +42,40 @@ def measure(name, fids, insts, D, algorithm, optimizer, steps, warmup=2, n_start
     return out
 
 
+def whole_c5(fids, insts, D=100):
+    """The whole C5 run on one GPU with the device optimiser: 150 runs x 750 BO iterations, n = 300 -> 1050."""
+    from pcabo_b200.bbob import BatchedBBOB
+    from pcabo_b200.engine import BatchedBOEngine
+    prob = BatchedBBOB(fids, insts, D, device="cuda")
+    budget, ndoe = 10 * D + 50, 3 * D
+    eng = BatchedBOEngine(prob, D, prob.bounds, budget, ndoe, [1000 * f + 10 * D + i for f, i in zip(fids, insts)],
+                          algorithm="pca", optimizer="device")
+    eng.initial_design()
+    torch.cuda.synchronize()
+    marks, t0 = [], time.perf_counter()
+    total = budget - ndoe
+    for s_ in range(total):
+        eng.step()
+        if (s_ + 1) % (total // 4) == 0 or s_ + 1 == total:
+            torch.cuda.synchronize()
+            marks.append((eng.n, time.perf_counter() - t0))
+    k = eng.k_host if getattr(eng, "k_host", None) is not None else None
+    out = {"config": "C5 whole run", "optimizer": "device", "runs": eng.B, "dim": D, "bo_iterations": eng.B * total,
+           "seconds": marks[-1][1], "iterations_per_s": eng.B * total / marks[-1][1],
+           "by_quarter": [{"n_end": n, "iterations_per_s": eng.B * (total // 4) / (t - (marks[i - 1][1] if i else 0.0))}
+                          for i, (n, t) in enumerate(marks[:4])],
+           "retries": eng.stats["retries"], "jitter_refits": eng.stats.get("jitter_refits", 0),
+           "k_final_mean": float(k.mean()) if k is not None else None, "k_final_max": int(k.max()) if k is not None else None,
+           "best_f_median": float(sorted(eng.current_best)[len(eng.current_best) // 2]) if hasattr(eng, "current_best") else None}
+    print(json.dumps(out), flush=True)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--only", default="")
+    ap.add_argument("--whole-c5", action="store_true")
     a = ap.parse_args()
     want = set(a.only.split(",")) if a.only else None
     if not want or "C1" in want:
@@ -62,8 +92,10 @@ def main():
         measure("C5", fids, insts, 100, "pca", "scipy", max(2, a.steps // 2), warmup=1)
         try:
             measure("C5", fids, insts, 100, "pca", "device", max(2, a.steps // 2), warmup=1)
-        except Exception as e:      # PCABO_E_UNSUPPORTED when the shared-memory need exceeds 227 KB
+        except Exception as e:
             print(json.dumps({"config": "C5", "optimizer": "device", "error": str(e)}), flush=True)
+        if a.whole_c5:
+            whole_c5(fids, insts)
 
 
 if __name__ == "__main__":
