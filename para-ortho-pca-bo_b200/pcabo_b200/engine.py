@@ -290,7 +290,7 @@ class BatchedBOEngine:
         t1 = self._sync_time()
         self._fit_gp()
         t2 = self._sync_time()
-        self.stats["kernel_launches"] += 3
+        self.stats["kernel_launches"] += ops.gp_fit_launches(self.n)
         self.timing_logs["SingleTaskGP"].append(t2 - t1)
         self._phase("pca_gp_kernels", tp)
         self._set_best_f()
@@ -333,7 +333,7 @@ class BatchedBOEngine:
             self._fit_gp(jitter=jitter.to(self.device))
             torch.cuda.current_stream().synchronize()
             self.stats["jitter_refits"] += len(bad)
-            self.stats["kernel_launches"] += 3
+            self.stats["kernel_launches"] += ops.gp_fit_launches(self.n)
             bad = np.nonzero(self.h_info.numpy())[0]
             if len(bad) == 0:
                 break

@@ -137,6 +137,13 @@ def gp_fit(buf: GPBuffers, Z, k, f, n, mode=0, fix_lo=None, fix_hi=None, lengths
     return buf
 
 
+def gp_fit_launches(n):
+    """Kernel launches of one pcabo_gp_fit + pcabo_gp_pack_w call: prep, kernel matrix, per 64-column block an update (+
+    a solve below the last), the triangular inverse, alpha, the transpose, the packing."""
+    nb = (int(n) + 63) // 64
+    return 2 + (2 * nb - 1) + (1 if nb > 1 else 0) + 2 + 1
+
+
 def gp_mll(buf: GPBuffers, f):
     lib = load_library()
     out = torch.empty(buf.B, dtype=torch.float64, device=f.device)
