@@ -282,14 +282,23 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
     if (!c.resident || !c.loaded) acp::mbar_wait(&bars[seq & (NBAR - 1)], (seq >> 4) & 1u);
     const double *pan = ring + poff[seq & (NPOFF - 1)];
     const int g0 = I * RT, ng = imin(RT, ngroups(n) - g0);    // groups of this panel (RT except at the end)
+    // offsets of the panel's groups inside the panel and their row strides (32-bit; the groups are consecutive)
+    int goff[RT], grs[RT];
+    {
+      int o = 0;
+#pragma unroll
+      for (int j = 0; j < RT; ++j) { goff[j] = o; grs[j] = grp_rs(g0 + j); o += 8 * grs[j]; }
+    }
     const int r0 = I * R, c1 = imin(r0 + 8 * ng, n);
-    const long long pbase = grp_off(g0);
     double *pbuf = part + (I & 1) * (NSPLIT * R * PLD);
     {
       double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, c0 = 0.0, c1v = 0.0, d0 = 0.0, d1 = 0.0;
       if (wrt < ng) {   // this warp's row tile (= group g0 + wrt) exists
         const int ksteps = 2 * (g0 + wrt) + 2;                 // its columns: 0 .. 8 (g0 + wrt) + 7
-        const double *pa = pan + (int)(grp_off(g0 + wrt) - pbase) + lr * grp_rs(g0 + wrt) + lc + 4 * wsp;
+        int my_off = 0, my_rs = 0;
+#pragma unroll
+        for (int j = 0; j < RT; ++j) if (j == wrt) { my_off = goff[j]; my_rs = grs[j]; }
+        const double *pa = pan + my_off + lr * my_rs + lc + 4 * wsp;
         // (the 8 - PT padding columns of the B operand repeat real points: whatever they produce is never read)
         const double *pb = kst + (lr < PT ? lr : lr - PT) * S + lc + 4 * wsp;
         int left = (ksteps - wsp + NSPLIT - 1) / NSPLIT;       // k steps wsp, wsp + NSPLIT, ... of this warp
@@ -333,11 +342,15 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
         for (int kq = 0; kq < KQ; ++kq) vacc = fma(bf[kq], bf[kq], vacc);
       }
       // A fragments of the transposed product: rows 4 kq + (lane & 3) of the panel live in group kq / 2
-      const double *acol[KQ];
+      // (a missing group at the end of the matrix has t = 0: the last existing group's address will do)
+      int aoff[KQ];
 #pragma unroll
       for (int kq = 0; kq < KQ; ++kq) {
-        const int gj = imin(kq >> 1, ng - 1);   // (a missing group has t = 0: any valid address will do)
-        acol[kq] = pan + (int)(grp_off(g0 + gj) - pbase) + ((4 * kq & 7) + lc) * grp_rs(g0 + gj) + lr;
+        const int gj = (kq >> 1) < ng ? (kq >> 1) : ng - 1;
+        int o = 0, r_ = 0;
+#pragma unroll
+        for (int j = 0; j < RT; ++j) if (j == gj) { o = goff[j]; r_ = grs[j]; }
+        aoff[kq] = o + ((4 * kq & 7) + lc) * r_ + lr;
       }
       const int ntile = (c1 + 7) >> 3;
       // tile outer, k step inner: the tiles are independent accumulator chains, and a tile right of the diagonal block
@@ -348,13 +361,13 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
         if (ct <= g0) {          // left of every group's diagonal block: all k steps, operands loaded up front
           double av[KQ];
 #pragma unroll
-          for (int kq = 0; kq < KQ; ++kq) av[kq] = acol[kq][ct * 8];
+          for (int kq = 0; kq < KQ; ++kq) av[kq] = pan[aoff[kq] + ct * 8];
 #pragma unroll
           for (int kq = 0; kq < KQ; ++kq) acp::dmma_8x8x4(sf[ti][0], sf[ti][1], av[kq], bf[kq]);
         } else if (ct < ntile) {  // a diagonal tile of the panel: only the groups at or below it hold something there
 #pragma unroll
           for (int kq = 0; kq < KQ; ++kq)
-            if (ct <= g0 + (kq >> 1)) acp::dmma_8x8x4(sf[ti][0], sf[ti][1], acol[kq][ct * 8], bf[kq]);
+            if (ct <= g0 + (kq >> 1)) acp::dmma_8x8x4(sf[ti][0], sf[ti][1], pan[aoff[kq] + ct * 8], bf[kq]);
         }
       }
     }

@@ -278,9 +278,13 @@ class BatchedBOEngine:
         self.timing_logs["pca"].append(t1 - t0)
 
     def _set_best_f(self):
-        """best_f as botorch stores it: torch.as_tensor(python float) -> float32 (PCA_BO.py:199-203)."""
-        bf = torch.tensor([float(torch.as_tensor(float(v))) for v in self.current_best], dtype=torch.float64)
-        self.gp.best_f.copy_(bf)
+        """best_f as botorch stores it: torch.as_tensor(python float) -> float32 (PCA_BO.py:199-203).
+        Staged through pinned memory: a copy from pageable memory would block the host thread until the model fit
+        enqueued just before it has finished (1.2 ms per call on the profile of round 2)."""
+        if getattr(self, "h_best_f", None) is None:
+            self.h_best_f = torch.zeros(self.B, dtype=torch.float64).pin_memory()
+        self.h_best_f.numpy()[:] = np.asarray(self.current_best, dtype=np.float64).astype(np.float32).astype(np.float64)
+        self.gp.best_f.copy_(self.h_best_f, non_blocking=True)
         self.stats["h2d_bytes"] += self.B * 8
 
     def _fit_models(self):
