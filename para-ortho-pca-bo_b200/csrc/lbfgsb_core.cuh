@@ -154,16 +154,27 @@ __device__ inline int chol_upper_warp(double *A, int lda, int n, int nsplit, dou
     sgn[q] = on && i >= nsplit;
   }
   int bad = 0;
+  double piv = A[0];
+  if (!(piv > 0.0)) { bad = 1; piv = 1.0; }
+  double pinv = 1.0 / piv;
   for (int k = 0; k < n; ++k) {
     const double *__restrict__ rk = A + k * lda;
-    double piv = rk[k];
     double a[EPL], ri[EPL], rj[EPL];
 #pragma unroll
     for (int q = 0; q < EPL; ++q) { a[q] = A[off[q]]; ri[q] = rk[oi[q]]; rj[q] = rk[oj[q]]; }
-    if (!(piv > 0.0)) { if (bad == 0) bad = k + 1; piv = 1.0; }
-    const double pinv = 1.0 / piv;
-    if (lane == 0) rdiag[k] = piv;      // turned into 1 / sqrt(piv) after the sweep
     const bool plus_k = k < nsplit;
+    // the NEXT pivot and its reciprocal, by every lane, ahead of the updates: the division (62 cycles) leaves the chain
+    double piv_n = 1.0, pinv_n = 1.0;
+    if (k + 1 < n) {
+      const double c = rk[k + 1];
+      const double pr = (c * pinv) * c;
+      double d = A[(k + 1) * lda + k + 1];
+      d = (plus_k && k + 1 >= nsplit) ? d + pr : d - pr;
+      if (!(d > 0.0)) { if (bad == 0) bad = k + 2; d = 1.0; }
+      piv_n = d;
+      pinv_n = 1.0 / d;
+    }
+    if (lane == 0) rdiag[k] = piv;      // turned into 1 / sqrt(piv) after the sweep
 #pragma unroll
     for (int q = 0; q < EPL; ++q) {
       const double prod = (ri[q] * pinv) * rj[q];
@@ -171,6 +182,7 @@ __device__ inline int chol_upper_warp(double *A, int lda, int n, int nsplit, dou
       if (row[q] > k) A[off[q]] = v;
     }
     __syncwarp();
+    piv = piv_n; pinv = pinv_n;
   }
   // unit factor: U_ij = a_ij / a_ii (j > i)
   const double pv = (lane < n) ? rdiag[lane] : 1.0;
