@@ -135,7 +135,10 @@ __device__ const unsigned short kTri20[224] = {
 // The 210 entries of the triangle are dealt flat to the 32 lanes (seven each, fixed for the whole factorisation). A
 // pivot costs: one reciprocal, then for all seven entries at once (branch free, so their FP64 latencies of 23 cycles
 // overlap) a_ij -= a_ki a_kj / a_kk from the UNSCALED pivot row, and one warp barrier. (Round 1 gave lane j the whole
-// column j and published the scaled pivot row through three warp barriers per pivot: 18.8 k cycles for 20 x 20.)
+// column j and published the scaled pivot row through three warp barriers per pivot: 18.8 k cycles for 20 x 20; this
+// one takes 14.5 k in isolation, tools/micro/chol_warp.cu. Measured and rejected in round 2: the matrix in registers with
+// shuffle-broadcast multipliers, fully unrolled (24.7 k), and computing the next pivot's reciprocal ahead of the updates
+// (18.7 k).)
 // Returns 0 or 1 + index of the first non-positive pivot.
 __device__ inline int chol_upper_warp(double *A, int lda, int n, int nsplit, double *rdiag) {
   const int lane = threadIdx.x & 31;
@@ -154,27 +157,16 @@ __device__ inline int chol_upper_warp(double *A, int lda, int n, int nsplit, dou
     sgn[q] = on && i >= nsplit;
   }
   int bad = 0;
-  double piv = A[0];
-  if (!(piv > 0.0)) { bad = 1; piv = 1.0; }
-  double pinv = 1.0 / piv;
   for (int k = 0; k < n; ++k) {
     const double *__restrict__ rk = A + k * lda;
+    double piv = rk[k];
     double a[EPL], ri[EPL], rj[EPL];
 #pragma unroll
     for (int q = 0; q < EPL; ++q) { a[q] = A[off[q]]; ri[q] = rk[oi[q]]; rj[q] = rk[oj[q]]; }
-    const bool plus_k = k < nsplit;
-    // the NEXT pivot and its reciprocal, by every lane, ahead of the updates: the division (62 cycles) leaves the chain
-    double piv_n = 1.0, pinv_n = 1.0;
-    if (k + 1 < n) {
-      const double c = rk[k + 1];
-      const double pr = (c * pinv) * c;
-      double d = A[(k + 1) * lda + k + 1];
-      d = (plus_k && k + 1 >= nsplit) ? d + pr : d - pr;
-      if (!(d > 0.0)) { if (bad == 0) bad = k + 2; d = 1.0; }
-      piv_n = d;
-      pinv_n = 1.0 / d;
-    }
+    if (!(piv > 0.0)) { if (bad == 0) bad = k + 1; piv = 1.0; }
+    const double pinv = 1.0 / piv;
     if (lane == 0) rdiag[k] = piv;      // turned into 1 / sqrt(piv) after the sweep
+    const bool plus_k = k < nsplit;
 #pragma unroll
     for (int q = 0; q < EPL; ++q) {
       const double prod = (ri[q] * pinv) * rj[q];
@@ -182,7 +174,6 @@ __device__ inline int chol_upper_warp(double *A, int lda, int n, int nsplit, dou
       if (row[q] > k) A[off[q]] = v;
     }
     __syncwarp();
-    piv = piv_n; pinv = pinv_n;
   }
   // unit factor: U_ij = a_ij / a_ii (j > i)
   const double pv = (lane < n) ? rdiag[lane] : 1.0;
@@ -644,28 +635,28 @@ LB_PHASE void subsm(T &tm, Work &w, int col, double theta) {
   }
   tm.sync();
   // d = (1/theta) r + (1/theta^2) Z'W wv ; projected step; remember xcp in xp
-  double iword_l = 0.0;
+  double iword_l = 0.0, ddp_l = 0.0;
   const double rtheta = 1.0 / theta;   // one reciprocal instead of a division per (variable, pair)
   for (int i = tm.tid; i < n; i += tm.nt) {
-    w.xp[i] = w.z[i];
+    const double zi = w.z[i];
+    w.xp[i] = zi;
+    double xk = zi;
     if (w.iwhere[i] <= 0) {
       double di = w.r[i];
       for (int j = 0; j < col; ++j) di += w.wy[j * w.ldp + i] * w.wv[j] * rtheta + w.ws[j * w.ldp + i] * w.wv[col + j];
       di *= rtheta;
       w.r[i] = di;  // r now holds the Newton direction on the free variables
-      double xk = w.z[i] + di;
+      xk = zi + di;
       xk = fmax(w.l[i], xk);
       xk = fmin(w.u[i], xk);
       w.z[i] = xk;
       if (xk == w.l[i] || xk == w.u[i]) iword_l = 1.0;
     }
+    ddp_l += (xk - w.x[i]) * w.g[i];   // sign of the directional derivative of the projected point (same pass)
   }
   const double iword = tm.max(iword_l);
+  const double ddp = tm.sum(ddp_l);
   if (iword == 0.0) { tm.sync(); return; }
-  // sign of the directional derivative of the projected point
-  double ddp = 0.0;
-  for (int i = tm.tid; i < n; i += tm.nt) ddp += (w.z[i] - w.x[i]) * w.g[i];
-  ddp = tm.sum(ddp);
   if (ddp > 0.0) {
     // fall back to the truncated (backtracked) step along d from xcp
     double alpha = 1.0;
@@ -852,11 +843,10 @@ LB_PHASE int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, do
     col = M - 1;
   }
   const int c = col;
-  for (int i = tm.tid; i < n; i += tm.nt) { w.ws[c * w.ldp + i] = w.d[i]; w.wy[c * w.ldp + i] = w.r[i]; }
-  tm.sync();
   tm.tick(13);
   theta = rr / dr;
-  // new row of S'Y (s_new . y_j) and new column of S'S (s_j . s_new)
+  // the new pair goes into row c and, in the same pass, the new row of S'Y (s_new . y_j) and the new column of S'S
+  // (s_j . s_new) are accumulated (all M rows: the sums of the rows >= c are never read)
   double part[M2];
 #ifdef __CUDA_ARCH__
 #pragma unroll
@@ -864,6 +854,8 @@ LB_PHASE int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, do
   for (int j = 0; j < M2; ++j) part[j] = 0.0;
   for (int i = tm.tid; i < n; i += tm.nt) {
     const double di = w.d[i];
+    w.ws[c * w.ldp + i] = di;
+    w.wy[c * w.ldp + i] = w.r[i];
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
@@ -959,35 +951,33 @@ LB_HD Result minimize(T &tm, Work &w, Fn &fn, int maxiter, double factr, double 
         subsm(tm, w, col, theta);
         tm.tick(4);
       }
-      // search direction and line search
-      double dtd_l = 0.0;
-      for (int i = tm.tid; i < n; i += tm.nt) {
-        const double di = w.z[i] - w.x[i];
-        w.d[i] = di;
-        dtd_l += di * di;
-      }
-      dtd = tm.sum(dtd_l);
-      if (iter == 0) stpmx = 1.0;
-      else {
-        double smx = BIG;
+      // search direction and line-search set-up in ONE pass over the variables: d = z - x, d'd, the largest feasible
+      // step, the saved iterate (t, r) = (x, g) and g'd; the three reductions are independent chains
+      {
+        double dtd_l = 0.0, gd_l = 0.0, smx = BIG;
         for (int i = tm.tid; i < n; i += tm.nt) {
-          const double a1 = w.d[i];
+          const double xi = w.x[i], gi = w.g[i];
+          const double a1 = w.z[i] - xi;
+          w.d[i] = a1;
+          w.t[i] = xi;
+          w.r[i] = gi;
+          dtd_l += a1 * a1;
+          gd_l += gi * a1;
           if (a1 < 0.0) {
-            const double a2 = w.l[i] - w.x[i];
+            const double a2 = w.l[i] - xi;
             if (a2 >= 0.0) smx = 0.0;
             else if (a1 * smx < a2) smx = a2 / a1;
           } else if (a1 > 0.0) {
-            const double a2 = w.u[i] - w.x[i];
+            const double a2 = w.u[i] - xi;
             if (a2 <= 0.0) smx = 0.0;
             else if (a1 * smx > a2) smx = a2 / a1;
           }
         }
-        stpmx = -tm.max(-smx);
+        dtd = tm.sum(dtd_l);
+        gd = tm.sum(gd_l);
+        stpmx = (iter == 0) ? 1.0 : -tm.max(-smx);   // (boxed problem: the first step is 1 as well)
+        tm.sync();
       }
-      // (boxed problem: the first step is 1 as well)
-      for (int i = tm.tid; i < n; i += tm.nt) { w.t[i] = w.x[i]; w.r[i] = w.g[i]; }
-      tm.sync();
-      gd = dot(tm, w.g, w.d, n);
       gdold = gd;
       if (gd >= 0.0) ls_failed = true;  // not a descent direction
       else if (dcsrch_start(ls, f, gd, stp, stpmx) < 0) ls_failed = true;
@@ -1029,21 +1019,28 @@ LB_HD Result minimize(T &tm, Work &w, Fn &fn, int maxiter, double factr, double 
     }
     tm.tick(8);
     ++iter;
-    sbgnrm = projgr(tm, w);
+    // projected-gradient norm of the new iterate and, in the same pass, the BFGS pair: r = g - g_old, r'r, d scaled by
+    // the accepted step (if one of the tests below ends the run, r and d are not looked at again)
+    double rr;
+    {
+      double sb = 0.0, rr_l = 0.0;
+      for (int i = tm.tid; i < n; i += tm.nt) {
+        const double gi = w.g[i], xi = w.x[i];
+        const double pg = (gi < 0.0) ? fmax(xi - w.u[i], gi) : fmin(xi - w.l[i], gi);
+        sb = fmax(sb, fabs(pg));
+        const double ri = gi - w.r[i];
+        w.r[i] = ri;
+        rr_l += ri * ri;
+        if (stp != 1.0) w.d[i] *= stp;
+      }
+      sbgnrm = tm.max(sb);
+      rr = tm.sum(rr_l);
+    }
     res.nit = iter;
     if (iter >= maxiter) { res.status = STOP_MAXITER; break; }       // scipy driver stops at NEW_X before the tests
     if (sbgnrm <= pgtol) { res.status = CONV_PGTOL; break; }
     const double ddum0 = fmax(fabs(fold), fmax(fabs(f), 1.0));
     if ((fold - f) <= EPSMCH * factr * ddum0) { res.status = CONV_FTOL; break; }
-    // BFGS update: r = g - g_old, d scaled by the accepted step
-    double rr_l = 0.0;
-    for (int i = tm.tid; i < n; i += tm.nt) {
-      const double ri = w.g[i] - w.r[i];
-      w.r[i] = ri;
-      rr_l += ri * ri;
-      if (stp != 1.0) w.d[i] *= stp;
-    }
-    const double rr = tm.sum(rr_l);
     double dr, ddum;
     if (stp == 1.0) { dr = gd - gdold; ddum = -gdold; }
     else { dr = (gd - gdold) * stp; ddum = -gdold * stp; }

@@ -83,3 +83,35 @@ def test_sweep_candidate_sharding_matches_single_launch():
         parts.append((float(v), int(i)))
     best = max(parts, key=lambda t: (t[0], -t[1]))
     assert best == whole
+
+
+def test_sweep_one_million_candidates_match_oracle():
+    """BASELINE config C4 at its smallest stated size: 2^20 scrambled-Sobol candidates (r = 16) against a GP with n = 450.
+    Every one of the 1 048 576 log-EI values within 1e-8 of the CPU oracle (evaluated in chunks), the fused arg-max equal
+    to numpy's first-occurrence arg-max, and the same winner when the range is split over 4 'ranks'."""
+    from pcabo_b200 import ops
+    from pcabo_b200.parallel import candidate_range
+    n, r, kmax, N = 450, 16, 16, 1 << 20
+    buf, acq, lo, hi = make_gp(n, r, kmax, seed=5)
+    eng, shift, sst = sobol_params(r, kmax, 1234)
+    ws = ops.SweepWorkspace(torch.device("cuda"))
+    vals = torch.empty(N, dtype=torch.float64, device="cuda")
+    bv, bi = ops.ei_sweep(buf, ws, N, 0, sobol=(shift, sst, lo, hi), vals=vals)
+    torch.cuda.synchronize()
+    got = vals.cpu().numpy()
+    pts = -1 / 3 + (4 / 3 + 1 / 3) * torch.quasirandom.SobolEngine(r, scramble=True, seed=1234).draw(N, dtype=torch.float64)
+    pts = torch.full((r,), -1 / 3, dtype=torch.float64) + (torch.full((r,), 4 / 3, dtype=torch.float64)
+                                                            - torch.full((r,), -1 / 3, dtype=torch.float64)) * \
+        torch.quasirandom.SobolEngine(r, scramble=True, seed=1234).draw(N, dtype=torch.float64)
+    ref = np.empty(N)
+    with torch.no_grad():
+        for a in range(0, N, 1 << 14):
+            ref[a:a + (1 << 14)] = acq(pts[a:a + (1 << 14)]).numpy()
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-6)) < 1e-8
+    assert int(bi) == int(np.argmax(ref)) and abs(float(bv) - ref.max()) <= 1e-8 * abs(ref.max())
+    parts = []
+    for rank in range(4):
+        a, b = candidate_range(N, rank, 4)
+        v, i = ops.ei_sweep(buf, ws, b - a, a, sobol=(shift, sst, lo, hi))
+        parts.append((float(v), int(i)))
+    assert max(parts, key=lambda t: (t[0], -t[1])) == (float(bv), int(bi))

@@ -57,29 +57,37 @@ def launch_summary(src, dst, header):
 
 
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     os.makedirs(PROF, exist_ok=True)
     j = lambda n: os.path.join(OUT, n)
-    if os.path.exists(j("launches_%s_final.csv" % tag)):
-        shutil.copy(j("launches_%s_final.csv" % tag), os.path.join(PROF, f"{tag}_launches_bench_steps3.csv"))
-        launch_summary(j("launches_%s_final.csv" % tag), os.path.join(PROF, f"{tag}_launch_summary.csv"),
-                       "ncu launch list summary (ncu --metrics gpu__time_duration.sum --clock-control none, "
-                       "bench.py --steps 3 --warmup 1 --no-cpu-baseline --sub-batches 1, device optimizer, n = 120..123); per-launch "
-                       "times are cold-cache and serialised: compare SHARES with bench.py's roofline.share_of_step")
+    for cand in ("launches_%s.csv" % tag, "launches_%s_final.csv" % tag):
+        if os.path.exists(j(cand)):
+            shutil.copy(j(cand), os.path.join(PROF, f"{tag}_launches_bench_steps3.csv"))
+            launch_summary(j(cand), os.path.join(PROF, f"{tag}_launch_summary.csv"),
+                           "ncu launch list summary (ncu --metrics gpu__time_duration.sum --clock-control none, "
+                           "bench.py --steps 3 --warmup 1 --no-cpu-baseline --no-sweep --sub-batches 1, device optimizer, stratified "
+                           "windows n = 121, 285, 430); per-launch times are cold-cache and serialised: compare SHARES with "
+                           "bench.py's roofline.share_of_step")
+            break
     for rep, dst, hd in [
+        (f"prof_lbfgsb_{tag}.ncu-rep", f"{tag}_lbfgsb_ncu_raw_summary.csv",
+         "ncu --set full, lbfgsb_logei_kernel<5, 32, 8, false> (resident W panels), tools/profile_lbfgsb.py 3 (n = 123, 90 runs x 2 chunks)"),
+        (f"lb_v8_late.ncu-rep", f"{tag}_lbfgsb_n430_ncu_raw_summary.csv",
+         "ncu --set full, lbfgsb_logei_kernel<5, 16, 8> streaming W panels at n ~ 430 (tools/profile_lbfgsb.py 310), mid-round build"),
+        (f"prof_chol_{tag}.ncu-rep", f"{tag}_chol_update_ncu_raw_summary.csv",
+         "ncu --set full, chol_update_kernel (one launch of the left-looking Cholesky pipeline), tools/measure_fp64.py"),
+        (f"prof_triinv_{tag}.ncu-rep", f"{tag}_tri_inverse_ncu_raw_summary.csv",
+         "ncu --set full, tri_inverse_kernel (block columns of L^-1), tools/measure_fp64.py"),
         (f"prof_lbfgsb_{tag}_final.ncu-rep", f"{tag}_lbfgsb_ncu_raw_summary.csv",
          "ncu --set full, lbfgsb_logei_kernel<5>, bench.py --steps 3 --warmup 1 --sub-batches 1, n = 122, 90 runs x 2 chunks"),
-        (f"prof_lbfgsb_{tag}_n390.ncu-rep", f"{tag}_lbfgsb_n390_ncu_raw_summary.csv",
-         "ncu --set full, lbfgsb_logei_kernel<5> at n ~ 390 (tools/profile_lbfgsb.py 280, launch 271), before the "
-         "uniform-trip-count / dual-accumulator changes"),
         (f"prof_sweep_{tag}_final.ncu-rep", f"{tag}_ei_sweep_ncu_raw_summary.csv",
          "ncu --set full, ei_sweep_kernel (v6: mbarrier K* ring, per-warp W staging, asynchronous epilogue), "
          "tools/bench_sweep.py --log2n 22 --dims 40 (n = 450)")]:
         if os.path.exists(j(rep)):
             raw_summary(j(rep), os.path.join(PROF, dst), hd)
     for src, dst in [("sweep_final.jsonl", f"{tag}_ei_sweep_bench.jsonl"), ("fp64_peaks2.json", f"{tag}_fp64_peaks.json"),
-                     ("lb_prof_n123_v8.json", f"{tag}_lbfgsb_phase_cycles_n123.json"),
-                     ("lb_prof_n400_v9.json", f"{tag}_lbfgsb_phase_cycles_n400.json"),
+                     (f"{tag}_lbfgsb_phase_cycles_n123.json", f"{tag}_lbfgsb_phase_cycles_n123.json"),
+                     (f"{tag}_lbfgsb_phase_cycles_n430.json", f"{tag}_lbfgsb_phase_cycles_n430.json"),
                      (f"bench_{tag}_final.json", f"{tag}_bench_c3_full_run.json"),
                      (f"bench_{tag}_reference.json", f"{tag}_bench_c3_full_run_reference_arm.json")]:
         if os.path.exists(j(src)):
