@@ -62,12 +62,12 @@ def main():
     j = lambda n: os.path.join(OUT, n)
     for cand in ("launches_%s.csv" % tag, "launches_%s_final.csv" % tag):
         if os.path.exists(j(cand)):
-            shutil.copy(j(cand), os.path.join(PROF, f"{tag}_launches_bench_steps3.csv"))
+            shutil.copy(j(cand), os.path.join(PROF, f"{tag}_launches_bench_steps2.csv"))
             launch_summary(j(cand), os.path.join(PROF, f"{tag}_launch_summary.csv"),
                            "ncu launch list summary (ncu --metrics gpu__time_duration.sum --clock-control none, "
-                           "bench.py --steps 3 --warmup 1 --no-cpu-baseline --no-sweep --sub-batches 1, device optimizer, stratified "
-                           "windows n = 121, 285, 430); per-launch times are cold-cache and serialised: compare SHARES with "
-                           "bench.py's roofline.share_of_step")
+                           "bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-sweep --sub-batches 1, device optimizer, n = 120..125; "
+                           "the cutlass d884gemm launches are the bench's own in-run DGEMM yardstick, not part of a step); per-launch "
+                           "times are cold-cache and serialised: compare SHARES with bench.py's roofline.share_of_step")
             break
     for rep, dst, hd in [
         (f"prof_lbfgsb_{tag}.ncu-rep", f"{tag}_lbfgsb_ncu_raw_summary.csv",
