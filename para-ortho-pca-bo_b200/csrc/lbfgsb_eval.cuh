@@ -280,6 +280,7 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
   for (int I = 0; I < L.npanels; ++I) {
     const unsigned seq = c.resident ? (unsigned)I : c.cons;
     if (!c.resident || !c.loaded) acp::mbar_wait(&bars[seq & (NBAR - 1)], (seq >> 4) & 1u);
+    ev_tick(c, 27);   // (profiling builds only: wait for the panel)
     const double *pan = ring + poff[seq & (NPOFF - 1)];
     const int g0 = I * RT, ng = imin(RT, ngroups(n) - g0);    // groups of this panel (RT except at the end)
     // offsets of the panel's groups inside the panel and their row strides (32-bit; the groups are consecutive)
@@ -322,7 +323,9 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
       *reinterpret_cast<double2 *>(pbuf + (wsp * R + wrt * 8 + lr) * PLD + 2 * lc) =
           make_double2((a0 + b0) + (c0 + d0), (a1 + b1) + (c1v + d1));
     }
+    ev_tick(c, 28);   // phase A
     cta_sync();
+    ev_tick(c, 29);   // barrier
     {
       double bf[KQ];
 #pragma unroll
@@ -356,21 +359,41 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
       // tile outer, k step inner: the tiles are independent accumulator chains, and a tile right of the diagonal block
       // is skipped by a uniform branch (predicated-off DMMAs measured slower than the chains they were meant to hide)
 #pragma unroll
-      for (int ti = 0; ti < TI; ++ti) {
-        const int ct = warp + NW * ti;
-        if (ct <= g0) {          // left of every group's diagonal block: all k steps, operands loaded up front
-          double av[KQ];
+      for (int ti = 0; ti < TI; ti += 2) {
+        const int ct = warp + NW * ti, ct2 = ct + NW;
+        if (ti + 1 < TI && ct2 <= g0) {
+          // two tiles left of every group's diagonal block: all k steps, operands loaded up front, the two accumulator
+          // chains interleaved (a DMMA that depends on the previous one waits ~30 cycles)
+          double av[KQ], aw[KQ];
 #pragma unroll
-          for (int kq = 0; kq < KQ; ++kq) av[kq] = pan[aoff[kq] + ct * 8];
+          for (int kq = 0; kq < KQ; ++kq) { av[kq] = pan[aoff[kq] + ct * 8]; aw[kq] = pan[aoff[kq] + ct2 * 8]; }
 #pragma unroll
-          for (int kq = 0; kq < KQ; ++kq) acp::dmma_8x8x4(sf[ti][0], sf[ti][1], av[kq], bf[kq]);
-        } else if (ct < ntile) {  // a diagonal tile of the panel: only the groups at or below it hold something there
+          for (int kq = 0; kq < KQ; ++kq) {
+            acp::dmma_8x8x4(sf[ti][0], sf[ti][1], av[kq], bf[kq]);
+            acp::dmma_8x8x4(sf[ti + 1][0], sf[ti + 1][1], aw[kq], bf[kq]);
+          }
+        } else {
 #pragma unroll
-          for (int kq = 0; kq < KQ; ++kq)
-            if (ct <= g0 + (kq >> 1)) acp::dmma_8x8x4(sf[ti][0], sf[ti][1], pan[aoff[kq] + ct * 8], bf[kq]);
+          for (int h = 0; h < 2; ++h) {
+            if (ti + h < TI) {
+              const int cth = ct + NW * h;
+              if (cth <= g0) {          // left of every group's diagonal block: all k steps
+                double av[KQ];
+#pragma unroll
+                for (int kq = 0; kq < KQ; ++kq) av[kq] = pan[aoff[kq] + cth * 8];
+#pragma unroll
+                for (int kq = 0; kq < KQ; ++kq) acp::dmma_8x8x4(sf[ti + h][0], sf[ti + h][1], av[kq], bf[kq]);
+              } else if (cth < ntile) {  // a diagonal tile of the panel: only the groups at or below it hold something there
+#pragma unroll
+                for (int kq = 0; kq < KQ; ++kq)
+                  if (cth <= g0 + (kq >> 1)) acp::dmma_8x8x4(sf[ti + h][0], sf[ti + h][1], pan[aoff[kq] + cth * 8], bf[kq]);
+              }
+            }
+          }
         }
       }
     }
+    ev_tick(c, 30);   // partial sums + phase B
     ++c.cons;
     if (!c.resident) {   // this warp is done with the panel
       __syncwarp();

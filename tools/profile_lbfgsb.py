@@ -14,7 +14,7 @@ from pcabo_b200.engine import BatchedBOEngine
 
 NAMES = ["tests", "cauchy_rest", "formk_chol", "cmprlb", "subsm", "ls_setup", "ls_step", "eval", "dcsrch", "update_formt_chol",
          "formk_products", "cauchy_pass1", "cauchy_bmv", "update_shift", "update_products", "x15",
-         "ev_kvec", "ev_sweep", "x18", "ev_coeff", "ev_grad", "x21", "ev_head", "fk_pre", "fk_sync1", "fk_work", "fk_sync2"] + [f"x{i}" for i in range(27, 32)]
+         "ev_kvec", "ev_sweep", "x18", "ev_coeff", "ev_grad", "x21", "ev_head", "fk_pre", "fk_sync1", "fk_work", "fk_sync2", "sw_wait", "sw_phaseA", "sw_barrier", "sw_phaseB", "x31"]
 NSLOT = 32
 
 
