@@ -9,21 +9,14 @@
 //   gp_prep_kernel   : per-dim min/max -> Normalize (0.1 pad) + search box (0.5 pad, min width 0.1); Standardize;
 //                      normalised inputs transposed (ZnT[c][i]) so later kernels read them coalesced.
 //   gp_kmat_kernel   : lower triangle of K = matern52(|zn_i - zn_j| / ell) + sigma^2 I, 64x64 tiles.
-//   gp_chol_kernel   : one CTA per run: blocked left-looking Cholesky (NB = 32, register-tiled FP64 panel GEMM,
-//                      diagonal blocks factored + inverted in shared memory, TRSM by forward substitution),
-//                      blocked triangular inverse W = L^-1, alpha = W^T (W y_s).
+//   (gp_chol.cu)     : Cholesky, W = L^-1, alpha = W^T (W y_s), W^T as a pipeline of tile kernels (pcabo_chol_pipeline)
+//   gp_pack_w_kernel : W repacked in 8-row groups for the bulk copies of the optimiser kernel (w_packed.cuh)
 #include "common.cuh"
 #include "w_packed.cuh"
 
 namespace {
 
 constexpr double SQRT5 = 2.23606797749978969640917366873128;
-constexpr int NB = 32;         // Cholesky block size
-constexpr int CH_THREADS = 256;
-constexpr int MT = 256;        // panel GEMM rows per pass
-constexpr int KB = 16;         // panel GEMM k-tile
-constexpr int AS_LD = MT + 2;  // k-major A tile leading dimension (even -> 16-byte aligned rows)
-constexpr int BS_LD = NB + 2;
 
 // --------------------------------------------------------------------------------------------- prep
 struct PrepArgs {
@@ -185,285 +178,6 @@ __global__ void __launch_bounds__(256) gp_kmat_kernel(int n, int kmax, int ld_n,
         Kb[(size_t)gi * ld_n + gj] = v;
       }
     }
-}
-
-// --------------------------------------------------------------------------------------------- Cholesky + inverse
-// C(r, c) (r < M, c < 32) = beta * C + alpha * sum_{k < K} A(r, k) * Bm(c, k)
-//   A(r, k) = Ap[r * a_rs + k * a_ks]  (a_lower_t: treat A(r, k) as zero when k < r + a_diag_off, for transposed lower W)
-//   Bm(c, k) = Bp[c * ldb + k]
-//   C(r, c) = Cp[r * c_rs + c * c_cs]
-struct Smem {
-  double As[KB][AS_LD];
-  double Bs[KB][BS_LD];
-  double D[NB][NB + 1];     // diagonal block
-  double Di[NB][NB + 1];    // its inverse
-  int info;
-};
-
-__device__ __noinline__ void panel_gemm(Smem &s, double *Cp, long c_rs, long c_cs, const double *Ap, long a_rs, long a_ks,
-                           const double *Bp, long ldb, int M, int K, int ncols, double alpha, double beta,
-                           bool a_k_fast, bool a_lower_t) {
-  const int tid = threadIdx.x;
-  const int tr = tid / 8, tc = tid % 8;
-  for (int m0 = 0; m0 < M; m0 += MT) {
-    double acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    const int rows = min(MT, M - m0);
-    // for the transposed-lower operand, A(r, k) == 0 whenever k < r: k-tiles entirely below m0 contribute nothing
-    int kstart = 0;
-    if (a_lower_t) kstart = (m0 / KB) * KB;
-    // The k-tiles are software pipelined: the global loads of tile k0 + KB are issued into registers before the FMAs of
-    // tile k0 and land while they run (the staging used to be load -> wait -> store -> barrier: 30 % of the kernel's
-    // stall cycles were L2 latency).
-    constexpr int A_PER = MT * KB / CH_THREADS, B_PER = NB * KB / CH_THREADS;
-    double ra[A_PER], rb[B_PER];
-    auto load_tile = [&](int k0) {
-#pragma unroll
-      for (int q = 0; q < A_PER; ++q) {
-        const int idx = tid + q * CH_THREADS;
-        int r, kk;
-        if (a_k_fast) { r = idx / KB; kk = idx % KB; } else { kk = idx / MT; r = idx % MT; }
-        double v = 0.0;
-        if (r < rows && k0 + kk < K && !(a_lower_t && (k0 + kk) < (m0 + r)))
-          v = Ap[(long)(m0 + r) * a_rs + (long)(k0 + kk) * a_ks];
-        ra[q] = v;
-      }
-#pragma unroll
-      for (int q = 0; q < B_PER; ++q) {
-        const int idx = tid + q * CH_THREADS;
-        const int c = idx / KB, kk = idx % KB;
-        double v = 0.0;
-        if (c < ncols && k0 + kk < K) v = Bp[(long)c * ldb + k0 + kk];
-        rb[q] = v;
-      }
-    };
-    auto store_tile = [&]() {
-#pragma unroll
-      for (int q = 0; q < A_PER; ++q) {
-        const int idx = tid + q * CH_THREADS;
-        int r, kk;
-        if (a_k_fast) { r = idx / KB; kk = idx % KB; } else { kk = idx / MT; r = idx % MT; }
-        s.As[kk][r] = ra[q];
-      }
-#pragma unroll
-      for (int q = 0; q < B_PER; ++q) {
-        const int idx = tid + q * CH_THREADS;
-        s.Bs[idx % KB][idx / KB] = rb[q];
-      }
-    };
-    if (kstart < K) load_tile(kstart);
-    for (int k0 = kstart; k0 < K; k0 += KB) {
-      store_tile();
-      __syncthreads();
-      if (k0 + KB < K) load_tile(k0 + KB);
-#pragma unroll
-      for (int kk = 0; kk < KB; ++kk) {
-        double av[8], bv[4];
-        const double2 *ap = reinterpret_cast<const double2 *>(&s.As[kk][tr * 8]);
-        const double2 *bp = reinterpret_cast<const double2 *>(&s.Bs[kk][tc * 4]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { const double2 t2 = ap[i]; av[2 * i] = t2.x; av[2 * i + 1] = t2.y; }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) { const double2 t2 = bp[j]; bv[2 * j] = t2.x; bv[2 * j + 1] = t2.y; }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-      }
-      __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = tr * 8 + i;
-      if (r < rows) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = tc * 4 + j;
-          if (c < ncols) {
-            double *p = Cp + (long)(m0 + r) * c_rs + (long)c * c_cs;
-            *p = (beta == 0.0 ? 0.0 : beta * (*p)) + alpha * acc[i][j];
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-}
-
-struct CholArgs {
-  int B, n, ld_n;
-  double *L, *W, *WT, *alpha;  // alpha holds y_s on entry
-  int *info;
-};
-
-__global__ void __launch_bounds__(CH_THREADS, 1) gp_chol_kernel(CholArgs a) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  Smem &s = *reinterpret_cast<Smem *>(smraw);
-  double *uvec = reinterpret_cast<double *>(smraw + sizeof(Smem));  // [n]
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int n = a.n;
-  const long ld = a.ld_n;
-  double *L = a.L + (size_t)b * ld * ld;
-  double *W = a.W + (size_t)b * ld * ld;
-  double *al = a.alpha + (size_t)b * ld;
-  if (tid == 0) s.info = 0;
-  __syncthreads();
-
-  // ---------------- blocked left-looking Cholesky
-  for (int j0 = 0; j0 < n; j0 += NB) {
-    const int nbj = min(NB, n - j0);
-    const int M = n - j0;
-    if (j0 > 0)
-      panel_gemm(s, L + (long)j0 * ld + j0, ld, 1, L + (long)j0 * ld, ld, 1, L + (long)j0 * ld, ld, M, j0, nbj, -1.0,
-                 1.0, true, false);
-    // diagonal block -> smem (lower), factor with warp 0
-    for (int idx = tid; idx < NB * NB; idx += CH_THREADS) {
-      const int r = idx / NB, c = idx % NB;
-      s.D[r][c] = (r < nbj && c <= r) ? L[(long)(j0 + r) * ld + j0 + c] : ((r == c) ? 1.0 : 0.0);
-    }
-    __syncthreads();
-    if (tid < 32) {
-      const int r = tid;
-      for (int c = 0; c < NB; ++c) {
-        // left-looking inside the block: column c
-        double v = s.D[r][c];
-        if (r >= c) {
-          for (int t = 0; t < c; ++t) v = fma(-s.D[r][t], s.D[c][t], v);
-        }
-        double dcc = __shfl_sync(0xffffffffu, v, c);
-        if (!(dcc > 0.0)) {
-          if (r == c && s.info == 0) s.info = j0 + c + 1;
-          dcc = 1e-300;
-        }
-        const double piv = sqrt(dcc);
-        if (r == c) s.D[r][c] = piv;
-        else if (r > c) s.D[r][c] = v / piv;
-        __syncwarp();
-      }
-      // inverse of the lower-triangular block: lane c solves L x = e_c
-      {
-        const int c = tid;
-        double x[NB];
-#pragma unroll
-        for (int r2 = 0; r2 < NB; ++r2) {
-          double v = (r2 == c) ? 1.0 : 0.0;
-#pragma unroll
-          for (int t = 0; t < r2; ++t) v = fma(-s.D[r2][t], x[t], v);
-          x[r2] = (r2 >= c) ? v / s.D[r2][r2] : 0.0;
-        }
-#pragma unroll
-        for (int r2 = 0; r2 < NB; ++r2) s.Di[r2][c] = x[r2];
-      }
-    }
-    __syncthreads();
-    // write back the factored diagonal block (lower; upper zero) and its inverse into W's diagonal block
-    for (int idx = tid; idx < NB * NB; idx += CH_THREADS) {
-      const int r = idx / NB, c = idx % NB;
-      if (r < nbj && c < nbj) {
-        L[(long)(j0 + r) * ld + j0 + c] = (c <= r) ? s.D[r][c] : 0.0;
-        W[(long)(j0 + r) * ld + j0 + c] = (c <= r) ? s.Di[r][c] : 0.0;
-      }
-    }
-    // TRSM below the diagonal block: row x <- x * Ljj^-T (forward substitution), one thread per row
-    for (int r = j0 + NB + tid; r < n; r += CH_THREADS) {
-      double *row = L + (long)r * ld + j0;
-      double x[NB];
-#pragma unroll
-      for (int c = 0; c < NB; ++c) x[c] = row[c];
-#pragma unroll
-      for (int c = 0; c < NB; ++c) {
-        double v = x[c];
-#pragma unroll
-        for (int t = 0; t < c; ++t) v = fma(-x[t], s.D[c][t], v);
-        x[c] = v / s.D[c][c];
-      }
-#pragma unroll
-      for (int c = 0; c < NB; ++c) row[c] = x[c];
-    }
-    __syncthreads();
-  }
-
-  // ---------------- blocked inverse W = L^-1 (lower). Diagonal blocks of W already hold inv(Ljj).
-  for (int i0 = NB; i0 < n; i0 += NB) {
-    const int nbi = min(NB, n - i0);
-    // T(r, c) = sum_k W[k][r] * L[i0 + c][k],  r in [0, i0), k in [r, i0)  -> stored at W[i0 + c][r]
-    panel_gemm(s, W + (long)i0 * ld, 1, ld, W, 1, ld, L + (long)i0 * ld, ld, i0, i0, nbi, 1.0, 0.0, false, true);
-    // W[i0 + :, r] <- - Wii * T[:, r]   (Wii = inv(Lii), lower), one thread per column r
-    for (int idx = tid; idx < NB * NB; idx += CH_THREADS) {
-      const int r = idx / NB, c = idx % NB;
-      s.Di[r][c] = (r < nbi && c < nbi) ? W[(long)(i0 + r) * ld + i0 + c] : 0.0;
-    }
-    __syncthreads();
-    for (int r = tid; r < i0; r += CH_THREADS) {
-      double v[NB];
-#pragma unroll
-      for (int c = 0; c < NB; ++c) v[c] = (c < nbi) ? W[(long)(i0 + c) * ld + r] : 0.0;
-#pragma unroll
-      for (int c = NB - 1; c >= 0; --c) {
-        double acc = 0.0;
-#pragma unroll
-        for (int t = 0; t <= c; ++t) acc = fma(s.Di[c][t], v[t], acc);
-        if (c < nbi) W[(long)(i0 + c) * ld + r] = -acc;
-      }
-    }
-    __syncthreads();
-  }
-
-  // ---------------- alpha = W^T (W y_s)
-  {
-    const int warp = tid >> 5, lane = tid & 31, nw = CH_THREADS >> 5;
-    for (int i = warp; i < n; i += nw) {
-      double acc = 0.0;
-      for (int j = lane; j <= i; j += 32) acc = fma(W[(long)i * ld + j], al[j], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) uvec[i] = acc;
-    }
-    __syncthreads();
-    for (int j = tid; j < n; j += CH_THREADS) {
-      double acc = 0.0;
-      for (int i = j; i < n; ++i) acc = fma(W[(long)i * ld + j], uvec[i], acc);
-      al[j] = acc;
-    }
-  }
-  // ---------------- WT = W^T (upper triangular, row-major): 32 x 32 tiles through shared memory, coalesced both ways
-  {
-    double *WT = a.WT + (size_t)b * ld * ld;
-    const int nb = (n + NB - 1) / NB;
-    for (int ti = 0; ti < nb; ++ti)
-      for (int tj = 0; tj <= ti; ++tj) {
-        __syncthreads();
-        for (int idx = tid; idx < NB * NB; idx += CH_THREADS) {
-          const int r = idx / NB, c = idx % NB;
-          const int i = ti * NB + r, j = tj * NB + c;
-          s.D[r][c] = (i < n && j <= i) ? W[(long)i * ld + j] : 0.0;
-        }
-        __syncthreads();
-        for (int idx = tid; idx < NB * NB; idx += CH_THREADS) {
-          const int r = idx / NB, c = idx % NB;
-          const int j = tj * NB + r, i = ti * NB + c;   // WT[j][i] = W[i][j]
-          if (i < n && j < n) {
-            if (j <= i) WT[(long)j * ld + i] = s.D[c][r];
-            else WT[(long)j * ld + i] = 0.0;     // strict lower part of a diagonal tile
-          }
-        }
-      }
-    // The evaluation kernels read whole 64 x 64 diagonal blocks of W and WT (uniform trip counts, coalesced rows): the
-    // off-diagonal 32 x 32 tile of each such block that lies above W's / below WT's diagonal is written as zero here.
-    __syncthreads();
-    for (int ti = 0; ti + 1 < nb; ti += 2)
-      for (int idx = tid; idx < NB * NB; idx += CH_THREADS) {
-        const int r = idx / NB, c = idx % NB;
-        const int i = ti * NB + r, j = (ti + 1) * NB + c;   // i < j
-        if (j < n) {
-          W[(long)i * ld + j] = 0.0;
-          WT[(long)j * ld + i] = 0.0;
-        }
-      }
-  }
-  if (tid == 0) a.info[b] = s.info;
 }
 
 // W (row-major lower triangle) -> the packed 8-row groups the optimiser kernel streams (w_packed.cuh). grid (groups, B).
@@ -636,23 +350,6 @@ extern "C" int pcabo_gp_fit_jitter(int B, int n, int kmax, int ld_n, int mode, c
                                    double *L, double *W, double *WT, double *alpha, int *info, void *stream) {
   return pcabo_gp_fit_hyper(B, n, kmax, ld_n, mode, Z, k, f, fix_lo, fix_hi, lengthscale, noise, nullptr, nullptr, jitter,
                             norm_off, norm_coef, box_lo, box_hi, ymean, ystd, ZnT, Zn, L, W, WT, alpha, info, stream);
-}
-
-extern "C" int pcabo_gp_fit_onecta(int B, int n, int kmax, int ld_n, double *L, double *W, double *WT, double *alpha,
-                                   int *info, void *stream) {
-  // round-1 factorisation (one thread block per run), kept as a yardstick for tools/measure_fp64.py: L holds K on entry
-  if (B <= 0 || n < 1 || ld_n < n || !L || !W || !WT || !alpha || !info) return PCABO_E_INVALID;
-  (void)kmax;
-  cudaStream_t st = as_stream(stream);
-  {
-    CholArgs a;
-    a.B = B; a.n = n; a.ld_n = ld_n; a.L = L; a.W = W; a.WT = WT; a.alpha = alpha; a.info = info;
-    const size_t smem = sizeof(Smem) + (size_t)n * sizeof(double);
-    PCABO_CUDA_CHECK(cudaFuncSetAttribute(gp_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gp_chol_kernel<<<B, CH_THREADS, smem, st>>>(a);
-    PCABO_LAUNCH_CHECK();
-  }
-  return PCABO_OK;
 }
 
 extern "C" int pcabo_gp_fit(int B, int n, int kmax, int ld_n, int mode, const double *Z, const int *k, const double *f,

@@ -277,3 +277,33 @@ def test_iohprofiler_writer_matches_reference_layout(tmp_path):
         if alg == "pca":
             assert run0["best"]["evals"] == kat["best"][str(fid)][inst]["evals"]
             assert abs(run0["best"]["y"] - kat["best"][str(fid)][inst]["y"]) < 1e-9
+
+
+def test_host_side_abi_planning_functions():
+    """The ABI's host-only planning functions need no GPU: the packed-W size (w_packed.cuh), the optimiser kernel's
+    shared-memory plan and its workspace need, for the configs of BASELINE (C1..C5)."""
+    from pcabo_b200 import ops
+    lib = ops.load_library()
+    # packed W: groups of 8 rows, row stride 8 g + (g odd ? 12 : 20), back to back
+    def packed(n):
+        return sum(8 * (8 * g + (12 if g & 1 else 20)) for g in range((n + 7) // 8))
+    for n in (1, 8, 9, 123, 150, 250, 450, 1050):
+        assert lib.pcabo_gp_packed_doubles(n) == packed(n)
+    assert lib.pcabo_gp_packed_doubles(0) == -1
+    # plans: everything resident while it fits (32-row panels), streaming 16- then 8-row panels beyond; always <= 227 KB;
+    # the BFGS pairs move to the caller's workspace only for the D = 100 stress config
+    for (n, kmax, k) in [(31, 10, 8), (150, 10, 10), (123, 40, 32)]:
+        p = ops.lbfgsb_plan(n, kmax, k)
+        assert p["resident"] == 1 and p["panel_rows"] == 32 and p["pairs_in_workspace"] == 0
+    for (n, kmax, k) in [(250, 20, 20), (300, 40, 40), (450, 40, 40), (303, 100, 90)]:
+        p = ops.lbfgsb_plan(n, kmax, k)
+        assert p["resident"] == 0 and p["panel_rows"] in (8, 16) and p["pairs_in_workspace"] == 0
+        assert p["smem_bytes"] <= 227 * 1024 and p["ring_doubles"] >= 2 * p["panel_rows"] * (n + 20) // 2 or p["panel_rows"] == 8
+        assert ops.lbfgsb_workspace_doubles(n, kmax, k) == 0
+    for k in (90, 100):
+        p = ops.lbfgsb_plan(1050, 100, k)
+        assert p["pairs_in_workspace"] == 1 and p["panel_rows"] == 8 and p["smem_bytes"] <= 227 * 1024
+        nvar = 5 * k
+        assert ops.lbfgsb_workspace_doubles(1050, 100, k, 10, 5, 7) == 7 * 2 * 2 * 10 * (((nvar + 15) & ~15) + 8)
+    assert ops.lbfgsb_workspace_doubles(450, 40, 40, 10, 8, 1) == -1        # batch_limit > 5 is not supported
+    assert ops.gp_fit_launches(450) == 2 + 15 + 1 + 2 + 1
