@@ -197,9 +197,9 @@ int pcabo_lbfgsb_logei_runs(const pcabo_gp_model *m, int nsel, const int *run_id
  * callee). pcabo_lbfgsb_workspace_doubles returns the number of doubles needed for `nsel` runs (0: shared memory
  * suffices and workspace may be NULL; -1: the problem does not fit either way -> PCABO_E_UNSUPPORTED).              */
 long long pcabo_lbfgsb_workspace_doubles(int n, int kmax, int k_bound, int num_restarts, int batch_limit, int nsel);
-/* The shared-memory plan the launcher would choose (host only, no device work): plan6 = {panel rows (8 / 16), ring
- * capacity in doubles, 1 if every panel of W stays resident in the ring, 1 if panels are released behind a barrier of
- * their own (small ring), 1 if the BFGS pairs live in the workspace, dynamic shared memory in bytes}.                */
+/* The shared-memory plan the launcher would choose (host only, no device work): plan6 = {panel rows (8 / 16 / 32), ring
+ * capacity in doubles, 1 if every panel of W stays resident in the ring, 0 (reserved), 1 if the BFGS pairs live in the
+ * workspace, dynamic shared memory in bytes}.                                                                         */
 int pcabo_lbfgsb_plan(int n, int kmax, int k_bound, int batch_limit, int have_workspace, int *plan6);
 int pcabo_lbfgsb_logei_runs_ws(const pcabo_gp_model *m, int nsel, const int *run_idx, int k_bound, int num_restarts,
                                int batch_limit, int maxiter, double factr, double pgtol, const double *ics,

@@ -6,6 +6,12 @@
 // inside the reference's optimize_acqf call (PCA_BO.py:607-614). The algorithm is
 // lbfgsb_core.cuh (validated on the host against scipy, tests/test_lbfgsb_core.py); tolerances are scipy's defaults
 // (factr = 2.22e-9 / eps = 1e7, pgtol = 1e-5, m = 10, maxls = 20).
+//
+// Block = 9 warps, one block per SM (up to 227 KB of shared memory): warp 0 is the optimiser ("brain": Cauchy point,
+// subspace minimisation, line search, BFGS update; small dense kernels warp-synchronous in shared memory), warps 0-7
+// evaluate log-EI value + gradient together (lbfgsb_eval.cuh: one sweep over the packed W on the FP64 tensor cores) and
+// share formk's O(m^2 n) products and the pair shift, warp 8 is the bulk-copy (TMA) producer of the W panel ring. The
+// compute warps synchronise on a named barrier the producer never joins; the brain posts commands through a mailbox.
 #include "lbfgsb_core.cuh"
 #include "lbfgsb_eval.cuh"
 
@@ -19,8 +25,8 @@ enum Cmd { CMD_EVAL = 1, CMD_FORMK = 2, CMD_EXIT = 3, CMD_SHIFT = 4 };
 // ROW of a block of the matrix (k = seg, seg + 8, ...): rows 0..col-1 of Y'ZZ'Y (entries j >= i), of S'AA'S (j >= i) and
 // of the mixed block (all jy for one iy), 3 col <= 30 row tasks = 240 threads, ONE pass. The row's own vector and the
 // free / active indicator are loaded once per k for up to 10 entries (round 1 dealt single entries to the lane groups:
-// three loads per FMA and seven passes, shared-memory bound at 14 k cycles). The free / active split is a 0/1 multiplier
-// instead of a branch; per entry the summation order is the same fixed xor-shuffle tree as before (bit-identical).
+// three loads per FMA and seven passes, 14 k cycles; now 8 k). The free / active split is a 0/1 multiplier folded into
+// the row's own value instead of a branch; the summation order per entry is a fixed xor-shuffle tree (deterministic).
 // (force-inlined into the kernel so that the pointers of `w` keep their shared-memory provenance: as a separate function
 // it reads them from the struct and every access becomes a generic load)
 __device__ __forceinline__ void formk_products_block(const lbfgsb::Work &w, int col, double theta) {

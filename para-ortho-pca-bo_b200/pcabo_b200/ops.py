@@ -222,12 +222,13 @@ def lbfgsb_workspace_doubles(n, kmax, k_bound, num_restarts=10, batch_limit=5, n
 
 
 def lbfgsb_plan(n, kmax, k_bound, batch_limit=5, have_workspace=True):
-    """The launcher's shared-memory plan as a dict (panel_rows, ring_doubles, resident, tight, pairs_in_workspace,
-    smem_bytes)."""
+    """The launcher's shared-memory plan as a dict (panel_rows, ring_doubles, resident, pairs_in_workspace, smem_bytes)."""
     out = (ctypes.c_int * 6)()
     check(load_library().pcabo_lbfgsb_plan(int(n), int(kmax), int(k_bound), int(batch_limit), int(bool(have_workspace)), out),
           "pcabo_lbfgsb_plan")
-    return dict(zip(("panel_rows", "ring_doubles", "resident", "tight", "pairs_in_workspace", "smem_bytes"), list(out)))
+    d = dict(zip(("panel_rows", "ring_doubles", "resident", "reserved", "pairs_in_workspace", "smem_bytes"), list(out)))
+    d.pop("reserved")
+    return d
 
 
 def lbfgsb_fits(n, kmax, k_bound, batch_limit=5):
