@@ -65,6 +65,82 @@ __device__ __forceinline__ void tile_mma(double (&acc)[8][2], const double *As, 
   }
 }
 
+// Factorisation D = L L^T of the 64 x 64 diagonal block in shared memory (lower triangle of D, row stride TLD) and
+// X = L^-1, by the 256 threads of the block. s_rdiag: 64 doubles of shared scratch; *s_info: first failed pivot (+ base).
+// All threads call; ends with a block barrier; `lane` = threadIdx.x & 31.
+__device__ __forceinline__ void diag_factor_invert(double *D, double *X, double *s_rdiag, int *s_info, int base) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  // right-looking on the UNSCALED columns: d_rs -= d_rc d_sc / d_cc for c < s <= r; one barrier per column
+  {
+    const int tr = tid >> 4, tc = tid & 15;
+    for (int c = 0; c < T - 1; ++c) {
+      double d = D[c * TLD + c];
+      if (!(d > 0.0)) {
+        if (tid == 0 && *s_info == 0) *s_info = base + c + 1;
+        d = 1e-300;
+      }
+      const double dinv = 1.0 / d;
+      double colr[4], cols[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int r = c + 1 + tr + 16 * a, s = c + 1 + tc + 16 * a;
+        colr[a] = (r < T) ? D[r * TLD + c] * dinv : 0.0;
+        cols[a] = (s < T) ? D[s * TLD + c] : 0.0;
+      }
+      // (loading all 16 entries up front and storing conditionally -- branch free -- measured slower: 58.7 k against 55 k
+      // cycles for the whole block, tools/micro/chol_diag.cu)
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const int r = c + 1 + tr + 16 * a, s = c + 1 + tc + 16 * bb;
+          if (r < T && s <= r) D[r * TLD + s] = fma(-colr[a], cols[bb], D[r * TLD + s]);
+        }
+      __syncthreads();
+    }
+    {
+      double d = D[(T - 1) * TLD + T - 1];
+      if (!(d > 0.0) && tid == 0 && *s_info == 0) *s_info = base + T;
+    }
+  }
+  // scale the columns: L_rc = d_rc / sqrt(d_cc) (a failed pivot is replaced by 1e-300 like the flag says)
+  {
+    const int c = tid & 63;
+    double d = D[c * TLD + c];
+    if (!(d > 0.0)) d = 1e-300;
+    const double rs = rsqrt(d);
+    __syncthreads();
+    for (int r = tid >> 6; r < T; r += NTH / 64)
+      if (r >= c) D[r * TLD + c] = (r == c) ? d * rs : D[r * TLD + c] * rs;
+  }
+  __syncthreads();
+  // X = D^-1 by column sweeps, four threads per column: thread (c, q) keeps the entries b_r, r = 4 m + q, of the
+  // right-hand side e_c in registers; step k: x_k = b_k / d_kk travels from its owner by a shuffle, b_r -= d_rk x_k for
+  // r > k (independent FMAs). Fully unrolled: the serial chain per step is one shuffle and one multiplication.
+  if (tid < T) s_rdiag[tid] = 1.0 / D[tid * TLD + tid];
+  __syncthreads();
+  {
+    const int c = tid >> 2, q = tid & 3;
+    double bv[T / 4];
+#pragma unroll
+    for (int m = 0; m < T / 4; ++m) bv[m] = (4 * m + q == c) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+      const int mk = k >> 2, qk = k & 3;
+      const double xk = __shfl_sync(0xffffffffu, bv[mk], (lane & ~3) | qk) * s_rdiag[k];
+      if (q == qk) bv[mk] = xk;
+#pragma unroll
+      for (int m = mk; m < T / 4; ++m) {
+        const int r = 4 * m + q;
+        if (m > mk || q > qk) bv[m] = fma(-D[r * TLD + k], xk, bv[m]);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < T / 4; ++m) X[(4 * m + q) * TLD + c] = bv[m];
+  }
+  __syncthreads();
+}
+
 struct CholP {
   int n, ld, j;
   double *L, *W;
@@ -128,74 +204,8 @@ __global__ void __launch_bounds__(NTH, 2) chol_update_kernel(CholP p) {
   __shared__ int s_info;
   if (tid == 0) s_info = 0;
   __syncthreads();
-  // right-looking on the UNSCALED columns: d_rs -= d_rc d_sc / d_cc for c < s <= r; one barrier per column
-  {
-    const int tr = tid >> 4, tc = tid & 15;
-    for (int c = 0; c < T - 1; ++c) {
-      double d = D[c * TLD + c];
-      if (!(d > 0.0)) {
-        if (tid == 0 && s_info == 0) s_info = j * T + c + 1;
-        d = 1e-300;
-      }
-      const double dinv = 1.0 / d;
-      double colr[4], cols[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int r = c + 1 + tr + 16 * a, s = c + 1 + tc + 16 * a;
-        colr[a] = (r < T) ? D[r * TLD + c] * dinv : 0.0;
-        cols[a] = (s < T) ? D[s * TLD + c] : 0.0;
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-          const int r = c + 1 + tr + 16 * a, s = c + 1 + tc + 16 * bb;
-          if (r < T && s <= r) D[r * TLD + s] = fma(-colr[a], cols[bb], D[r * TLD + s]);
-        }
-      __syncthreads();
-    }
-    {
-      double d = D[(T - 1) * TLD + T - 1];
-      if (!(d > 0.0) && tid == 0 && s_info == 0) s_info = j * T + T;
-    }
-  }
-  // scale the columns: L_rc = d_rc / sqrt(d_cc) (a failed pivot is replaced by 1e-300 like the flag says)
-  {
-    const int c = tid & 63;
-    double d = D[c * TLD + c];
-    if (!(d > 0.0)) d = 1e-300;
-    const double rs = rsqrt(d);
-    __syncthreads();
-    for (int r = tid >> 6; r < T; r += NTH / 64)
-      if (r >= c) D[r * TLD + c] = (r == c) ? d * rs : D[r * TLD + c] * rs;
-  }
-  __syncthreads();
-  // X = D^-1 by column sweeps, four threads per column: thread (c, q) keeps the entries b_r, r = 4 m + q, of the
-  // right-hand side e_c in registers; step k: x_k = b_k / d_kk travels from its owner by a shuffle, b_r -= d_rk x_k for
-  // r > k (independent FMAs). Fully unrolled: the serial chain per step is one shuffle and one multiplication.
   __shared__ double s_rdiag[T];
-  if (tid < T) s_rdiag[tid] = 1.0 / D[tid * TLD + tid];
-  __syncthreads();
-  {
-    const int c = tid >> 2, q = tid & 3;
-    double bv[T / 4];
-#pragma unroll
-    for (int m = 0; m < T / 4; ++m) bv[m] = (4 * m + q == c) ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = 0; k < T; ++k) {
-      const int mk = k >> 2, qk = k & 3;
-      const double xk = __shfl_sync(0xffffffffu, bv[mk], (lane & ~3) | qk) * s_rdiag[k];
-      if (q == qk) bv[mk] = xk;
-#pragma unroll
-      for (int m = mk; m < T / 4; ++m) {
-        const int r = 4 * m + q;
-        if (m > mk || q > qk) bv[m] = fma(-D[r * TLD + k], xk, bv[m]);
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < T / 4; ++m) X[(4 * m + q) * TLD + c] = bv[m];
-  }
-  __syncthreads();
+  diag_factor_invert(D, X, s_rdiag, &s_info, j * T);
   double *W = p.W + (size_t)b * ld * ld;
   for (int idx = tid; idx < T * T; idx += NTH) {
     const int r = idx >> 6, c = idx & 63, g_r = j * T + r, g_c = j * T + c;
