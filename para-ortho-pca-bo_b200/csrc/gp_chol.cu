@@ -14,7 +14,7 @@
 //     chol_solve_kernel   grid (tiles i > j, runs): L[i][j] = C[i][j] W[j][j]^T
 //   tri_inverse_kernel    grid (block columns J, runs): W[i][J] = -W[i][i] sum_{k=J}^{i-1} L[i][k] W[k][J], i = J+1, ...
 //                         (the block columns of L^-1 are independent of each other)
-//   alpha_kernel          grid (runs): alpha = W^T (W y_s)
+//   alpha_u / alpha_wt    grid (runs, 64-row blocks): u = W y_s, alpha = W^T u
 //   transpose_kernel      grid (lower tiles, runs): WT = W^T
 #include "async_copy.cuh"
 #include "common.cuh"
@@ -151,7 +151,9 @@ struct CholP {
 __global__ void __launch_bounds__(NTH, 2) chol_update_kernel(CholP p) {
   extern __shared__ __align__(16) double sm[];
   double *As = sm, *Bs = sm + T * TLD;      // later: D = As (factor), X = Bs (inverse)
-  const int b = blockIdx.y, j = p.j, i = j + blockIdx.x;
+  // (the run index is the fastest grid dimension: the long diagonal-block CTAs (blockIdx.y = 0) of all runs are
+  // scheduled first and spread one per SM, instead of sharing an SM with each other behind the short off-diagonal ones)
+  const int b = blockIdx.x, j = p.j, i = j + blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
   const int n = p.n;
   const long ld = p.ld;
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(NTH, 2) chol_update_kernel(CholP p) {
 __global__ void __launch_bounds__(NTH, 2) chol_solve_kernel(CholP p) {
   extern __shared__ __align__(16) double sm[];
   double *As = sm, *Bs = sm + T * TLD;
-  const int b = blockIdx.y, j = p.j, i = j + 1 + blockIdx.x;
+  const int b = blockIdx.x, j = p.j, i = j + 1 + blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
   const int n = p.n;
   const long ld = p.ld;
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(NTH, 2) chol_solve_kernel(CholP p) {
 __global__ void __launch_bounds__(NTH, 2) tri_inverse_kernel(int n, int ld_n, const double *Lg, double *Wg) {
   extern __shared__ __align__(16) double sm[];
   double *As = sm, *Bs = sm + T * TLD;
-  const int b = blockIdx.y, J = blockIdx.x;
+  const int b = blockIdx.x, J = blockIdx.y;   // (J = 0, the longest block column, first)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
   const long ld = ld_n;
   const double *L = Lg + (size_t)b * ld * ld;
@@ -302,37 +304,52 @@ __global__ void __launch_bounds__(NTH, 2) tri_inverse_kernel(int n, int ld_n, co
   }
 }
 
-// ---- alpha = W^T (W y_s); alpha holds y_s on entry. One block per run.
-__global__ void __launch_bounds__(NTH) alpha_kernel(int n, int ld_n, const double *Wg, double *alpha) {
-  extern __shared__ __align__(16) double sm[];
-  double *u = sm, *y = sm + ((n + 1) & ~1);
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+// ---- alpha = W^T (W y_s) in two kernels of (64-row / 64-column blocks) x runs (one block per run took 225 us at
+//      90 x 450: a chain of L2 round trips; the 8 x 90 blocks of each kernel overlap theirs).
+//      u = W y_s: warp per row, lanes over the columns j <= i; y_s is read from `alpha`, u goes to `u_out`.
+__global__ void __launch_bounds__(NTH) alpha_u_kernel(int n, int ld_n, const double *Wg, const double *alpha, double *u_out) {
+  const int b = blockIdx.x, i0 = blockIdx.y * T, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long ld = ld_n;
   const double *W = Wg + (size_t)b * ld * ld;
-  double *al = alpha + (size_t)b * ld;
-  for (int i = tid; i < n; i += NTH) y[i] = al[i];
-  __syncthreads();
-  for (int i = warp; i < n; i += NTH / 32) {
-    double a0 = 0.0, a1 = 0.0;
-    int jj = lane;
-    for (; jj + 32 <= i; jj += 64) { a0 = fma(W[(long)i * ld + jj], y[jj], a0); a1 = fma(W[(long)i * ld + jj + 32], y[jj + 32], a1); }
-    for (; jj <= i; jj += 32) a0 = fma(W[(long)i * ld + jj], y[jj], a0);
-    const double s = warp_sum(a0 + a1);
-    if (lane == 0) u[i] = s;
-  }
-  __syncthreads();
-  for (int jj = tid; jj < n; jj += NTH) {
+  const double *y = alpha + (size_t)b * ld;
+  for (int i = i0 + warp; i < min(i0 + T, n); i += NTH / 32) {
+    const double *row = W + (long)i * ld;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int i = jj;
-    for (; i + 3 < n; i += 4) {
-      a0 = fma(W[(long)i * ld + jj], u[i], a0);
-      a1 = fma(W[(long)(i + 1) * ld + jj], u[i + 1], a1);
-      a2 = fma(W[(long)(i + 2) * ld + jj], u[i + 2], a2);
-      a3 = fma(W[(long)(i + 3) * ld + jj], u[i + 3], a3);
+    int jj = lane;
+    for (; jj + 96 <= i; jj += 128) {
+      const double w0 = row[jj], w1 = row[jj + 32], w2 = row[jj + 64], w3 = row[jj + 96];
+      a0 = fma(w0, y[jj], a0); a1 = fma(w1, y[jj + 32], a1); a2 = fma(w2, y[jj + 64], a2); a3 = fma(w3, y[jj + 96], a3);
     }
-    for (; i < n; ++i) a0 = fma(W[(long)i * ld + jj], u[i], a0);
-    al[jj] = (a0 + a1) + (a2 + a3);
+    for (; jj <= i; jj += 32) a0 = fma(row[jj], y[jj], a0);
+    const double s = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) u_out[(size_t)b * ld * ld + i] = s;   // first row of this run's scratch matrix
   }
+}
+
+//      alpha = W^T u: block = 64 columns; thread (q, c): column j0 + c, rows i = j0 + q, j0 + q + 4, ... (coalesced over
+//      c), eight loads in flight; the four row classes are combined through shared memory.
+__global__ void __launch_bounds__(NTH) alpha_wt_kernel(int n, int ld_n, const double *Wg, const double *u_in, double *alpha) {
+  __shared__ double red[4][T];
+  const int b = blockIdx.x, j0 = blockIdx.y * T, tid = threadIdx.x, c = tid & 63, q = tid >> 6;
+  const long ld = ld_n;
+  const double *W = Wg + (size_t)b * ld * ld;
+  const double *u = u_in + (size_t)b * ld * ld;
+  const int jj = j0 + c;
+  double a0 = 0.0, a1 = 0.0;
+  if (jj < n) {
+    int i = j0 + q;     // rows above the diagonal of this column hold zeros inside the 64 x 64 diagonal tile
+    for (; i + 28 < n; i += 32) {
+      double w8[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) w8[t] = W[(long)(i + 4 * t) * ld + jj];
+#pragma unroll
+      for (int t = 0; t < 8; t += 2) { a0 = fma(w8[t], u[i + 4 * t], a0); a1 = fma(w8[t + 1], u[i + 4 * t + 4], a1); }
+    }
+    for (; i < n; i += 4) a0 = fma(W[(long)i * ld + jj], u[i], a0);
+  }
+  red[q][c] = a0 + a1;
+  __syncthreads();
+  if (q == 0 && jj < n) alpha[(size_t)b * ld + jj] = (red[0][c] + red[1][c]) + (red[2][c] + red[3][c]);
 }
 
 // ---- WT = W^T by 64 x 64 tiles (lower tiles of W -> upper tiles of WT); in a diagonal tile both triangles are written
@@ -376,18 +393,21 @@ int pcabo_chol_pipeline(int B, int n, int ld_n, double *L, double *W, double *WT
   p.n = n; p.ld = ld_n; p.L = L; p.W = W; p.info = info;
   for (int j = 0; j < nb; ++j) {
     p.j = j;
-    chol_update_kernel<<<dim3(nb - j, B), NTH, smem, st>>>(p);
+    chol_update_kernel<<<dim3(B, j == 0 ? 1 : nb - j), NTH, smem, st>>>(p);   // (j = 0: only the diagonal block changes)
     PCABO_LAUNCH_CHECK();
     if (j + 1 < nb) {
-      chol_solve_kernel<<<dim3(nb - j - 1, B), NTH, smem, st>>>(p);
+      chol_solve_kernel<<<dim3(B, nb - j - 1), NTH, smem, st>>>(p);
       PCABO_LAUNCH_CHECK();
     }
   }
   if (nb > 1) {
-    tri_inverse_kernel<<<dim3(nb - 1, B), NTH, smem, st>>>(n, ld_n, L, W);
+    tri_inverse_kernel<<<dim3(B, nb - 1), NTH, smem, st>>>(n, ld_n, L, W);
     PCABO_LAUNCH_CHECK();
   }
-  alpha_kernel<<<B, NTH, (size_t)2 * ((n + 1) & ~1) * sizeof(double), st>>>(n, ld_n, W, alpha);
+  // u = W y_s lands in the first row of WT of each run (WT is only written by the transpose below), alpha = W^T u
+  alpha_u_kernel<<<dim3(B, nb), NTH, 0, st>>>(n, ld_n, W, alpha, WT);
+  PCABO_LAUNCH_CHECK();
+  alpha_wt_kernel<<<dim3(B, nb), NTH, 0, st>>>(n, ld_n, W, WT, alpha);
   PCABO_LAUNCH_CHECK();
   transpose_kernel<<<dim3(nb * (nb + 1) / 2, B), NTH, 0, st>>>(n, ld_n, W, WT);
   PCABO_LAUNCH_CHECK();

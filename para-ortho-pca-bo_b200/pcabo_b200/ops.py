@@ -141,7 +141,7 @@ def gp_fit_launches(n):
     """Kernel launches of one pcabo_gp_fit + pcabo_gp_pack_w call: prep, kernel matrix, per 64-column block an update (+
     a solve below the last), the triangular inverse, alpha, the transpose, the packing."""
     nb = (int(n) + 63) // 64
-    return 2 + (2 * nb - 1) + (1 if nb > 1 else 0) + 2 + 1
+    return 2 + (2 * nb - 1) + (1 if nb > 1 else 0) + 3 + 1
 
 
 def gp_mll(buf: GPBuffers, f):

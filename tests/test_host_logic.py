@@ -306,4 +306,4 @@ def test_host_side_abi_planning_functions():
         nvar = 5 * k
         assert ops.lbfgsb_workspace_doubles(1050, 100, k, 10, 5, 7) == 7 * 2 * 2 * 10 * (((nvar + 15) & ~15) + 8)
     assert ops.lbfgsb_workspace_doubles(450, 40, 40, 10, 8, 1) == -1        # batch_limit > 5 is not supported
-    assert ops.gp_fit_launches(450) == 2 + 15 + 1 + 2 + 1
+    assert ops.gp_fit_launches(450) == 2 + 15 + 1 + 3 + 1
