@@ -219,6 +219,15 @@ int pcabo_ei_sweep(const pcabo_gp_model *m, int run, long long ncand, long long 
                    double *part_val, long long *part_idx, int nparts, double *best_val, long long *best_idx,
                    void *stream);
 
+/* The raw-sample scoring pass of optimize_acqf for ALL runs of the batch in one launch (PCA_BO.py:607-614: botorch scores
+ * raw_samples = 512 scrambled-Sobol points per optimize_acqf call with LogExpectedImprovement, 5 at a time): the tile
+ * pipeline of pcabo_ei_sweep (FP64 tensor cores, DMMA.8x8x4) with one row of `ctas_per_run` CTAs per run (0: chosen so
+ * that the launch is one wave of the SMs), values out, no arg-max.  X [B][npts][kmax] raw-space points, val [B][npts].
+ * Same limits as pcabo_ei_sweep (log-EI only, n <= 512, even ld_n and kmax); PCABO_E_UNSUPPORTED otherwise -- the
+ * caller then scores with pcabo_logei, which has no such limits.                                                     */
+int pcabo_logei_raw_runs(const pcabo_gp_model *m, int npts, const double *X, double *val, int ctas_per_run,
+                         void *stream);
+
 /* Scrambled Sobol raw samples scaled to the search box, generated on the device from host-drawn scramble bits
  * (replaces botorch draw_sobol_samples / torch SobolEngine(k, scramble=True).draw(npts, float64) inside optimize_acqf,
  * PCA_BO.py:607-614; bit-identical to torch).  shift [B][kmax] (30-bit), ltm_dots [B][kmax][30] (rows of the random
@@ -245,6 +254,21 @@ int pcabo_gather_rows(int B, int npts, int nsel, int kmax, const double *X, cons
 int pcabo_select_initial_conditions(int B, int nraw, int nsel, int kmax, double eta, const double *vals,
                                     unsigned *mt_state, int *mt_pos, const double *X, double *ics, int *idx,
                                     int *flag, void *stream);
+
+/* optimize_acqf's return value (PCA_BO.py:607-614, 618-619): torch.argmax over the final log-EI values of the restarts
+ * (first occurrence) and the winning candidate.  vals [B][R], cand [B][R][D] -> z_new [B][D], best_val [B], best_idx [B]
+ * (may be NULL).                                                                                                    */
+int pcabo_pick_best(int B, int R, int D, const double *vals, const double *cand, double *z_new, double *best_val,
+                    int *best_idx, void *stream);
+
+/* The bookkeeping tail of PCA_BO.__call__ (PCA_BO.py:239-281) on the device, so that the host never waits for it:
+ * f = oob ? penalty : f_new (an outside point is not evaluated, :259-263), X[b][n] = x_new[b], f[b][n] = f,
+ * best[b] = min / max(best[b], f) (AbstractBayesianOptimizer.assign_new_best :196-208) and best_f[b] = best[b] rounded
+ * to float32 as botorch will store it in the next iteration's acquisition (:199-203).  oob, z_new, acq, rec may be NULL;
+ * rec [B][2 D + 3] = (x_new, z_new, f, oob, acq) is the packed record the host reads back asynchronously.          */
+int pcabo_append_observation(int B, int D, int ld_n, int n, const double *x_new, const double *z_new,
+                             const double *f_new, const int *oob, const double *acq, double penalty, int maximization,
+                             double *X, double *f, double *best, double *best_f, double *rec, void *stream);
 
 /* Batched BBOB objectives f15 / f16 / f17 / f20 (the synthetic workloads of BASELINE configs C1-C3), one block per
  * (problem, point): replaces the per-iteration host call problem(x) of the reference (PCA_BO.py:263,

@@ -61,8 +61,10 @@ struct SweepArgs {
   const int *shift, *sstate;   // Sobol: [kmax] shifts and [kmax][30] scrambled direction numbers
   const double *lo, *hi;       // box [kmax]
   double *vals;                // optional [ncand]
-  double *best_val;            // [gridDim.x]
+  double *best_val;            // [gridDim.x] (nullptr in the multi-run form: values only)
   long long *best_idx;         // [gridDim.x] global indices
+  int multi;                   // 1: one row of CTAs per run (run = blockIdx.y), X / vals advance by x_stride / ncand per run
+  long long x_stride;          // doubles between the candidate sets of consecutive runs (multi-run form)
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -191,7 +193,9 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = m.n, kmax = m.kmax;
   const long ld = m.ld_n;
-  const int b = a.b;
+  const int b = a.multi ? (int)blockIdx.y : a.b;
+  const double *const Xc = (a.X != nullptr && a.multi) ? a.X + (size_t)b * a.x_stride : a.X;
+  double *const valsc = (a.vals != nullptr && a.multi) ? a.vals + (size_t)b * a.ncand : a.vals;
   const int kk = m.k ? m.k[b] : kmax;
   const int kk4 = (kk + 3) / 4;               // k-steps of the distance MMA
   const int zld = sweep_zld(kmax);
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
   const double d0 = 1e-15;
   const double kss = (SQRT5 * d0 + 1.0 + (5.0 / 3.0) * (d0 * d0)) * exp(-SQRT5 * d0);
 
-  if (a.X == nullptr)
+  if (Xc == nullptr)
     for (int i = tid; i < kk * MAXBIT; i += SW_THREADS) ssst[i] = a.sstate[i];
   // squared norms of the training rows and alpha (once per CTA); zero padding of the candidate buffers
   for (int j = tid; j < rows16; j += SW_THREADS) {
@@ -259,8 +263,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       for (int j = lane; j < kk; j += 32) {
         double x = 0.0;
         if (ci < a.ncand) {
-          if (a.X != nullptr) {
-            x = a.X[(size_t)ci * kmax + j];
+          if (Xc != nullptr) {
+            x = Xc[(size_t)ci * kmax + j];
           } else {
             const unsigned long long g = (unsigned long long)(a.idx0 + ci);
             const int sh = a.shift[j];
@@ -543,7 +547,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
       double val = lh + log(sg);
       const long long ci = c0 + c;
       if (ci < a.ncand) {
-        if (a.vals) a.vals[ci] = val;
+        if (valsc) valsc[ci] = val;
       } else {
         val = -INFINITY;
       }
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
   long long *fin_i = reinterpret_cast<long long *>(sred + NWARP);
   if (lane == 0) { fin_v[warp] = cta_best; fin_i[warp] = cta_idx; }
   __syncthreads();
-  if (tid == 0) {
+  if (tid == 0 && a.best_val != nullptr) {
     double bv = -INFINITY;
     long long bi = 0x7fffffffffffffffLL;
     for (int w8 = 0; w8 < NWARP; ++w8)
@@ -636,13 +640,43 @@ extern "C" int pcabo_ei_sweep(const pcabo_gp_model *m, int run, long long ncand,
   PCABO_CUDA_CHECK(cudaFuncSetAttribute(ei_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SweepArgs a;
   a.m = *m; a.b = run; a.ncand = ncand; a.idx0 = idx0; a.X = X; a.shift = shift; a.sstate = sstate; a.lo = lo; a.hi = hi;
-  a.vals = vals; a.best_val = part_val; a.best_idx = part_idx;
+  a.vals = vals; a.best_val = part_val; a.best_idx = part_idx; a.multi = 0; a.x_stride = 0;
   const long long ntiles = (ncand + TC - 1) / TC;
   const int grid = (int)(ntiles < nparts ? ntiles : nparts);
   cudaStream_t st = as_stream(stream);
   ei_sweep_kernel<<<grid, SW_THREADS, smem, st>>>(a);
   PCABO_LAUNCH_CHECK();
   sweep_final_kernel<<<1, 256, 0, st>>>(grid, part_val, part_idx, best_val, best_idx);
+  PCABO_LAUNCH_CHECK();
+  return PCABO_OK;
+}
+
+// Multi-run form of the sweep: the raw-sample scoring pass of optimize_acqf (PCA_BO.py:607-614; 512 scrambled-Sobol
+// points per run) for ALL runs of the batch in one launch, values out, no arg-max. Each run gets a row of `ctas_per_run`
+// CTAs that share its candidate tiles (32 candidates each).
+extern "C" int pcabo_logei_raw_runs(const pcabo_gp_model *m, int npts, const double *X, double *val, int ctas_per_run,
+                                    void *stream) {
+  if (!m || npts <= 0 || !X || !val || m->B <= 0 || !m->W || !m->Zn || !m->alpha || !m->norm_off || !m->norm_coef ||
+      !m->ymean || !m->ystd || !m->best_f || (!m->lengthscales && !(m->lengthscale > 0.0)))
+    return PCABO_E_INVALID;
+  if (m->acq != PCABO_ACQ_LOG_EI) return PCABO_E_UNSUPPORTED;
+  if (m->n > 8 * NWARP * RT_MAX || m->n < 2 || (m->ld_n & 1) || (m->kmax & 1) || m->kmax > 104 || m->B > 65535)
+    return PCABO_E_UNSUPPORTED;
+  const size_t smem = sweep_smem_bytes(m->n, m->kmax);
+  if (smem > 227 * 1024) return PCABO_E_UNSUPPORTED;
+  PCABO_CUDA_CHECK(cudaFuncSetAttribute(ei_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SweepArgs a;
+  a.m = *m; a.b = 0; a.ncand = npts; a.idx0 = 0; a.X = X; a.shift = nullptr; a.sstate = nullptr; a.lo = nullptr;
+  a.hi = nullptr; a.vals = val; a.best_val = nullptr; a.best_idx = nullptr; a.multi = 1;
+  a.x_stride = (long long)npts * m->kmax;
+  const int ntiles = (npts + TC - 1) / TC;
+  if (ctas_per_run <= 0) {   // as many CTAs per run as keep the whole launch within one wave of the 148 SMs
+    ctas_per_run = 1;
+    while (2 * ctas_per_run <= ntiles && 2 * ctas_per_run * m->B <= 148) ctas_per_run *= 2;
+  }
+  if (ctas_per_run > ntiles) ctas_per_run = ntiles;
+  dim3 grid(ctas_per_run, m->B);
+  ei_sweep_kernel<<<grid, SW_THREADS, smem, as_stream(stream)>>>(a);
   PCABO_LAUNCH_CHECK();
   return PCABO_OK;
 }

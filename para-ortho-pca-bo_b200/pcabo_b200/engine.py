@@ -148,6 +148,7 @@ class BatchedBOEngine:
         self.d_mt_state = self.d_mt_pos = self.ic_out = None
         self.gens_on_host = True       # False: the device-resident MT19937 states are ahead of the torch CPU generators
         self.force_host_ic = False     # tests: always take the host path for the Boltzmann pick
+        self.raw_scoring = "tensor"    # "scalar": always score the raw samples with pcabo_logei (tests, comparisons)
         self.pending = None         # state of a step between step_begin() and step_end()
         self.phase_times = None     # set to {} to accumulate host wall time per phase (adds device syncs)
         self.kernel_events = None   # set to [] to record CUDA-event pairs around every value+grad log-EI launch
@@ -355,6 +356,14 @@ class BatchedBOEngine:
             self.gen_io.restore(self.torch_gens, self.d_mt_state.cpu(), self.d_mt_pos.cpu())
             self.gens_on_host = True
 
+    def _score_raw(self, x_raw):
+        """log-EI of the raw Sobol samples of every run (botorch scores them 5 at a time, PCA_BO.py:607-614): the tile
+        pipeline of the candidate sweep on the FP64 tensor cores when the model is within its limits (log-EI, n <= 512,
+        even capacities), the general value kernel otherwise (config C5, PI, odd D)."""
+        if self.raw_scoring == "tensor" and ops.logei_raw_supported(self.gp, self.n):
+            return ops.logei_raw(self.gp, x_raw)["val"]
+        return ops.logei(self.gp, x_raw)["val"]
+
     def _ic_launch_fast(self):
         """_ic_launch for the common case (all runs, 512 raw samples, log-EI, generators owned by the engine): the
         Boltzmann pick itself runs on the device too (pcabo_select_initial_conditions replays torch.multinomial from
@@ -373,7 +382,7 @@ class BatchedBOEngine:
         self.d_mt_pos_prev.copy_(self.d_mt_pos)
         d_shift, d_dots = ops.sobol_scramble_bits(k_dev, self.d_mt_state, self.d_mt_pos, D)
         x_raw = ops.sobol_points(self.raw_samples, k_dev, d_shift, d_dots, self.state0, self.gp.box_lo, self.gp.box_hi)
-        vals_dev = ops.logei(self.gp, x_raw)["val"]
+        vals_dev = self._score_raw(x_raw)
         self.ic_out = ops.select_initial_conditions(vals_dev, self.d_mt_state, self.d_mt_pos, x_raw, R, out=self.ic_out)
         if self.h_flag is None:
             self.h_flag = torch.zeros(B, dtype=torch.int32).pin_memory()
@@ -408,7 +417,7 @@ class BatchedBOEngine:
             k_dev = kk.to(self.device)
         d_shift, d_dots = ops.sobol_scramble_bits(k_dev, d_state, d_pos, D)
         x_raw = ops.sobol_points(nraw, k_dev, d_shift, d_dots, self.state0, self.gp.box_lo, self.gp.box_hi)
-        vals_dev = ops.logei(self.gp, x_raw)["val"]
+        vals_dev = self._score_raw(x_raw)
         if self.h_vals is None or self.h_vals.shape != vals_dev.shape:
             self.h_vals = torch.zeros(vals_dev.shape, dtype=torch.float64).pin_memory()
         if self.h_state_back is None:

@@ -199,6 +199,28 @@ def logei(buf: GPBuffers, X, want_grad=False, want_posterior=False, out=None):
     return out
 
 
+def logei_raw_supported(buf: GPBuffers, n=None) -> bool:
+    """True when pcabo_logei_raw_runs (the tensor-core tile pipeline) covers this model: log-EI, n <= 512, even row
+    capacity and column capacity."""
+    n = buf.n if n is None else n
+    return buf.acq == ACQ_LOG_EI and 2 <= n <= 512 and buf.ld_n % 2 == 0 and buf.kmax % 2 == 0 and buf.kmax <= 104
+
+
+def logei_raw(buf: GPBuffers, X, out=None, ctas_per_run=0):
+    """Value-only log-EI of the raw samples X [B, npts, kmax] of every run in one launch of the sweep pipeline on the FP64
+    tensor cores (pcabo_logei_raw_runs) -> dict(val [B, npts])."""
+    lib = load_library()
+    B, npts, kmax = X.shape
+    if B != buf.B or kmax != buf.kmax:
+        raise PcaboError("logei_raw: shape mismatch with the GP buffers")
+    if out is None:
+        out = dict(val=torch.empty(B, npts, dtype=torch.float64, device=X.device))
+    m = model_struct(buf)
+    check(lib.pcabo_logei_raw_runs(ctypes.byref(m), npts, _d(X, "X"), _d(out["val"], "val"), int(ctas_per_run), _stream()),
+          "pcabo_logei_raw_runs")
+    return out
+
+
 def argmax(v):
     """v [B, m] -> (best_val [B], best_idx [B] int32), first occurrence on ties."""
     lib = load_library()
@@ -207,6 +229,31 @@ def argmax(v):
     bi = torch.empty(B, dtype=torch.int32, device=v.device)
     check(lib.pcabo_argmax(B, m, _d(v, "v"), _d(bv, "best_val"), _i(bi, "best_idx"), _stream()), "pcabo_argmax")
     return bv, bi
+
+
+def pick_best(vals, cand, out=None):
+    """vals [B, R], cand [B, R, D] -> dict(z [B, D], val [B], idx [B] int32): first-occurrence arg-max over the restarts
+    and the winning candidate (what optimize_acqf returns)."""
+    lib = load_library()
+    B, R, D = cand.shape
+    if out is None:
+        out = dict(z=torch.empty(B, D, dtype=torch.float64, device=cand.device),
+                   val=torch.empty(B, dtype=torch.float64, device=cand.device),
+                   idx=torch.empty(B, dtype=torch.int32, device=cand.device))
+    check(lib.pcabo_pick_best(B, R, D, _d(vals, "vals"), _d(cand, "cand"), _d(out["z"], "z"), _d(out["val"], "val"),
+                              _i(out["idx"], "idx"), _stream()), "pcabo_pick_best")
+    return out
+
+
+def append_observation(X, f, n, x_new, z_new, f_new, oob, acq, penalty, maximization, best, best_f, rec):
+    """Device-side tail of a BO iteration (pcabo_append_observation): penalty for out-of-bounds proposals, append to the
+    history X [B, ld_n, D] / f [B, ld_n] at row n, running best and its float32 rounding, packed record rec [B, 2D+3]."""
+    lib = load_library()
+    B, ld_n, D = X.shape
+    check(lib.pcabo_append_observation(B, D, ld_n, int(n), _d(x_new, "x_new"), _d(z_new, "z_new"), _d(f_new, "f_new"),
+                                       _i(oob, "oob"), _d(acq, "acq"), float(penalty), int(bool(maximization)),
+                                       _d(X, "X"), _d(f, "f"), _d(best, "best"), _d(best_f, "best_f"), _d(rec, "rec"),
+                                       _stream()), "pcabo_append_observation")
 
 
 LBFGSB_STATUS = {0: "CONVERGENCE: NORM OF PROJECTED GRADIENT <= PGTOL", 1: "CONVERGENCE: RELATIVE REDUCTION OF F <= FACTR*EPSMCH",

@@ -187,6 +187,54 @@ def test_logei_value_grad(D, n, npts, maximization):
         assert float(out["grad"][b, :, k:].abs().max()) == 0.0 if k < D else True
 
 
+@pytest.mark.parametrize("D,n,npts,B", [(10, 77, 512, 3), (20, 250, 512, 2), (40, 120, 512, 4), (40, 331, 517, 3),
+                                        (40, 450, 512, 5), (40, 450, 1024, 2), (12, 64, 40, 1)])
+@pytest.mark.parametrize("maximization", [False, True])
+def test_logei_raw_runs_matches_oracle(D, n, npts, B, maximization):
+    """The raw-sample scoring pass of the BO loop on the tensor-core tile pipeline (pcabo_logei_raw_runs: all runs of the
+    batch in one launch, per-run k, PCA-mode normalisation): every value within 1e-8 of the CPU oracle and of the scalar
+    value kernel, for every way of dealing the tiles to CTAs."""
+    ops, hist, X, f, pca, buf = _fit_gp_batch(D, n, B, maximization, ld_n=n + (n & 1))
+    from oracle import gp, acqf
+    rng = np.random.RandomState(11)
+    pts = torch.zeros(B, npts, D, dtype=torch.float64)
+    refs = []
+    for b in range(B):
+        k = int(pca["k"][b])
+        Z = pca["Z"][b, :n, :k].cpu().numpy()
+        fb = hist[b][1]
+        model = gp.GPModel(Z, fb, norm_bounds=acqf.normalize_box_pca(Z))
+        best = float(np.max(fb) if maximization else np.min(fb))
+        acq = gp.LogExpectedImprovement(model, best, maximize=maximization)
+        box = acqf.search_box_pca(Z)
+        P = box[0] + (box[1] - box[0]) * rng.rand(npts, k)
+        P[0] = Z[rng.randint(n)]                                   # on a training point
+        P[1] = Z[int(np.argmin(fb))] + 1e-3 * rng.randn(k)          # next to the incumbent
+        P[2] = box[0]
+        pts[b, :, :k] = torch.from_numpy(P)
+        buf.best_f[b] = gp.best_f_as_botorch(best)
+        with torch.no_grad():
+            refs.append(acq(torch.from_numpy(P)).numpy())
+    buf.maximize = maximization
+    assert ops.logei_raw_supported(buf, n)
+    ptsd = pts.cuda()
+    scalar = ops.logei(buf, ptsd)["val"].cpu().numpy()
+    for cpr in (0, 1, 3, 16, 64):
+        got = ops.logei_raw(buf, ptsd, ctas_per_run=cpr)["val"].cpu().numpy()
+        for b in range(B):
+            assert rel_err(got[b], refs[b], 1e-6) < RTOL, f"run {b}, {cpr} CTAs per run: log-EI vs oracle"
+            assert rel_err(got[b], scalar[b], 1e-6) < RTOL, f"run {b}, {cpr} CTAs per run: log-EI vs pcabo_logei"
+
+
+def test_logei_raw_runs_limits():
+    """Outside the limits of the tile pipeline the entry point refuses (no silent fallback inside the library)."""
+    ops, hist, X, f, pca, buf = _fit_gp_batch(5, 12, 1)             # odd column capacity
+    from pcabo_b200.lib import PcaboError
+    assert not ops.logei_raw_supported(buf, 12)
+    with pytest.raises(PcaboError):
+        ops.logei_raw(buf, torch.zeros(1, 32, 5, dtype=torch.float64, device="cuda"))
+
+
 def test_logei_branches():
     """All three branches of log_h (u > -1, -1e6 < u <= -1, u <= -1e6) against the oracle's helper."""
     B, D, n = 1, 5, 12

@@ -49,6 +49,7 @@ def main():
     tot = p[:, :16].sum(1)
     worst = int(np.argmax(tot))
     res = {"kernel_ms": e0.elapsed_time(e1), "n": eng.n, "k_mean": float(k_host.mean()),
+           "nit_hist_25": np.bincount(np.minimum(nit // 25, 8), minlength=9).tolist(),   # [0,25), [25,50) ... [175,200), 200
            "nit_mean": float(nit.mean()), "nit_max": int(nit.max()), "nfev_mean": float(nfev.mean()), "nfev_max": int(nfev.max()),
            "cycles_per_iteration_mean": {nm: float((p[:, i] / np.maximum(nit, 1)).mean()) for i, nm in enumerate(NAMES)},
            "share_mean": {nm: float(p[:, i].sum() / tot.sum()) for i, nm in enumerate(NAMES)},
