@@ -10,7 +10,7 @@ communication with all runs' restart problems sharing one value+gradient kernel 
 import math
 import os
 from concurrent.futures import ThreadPoolExecutor
-from time import perf_counter
+from time import perf_counter, sleep
 
 import numpy as np
 import torch
@@ -149,6 +149,26 @@ class BatchedBOEngine:
         self.gens_on_host = True       # False: the device-resident MT19937 states are ahead of the torch CPU generators
         self.force_host_ic = False     # tests: always take the host path for the Boltzmann pick
         self.raw_scoring = "tensor"    # "scalar": always score the raw samples with pcabo_logei (tests, comparisons)
+        # asynchronous tail (PipelinedEngines sets it): penalty / append / best-so-far run on the device
+        # (pcabo_append_observation) and the host lists are brought up to date later from packed records read back
+        # asynchronously (_drain), so step_end() returns without waiting for the GPU
+        self.async_tail = False
+        self.best_dev = torch.zeros(B, **f64)        # running best of every run (unrounded)
+        self.best_dev_valid = False                  # best_dev / gp.best_f are maintained by the device tail
+        self.rec_dev = torch.zeros(B, 2 * D + 3, **f64)
+        self.pending_host = []                       # [(n, pinned record, event, k)] of iterations not yet in the host lists
+        self.rec_free = []
+        self.pick_out = self.im_out = None
+        # optional low-priority side stream for the optimiser kernel (PipelinedEngines): its blocks hold a whole SM for
+        # milliseconds, and the short kernels of the other sub-batches' model fits must not queue behind them
+        self.opt_stream = None
+        # longest-first dispatch of the optimiser kernel's blocks: 2 B chunk problems want more SMs than the GPU has (180
+        # against 148 for 90 runs), the blocks dispatched last start when the first chunks finish, and the launch lasts as
+        # long as its last block -- so the runs whose chunks took longest in the PREVIOUS iteration are dispatched first
+        self.lpt_dispatch = True
+        self.prev_cost = None          # [B] iterations + evaluations of each run's slowest chunk in the last full launch
+        self.h_order = self.d_order = None
+        self.d_ics_buf = None
         self.pending = None         # state of a step between step_begin() and step_end()
         self.phase_times = None     # set to {} to accumulate host wall time per phase (adds device syncs)
         self.kernel_events = None   # set to [] to record CUDA-event pairs around every value+grad log-EI launch
@@ -195,6 +215,8 @@ class BatchedBOEngine:
     def attach_history(self, x_lists, f_lists):
         """Adopt already evaluated points (the caller's own list objects are kept and appended to)."""
         B = self.B
+        self._drain(True)
+        self.best_dev_valid = False
         n0 = len(f_lists[0])
         if any(len(f) != n0 for f in f_lists) or n0 > self.cap:
             raise PcaboError("attach_history: all runs of a batch must hold the same number of points (<= budget)")
@@ -282,11 +304,20 @@ class BatchedBOEngine:
         """best_f as botorch stores it: torch.as_tensor(python float) -> float32 (PCA_BO.py:199-203).
         Staged through pinned memory: a copy from pageable memory would block the host thread until the model fit
         enqueued just before it has finished (1.2 ms per call on the profile of round 2)."""
+        if self.async_tail and self.best_dev_valid:
+            return      # kept up to date on the device by pcabo_append_observation
+        self._drain(True)
         if getattr(self, "h_best_f", None) is None:
-            self.h_best_f = torch.zeros(self.B, dtype=torch.float64).pin_memory()
-        self.h_best_f.numpy()[:] = np.asarray(self.current_best, dtype=np.float64).astype(np.float32).astype(np.float64)
-        self.gp.best_f.copy_(self.h_best_f, non_blocking=True)
+            self.h_best_f = torch.zeros(2, self.B, dtype=torch.float64).pin_memory()
+        cb = np.asarray(self.current_best, dtype=np.float64)
+        self.h_best_f.numpy()[0] = cb.astype(np.float32).astype(np.float64)
+        self.h_best_f.numpy()[1] = cb
+        self.gp.best_f.copy_(self.h_best_f[0], non_blocking=True)
         self.stats["h2d_bytes"] += self.B * 8
+        if self.async_tail:
+            self.best_dev.copy_(self.h_best_f[1], non_blocking=True)
+            self.best_dev_valid = True
+            self.stats["h2d_bytes"] += self.B * 8
 
     def _fit_models(self):
         tp = perf_counter()
@@ -483,7 +514,9 @@ class BatchedBOEngine:
         (rows of `runs` updated)."""
         B, D, R = self.B, self.D, self.num_restarts
         if d_ics is None:
-            d_ics = torch.zeros(B, R, D, dtype=torch.float64, device=self.device)
+            if self.d_ics_buf is None:
+                self.d_ics_buf = torch.zeros(B, R, D, dtype=torch.float64, device=self.device)
+            d_ics = self.d_ics_buf      # (every row is rewritten below; columns >= k stay zero)
         pending = list(runs)
         factor = 1
         while pending and factor < 5:
@@ -572,24 +605,43 @@ class BatchedBOEngine:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
         run_idx = None if runs is None else torch.tensor(sel, dtype=torch.int32).to(self.device, non_blocking=True)
+        if runs is None and self.lpt_dispatch and self.prev_cost is not None and B > 1:
+            if self.h_order is None:
+                self.h_order = torch.zeros(B, dtype=torch.int32).pin_memory()
+                self.d_order = torch.zeros(B, dtype=torch.int32, device=self.device)
+            self.h_order.numpy()[:] = np.argsort(-self.prev_cost, kind="stable")
+            self.d_order.copy_(self.h_order, non_blocking=True)
+            run_idx = self.d_order       # (results are indexed by run: the order changes nothing but the dispatch)
         k_bound = int(max(k_host[b] for b in sel))
         need = ops.lbfgsb_workspace_doubles(self.n, self.D, k_bound, self.num_restarts, self.batch_limit, len(sel))
         if need > 0 and (self.lb_ws is None or self.lb_ws.numel() < need):
             # sized once for the whole batch at the largest k (never reallocated inside the loop after that)
             full = ops.lbfgsb_workspace_doubles(self.n, self.D, self.D, self.num_restarts, self.batch_limit, B)
             self.lb_ws = torch.empty(max(need, full), dtype=torch.float64, device=self.device)
-        out = ops.lbfgsb_logei(self.gp, d_x, self.gp.box_lo, self.gp.box_hi, self.batch_limit, self.maxiter, out=out,
-                               run_idx=run_idx, k_bound=k_bound, workspace=self.lb_ws)
-        if ev is not None:
-            ev[1].record()
-        if self.h_status is None or self.h_status.shape != out["status"].shape:
-            self.h_status = torch.zeros(out["status"].shape, dtype=torch.int32).pin_memory()
-            self.h_nfev, self.h_nit = torch.zeros_like(self.h_status).pin_memory(), torch.zeros_like(self.h_status).pin_memory()
-        self.h_status.copy_(out["status"], non_blocking=True)
-        self.h_nfev.copy_(out["nfev"], non_blocking=True)
-        self.h_nit.copy_(out["nit"], non_blocking=True)
-        done = torch.cuda.Event()
-        done.record()
+        side = self.opt_stream
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream())
+            main = torch.cuda.current_stream()
+            torch.cuda.set_stream(side)
+        try:
+            if ev is not None and side is not None:
+                ev[0].record()      # (time the kernel on the stream it runs on)
+            out = ops.lbfgsb_logei(self.gp, d_x, self.gp.box_lo, self.gp.box_hi, self.batch_limit, self.maxiter, out=out,
+                                   run_idx=run_idx, k_bound=k_bound, workspace=self.lb_ws)
+            if ev is not None:
+                ev[1].record()
+            if self.h_status is None or self.h_status.shape != out["status"].shape:
+                self.h_status = torch.zeros(out["status"].shape, dtype=torch.int32).pin_memory()
+                self.h_nfev, self.h_nit = torch.zeros_like(self.h_status).pin_memory(), torch.zeros_like(self.h_status).pin_memory()
+            self.h_status.copy_(out["status"], non_blocking=True)
+            self.h_nfev.copy_(out["nfev"], non_blocking=True)
+            self.h_nit.copy_(out["nit"], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        finally:
+            if side is not None:
+                torch.cuda.set_stream(main)
+                main.wait_event(done)     # whatever follows on the sub-batch's own stream sees the candidates
         if self.overlap_hook is not None:        # host work that does not depend on the result runs under the kernel
             hook, self.overlap_hook = self.overlap_hook, None
             hook()
@@ -609,20 +661,28 @@ class BatchedBOEngine:
             n = self.n
             # algorithmic bytes of one value+gradient evaluation of one chunk: the n x n lower-triangular FP64 cache
             # L^-1 once (4 n^2), the training set and alpha (8 n k + 8 n); times the evaluations actually done
-            nbytes = sum(int(nfev[b, c]) * (4 * n * n + 8 * n * int(k_host[b]) + 8 * n)
-                         for b in sel for c in range(nfev.shape[1]))
+            ks = np.asarray(k_host, dtype=np.int64)[sel]
+            ev_run = nfev[sel].astype(np.int64)                       # [runs, chunks] evaluations
+            nbytes = int((ev_run.sum(axis=1) * (4 * n * n + 8 * n * ks + 8 * n)).sum())
             # algorithmic flops: F_vg = 2 n^2 + 11 n k + 16 n per point and value+gradient evaluation
-            nflops = sum(int(nfev[b, c]) * min(self.batch_limit, self.num_restarts - c * self.batch_limit)
-                         * (2 * n * n + 11 * n * int(k_host[b]) + 16 * n)
-                         for b in sel for c in range(nfev.shape[1]))
+            pts = np.array([min(self.batch_limit, self.num_restarts - c * self.batch_limit) for c in range(nfev.shape[1])],
+                           dtype=np.int64)
+            nflops = int(((ev_run * pts[None, :]).sum(axis=1) * (2 * n * n + 11 * n * ks + 16 * n)).sum())
             self.kernel_events.append((ev[0], ev[1], nbytes, nflops))
         self.stats["kernel_launches"] += 1
         self.stats["lbfgsb_rounds"] += int(nfev[sel].max())
         self.stats["d2h_bytes"] += status.size * 12
-        warned = {b: bool((status[b] == 3).any()) for b in sel}
+        if len(sel) == self.B:
+            # (a decaying maximum: a run that needed the full 200 iterations tends to need them again soon)
+            cost = (nit.astype(np.int64) + nfev).max(axis=1).astype(np.float64)
+            self.prev_cost = cost if self.prev_cost is None else np.maximum(cost, 0.7 * self.prev_cost)
+        w3 = (status == 3).any(axis=1)
+        warned = {b: bool(w3[b]) for b in sel}
+        nl, fl = nit.tolist(), nfev.tolist()
+        dn, df = self.last.setdefault("nit", {}), self.last.setdefault("nfev", {})
         for b in sel:
-            self.last.setdefault("nit", {})[b] = nit[b].tolist()
-            self.last.setdefault("nfev", {})[b] = nfev[b].tolist()
+            dn[b] = nl[b]
+            df[b] = fl[b]
         return out, warned
 
     def _optimize_device(self, d_x, k_host, runs=None, out=None):
@@ -691,10 +751,9 @@ class BatchedBOEngine:
                 self._phase("lbfgsb_kernel_retry", tp)
             d_c = self.lb_out["cand"]
         vals = ops.logei(self.gp, d_c)["val"]                        # final no-grad evaluation of the candidates
-        best_val, best_idx = ops.argmax(vals)                        # torch.argmax over the restarts
-        z_new = d_c[torch.arange(B, device=self.device), best_idx.long()]
+        self.pick_out = ops.pick_best(vals, d_c, out=self.pick_out)  # torch.argmax over the restarts + the winner
         self.stats["kernel_launches"] += 2
-        return z_new.contiguous(), best_val
+        return self.pick_out["z"], self.pick_out["val"]
 
     def step_launch(self):
         """Phase A of a BO iteration: model fit and raw-sample scoring enqueued; returns without waiting for the GPU.
@@ -738,6 +797,12 @@ class BatchedBOEngine:
         self.timing_logs["optimize_acqf"].append(t1 - self.pending["t0"])
         self.pending = None
         tp = perf_counter()
+        if self.async_tail and self.batched_problem is not None:
+            self._step_end_async(z_new, acq_val)
+            self._phase("inverse_map_objective_bookkeeping", tp)
+            return True
+        self._drain(True)
+        self.best_dev_valid = False     # the host lists are the truth on this path
         if self.algorithm == "pca":
             im = ops.inverse_map(z_new, self.pca["k"], self.pca["V"], self.pca["m2"], self.pca["xbar"], self.lo, self.hi)
             self.stats["kernel_launches"] += 1
@@ -770,11 +835,61 @@ class BatchedBOEngine:
         return True
 
 
+    def _step_end_async(self, z_new, acq_val):
+        """The tail of PCA_BO.__call__ (:239-281) without a host round trip: inverse map, objective, penalty, append and
+        best-so-far on the device; ONE packed record per iteration is read back asynchronously for the host lists."""
+        B, D, n = self.B, self.D, self.n
+        if not self.best_dev_valid:
+            self._set_best_f()
+        if self.algorithm == "pca":
+            self.im_out = ops.inverse_map(z_new, self.pca["k"], self.pca["V"], self.pca["m2"], self.pca["xbar"], self.lo,
+                                          self.hi, out=self.im_out)
+            x_dev, oob = self.im_out["x"], self.im_out["oob"]
+            self.stats["kernel_launches"] += 1
+        else:
+            x_dev, oob = z_new, None
+        f_dev = self.batched_problem(x_dev)
+        ops.append_observation(self.X, self.f, n, x_dev, z_new, f_dev, oob, acq_val,
+                               -1000.0 if self.maximization else 1000.0, self.maximization,   # PCA_BO.py:260-261
+                               self.best_dev, self.gp.best_f, self.rec_dev)
+        rec = self.rec_free.pop() if self.rec_free else torch.zeros(B, 2 * D + 3, dtype=torch.float64).pin_memory()
+        rec.copy_(self.rec_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.pending_host.append((n, rec, ev, self.k_host.copy()))
+        self.stats["kernel_launches"] += 2
+        self.stats["d2h_bytes"] += rec.numel() * 8
+        self.n = n + 1
+        self._drain(False)
+
+    def _drain(self, wait):
+        """Bring the host lists (x_evals, f_evals, oob_evals, best tracking, `last`) up to date with the iterations whose
+        packed records have arrived; wait=True blocks until all of them have."""
+        D = self.D
+        while self.pending_host:
+            n, rec, ev, k = self.pending_host[0]
+            if wait:
+                ev.synchronize()
+            elif not ev.query():
+                break
+            self.pending_host.pop(0)
+            r = rec.numpy()
+            for b in range(self.B):
+                self.x_evals[b].append(r[b, :D].copy())
+                self.f_evals[b].append(float(r[b, 2 * D]))
+                self.oob_evals[b].append(bool(r[b, 2 * D + 1] != 0.0))
+                self._update_best_with_last(b)
+            self.last.update(z_new=r[:, D:2 * D].copy(), x_new=r[:, :D].copy(), new_f=r[:, 2 * D].copy(),
+                             oob=r[:, 2 * D + 1] != 0.0, acq_val=r[:, 2 * D + 2].copy(), k=k)
+            self.rec_free.append(rec)
+
     def step(self):
         """One BO iteration for all runs (PCA_BO.py:178-281)."""
         if not self.step_begin():
             return False
-        return self.step_end()
+        ok = self.step_end()
+        self._drain(True)
+        return ok
 
     def run(self, max_iterations=None):
         if self.n == 0:
@@ -794,14 +909,21 @@ class PipelinedEngines:
     the kernel of one sub-batch is in flight the host prepares the next sub-batch (model fit, raw samples, multinomial)
     and launches its kernel too: step_begin() of every engine returns with its kernel running, step_end() collects."""
 
-    def __init__(self, engines):
+    def __init__(self, engines, async_tail=True):
         self.engines = list(engines)
-        self.streams = [torch.cuda.Stream(device=e.device) for e in self.engines]
+        # the sub-batches' own streams are high priority, the optimiser kernels go to low-priority side streams: when an
+        # SM frees up, the short kernels of a model fit get it before the queued blocks of another optimiser kernel
+        self.streams = [torch.cuda.Stream(device=e.device, priority=-1) for e in self.engines]
+        for e in self.engines:
+            e.opt_stream = torch.cuda.Stream(device=e.device, priority=0)
         # the engines' buffers were allocated and zero-filled on the stream that was current at construction: order the
         # side streams after that work before their first use
         for e, st in zip(self.engines, self.streams):
             st.wait_stream(torch.cuda.current_stream(e.device))
+            # device objective + device optimiser: nothing in the tail of an iteration needs the host
+            e.async_tail = bool(async_tail) and e.batched_problem is not None and e.optimizer == "device"
         self.B = sum(e.B for e in self.engines)
+        self.idle_s = 0.0       # host time spent polling with nothing to do
 
     def initial_design(self):
         for e, st in zip(self.engines, self.streams):
@@ -810,24 +932,59 @@ class PipelinedEngines:
         torch.cuda.synchronize(self.engines[0].device)
 
     def run_steps(self, k):
-        """k lock-step iterations of every sub-batch, software-pipelined across the sub-batches: after the optimiser
-        kernel of one sub-batch is launched (step_begin) the host turns to the next sub-batch, and comes back to collect
-        (step_end) one round later. A finer, event-driven schedule (run the next phase of whichever engine's CUDA event
-        has completed) was measured and is worse: it lets the optimiser kernels of all sub-batches start together, after
-        which the host has nothing to overlap with them."""
+        """k lock-step iterations of every sub-batch, interleaved by ONE host thread. Per sub-batch and iteration the
+        host does three short things: E (after its optimiser kernel: enqueue the tail of the iteration), A (enqueue the
+        next iteration's model fit and raw-sample scoring) and B (read k / flags of phase A, launch the optimiser
+        kernel). With the asynchronous tail none of them waits for the GPU, so the schedule is event driven: launch the
+        optimiser of any sub-batch whose phase A has completed, else serve (E + A) any sub-batch whose optimiser has
+        finished, else block on the oldest outstanding event (a phase A before an optimiser kernel)."""
         if k <= 0:
             return
+        remaining = {id(e): k for e in self.engines}
+        a_wait, o_wait = [], []          # sub-batches with phase A / with the optimiser kernel in flight, oldest first
         for e, st in zip(self.engines, self.streams):
             with torch.cuda.stream(st):
+                e.step_launch()
+            a_wait.append((e, st))
+
+        def done(item):
+            ev = item[0].wait_event()
+            return ev is None or ev.query()
+
+        def phase_b(item):
+            e, st = item
+            with torch.cuda.stream(st):
                 e.step_begin()
-        for it in range(k):
-            for e, st in zip(self.engines, self.streams):
-                with torch.cuda.stream(st):
-                    e.step_end()
-                    if it + 1 < k:
-                        e.step_begin()
+            o_wait.append(item)
+
+        def phase_ea(item):
+            e, st = item
+            with torch.cuda.stream(st):
+                e.step_end()
+                remaining[id(e)] -= 1
+                if remaining[id(e)] > 0:
+                    e.step_launch()
+                    a_wait.append(item)
+
+        while a_wait or o_wait:
+            i = next((i for i, it in enumerate(a_wait) if done(it)), None)
+            if i is not None:
+                phase_b(a_wait.pop(i))
+                continue
+            i = next((i for i, it in enumerate(o_wait) if done(it)), None)
+            if i is not None:
+                phase_ea(o_wait.pop(i))
+                continue
+            # nothing has completed: poll (blocking on one particular event would leave a sub-batch that finishes
+            # earlier than that one unattended)
+            t0 = perf_counter()
+            while not any(done(it) for it in a_wait) and not any(done(it) for it in o_wait):
+                sleep(2e-5)
+            self.idle_s += perf_counter() - t0
         for st in self.streams:
             st.synchronize()
+        for e in self.engines:
+            e._drain(True)
 
     def step(self):
         self.run_steps(1)
@@ -843,4 +1000,5 @@ class PipelinedEngines:
         for e in self.engines:
             for k, v in e.stats.items():
                 out[k] = out.get(k, 0) + v
+        out["idle_poll_s"] = self.idle_s
         return out

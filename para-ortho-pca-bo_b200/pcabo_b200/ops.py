@@ -30,7 +30,13 @@ def _i(t, name):
     return _dev_ptr(t, torch.int32, name)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    # (torch.cuda.current_stream() builds a Stream object: ~10 us per call, a dozen calls per sub-batch and iteration)
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -164,6 +170,18 @@ def gp_mll_grad(buf: GPBuffers):
 
 
 def model_struct(buf: GPBuffers) -> GpModelStruct:
+    # (built three or four times per sub-batch and iteration from the same fields: cached on those fields)
+    key = (buf.n, None if buf.k is None else buf.k.data_ptr(), int(buf.acq), bool(buf.maximize), float(buf.lengthscale),
+           None if buf.lengthscales is None else buf.lengthscales.data_ptr(), buf.best_f.data_ptr(), buf.Wp.data_ptr(),
+           buf.W.data_ptr(), buf.alpha.data_ptr())
+    if getattr(buf, "_ms_key", None) == key:
+        return buf._ms
+    m = _model_struct(buf)
+    buf._ms_key, buf._ms = key, m
+    return m
+
+
+def _model_struct(buf: GPBuffers) -> GpModelStruct:
     m = GpModelStruct()
     m.B, m.n, m.kmax, m.ld_n = buf.B, buf.n, buf.kmax, buf.ld_n
     m.maximize = int(bool(buf.maximize))

@@ -303,6 +303,27 @@ def test_pipelined_sub_batches_equal_one_batch():
             assert np.allclose(xa[:ndoe + 1], xb[:ndoe + 1], rtol=1e-9, atol=1e-9), (s, j)
             same += int(np.allclose(xa, xb, rtol=1e-6, atol=1e-6))
     assert same >= 5
+    # the asynchronous tail (device-side penalty / append / best-so-far, host lists filled from packed records) against
+    # the synchronous one on the same sub-batches: every number identical
+    assert all(e.async_tail for e in subs)
+    subs2 = [make(list(range(s, 6, S))) for s in range(S)]
+    pipe2 = PipelinedEngines(subs2, async_tail=False)
+    pipe2.initial_design()
+    pipe2.run_steps(steps)
+    assert not any(e.async_tail for e in subs2)
+    for e, e2 in zip(subs, subs2):
+        assert not e.pending_host
+        for j in range(e.B):
+            assert e.f_evals[j] == e2.f_evals[j] and e.oob_evals[j] == e2.oob_evals[j], j
+            assert np.array_equal(np.array(e.x_evals[j]), np.array(e2.x_evals[j])), j
+        assert e.current_best == e2.current_best and e.current_best_index == e2.current_best_index
+        assert np.array_equal(e.last["z_new"], e2.last["z_new"]) and np.array_equal(e.last["acq_val"], e2.last["acq_val"])
+        assert torch.equal(e.X[:, :e.n], e2.X[:, :e2.n]) and torch.equal(e.f[:, :e.n], e2.f[:, :e2.n])
+    # one more step through the plain API on an engine that used the asynchronous tail: the host lists are complete
+    e = subs[0]
+    with torch.cuda.stream(pipe.streams[0]):
+        e.step()
+    assert len(e.f_evals[0]) == e.n and not e.pending_host
 
 
 def test_engine_probability_of_improvement_matches_oracle():
