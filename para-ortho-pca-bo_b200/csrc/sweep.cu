@@ -187,15 +187,17 @@ __host__ __device__ inline size_t sweep_smem_bytes(int n, int kmax) {
   return d * sizeof(double) + (size_t)kmax * MAXBIT * sizeof(int);
 }
 
+// MULTI: one row of CTAs per run (run = blockIdx.y), values only -- the raw-sample scoring pass of the BO loop
+template <bool MULTI>
 __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
   extern __shared__ __align__(16) double smd[];
   const pcabo_gp_model &m = a.m;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = m.n, kmax = m.kmax;
   const long ld = m.ld_n;
-  const int b = a.multi ? (int)blockIdx.y : a.b;
-  const double *const Xc = (a.X != nullptr && a.multi) ? a.X + (size_t)b * a.x_stride : a.X;
-  double *const valsc = (a.vals != nullptr && a.multi) ? a.vals + (size_t)b * a.ncand : a.vals;
+  const int b = MULTI ? (int)blockIdx.y : a.b;
+  const double *const Xc = MULTI ? a.X + (size_t)b * a.x_stride : a.X;
+  double *const valsc = MULTI ? a.vals + (size_t)b * a.ncand : a.vals;
   const int kk = m.k ? m.k[b] : kmax;
   const int kk4 = (kk + 3) / 4;               // k-steps of the distance MMA
   const int zld = sweep_zld(kmax);
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) ei_sweep_kernel(SweepArgs a) {
   long long *fin_i = reinterpret_cast<long long *>(sred + NWARP);
   if (lane == 0) { fin_v[warp] = cta_best; fin_i[warp] = cta_idx; }
   __syncthreads();
-  if (tid == 0 && a.best_val != nullptr) {
+  if (!MULTI && tid == 0) {
     double bv = -INFINITY;
     long long bi = 0x7fffffffffffffffLL;
     for (int w8 = 0; w8 < NWARP; ++w8)
@@ -637,14 +639,14 @@ extern "C" int pcabo_ei_sweep(const pcabo_gp_model *m, int run, long long ncand,
   if (m->n > 8 * NWARP * RT_MAX || m->n < 2 || (m->ld_n & 1) || (m->kmax & 1) || m->kmax > 104) return PCABO_E_UNSUPPORTED;
   const size_t smem = sweep_smem_bytes(m->n, m->kmax);
   if (smem > 227 * 1024) return PCABO_E_UNSUPPORTED;
-  PCABO_CUDA_CHECK(cudaFuncSetAttribute(ei_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PCABO_CUDA_CHECK(cudaFuncSetAttribute(ei_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SweepArgs a;
   a.m = *m; a.b = run; a.ncand = ncand; a.idx0 = idx0; a.X = X; a.shift = shift; a.sstate = sstate; a.lo = lo; a.hi = hi;
   a.vals = vals; a.best_val = part_val; a.best_idx = part_idx; a.multi = 0; a.x_stride = 0;
   const long long ntiles = (ncand + TC - 1) / TC;
   const int grid = (int)(ntiles < nparts ? ntiles : nparts);
   cudaStream_t st = as_stream(stream);
-  ei_sweep_kernel<<<grid, SW_THREADS, smem, st>>>(a);
+  ei_sweep_kernel<false><<<grid, SW_THREADS, smem, st>>>(a);
   PCABO_LAUNCH_CHECK();
   sweep_final_kernel<<<1, 256, 0, st>>>(grid, part_val, part_idx, best_val, best_idx);
   PCABO_LAUNCH_CHECK();
@@ -664,7 +666,7 @@ extern "C" int pcabo_logei_raw_runs(const pcabo_gp_model *m, int npts, const dou
     return PCABO_E_UNSUPPORTED;
   const size_t smem = sweep_smem_bytes(m->n, m->kmax);
   if (smem > 227 * 1024) return PCABO_E_UNSUPPORTED;
-  PCABO_CUDA_CHECK(cudaFuncSetAttribute(ei_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PCABO_CUDA_CHECK(cudaFuncSetAttribute(ei_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SweepArgs a;
   a.m = *m; a.b = 0; a.ncand = npts; a.idx0 = 0; a.X = X; a.shift = nullptr; a.sstate = nullptr; a.lo = nullptr;
   a.hi = nullptr; a.vals = val; a.best_val = nullptr; a.best_idx = nullptr; a.multi = 1;
@@ -676,7 +678,7 @@ extern "C" int pcabo_logei_raw_runs(const pcabo_gp_model *m, int npts, const dou
   }
   if (ctas_per_run > ntiles) ctas_per_run = ntiles;
   dim3 grid(ctas_per_run, m->B);
-  ei_sweep_kernel<<<grid, SW_THREADS, smem, as_stream(stream)>>>(a);
+  ei_sweep_kernel<true><<<grid, SW_THREADS, smem, as_stream(stream)>>>(a);
   PCABO_LAUNCH_CHECK();
   return PCABO_OK;
 }
