@@ -479,7 +479,10 @@ def run_ours(args):
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650",
                         "bytes_note": "algorithmic: nfev x (4 n^2 + 8 n k + 8 n) per chunk (served from L2)"},
                 "launches": len(evs), "concurrent_launches": S, "avg_launch_us": 1e3 * tot_ms / len(evs),
-                "share_of_step": tot_ms * 1e-3 / secs / S}
+                "share_of_step": tot_ms * 1e-3 / secs / S,
+                # `achieved` is PER LAUNCH (one sub-batch of runs); S launches are in flight at a time on different SMs
+                "all_concurrent_launches": {"achieved": tf * S, "unit": "TFLOP/s", "frac": tf * S / dgemm,
+                                            "note": "per-launch figure x the S launches that overlap (one per sub-batch)"}}
 
     cpu_base = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:

@@ -290,6 +290,54 @@ def test_inverse_map_and_argmax():
     assert int(bi[1]) == 77
 
 
+@pytest.mark.parametrize("maximization", [False, True])
+def test_pick_best_and_append_observation(maximization):
+    """The device-side tail of an iteration against its plain restatement: first-occurrence arg-max over the restarts and
+    the winning candidate (optimize_acqf's return); out-of-bounds penalty instead of the objective value, append to the
+    history, running best and its float32 rounding (PCA_BO.py:239-281, 199-203), packed record."""
+    ops = _ops()
+    rng = np.random.RandomState(3)
+    B, R, D, ld_n, n = 7, 10, 6, 12, 9
+    vals = rng.randn(B, R)
+    vals[1, 4] = vals[1, 7] = vals[1].max() + 1.0          # a tie: the first occurrence wins
+    vals[2, :] = -np.inf                                    # all equal
+    vals[3, 2] = np.nan                                     # NaNs are skipped (like pcabo_argmax)
+    cand = rng.randn(B, R, D)
+    out = ops.pick_best(torch.from_numpy(vals).cuda(), torch.from_numpy(cand).cuda())
+    idx = out["idx"].cpu().numpy()
+    ref_idx = np.array([int(np.nanargmax(np.where(np.isnan(v), -np.inf, v))) for v in vals])
+    assert np.array_equal(idx, ref_idx) and idx[1] == 4 and idx[2] == 0
+    assert np.array_equal(out["z"].cpu().numpy(), cand[np.arange(B), ref_idx])
+    assert np.array_equal(out["val"].cpu().numpy(), vals[np.arange(B), ref_idx])
+    X = torch.from_numpy(rng.randn(B, ld_n, D)).cuda()
+    f = torch.from_numpy(rng.randn(B, ld_n)).cuda()
+    X0, f0 = X.clone(), f.clone()
+    x_new, z_new, f_new, acq = rng.randn(B, D), rng.randn(B, D), 100.0 * rng.randn(B), rng.randn(B)
+    oob = np.array([0, 1, 0, 0, 1, 0, 0], dtype=np.int32)
+    best0 = 10.0 * rng.randn(B)
+    best = torch.from_numpy(best0.copy()).cuda()
+    best_f = torch.zeros(B, dtype=torch.float64, device="cuda")
+    rec = torch.zeros(B, 2 * D + 3, dtype=torch.float64, device="cuda")
+    pen = -1000.0 if maximization else 1000.0
+    ops.append_observation(X, f, n, torch.from_numpy(x_new).cuda(), torch.from_numpy(z_new).cuda(),
+                           torch.from_numpy(f_new).cuda(), torch.from_numpy(oob).cuda(), torch.from_numpy(acq).cuda(),
+                           pen, maximization, best, best_f, rec)
+    fv = np.where(oob != 0, pen, f_new)
+    nb = np.maximum(best0, fv) if maximization else np.minimum(best0, fv)
+    assert np.array_equal(X[:, n].cpu().numpy(), x_new) and np.array_equal(f[:, n].cpu().numpy(), fv)
+    keep = [i for i in range(ld_n) if i != n]
+    assert torch.equal(X[:, keep], X0[:, keep]) and torch.equal(f[:, keep], f0[:, keep])
+    assert np.array_equal(best.cpu().numpy(), nb)
+    assert np.array_equal(best_f.cpu().numpy(), nb.astype(np.float32).astype(np.float64))
+    r = rec.cpu().numpy()
+    assert np.array_equal(r[:, :D], x_new) and np.array_equal(r[:, D:2 * D], z_new) and np.array_equal(r[:, 2 * D], fv)
+    assert np.array_equal(r[:, 2 * D + 1], oob.astype(np.float64)) and np.array_equal(r[:, 2 * D + 2], acq)
+    # vanilla BO: no reduced space and no bounds test (z = x, nothing is ever outside)
+    ops.append_observation(X, f, n + 1, torch.from_numpy(x_new).cuda(), None, torch.from_numpy(f_new).cuda(), None, None,
+                           pen, maximization, best, best_f, rec)
+    assert np.array_equal(f[:, n + 1].cpu().numpy(), f_new) and np.array_equal(rec.cpu().numpy()[:, D:2 * D], x_new)
+
+
 def test_errors_are_loud():
     """The product path refuses CPU tensors and wrong dtypes instead of falling back."""
     ops = _ops()
