@@ -227,6 +227,8 @@ int pcabo_ei_sweep(const pcabo_gp_model *m, int run, long long ncand, long long 
  * caller then scores with pcabo_logei, which has no such limits.                                                     */
 int pcabo_logei_raw_runs(const pcabo_gp_model *m, int npts, const double *X, double *val, int ctas_per_run,
                          void *stream);
+/* Host only: 1 if pcabo_logei_raw_runs supports a model of this shape (n, kmax, ld_n, acq), else 0. */
+int pcabo_logei_raw_supported(int n, int kmax, int ld_n, int acq);
 
 /* Scrambled Sobol raw samples scaled to the search box, generated on the device from host-drawn scramble bits
  * (replaces botorch draw_sobol_samples / torch SobolEngine(k, scramble=True).draw(npts, float64) inside optimize_acqf,

@@ -653,6 +653,14 @@ extern "C" int pcabo_ei_sweep(const pcabo_gp_model *m, int run, long long ncand,
   return PCABO_OK;
 }
 
+// Host-only: 1 when pcabo_logei_raw_runs covers a model of this shape (the tile pipeline keeps n x 32 accumulators in
+// registers and stages candidates, K* panels and per-warp W tiles in shared memory), 0 otherwise.
+extern "C" int pcabo_logei_raw_supported(int n, int kmax, int ld_n, int acq) {
+  if (acq != PCABO_ACQ_LOG_EI) return 0;
+  if (n > 8 * NWARP * RT_MAX || n < 2 || ld_n < n || (ld_n & 1) || (kmax & 1) || kmax < 2 || kmax > 104) return 0;
+  return sweep_smem_bytes(n, kmax) <= 227 * 1024 ? 1 : 0;
+}
+
 // Multi-run form of the sweep: the raw-sample scoring pass of optimize_acqf (PCA_BO.py:607-614; 512 scrambled-Sobol
 // points per run) for ALL runs of the batch in one launch, values out, no arg-max. Each run gets a row of `ctas_per_run`
 // CTAs that share its candidate tiles (32 candidates each).

@@ -10,7 +10,7 @@ EXPORTED_SYMBOLS = [
     "pcabo_weights_pca_fit", "pcabo_inverse_map", "pcabo_gp_fit", "pcabo_gp_fit_jitter", "pcabo_gp_fit_hyper", "pcabo_gp_mll_grad_hyper", "pcabo_gp_pack_w",
     "pcabo_gp_packed_doubles", "pcabo_gp_mll", "pcabo_gp_mll_grad",
     "pcabo_logei", "pcabo_argmax", "pcabo_lbfgsb_logei", "pcabo_lbfgsb_logei_prof", "pcabo_lbfgsb_logei_runs", "pcabo_lbfgsb_logei_runs_ws",
-    "pcabo_lbfgsb_workspace_doubles", "pcabo_lbfgsb_plan", "pcabo_ei_sweep", "pcabo_logei_raw_runs", "pcabo_pick_best", "pcabo_append_observation",
+    "pcabo_lbfgsb_workspace_doubles", "pcabo_lbfgsb_plan", "pcabo_ei_sweep", "pcabo_logei_raw_runs", "pcabo_logei_raw_supported", "pcabo_pick_best", "pcabo_append_observation",
     "pcabo_sobol_points", "pcabo_sobol_scramble_bits", "pcabo_gather_rows", "pcabo_bbob_eval", "pcabo_bbob_eval_aux", "pcabo_select_initial_conditions",
 ]
 
@@ -95,6 +95,8 @@ def load_library(build_if_missing: bool = False):
     lib.pcabo_ei_sweep.restype = ci
     lib.pcabo_ei_sweep.argtypes = [ctypes.POINTER(GpModelStruct), ci, ctypes.c_longlong, ctypes.c_longlong] + [vp] * 8 + \
                                   [ci, vp, vp, vp]
+    lib.pcabo_logei_raw_supported.restype = ci
+    lib.pcabo_logei_raw_supported.argtypes = [ci, ci, ci, ci]
     lib.pcabo_logei_raw_runs.restype = ci
     lib.pcabo_logei_raw_runs.argtypes = [ctypes.POINTER(GpModelStruct), ci, vp, vp, ci, vp]
     lib.pcabo_pick_best.restype = ci

@@ -219,9 +219,9 @@ def logei(buf: GPBuffers, X, want_grad=False, want_posterior=False, out=None):
 
 def logei_raw_supported(buf: GPBuffers, n=None) -> bool:
     """True when pcabo_logei_raw_runs (the tensor-core tile pipeline) covers this model: log-EI, n <= 512, even row
-    capacity and column capacity."""
+    capacity and column capacity, shared memory of the pipeline within 227 KB (the library decides)."""
     n = buf.n if n is None else n
-    return buf.acq == ACQ_LOG_EI and 2 <= n <= 512 and buf.ld_n % 2 == 0 and buf.kmax % 2 == 0 and buf.kmax <= 104
+    return bool(load_library().pcabo_logei_raw_supported(int(n), int(buf.kmax), int(buf.ld_n), int(buf.acq)))
 
 
 def logei_raw(buf: GPBuffers, X, out=None, ctas_per_run=0):

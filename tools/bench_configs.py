@@ -16,6 +16,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "para-ortho-pca-bo_b200"))
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import torch
 
 
@@ -42,25 +43,46 @@ def measure(name, fids, insts, D, algorithm, optimizer, steps, warmup=2, n_start
     return out
 
 
-def whole_c5(fids, insts, D=100):
-    """The whole C5 run on one GPU with the device optimiser: 150 runs x 750 BO iterations, n = 300 -> 1050."""
+def whole_c5(fids, insts, D=100, S=1):
+    """The whole C5 run on one GPU with the device optimiser: 150 runs x 750 BO iterations, n = 300 -> 1050. S > 1: the
+    runs advance as S sub-batches (PipelinedEngines: asynchronous tail, event-driven schedule)."""
     from pcabo_b200.bbob import BatchedBBOB
-    from pcabo_b200.engine import BatchedBOEngine
-    prob = BatchedBBOB(fids, insts, D, device="cuda")
+    from pcabo_b200.engine import BatchedBOEngine, PipelinedEngines
     budget, ndoe = 10 * D + 50, 3 * D
-    eng = BatchedBOEngine(prob, D, prob.bounds, budget, ndoe, [1000 * f + 10 * D + i for f, i in zip(fids, insts)],
-                          algorithm="pca", optimizer="device")
+    subs = []
+    for s_ in range(S):
+        sel = list(range(s_, len(fids), S))
+        prob = BatchedBBOB([fids[i] for i in sel], [insts[i] for i in sel], D, device="cuda")
+        subs.append(BatchedBOEngine(prob, D, prob.bounds, budget, ndoe,
+                                    [1000 * fids[i] + 10 * D + insts[i] for i in sel], algorithm="pca", optimizer="device"))
+    eng = subs[0] if S == 1 else PipelinedEngines(subs)
     eng.initial_design()
     torch.cuda.synchronize()
     marks, t0 = [], time.perf_counter()
     total = budget - ndoe
-    for s_ in range(total):
-        eng.step()
-        if (s_ + 1) % (total // 4) == 0 or s_ + 1 == total:
+    if S == 1:
+        for s_ in range(total):
+            eng.step()
+            if (s_ + 1) % (total // 4) == 0 or s_ + 1 == total:
+                torch.cuda.synchronize()
+                marks.append((eng.n, time.perf_counter() - t0))
+    else:
+        done = 0
+        while done < total:
+            q = min(total // 4, total - done)
+            eng.run_steps(q)
+            done += q
             torch.cuda.synchronize()
             marks.append((eng.n, time.perf_counter() - t0))
+
+    class _All:      # the view of all runs the summary below needs
+        B = len(fids)
+        stats = eng.stats
+        k_host = __import__("numpy").concatenate([e.k_host for e in subs])
+        current_best = [v for e in subs for v in e.current_best]
+    eng = _All
     k = eng.k_host if getattr(eng, "k_host", None) is not None else None
-    out = {"config": "C5 whole run", "optimizer": "device", "runs": eng.B, "dim": D, "bo_iterations": eng.B * total,
+    out = {"config": "C5 whole run", "optimizer": "device", "sub_batches": S, "runs": eng.B, "dim": D, "bo_iterations": eng.B * total,
            "seconds": marks[-1][1], "iterations_per_s": eng.B * total / marks[-1][1],
            "by_quarter": [{"n_end": n, "iterations_per_s": eng.B * (total // 4) / (t - (marks[i - 1][1] if i else 0.0))}
                           for i, (n, t) in enumerate(marks[:4])],
@@ -76,6 +98,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--only", default="")
     ap.add_argument("--whole-c5", action="store_true")
+    ap.add_argument("--sub-batches", type=int, default=1, help="--whole-c5: sub-batches (PipelinedEngines)")
+    ap.add_argument("--skip-short", action="store_true", help="--whole-c5 only, without the short C5 measurements")
     a = ap.parse_args()
     want = set(a.only.split(",")) if a.only else None
     if not want or "C1" in want:
@@ -89,13 +113,14 @@ def main():
     if not want or "C5" in want:
         fids = [f for f in (20, 21, 22, 23, 24) for _ in range(30)]
         insts = [i for _ in range(5) for i in range(30)]
-        measure("C5", fids, insts, 100, "pca", "scipy", max(2, a.steps // 2), warmup=1)
-        try:
-            measure("C5", fids, insts, 100, "pca", "device", max(2, a.steps // 2), warmup=1)
-        except Exception as e:
-            print(json.dumps({"config": "C5", "optimizer": "device", "error": str(e)}), flush=True)
+        if not a.skip_short:
+            measure("C5", fids, insts, 100, "pca", "scipy", max(2, a.steps // 2), warmup=1)
+            try:
+                measure("C5", fids, insts, 100, "pca", "device", max(2, a.steps // 2), warmup=1)
+            except Exception as e:
+                print(json.dumps({"config": "C5", "optimizer": "device", "error": str(e)}), flush=True)
         if a.whole_c5:
-            whole_c5(fids, insts)
+            whole_c5(fids, insts, S=a.sub_batches)
 
 
 if __name__ == "__main__":
