@@ -645,7 +645,8 @@ class BatchedBOEngine:
         if self.overlap_hook is not None:        # host work that does not depend on the result runs under the kernel
             hook, self.overlap_hook = self.overlap_hook, None
             hook()
-        return dict(out=out, sel=sel, ev=ev, done=done, k_host=k_host)
+        # (run_idx stays referenced until the launch has been collected: it may have been used on the side stream)
+        return dict(out=out, sel=sel, ev=ev, done=done, k_host=k_host, run_idx=run_idx)
 
     def _finish_device(self, h):
         """Wait for the optimiser kernel of `h`. Returns (the output dict with the device tensor of clamped candidates
