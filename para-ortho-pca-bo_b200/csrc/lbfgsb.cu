@@ -117,6 +117,10 @@ struct Mailbox {
 // The L-BFGS-B "team" on the device is ONE warp: reductions are shuffles, sync is __syncwarp (no block barriers).
 struct CudaWarpTeam {
   static constexpr bool kWarpRegs = true;
+  // warp 1 computes cmprlb and the first products of subsm while warp 0 factors K (they only need the Cauchy point and the
+  // factor of T): a named barrier of the two warps joins them (6.6 k + 3 k cycles hidden behind the 11 k of the Cholesky)
+  static constexpr bool kAsyncHelper = true;
+  __device__ void join_helper() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
   int tid, nt, lane, nl;
   bool w0;
   Mailbox *mb;
@@ -290,8 +294,18 @@ __global__ void __launch_bounds__(lbeval::NT_ALL, 1) lbfgsb_logei_kernel(LbArgs 
         if (c == CMD_EVAL) {
           obj.run(w.x, w.g);
         } else if (c == CMD_FORMK) {
-          formk_products_block(w, mb->col, mb->theta);
+          const int fcol = mb->col;
+          const double ftheta = mb->theta;
+          formk_products_block(w, fcol, ftheta);
           lbeval::cta_sync();
+          if (tid < 64) {   // warp 1: the helper team (see CudaWarpTeam::kAsyncHelper)
+            CudaWarpTeam th;
+            th.tid = tid - 32; th.nt = 32; th.lane = tid - 32; th.nl = 32; th.w0 = true; th.mb = mb; th.wk = &w;
+            th.prof = nullptr; th.red = tred + 720; th.last = 0;
+            lbfgsb::cmprlb(th, w, fcol, ftheta);
+            lbfgsb::subsm_products(th, w, fcol, ftheta);
+            th.join_helper();
+          }
         } else if (c == CMD_SHIFT) {
           shift_pairs_block(w);
           lbeval::cta_sync();

@@ -44,6 +44,10 @@ struct HostTeam {
   static constexpr int tid = 0, nt = 1, lane = 0, nl = 1;
   static constexpr bool w0 = true;
   static constexpr bool kWarpRegs = false;   // true: the team is one CUDA warp with register/shuffle small-matrix kernels
+  // true: a helper team computes cmprlb and the first products of subsm WHILE this team factors K in formk (they do not
+  // depend on the factor); the team then only joins the helper (join_helper) instead of running them itself
+  static constexpr bool kAsyncHelper = false;
+  void join_helper() {}
   void sync() {}
   void wsync() {}
   double sum(double v) { return v; }
@@ -595,8 +599,9 @@ LB_PHASE void cmprlb(T &tm, Work &w, int col, double theta) {
 
 // Subspace minimisation with the projected (Morales-Nocedal) safeguard. On entry w.z = xcp, w.r = reduced gradient;
 // on exit w.z holds the subspace minimiser. xk = w.x, gk = w.g.
+// wv = (Y'Z r, theta S'Z r): the right-hand side of the subspace system (does not need the factor of K)
 template <class T>
-LB_PHASE void subsm(T &tm, Work &w, int col, double theta) {
+LB_PHASE void subsm_products(T &tm, Work &w, int col, double theta) {
   const int n = w.n;
   double part[M2];
 #ifdef __CUDA_ARCH__
@@ -618,6 +623,12 @@ LB_PHASE void subsm(T &tm, Work &w, int col, double theta) {
       for (int j = 0; j < col; ++j) { w.wv[j] = S[j]; w.wv[col + j] = theta * S[M + j]; }
   }
   tm.sync();
+}
+
+template <class T>
+LB_PHASE void subsm(T &tm, Work &w, int col, double theta) {
+  const int n = w.n;
+  if constexpr (!T::kAsyncHelper) subsm_products(tm, w, col, theta);
   // wv <- K^-1 wv through the LEL^T factor
 #ifdef __CUDA_ARCH__
   if constexpr (T::kWarpRegs) {
@@ -941,12 +952,13 @@ LB_HD Result minimize(T &tm, Work &w, Fn &fn, int maxiter, double factr, double 
       const int nfree = (int)(tm.sum(nfree_l) + 0.5);
       if (nfree != 0 && col != 0) {
         const int info = formk(tm, w, col, theta, flag);
+        if constexpr (T::kAsyncHelper) tm.join_helper();   // cmprlb + subsm_products were computed meanwhile
         if (info != 0) {  // refresh the memory and restart the iteration
           col = 0; theta = 1.0; updatd = false;
           continue;
         }
         tm.tick(2);
-        cmprlb(tm, w, col, theta);
+        if constexpr (!T::kAsyncHelper) cmprlb(tm, w, col, theta);
         tm.tick(3);
         subsm(tm, w, col, theta);
         tm.tick(4);
