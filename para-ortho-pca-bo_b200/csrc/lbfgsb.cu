@@ -19,7 +19,7 @@ namespace {
 
 constexpr int LB_THREADS = lbeval::NT;
 
-enum Cmd { CMD_EVAL = 1, CMD_FORMK = 2, CMD_EXIT = 3, CMD_SHIFT = 4 };
+enum Cmd { CMD_EVAL = 1, CMD_FORMK = 2, CMD_EXIT = 3, CMD_SHIFT = 4, CMD_CAUCHY1 = 5 };
 
 // Raw inner products of formk (see lbfgsb::formk_products_range for the layout) by the whole block. 8 lanes share one
 // ROW of a block of the matrix (k = seg, seg + 8, ...): rows 0..col-1 of Y'ZZ'Y (entries j >= i), of S'AA'S (j >= i) and
@@ -121,6 +121,11 @@ struct CudaWarpTeam {
   // factor of T): a named barrier of the two warps joins them (6.6 k + 3 k cycles hidden behind the 11 k of the Cholesky)
   static constexpr bool kAsyncHelper = true;
   __device__ void join_helper() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
+  // wakes the block; warp 1 runs lbfgsb::cauchy_pass1 for the next iteration and joins at the end of update_pairs
+  __device__ void start_cauchy_pass1(const lbfgsb::Work &, int col, double theta) {
+    if (lane == 0) { mb->cmd = CMD_CAUCHY1; mb->col = col; mb->theta = theta; }
+    lbeval::cta_sync();
+  }
   int tid, nt, lane, nl;
   bool w0;
   Mailbox *mb;
@@ -309,6 +314,18 @@ __global__ void __launch_bounds__(lbeval::NT_ALL, 1) lbfgsb_logei_kernel(LbArgs 
         } else if (c == CMD_SHIFT) {
           shift_pairs_block(w);
           lbeval::cta_sync();
+        } else if (c == CMD_CAUCHY1) {
+          if (tid < 64) {   // warp 1: first pass of the next Cauchy point while warp 0 forms and factors T
+            const int ccol = mb->col;
+            const double ctheta = mb->theta;
+            CudaWarpTeam th;
+            th.tid = tid - 32; th.nt = 32; th.lane = tid - 32; th.nl = 32; th.w0 = true; th.mb = mb; th.wk = &w;
+            th.prof = nullptr; th.red = tred + 720; th.last = 0;
+            double f1;
+            int nbreak;
+            lbfgsb::cauchy_pass1(th, w, ccol, ctheta, f1, nbreak);
+            th.join_helper();
+          }
         } else {
           break;
         }

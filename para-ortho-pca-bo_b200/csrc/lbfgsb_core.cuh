@@ -48,6 +48,7 @@ struct HostTeam {
   // depend on the factor); the team then only joins the helper (join_helper) instead of running them itself
   static constexpr bool kAsyncHelper = false;
   void join_helper() {}
+  void start_cauchy_pass1(const struct Work &, int, double) {}
   void sync() {}
   void wsync() {}
   double sum(double v) { return v; }
@@ -68,6 +69,7 @@ struct Work {
   double *wn;                                    // [M2][M2]
   double *p, *c, *wbp, *v, *wv;                  // [M2]
   double *tbrk;                                  // [n] breakpoints (negative: none / consumed)
+  double *pre;                                   // [2] f1 and the breakpoint count of a Cauchy first pass computed ahead
   int *iwhere;                                   // [n]
   // reciprocals kept next to the factors (warp-register path): 1/sy_kk, 1/sqrt(sy_kk), 1/diag(wt), 1/diag(wn)
   double *rsy, *rsq, *wt_rd, *wn_rd;
@@ -100,6 +102,7 @@ LB_HD inline void carve(Work &w, int n, double *base, double *pairs = nullptr) {
   w.wn = q; q += M2 * M2;
   w.p = q; q += M2; w.c = q; q += M2; w.wbp = q; q += M2; w.v = q; q += M2; w.wv = q; q += M2;
   w.tbrk = q; q += n;
+  w.pre = q; q += 2;     // (two of the four spare doubles of work_doubles)
   w.iwhere = reinterpret_cast<int *>(q);
 }
 
@@ -356,15 +359,13 @@ LB_HD double projgr(T &tm, const Work &w) {
 }
 
 // ------------------------------------------------------------------------------------------------ Cauchy point
+// First pass of the generalized Cauchy point: variable classification, breakpoints, d = -g on the free variables, z = x,
+// p = W'd and c = 0. Needs the stored pairs but NOT the factor of T, so on the device a helper warp runs it for the NEXT
+// iteration while the optimiser warp forms and factors T (update_pairs). f1 = -d'd and the number of breakpoints are
+// returned and left in w.pre.
 template <class T>
-LB_PHASE void cauchy(T &tm, Work &w, int col, double theta, double sbgnrm, int &nseg) {
+LB_PHASE void cauchy_pass1(T &tm, Work &w, int col, double theta, double &f1_out, int &nbreak_out) {
   const int n = w.n;
-  nseg = 0;
-  if (sbgnrm <= 0.0) {
-    for (int i = tm.tid; i < n; i += tm.nt) w.z[i] = w.x[i];
-    tm.sync();
-    return;
-  }
   double f1 = 0.0;
   double part[M2];
 #ifdef __CUDA_ARCH__
@@ -416,9 +417,29 @@ LB_PHASE void cauchy(T &tm, Work &w, int col, double theta, double sbgnrm, int &
     if (tm.tid == 0) {
       for (int j = 0; j < col; ++j) { w.p[j] = S[j]; w.p[col + j] = theta * S[M + j]; }
       for (int j = 0; j < 2 * col; ++j) w.c[j] = 0.0;
+      w.pre[0] = f1;
+      w.pre[1] = (double)nbreak;
     }
   }
   tm.sync();
+  f1_out = f1;
+  nbreak_out = nbreak;
+}
+
+// pass1_ready: cauchy_pass1 has been run for this iterate already (w.pre holds its two scalars)
+template <class T>
+LB_PHASE void cauchy(T &tm, Work &w, int col, double theta, double sbgnrm, int &nseg, bool pass1_ready = false) {
+  const int n = w.n;
+  nseg = 0;
+  if (sbgnrm <= 0.0) {
+    for (int i = tm.tid; i < n; i += tm.nt) w.z[i] = w.x[i];
+    tm.sync();
+    return;
+  }
+  double f1 = 0.0;
+  int nbreak = 0;
+  if (pass1_ready) { f1 = w.pre[0]; nbreak = (int)(w.pre[1] + 0.5); }
+  else cauchy_pass1(tm, w, col, theta, f1, nbreak);
   tm.tick(11);
   if (nbreak == 0) return;  // no variable can move: xcp = x (all boxed, so "nfree == n + 1" of the original holds)
   double f2 = -theta * f1;
@@ -883,6 +904,8 @@ LB_PHASE int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, do
   col = c + 1;
   tm.sync();
   tm.tick(14);
+  // the pairs are in place: the first pass of the NEXT iteration's Cauchy point can start (helper team, if there is one)
+  if constexpr (T::kAsyncHelper) tm.start_cauchy_pass1(w, col, theta);
   for (int k = tm.tid; k < col; k += tm.nt) { w.rsy[k] = 1.0 / w.sy[k * M + k]; w.rsq[k] = 1.0 / sqrt(w.sy[k * M + k]); }
   tm.sync();
   // formt: upper triangle of T
@@ -896,7 +919,11 @@ LB_PHASE int update_pairs(T &tm, Work &w, int &col, double &theta, double rr, do
   }
   tm.sync();
 #ifdef __CUDA_ARCH__
-  if constexpr (T::kWarpRegs) return dev::chol_upper_warp(w.wt, M, col, col, w.wt_rd) != 0 ? -3 : 0;
+  if constexpr (T::kWarpRegs) {
+    const int bad = dev::chol_upper_warp(w.wt, M, col, col, w.wt_rd);
+    if constexpr (T::kAsyncHelper) tm.join_helper();
+    return bad != 0 ? -3 : 0;
+  }
 #endif
   return chol_upper(tm, w.wt, M, col, flag) != 0 ? -3 : 0;
 }
@@ -934,6 +961,7 @@ LB_HD Result minimize(T &tm, Work &w, Fn &fn, int maxiter, double factr, double 
   int iter = 0;
   int passes = 0;
   bool first = true;
+  bool pass1_ready = false;   // the helper team ran cauchy_pass1 for the current iterate during update_pairs
   while (true) {
     double dtd = 0.0, stpmx = BIG, stp = 1.0, fold = f, gd = 0.0, gdold = 0.0;
     int ifun = 0, iback = 0;
@@ -944,7 +972,8 @@ LB_HD Result minimize(T &tm, Work &w, Fn &fn, int maxiter, double factr, double 
       if (++passes > 3 * maxiter + 20) { res.status = ABNORMAL; break; }
       int nseg;
       tm.tick(0);
-      cauchy(tm, w, col, theta, sbgnrm, nseg);
+      cauchy(tm, w, col, theta, sbgnrm, nseg, pass1_ready);
+      pass1_ready = false;
       tm.tick(1);
       // free variables at the Cauchy point
       double nfree_l = 0.0;
@@ -1060,6 +1089,7 @@ LB_HD Result minimize(T &tm, Work &w, Fn &fn, int maxiter, double factr, double 
     updatd = true;
     const int info = update_pairs(tm, w, col, theta, rr, dr, stp, dtd, flag);
     tm.tick(9);
+    pass1_ready = T::kAsyncHelper && info == 0;   // (a failed factorisation discards the memory: col and theta change)
     if (info != 0) { col = 0; theta = 1.0; updatd = false; }
   }
   res.f = f;
