@@ -414,44 +414,11 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     if (lc == 0) red[NW * PT + warp * 8 + lr] = v;
   }
-  cta_sync();
-  ev_tick(c, 17);
-  double *res = red + NW * PT + NW * 8;   // [2][PT]: d value / d mu_s, d value / d var_s
-  if (tid < PT) {
-    const int p = tid;
-    double ms = 0.0, v = 0.0;
-    for (int w8 = 0; w8 < NW; ++w8) ms += red[w8 * PT + p];
-    for (int w8 = 0; w8 < NW; ++w8) v += red[NW * PT + w8 * 8 + p];
-    // k(x*, x*) as gpytorch evaluates it: distance clamped to sqrt(1e-30)
-    const double d0 = 1e-15;
-    const double kss = (SQRT5 * d0 + 1.0 + (5.0 / 3.0) * (d0 * d0)) * exp(-SQRT5 * d0);
-    const double ystd = c.ystd;
-    const double mu = c.ymean + ystd * ms;
-    const double var_raw = ystd * ystd * (kss - v);
-    const bool clamped = !(var_raw >= 1e-10);
-    const double var = clamped ? 1e-10 : var_raw;
-    const double sg = sqrt(var);
-    const double u = c.sgn * (mu - c.best_f) / sg;
-    double value, dmu, dvar;
-    if (c.acq == PCABO_ACQ_PI) {
-      value = 0.5 * erfc(-logei::INV_SQRT2 * u);
-      const double phi = logei::INV_SQRT_2PI * exp(-0.5 * u * u);
-      dmu = phi * c.sgn * ystd / sg;
-      dvar = clamped ? 0.0 : -phi * u * ystd * ystd / (2.0 * var);
-    } else {
-      double lh, dlh;
-      logei::log_h_and_grad(u, lh, dlh);
-      value = lh + log(sg);
-      dmu = dlh * c.sgn * ystd / sg;
-      dvar = clamped ? 0.0 : (1.0 - u * dlh) * ystd * ystd / (2.0 * var);
-    }
-    if (p < pcount) val[p] = value;
-    res[p] = dmu;
-    res[PT + p] = dvar;
-  }
-  cta_sync();
-  ev_tick(c, 22);
-  // ---- gradient coefficients straight from the accumulators: c_j = gf_j (dmu alpha_j - 2 dvar s_j), over the k vector
+  // ---- the gradient is linear in the two head results (d value / d mu_s, d value / d var_s):
+  //          grad_j = A sum_i gf_i alpha_i (xn_j - zn_ij) - 2 B sum_i gf_i s_i (xn_j - zn_ij),
+  //      so its two sums do not wait for the head (erfc / erfcx / log chains of five lanes, ~4 k cycles): the factors
+  //      gf alpha and gf s go over the k vector and gf straight from the accumulators, then warp 0 evaluates the head WHILE
+  //      warps 1..7 accumulate the two sums; they meet at the barrier before the partials are combined.
 #pragma unroll
   for (int ti = 0; ti < TI; ++ti) {
     const int j = (warp + NW * ti) * 8 + lr;
@@ -460,48 +427,99 @@ __device__ void eval(Ctx &c, int pcount, const double *X, double *val, double *g
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int p = 2 * lc + h;
-        if (p < PT) kst[p * S + j] = gf[p * S + j] * (res[p] * al - 2.0 * res[PT + p] * sf[ti][h]);
+        if (p < PT) {
+          const double g0 = gf[p * S + j];
+          kst[p * S + j] = g0 * al;
+          gf[p * S + j] = g0 * sf[ti][h];
+        }
       }
     }
   }
   cta_sync();
+  ev_tick(c, 17);
+  double *res = red + NW * PT + NW * 8;   // [2][PT]: d value / d mu_s, d value / d var_s
+  constexpr int NTG = NT - 32;            // threads of the gradient sums (warps 1..7)
+  const int IG = NTG / kk;                // >= 2 for kk <= 104
+  const int gt = tid - 32, ig = gt / kk, j = gt % kk;
+  double acc1[PT], acc2[PT];
+#pragma unroll
+  for (int p = 0; p < PT; ++p) { acc1[p] = 0.0; acc2[p] = 0.0; }
+  if (warp == 0) {
+    if (tid < PT) {
+      const int p = tid;
+      double ms = 0.0, v = 0.0;
+      for (int w8 = 0; w8 < NW; ++w8) ms += red[w8 * PT + p];
+      for (int w8 = 0; w8 < NW; ++w8) v += red[NW * PT + w8 * 8 + p];
+      // k(x*, x*) as gpytorch evaluates it: distance clamped to sqrt(1e-30)
+      const double d0 = 1e-15;
+      const double kss = (SQRT5 * d0 + 1.0 + (5.0 / 3.0) * (d0 * d0)) * exp(-SQRT5 * d0);
+      const double ystd = c.ystd;
+      const double mu = c.ymean + ystd * ms;
+      const double var_raw = ystd * ystd * (kss - v);
+      const bool clamped = !(var_raw >= 1e-10);
+      const double var = clamped ? 1e-10 : var_raw;
+      const double sg = sqrt(var);
+      const double u = c.sgn * (mu - c.best_f) / sg;
+      double value, dmu, dvar;
+      if (c.acq == PCABO_ACQ_PI) {
+        value = 0.5 * erfc(-logei::INV_SQRT2 * u);
+        const double phi = logei::INV_SQRT_2PI * exp(-0.5 * u * u);
+        dmu = phi * c.sgn * ystd / sg;
+        dvar = clamped ? 0.0 : -phi * u * ystd * ystd / (2.0 * var);
+      } else {
+        double lh, dlh;
+        logei::log_h_and_grad(u, lh, dlh);
+        value = lh + log(sg);
+        dmu = dlh * c.sgn * ystd / sg;
+        dvar = clamped ? 0.0 : (1.0 - u * dlh) * ystd * ystd / (2.0 * var);
+      }
+      if (p < pcount) val[p] = value;
+      res[p] = dmu;
+      res[PT + p] = dvar;
+    }
+  } else if (ig < IG) {
+    // thread (ig, j) of warps 1..7: every IG-th training point
+    double xj[PT];
+#pragma unroll
+    for (int p = 0; p < PT; ++p) xj[p] = xn[p * kmax + j];
+    int i = ig;
+    for (; i + 7 * IG < n; i += 8 * IG) {
+      double z8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) z8[u] = c.Zn[(size_t)(i + u * IG) * kmax + j];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int p = 0; p < PT; ++p) {
+          const double dz = xj[p] - z8[u];
+          acc1[p] = fma(kst[p * S + i + u * IG], dz, acc1[p]);
+          acc2[p] = fma(gf[p * S + i + u * IG], dz, acc2[p]);
+        }
+    }
+    for (; i < n; i += IG) {
+      const double z = c.Zn[(size_t)i * kmax + j];
+#pragma unroll
+      for (int p = 0; p < PT; ++p) {
+        const double dz = xj[p] - z;
+        acc1[p] = fma(kst[p * S + i], dz, acc1[p]);
+        acc2[p] = fma(gf[p * S + i], dz, acc2[p]);
+      }
+    }
+  }
+  cta_sync();
+  ev_tick(c, 22);
+  // ---- combine with the head results: partial of grad[p][j] over this thread's training points
+  if (warp != 0 && ig < IG) {
+#pragma unroll
+    for (int p = 0; p < PT; ++p) part[(ig * PT + p) * kk + j] = res[p] * acc1[p] - 2.0 * res[PT + p] * acc2[p];
+  }
+  cta_sync();
   ev_tick(c, 19);
-  // ---- grad[p][j] = gscale (1 / coef_j) sum_i c_i (xn_j - zn_ij): thread (ig, j), every IG-th training point
-  {
-    const int IG = NT / kk;   // >= 2 for kk <= 104
-    const int ig = tid / kk, j = tid % kk;
-    double acc[PT];
-#pragma unroll
-    for (int p = 0; p < PT; ++p) acc[p] = 0.0;
-    if (ig < IG) {
-      double xj[PT];
-#pragma unroll
-      for (int p = 0; p < PT; ++p) xj[p] = xn[p * kmax + j];
-      int i = ig;
-      for (; i + 7 * IG < n; i += 8 * IG) {
-        double z8[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) z8[u] = c.Zn[(size_t)(i + u * IG) * kmax + j];
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-#pragma unroll
-          for (int p = 0; p < PT; ++p) acc[p] = fma(kst[p * S + i + u * IG], xj[p] - z8[u], acc[p]);
-      }
-      for (; i < n; i += IG) {
-        const double z = c.Zn[(size_t)i * kmax + j];
-#pragma unroll
-        for (int p = 0; p < PT; ++p) acc[p] = fma(kst[p * S + i], xj[p] - z, acc[p]);
-      }
-#pragma unroll
-      for (int p = 0; p < PT; ++p) part[(ig * PT + p) * kk + j] = acc[p];
-    }
-    cta_sync();
-    for (int idx = tid; idx < pcount * kk; idx += NT) {
-      const int p = idx / kk, jj = idx % kk;
-      double sv = 0.0;
-      for (int q = 0; q < IG; ++q) sv += part[(q * PT + p) * kk + jj];
-      grad[idx] = gscale * sv / c.coef[jj];
-    }
+  for (int idx = tid; idx < pcount * kk; idx += NT) {
+    const int p = idx / kk, jj = idx % kk;
+    double sv = 0.0;
+    for (int q = 0; q < IG; ++q) sv += part[(q * PT + p) * kk + jj];
+    grad[idx] = gscale * sv / c.coef[jj];
   }
   cta_sync();
   ev_tick(c, 20);
