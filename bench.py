@@ -324,7 +324,9 @@ def ncu_traffic():
     """DRAM bytes per launch of the optimiser kernel from the committed ncu capture (profiles/, one `ncu --set full`
     launch; a number taken under a profiler is only quoted, never timed): traffic far below the algorithmic bytes says
     the kernel is served from shared memory / L2."""
-    path = os.path.join(ROOT, "profiles", "r02_lbfgsb_ncu_raw_summary.csv")
+    name = next((f for f in ("r02b_lbfgsb_ncu_raw_summary.csv", "r02_lbfgsb_ncu_raw_summary.csv")
+                 if os.path.exists(os.path.join(ROOT, "profiles", f))), "r02b_lbfgsb_ncu_raw_summary.csv")
+    path = os.path.join(ROOT, "profiles", name)
     try:
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         tot, head = 0.0, ""
@@ -335,7 +337,7 @@ def ncu_traffic():
                 _, unit, val = line.strip().split(",")
                 tot += float(val) * scale[unit]
         return {"traffic": tot, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, " + head +
-                                                " (profiles/r02_lbfgsb_ncu_raw_summary.csv)"}
+                                                " (90 runs in the launch; profiles/" + name + ")"}
     except Exception:
         return {"traffic": None, "traffic_note": "no committed ncu capture found under profiles/"}
 
