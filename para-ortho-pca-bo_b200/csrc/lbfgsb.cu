@@ -123,12 +123,15 @@ struct CudaWarpTeam {
   __device__ void join_helper() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
   // wakes the block; warp 1 runs lbfgsb::cauchy_pass1 for the next iteration and joins at the end of update_pairs
   __device__ void start_cauchy_pass1(const lbfgsb::Work &, int col, double theta) {
-    if (lane == 0) { mb->cmd = CMD_CAUCHY1; mb->col = col; mb->theta = theta; }
+    Mailbox *m = post_slot();
+    if (lane == 0) { m->cmd = CMD_CAUCHY1; m->col = col; m->theta = theta; }
     lbeval::cta_sync();
   }
   int tid, nt, lane, nl;
   bool w0;
-  Mailbox *mb;
+  Mailbox *mb;          // TWO entries used alternately: a command is never overwritten while a warp may still be reading it
+  int par;              // entry of the next command (every warp of the block counts the command rounds the same way)
+  __device__ Mailbox *post_slot() { Mailbox *m = mb + par; par ^= 1; return m; }
   const lbfgsb::Work *wk;
   long long *prof;      // optional [16] cycle counters of this block (lane 0), or nullptr
   double *red;          // shared-memory scratch of sum_n: [20][33] + [20]
@@ -172,7 +175,8 @@ struct CudaWarpTeam {
   }
   __device__ void formk_products(const lbfgsb::Work &w, int col, double theta) {
     tick(23);
-    if (lane == 0) { mb->cmd = CMD_FORMK; mb->col = col; mb->theta = theta; }
+    Mailbox *m = post_slot();
+    if (lane == 0) { m->cmd = CMD_FORMK; m->col = col; m->theta = theta; }
     lbeval::cta_sync();
     tick(24);
     formk_products_block(w, col, theta);
@@ -181,7 +185,8 @@ struct CudaWarpTeam {
     tick(26);
   }
   __device__ void shift_pairs(const lbfgsb::Work &w) {
-    if (lane == 0) mb->cmd = CMD_SHIFT;
+    Mailbox *m = post_slot();
+    if (lane == 0) m->cmd = CMD_SHIFT;
     lbeval::cta_sync();
     shift_pairs_block(w);
     lbeval::cta_sync();
@@ -195,7 +200,8 @@ struct LogEiObjective {
   double *vals;  // smem [8]
   // called by warp 0 (the team); posts the evaluation to the whole block
   __device__ double operator()(CudaWarpTeam &tm, const double *x, double *g) {
-    if (tm.lane == 0) tm.mb->cmd = CMD_EVAL;
+    Mailbox *m = tm.post_slot();
+    if (tm.lane == 0) m->cmd = CMD_EVAL;
     lbeval::cta_sync();
     return run(x, g);
   }
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(lbeval::NT_ALL, 1) lbfgsb_logei_kernel(LbArgs 
   double *wsy = PG ? a.wsy + ((size_t)blockIdx.y * nchunks + chunk) * (size_t)(2 * lbfgsb::M) * lbfgsb::pair_stride(a.nvar_max) : nullptr;
   lbfgsb::carve<PG>(w, nvar, q, wsy);   // PG: the BFGS pairs live in the caller's workspace (global memory)
   q += lbfgsb::work_doubles(nvar, PG);
-  Mailbox *mb = reinterpret_cast<Mailbox *>(q); q += 2;
+  Mailbox *mb = reinterpret_cast<Mailbox *>(q); q += 4;   // two entries
   obj.vals = q; q += 8;
   int *flag = reinterpret_cast<int *>(q); q += 2;
   long long *sprof = reinterpret_cast<long long *>(q); q += 32;   // cycle counters live in shared memory, flushed at the end
@@ -285,27 +291,33 @@ __global__ void __launch_bounds__(lbeval::NT_ALL, 1) lbfgsb_logei_kernel(LbArgs 
     lbeval::cta_sync();
     if (tid < 32) {
       CudaWarpTeam tm;
-      tm.tid = tid; tm.nt = 32; tm.lane = tid; tm.nl = 32; tm.w0 = true; tm.mb = mb; tm.wk = &w;
+      tm.tid = tid; tm.nt = 32; tm.lane = tid; tm.nl = 32; tm.w0 = true; tm.mb = mb; tm.par = 0; tm.wk = &w;
       tm.prof = a.prof ? sprof : nullptr;
       tm.red = tred;
       tm.last = clock64();
       r = lbfgsb::minimize(tm, w, obj, a.maxiter, a.factr, a.pgtol, flag);
-      if (tid == 0) { mb->cmd = CMD_EXIT; lbeval::signal_exit(obj.ctx); }
+      {
+        Mailbox *m = tm.post_slot();
+        if (tid == 0) { m->cmd = CMD_EXIT; lbeval::signal_exit(obj.ctx); }
+      }
       lbeval::cta_sync();
     } else {
+      int par = 0;
       for (;;) {
         lbeval::cta_sync();
-        const int c = mb->cmd;
+        const Mailbox *cm = mb + par;
+        par ^= 1;
+        const int c = cm->cmd;
         if (c == CMD_EVAL) {
           obj.run(w.x, w.g);
         } else if (c == CMD_FORMK) {
-          const int fcol = mb->col;
-          const double ftheta = mb->theta;
+          const int fcol = cm->col;
+          const double ftheta = cm->theta;
           formk_products_block(w, fcol, ftheta);
           lbeval::cta_sync();
           if (tid < 64) {   // warp 1: the helper team (see CudaWarpTeam::kAsyncHelper)
             CudaWarpTeam th;
-            th.tid = tid - 32; th.nt = 32; th.lane = tid - 32; th.nl = 32; th.w0 = true; th.mb = mb; th.wk = &w;
+            th.tid = tid - 32; th.nt = 32; th.lane = tid - 32; th.nl = 32; th.w0 = true; th.mb = mb; th.par = 0; th.wk = &w;
             th.prof = nullptr; th.red = tred + 720; th.last = 0;
             lbfgsb::cmprlb(th, w, fcol, ftheta);
             lbfgsb::subsm_products(th, w, fcol, ftheta);
@@ -316,10 +328,10 @@ __global__ void __launch_bounds__(lbeval::NT_ALL, 1) lbfgsb_logei_kernel(LbArgs 
           lbeval::cta_sync();
         } else if (c == CMD_CAUCHY1) {
           if (tid < 64) {   // warp 1: first pass of the next Cauchy point while warp 0 forms and factors T
-            const int ccol = mb->col;
-            const double ctheta = mb->theta;
+            const int ccol = cm->col;
+            const double ctheta = cm->theta;
             CudaWarpTeam th;
-            th.tid = tid - 32; th.nt = 32; th.lane = tid - 32; th.nl = 32; th.w0 = true; th.mb = mb; th.wk = &w;
+            th.tid = tid - 32; th.nt = 32; th.lane = tid - 32; th.nl = 32; th.w0 = true; th.mb = mb; th.par = 0; th.wk = &w;
             th.prof = nullptr; th.red = tred + 720; th.last = 0;
             double f1;
             int nbreak;
@@ -346,7 +358,7 @@ __global__ void __launch_bounds__(lbeval::NT_ALL, 1) lbfgsb_logei_kernel(LbArgs 
 }
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
-constexpr int TAIL_DOUBLES = 2 + 8 + 2 + 32 + 8;
+constexpr int TAIL_DOUBLES = 4 + 8 + 2 + 32 + 8;   // mailbox (two entries), values, flag, cycle counters, slack
 
 // Shared-memory plan of one launch: panel height, ring capacity, where the BFGS pairs live.
 struct Plan {
