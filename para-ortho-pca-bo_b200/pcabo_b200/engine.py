@@ -902,6 +902,53 @@ class BatchedBOEngine:
         return self
 
 
+def schedule_sub_batches(items, k, context, pause=lambda: sleep(2e-5)):
+    """The event-driven schedule of PipelinedEngines.run_steps (pure host logic: the engines only have to offer
+    step_launch / step_begin / step_end / wait_event). items: [(engine, token)], `context(token)` a context manager entered
+    around every engine call (the sub-batch's CUDA stream), `pause()` what to do when nothing has completed. Every engine
+    gets exactly k iterations, each as A (step_launch) -> B (step_begin) -> E (step_end), B and E only once the event of
+    the phase before has completed -- unless nothing at all is ready, then the loop pauses and looks again. Returns the
+    seconds spent pausing."""
+    remaining = {id(e): k for e, _ in items}
+    a_wait, o_wait = [], []          # sub-batches with phase A / with the optimiser kernel in flight, oldest first
+    idle = 0.0
+    for item in items:
+        with context(item[1]):
+            item[0].step_launch()
+        a_wait.append(item)
+
+    def done(item):
+        ev = item[0].wait_event()
+        return ev is None or ev.query()
+
+    while a_wait or o_wait:
+        i = next((i for i, it in enumerate(a_wait) if done(it)), None)
+        if i is not None:
+            item = a_wait.pop(i)
+            with context(item[1]):
+                item[0].step_begin()
+            o_wait.append(item)
+            continue
+        i = next((i for i, it in enumerate(o_wait) if done(it)), None)
+        if i is not None:
+            item = o_wait.pop(i)
+            e = item[0]
+            with context(item[1]):
+                e.step_end()
+                remaining[id(e)] -= 1
+                if remaining[id(e)] > 0:
+                    e.step_launch()
+                    a_wait.append(item)
+            continue
+        # nothing has completed: poll (blocking on one particular event would leave a sub-batch that finishes earlier
+        # than that one unattended)
+        t0 = perf_counter()
+        while not any(done(it) for it in a_wait) and not any(done(it) for it in o_wait):
+            pause()
+        idle += perf_counter() - t0
+    return idle
+
+
 class PipelinedEngines:
     """S independent sub-batches of runs, each a BatchedBOEngine on its own CUDA stream, interleaved by ONE host thread.
 
@@ -941,47 +988,9 @@ class PipelinedEngines:
         finished, else block on the oldest outstanding event (a phase A before an optimiser kernel)."""
         if k <= 0:
             return
-        remaining = {id(e): k for e in self.engines}
-        a_wait, o_wait = [], []          # sub-batches with phase A / with the optimiser kernel in flight, oldest first
-        for e, st in zip(self.engines, self.streams):
-            with torch.cuda.stream(st):
-                e.step_launch()
-            a_wait.append((e, st))
 
-        def done(item):
-            ev = item[0].wait_event()
-            return ev is None or ev.query()
-
-        def phase_b(item):
-            e, st = item
-            with torch.cuda.stream(st):
-                e.step_begin()
-            o_wait.append(item)
-
-        def phase_ea(item):
-            e, st = item
-            with torch.cuda.stream(st):
-                e.step_end()
-                remaining[id(e)] -= 1
-                if remaining[id(e)] > 0:
-                    e.step_launch()
-                    a_wait.append(item)
-
-        while a_wait or o_wait:
-            i = next((i for i, it in enumerate(a_wait) if done(it)), None)
-            if i is not None:
-                phase_b(a_wait.pop(i))
-                continue
-            i = next((i for i, it in enumerate(o_wait) if done(it)), None)
-            if i is not None:
-                phase_ea(o_wait.pop(i))
-                continue
-            # nothing has completed: poll (blocking on one particular event would leave a sub-batch that finishes
-            # earlier than that one unattended)
-            t0 = perf_counter()
-            while not any(done(it) for it in a_wait) and not any(done(it) for it in o_wait):
-                sleep(2e-5)
-            self.idle_s += perf_counter() - t0
+        # (every call of a sub-batch runs with its own stream current)
+        self.idle_s += schedule_sub_batches(list(zip(self.engines, self.streams)), k, torch.cuda.stream)
         for st in self.streams:
             st.synchronize()
         for e in self.engines:

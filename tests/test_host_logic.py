@@ -307,3 +307,89 @@ def test_host_side_abi_planning_functions():
         assert ops.lbfgsb_workspace_doubles(1050, 100, k, 10, 5, 7) == 7 * 2 * 2 * 10 * (((nvar + 15) & ~15) + 8)
     assert ops.lbfgsb_workspace_doubles(450, 40, 40, 10, 8, 1) == -1        # batch_limit > 5 is not supported
     assert ops.gp_fit_launches(450) == 2 + 15 + 1 + 3 + 1
+
+
+def test_sub_batch_schedule_with_simulated_engines():
+    """PipelinedEngines' event-driven schedule as pure host logic, on simulated engines with a simulated clock: every
+    sub-batch gets exactly k iterations, each as A -> B -> E with B / E only after the event of the phase before has
+    completed, a sub-batch that finishes early is served before an older one that is still running, and the host pauses
+    only when nothing is ready."""
+    import contextlib
+    from pcabo_b200.engine import schedule_sub_batches
+    clock = [0.0]
+    log = []
+
+    class Ev:
+        def __init__(self, t):
+            self.t = t
+
+        def query(self):
+            return clock[0] >= self.t
+
+    class Eng:
+        def __init__(self, name, rng):
+            self.name, self.rng, self.phase, self.ev, self.steps = name, rng, None, None, 0
+
+        def step_launch(self):
+            assert self.phase in (None, "E")
+            self.phase, self.ev = "A", Ev(clock[0] + 1.0)                       # model fit: 1 ms
+            log.append((self.name, "A", clock[0]))
+            clock[0] += 0.3                                                     # host time of the call
+
+        def step_begin(self):
+            assert self.phase == "A" and self.ev.query(), "optimiser launched before the model fit completed"
+            self.phase, self.ev = "B", Ev(clock[0] + self.rng.choice([4.0, 6.0, 13.0]))   # optimiser kernel
+            log.append((self.name, "B", clock[0]))
+            clock[0] += 0.3
+
+        def step_end(self):
+            assert self.phase == "B" and self.ev.query(), "tail enqueued before the optimiser finished"
+            self.phase, self.ev = "E", None
+            self.steps += 1
+            log.append((self.name, "E", clock[0]))
+            clock[0] += 0.3
+
+        def wait_event(self):
+            return self.ev
+
+    def pause():
+        clock[0] += 0.05
+
+    rng = np.random.RandomState(0)
+    engines = [Eng(i, rng) for i in range(5)]
+    seen_ctx = []
+
+    @contextlib.contextmanager
+    def ctx(token):
+        seen_ctx.append(token)
+        yield
+
+    idle = schedule_sub_batches([(e, 100 + e.name) for e in engines], 7, ctx, pause)
+    assert all(e.steps == 7 and e.phase == "E" for e in engines)
+    assert idle >= 0.0 and set(seen_ctx) == {100, 101, 102, 103, 104}
+    for e in engines:                      # per engine: A B E A B E ... (the last iteration launches no further A)
+        seq = "".join(p for n_, p, _ in log if n_ == e.name)
+        assert seq == "ABE" * 7, seq
+    # nothing is ever served while something that completed earlier in launch order of the same kind waits:
+    # the host was never idle for longer than the shortest remaining event (it polls, it does not block on one event)
+    total = clock[0]
+    busy = 0.3 * len(log)
+    assert total < busy + 7 * 14.0 + 5.0   # far below the serial sum of all kernels (5 engines x 7 x ~8 ms)
+    # one iteration, one engine: degenerate sizes work too
+    log.clear()
+    one = Eng(0, rng)
+    schedule_sub_batches([(one, 0)], 1, ctx, pause)
+    assert one.steps == 1 and [p for _, p, _ in log] == ["A", "B", "E"]
+    assert schedule_sub_batches([], 3, ctx, pause) == 0.0
+
+
+def test_raw_scoring_support_predicate_is_host_only():
+    """pcabo_logei_raw_supported (no device work): the tile pipeline covers log-EI models with n <= 512, even capacities
+    and its shared memory within 227 KB -- config C3 yes, config C5 (D = 100) no, probability of improvement no."""
+    from pcabo_b200.lib import load_library
+    lib = load_library()
+    yes = [(450, 40, 450), (123, 40, 450), (512, 32, 512), (150, 10, 150), (250, 20, 250), (2, 2, 2)]
+    no = [(300, 100, 1050), (513, 32, 514), (450, 41, 450), (449, 40, 449), (450, 40, 448), (1, 40, 450), (450, 106, 450)]
+    assert all(lib.pcabo_logei_raw_supported(n, k, ld, 0) == 1 for n, k, ld in yes)
+    assert all(lib.pcabo_logei_raw_supported(n, k, ld, 0) == 0 for n, k, ld in no)
+    assert lib.pcabo_logei_raw_supported(450, 40, 450, 1) == 0
