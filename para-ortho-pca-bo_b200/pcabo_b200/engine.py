@@ -619,6 +619,7 @@ class BatchedBOEngine:
             full = ops.lbfgsb_workspace_doubles(self.n, self.D, self.D, self.num_restarts, self.batch_limit, B)
             self.lb_ws = torch.empty(max(need, full), dtype=torch.float64, device=self.device)
         side = self.opt_stream
+        done = None
         if side is not None:
             side.wait_stream(torch.cuda.current_stream())
             main = torch.cuda.current_stream()
@@ -641,7 +642,8 @@ class BatchedBOEngine:
         finally:
             if side is not None:
                 torch.cuda.set_stream(main)
-                main.wait_event(done)     # whatever follows on the sub-batch's own stream sees the candidates
+                if done is not None:
+                    main.wait_event(done)     # whatever follows on the sub-batch's own stream sees the candidates
         if self.overlap_hook is not None:        # host work that does not depend on the result runs under the kernel
             hook, self.overlap_hook = self.overlap_hook, None
             hook()
@@ -985,7 +987,7 @@ class PipelinedEngines:
         next iteration's model fit and raw-sample scoring) and B (read k / flags of phase A, launch the optimiser
         kernel). With the asynchronous tail none of them waits for the GPU, so the schedule is event driven: launch the
         optimiser of any sub-batch whose phase A has completed, else serve (E + A) any sub-batch whose optimiser has
-        finished, else block on the oldest outstanding event (a phase A before an optimiser kernel)."""
+        finished, else poll until one of the outstanding events completes (schedule_sub_batches)."""
         if k <= 0:
             return
 
